@@ -1,0 +1,339 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of oracle/liboracle.so and oracle/_ref/libikdtree_ref.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libikdtree_ref.so")
+
+
+class State18(C.Structure):
+    """flo_state18 (oracle/flo_oracle.h) == StatesGroup, reference include/common_lib.h:296-381."""
+    _fields_ = [("rot", C.c_double * 9), ("pos", C.c_double * 3), ("vel", C.c_double * 3),
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("grav", C.c_double * 3),
+                ("cov", C.c_double * 324)]
+
+    @classmethod
+    def make(cls, R, p, vel=None, bg=None, ba=None, grav=None, cov=None):
+        s = cls()
+        s.rot[:] = np.asarray(R, np.float64).ravel()
+        s.pos[:] = np.asarray(p, np.float64)
+        s.vel[:] = np.zeros(3) if vel is None else vel
+        s.bg[:] = np.zeros(3) if bg is None else bg
+        s.ba[:] = np.zeros(3) if ba is None else ba
+        s.grav[:] = np.zeros(3) if grav is None else grav
+        s.cov[:] = (np.eye(18) if cov is None else np.asarray(cov, np.float64)).ravel()
+        return s
+
+    def copy(self):
+        o = State18()
+        C.memmove(C.byref(o), C.byref(self), C.sizeof(State18))
+        return o
+
+    @property
+    def R(self):
+        return np.array(self.rot[:]).reshape(3, 3)
+
+    @property
+    def p(self):
+        return np.array(self.pos[:])
+
+    @property
+    def P(self):
+        return np.array(self.cov[:]).reshape(18, 18)
+
+    def vector(self):
+        """All 18 'coordinates' + rotation entries flattened (for tolerance comparisons)."""
+        return np.concatenate([self.rot[:], self.pos[:], self.vel[:], self.bg[:], self.ba[:], self.grav[:]])
+
+
+class LioParams(C.Structure):
+    _fields_ = [("R_LI", C.c_double * 9), ("t_LI", C.c_double * 3), ("laser_point_cov", C.c_double),
+                ("max_iteration", C.c_int), ("conv_rot_deg", C.c_double), ("conv_pos_cm", C.c_double),
+                ("nthreads", C.c_int)]
+
+
+class LioReport(C.Structure):
+    _fields_ = [("passes", C.c_int), ("knn_passes", C.c_int), ("n_eff_last", C.c_int),
+                ("res_mean_last", C.c_double), ("rows_total", C.c_int64), ("converged_last", C.c_int)]
+
+
+class Cam(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("d", C.c_double * 5)]
+
+
+class VioParams(C.Structure):
+    _fields_ = [("Rcl", C.c_double * 9), ("Pcl", C.c_double * 3), ("R_LI", C.c_double * 9),
+                ("t_LI", C.c_double * 3), ("img_point_cov", C.c_double), ("max_iteration", C.c_int),
+                ("conv_rot_deg", C.c_float), ("conv_pos_cm", C.c_float), ("force_all_passes", C.c_int)]
+
+
+class VioReport(C.Structure):
+    _fields_ = [("passes", C.c_int * 3), ("last_error", C.c_float * 3), ("rows_total", C.c_int64),
+                ("skipped_last", C.c_int), ("cov_updated", C.c_int)]
+
+
+KNN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+
+
+def build(force: bool = False) -> None:
+    """Compile the checker (and, when /root/reference is present, the reference ikd-Tree)."""
+    need = force or not os.path.exists(_LIB) or \
+        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_oracle.h"))
+    if need:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    if os.path.isdir("/root/reference/include/ikd-Tree") and (force or not os.path.exists(_REF)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.flo_knn_brute_ctx.restype = C.c_void_p
+        L.flo_knn_brute_ctx.argtypes = [C.c_void_p, C.c_int]
+        L.flo_free.argtypes = [C.c_void_p]
+        L.flo_knn_brute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.flo_esti_plane.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        L.flo_lio_create.restype = C.c_void_p
+        L.flo_lio_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.flo_lio_destroy.argtypes = [C.c_void_p]
+        L.flo_lio_pass.restype = C.c_int
+        L.flo_lio_pass.argtypes = [C.c_void_p, C.POINTER(LioParams), C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 15
+        L.flo_lio_update.argtypes = [C.c_void_p, C.POINTER(LioParams), C.POINTER(State18), C.POINTER(State18),
+                                     C.POINTER(LioReport)]
+        L.flo_vio_create.restype = C.c_void_p
+        L.flo_vio_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.POINTER(Cam)]
+        L.flo_vio_destroy.argtypes = [C.c_void_p]
+        L.flo_vio_pass.restype = C.c_float
+        L.flo_vio_pass.argtypes = [C.c_void_p, C.POINTER(VioParams), C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.flo_vio_update.argtypes = [C.c_void_p, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18),
+                                     C.POINTER(VioReport)]
+        L.flo_world2cam.argtypes = [C.POINTER(Cam), C.c_void_p, C.c_void_p]
+        L.flo_exp3.argtypes = [C.c_void_p, C.c_void_p]
+        L.flo_log3.argtypes = [C.c_void_p, C.c_void_p]
+        L.flo_state_boxplus.argtypes = [C.POINTER(State18), C.c_void_p]
+        L.flo_state_boxminus.argtypes = [C.POINTER(State18), C.POINTER(State18), C.c_void_p]
+        L.flo_inverse.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own ikd-Tree (None if oracle/_ref was never built)."""
+    global _ref
+    if _ref is None:
+        build()
+        if not os.path.exists(_REF):
+            return None
+        R = C.CDLL(_REF)
+        R.ikdref_build.restype = C.c_void_p
+        R.ikdref_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        R.ikdref_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        R.ikdref_size.argtypes = [C.c_void_p]
+        _ref = R
+    return _ref
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------ kNN
+def knn_brute(map_xyz, q, k=5, nthreads=8):
+    L = lib()
+    m, q = f32(map_xyz), f32(q)
+    ctx = L.flo_knn_brute_ctx(_p(m), len(m))
+    idx = np.empty((len(q), k), np.int32)
+    d2 = np.empty((len(q), k), np.float32)
+    L.flo_knn_brute(ctx, _p(q), len(q), k, _p(idx), _p(d2), nthreads)
+    L.flo_free(ctx)
+    return idx, d2
+
+
+class IkdTreeRef:
+    """The reference's KD_TREE (include/ikd-Tree/ikd_Tree.cpp), built once, never destroyed."""
+
+    def __init__(self, map_xyz):
+        R = ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libikdtree_ref.so missing (built only where /root/reference exists)")
+        self._R = R
+        m = f32(map_xyz)
+        self.handle = R.ikdref_build(_p(m), len(m), 3)
+
+    def knn(self, q, k=5, nthreads=4):
+        q = f32(q)
+        idx = np.empty((len(q), k), np.int32)
+        d2 = np.empty((len(q), k), np.float32)
+        self._R.ikdref_knn(self.handle, _p(q), len(q), k, _p(idx), _p(d2), nthreads)
+        return idx, d2
+
+    @property
+    def fn_ptr(self):
+        return C.cast(self._R.ikdref_knn, C.c_void_p)
+
+
+def esti_plane(nb, threshold=0.1):
+    nb = f32(nb).reshape(15)
+    out = np.zeros(4, np.float32)
+    ok = lib().flo_esti_plane(_p(nb), C.c_float(threshold), _p(out))
+    return bool(ok), out
+
+
+# ------------------------------------------------------------------------------ LIO
+def lio_params(frame, max_iteration, nthreads=4, early_stop=True):
+    p = LioParams()
+    p.R_LI[:] = f64(frame["R_LI"]).ravel()
+    p.t_LI[:] = f64(frame["t_LI"])
+    p.laser_point_cov = frame["cfg"].laser_point_cov
+    p.max_iteration = max_iteration
+    p.conv_rot_deg = 0.01 if early_stop else 0.0
+    p.conv_pos_cm = 0.015 if early_stop else 0.0
+    p.nthreads = nthreads
+    return p
+
+
+class Lio:
+    def __init__(self, map_xyz, scan_body, tree: IkdTreeRef | None = None):
+        self.L = lib()
+        self.map = f32(map_xyz)
+        self.scan = f32(scan_body)
+        self.N = len(self.scan)
+        self.tree = tree
+        fn = tree.fn_ptr if tree is not None else None
+        ctx = tree.handle if tree is not None else None
+        self.h = self.L.flo_lio_create(_p(self.map), len(self.map), _p(self.scan), self.N, fn, ctx)
+
+    def __del__(self):
+        try:
+            self.L.flo_lio_destroy(self.h)
+        except Exception:
+            pass
+
+    def run_pass(self, prm: LioParams, R, p, rematch: bool, rows12=False):
+        N = self.N
+        out = dict(world=np.zeros((N, 3), np.float32), nn_idx=np.zeros((N, 5), np.int32),
+                   nn_d2=np.zeros((N, 5), np.float32), pabcd=np.zeros((N, 4), np.float32),
+                   pd2=np.zeros(N, np.float32), selected=np.zeros(N, np.uint8),
+                   Hsub=np.zeros((N, 6)), h_x=np.zeros((N, 12)) if rows12 else None, meas=np.zeros(N),
+                   sel_idx=np.zeros(N, np.int32), HTH6=np.zeros((6, 6)), HTz6=np.zeros(6),
+                   HTH12=np.zeros((12, 12)) if rows12 else None, HTh12=np.zeros(12) if rows12 else None)
+        tot = np.zeros(1)
+        R = f64(R)
+        p = f64(p)
+        n = self.L.flo_lio_pass(self.h, C.byref(prm), _p(R), _p(p), int(rematch), _p(out["world"]), _p(out["nn_idx"]),
+                                _p(out["nn_d2"]), _p(out["pabcd"]), _p(out["pd2"]), _p(out["selected"]), _p(out["Hsub"]),
+                                _p(out["h_x"]), _p(out["meas"]), _p(out["sel_idx"]), _p(out["HTH6"]), _p(out["HTz6"]),
+                                _p(out["HTH12"]), _p(out["HTh12"]), _p(tot))
+        out["n"] = n
+        out["total_residual"] = float(tot[0])
+        for k in ("Hsub", "h_x", "meas", "sel_idx"):
+            if out[k] is not None:
+                out[k] = out[k][:n]
+        return out
+
+    def update(self, prm: LioParams, x: State18, x_prop: State18):
+        rep = LioReport()
+        self.L.flo_lio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep))
+        return rep
+
+
+# ------------------------------------------------------------------------------ VIO
+def make_cam(cam: dict) -> Cam:
+    c = Cam()
+    c.width, c.height = cam["width"], cam["height"]
+    c.fx, c.fy, c.cx, c.cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    c.d[:] = cam["d"]
+    return c
+
+
+def vio_params(frame, max_iteration, early_stop=True, force_all_passes=False):
+    p = VioParams()
+    p.Rcl[:] = f64(frame["Rcl"]).ravel()
+    p.Pcl[:] = f64(frame["Pcl"])
+    p.R_LI[:] = f64(frame["R_LI"]).ravel()
+    p.t_LI[:] = f64(frame["t_LI"])
+    p.img_point_cov = frame["cfg"].img_point_cov
+    p.max_iteration = max_iteration
+    p.conv_rot_deg = 0.001 if early_stop else 0.0
+    p.conv_pos_cm = 0.001 if early_stop else 0.0
+    p.force_all_passes = int(force_all_passes)
+    return p
+
+
+class Vio:
+    def __init__(self, image, patch_pos, patch_ref, patch_level, cam: dict):
+        self.L = lib()
+        self.img = np.ascontiguousarray(image, np.uint8)
+        self.pos = f64(patch_pos)
+        self.patch = f32(patch_ref).reshape(len(self.pos), 192)
+        self.level = np.ascontiguousarray(patch_level, np.int32)
+        self.Pn = len(self.pos)
+        self.cam = make_cam(cam)
+        h, w = self.img.shape
+        self.h = self.L.flo_vio_create(_p(self.img), w, h, w, _p(self.pos), _p(self.patch), _p(self.level), self.Pn,
+                                       C.byref(self.cam))
+
+    def __del__(self):
+        try:
+            self.L.flo_vio_destroy(self.h)
+        except Exception:
+            pass
+
+    def run_pass(self, prm: VioParams, R, p, level: int, rows=True):
+        Pn = self.Pn
+        z = np.zeros(Pn * 64) if rows else None
+        H = np.zeros((Pn * 64, 6)) if rows else None
+        err = np.zeros(Pn, np.float32)
+        HTH, HTz = np.zeros((6, 6)), np.zeros(6)
+        nm = np.zeros(1, np.int64)
+        sk = np.zeros(1, np.int32)
+        R, p = f64(R), f64(p)
+        e = self.L.flo_vio_pass(self.h, C.byref(prm), _p(R), _p(p), level, _p(z), _p(H), _p(err), _p(HTH), _p(HTz),
+                                _p(nm), _p(sk))
+        return dict(error=np.float32(e), z=z, H_sub=H, errors=err, HTH6=HTH, HTz6=HTz, n_meas=int(nm[0]),
+                    skipped=int(sk[0]))
+
+    def update(self, prm: VioParams, x: State18, x_prop: State18):
+        rep = VioReport()
+        self.L.flo_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep))
+        return rep
+
+
+def world2cam(cam: dict, pf):
+    c = make_cam(cam)
+    pf = f64(pf)
+    out = np.zeros(2)
+    lib().flo_world2cam(C.byref(c), _p(pf), _p(out))
+    return out
+
+
+def state_from_frame(frame, prop=True) -> State18:
+    R = frame["R_prop"] if prop else frame["R_true"]
+    p = frame["p_prop"] if prop else frame["p_true"]
+    return State18.make(R, p, frame["vel"], frame["bg"], frame["ba"], frame["grav"], frame["cov"])
