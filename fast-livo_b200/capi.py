@@ -1,0 +1,387 @@
+"""ctypes binding of libfastlivo_b200.so (include/fastlivo_b200.h).
+
+No CPU fallback: if the library is missing it is built with nvcc; if there is no CUDA
+device ``Handle()`` raises ``FlbError`` (FLB_ERR_NO_DEVICE).  Nothing here imports the
+oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfastlivo_b200.so")
+
+FLB_OK = 0
+ERRORS = {-1: "FLB_ERR_INVALID", -2: "FLB_ERR_CUDA", -3: "FLB_ERR_NO_DEVICE", -4: "FLB_ERR_STATE",
+          -5: "FLB_ERR_NUMERIC", -6: "FLB_ERR_COMM", -7: "FLB_ERR_TIMEOUT"}
+
+
+class FlbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("cell_size", C.c_double), ("knn_max_d2", C.c_double),
+                ("plane_threshold", C.c_double), ("persistent", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class State18(C.Structure):
+    _fields_ = [("rot", C.c_double * 9), ("pos", C.c_double * 3), ("vel", C.c_double * 3),
+                ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("grav", C.c_double * 3),
+                ("cov", C.c_double * 324)]
+
+    @classmethod
+    def make(cls, R, p, vel=None, bg=None, ba=None, grav=None, cov=None):
+        s = cls()
+        s.rot[:] = np.asarray(R, np.float64).ravel()
+        s.pos[:] = np.asarray(p, np.float64)
+        s.vel[:] = np.zeros(3) if vel is None else vel
+        s.bg[:] = np.zeros(3) if bg is None else bg
+        s.ba[:] = np.zeros(3) if ba is None else ba
+        s.grav[:] = np.zeros(3) if grav is None else grav
+        s.cov[:] = (np.eye(18) if cov is None else np.asarray(cov, np.float64)).ravel()
+        return s
+
+    @classmethod
+    def from_frame(cls, frame, prop=True):
+        R = frame["R_prop"] if prop else frame["R_true"]
+        p = frame["p_prop"] if prop else frame["p_true"]
+        return cls.make(R, p, frame["vel"], frame["bg"], frame["ba"], frame["grav"], frame["cov"])
+
+    def copy(self):
+        o = State18()
+        C.memmove(C.byref(o), C.byref(self), C.sizeof(State18))
+        return o
+
+    @property
+    def R(self):
+        return np.array(self.rot[:]).reshape(3, 3)
+
+    @property
+    def p(self):
+        return np.array(self.pos[:])
+
+    @property
+    def P(self):
+        return np.array(self.cov[:]).reshape(18, 18)
+
+    def vector(self):
+        return np.concatenate([self.rot[:], self.pos[:], self.vel[:], self.bg[:], self.ba[:], self.grav[:]])
+
+
+class LioParams(C.Structure):
+    _fields_ = [("R_LI", C.c_double * 9), ("t_LI", C.c_double * 3), ("laser_point_cov", C.c_double),
+                ("max_iteration", C.c_int), ("conv_rot_deg", C.c_double), ("conv_pos_cm", C.c_double)]
+
+
+class LioReport(C.Structure):
+    _fields_ = [("passes", C.c_int), ("knn_passes", C.c_int), ("n_eff_last", C.c_int),
+                ("res_mean_last", C.c_double), ("rows_total", C.c_int64), ("converged_last", C.c_int),
+                ("status", C.c_int)]
+
+
+class NormalEq(C.Structure):
+    _fields_ = [("width", C.c_int), ("n_eff", C.c_int), ("sum_abs_res", C.c_double),
+                ("HTH", C.c_double * 144), ("HTh", C.c_double * 12)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("d", C.c_double * 5)]
+
+
+class VioParams(C.Structure):
+    _fields_ = [("Rcl", C.c_double * 9), ("Pcl", C.c_double * 3), ("R_LI", C.c_double * 9),
+                ("t_LI", C.c_double * 3), ("img_point_cov", C.c_double), ("max_iteration", C.c_int),
+                ("conv_rot_deg", C.c_float), ("conv_pos_cm", C.c_float), ("force_all_passes", C.c_int)]
+
+
+class VioReport(C.Structure):
+    _fields_ = [("passes", C.c_int * 3), ("last_error", C.c_float * 3), ("rows_total", C.c_int64),
+                ("skipped_last", C.c_int), ("cov_updated", C.c_int), ("status", C.c_int)]
+
+
+class VioEq(C.Structure):
+    _fields_ = [("HTH", C.c_double * 36), ("HTz", C.c_double * 6), ("error", C.c_float),
+                ("n_meas", C.c_int64), ("skipped", C.c_int)]
+
+
+# every symbol include/fastlivo_b200.h declares (checked by the CPU-only test tier)
+SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "flb_set_stream", "flb_synchronize",
+           "flb_map_upload", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update",
+           "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
+           "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
+           "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_profile_start", "flb_profile_stop",
+           "flb_launch_count", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy"]
+
+
+def lib_path() -> str:
+    return _SO
+
+
+def build(force: bool = False) -> str:
+    """Compile libfastlivo_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "fastlivo_b200.h"))
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs)
+    if force or stale:
+        if not os.path.exists("/usr/local/cuda/bin/nvcc") and os.path.exists(_SO):
+            return _SO  # a box without nvcc: use the prebuilt library that travelled with the repo
+        subprocess.check_call(["bash", os.path.join(_HERE, "build.sh")])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp = C.c_void_p
+        L.flb_abi_version.restype = C.c_int
+        L.flb_last_error.restype = C.c_char_p
+        L.flb_last_error.argtypes = [vp]
+        L.flb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.flb_destroy.argtypes = [vp]
+        L.flb_set_stream.argtypes = [vp, vp]
+        L.flb_synchronize.argtypes = [vp]
+        L.flb_map_upload.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.flb_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.flb_knn.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.flb_lio_pass.argtypes = [vp, C.POINTER(LioParams), vp, vp, C.c_int, C.c_int, C.POINTER(NormalEq)]
+        L.flb_lio_export.argtypes = [vp] + [vp] * 9 + [C.POINTER(C.c_int)]
+        L.flb_lio_update.argtypes = [vp, C.POINTER(LioParams), C.POINTER(State18), C.POINTER(State18), C.POINTER(LioReport)]
+        L.flb_image_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        L.flb_patches_upload.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.flb_camera_set.argtypes = [vp, C.POINTER(Camera)]
+        L.flb_vio_pass.argtypes = [vp, C.POINTER(VioParams), vp, vp, C.c_int, C.POINTER(VioEq)]
+        L.flb_vio_export.argtypes = [vp, vp, vp, vp]
+        L.flb_vio_update.argtypes = [vp, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18), C.POINTER(VioReport)]
+        L.flb_state_upload.argtypes = [vp, C.POINTER(State18), C.POINTER(State18)]
+        L.flb_state_download.argtypes = [vp, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
+        L.flb_lio_update_enqueue.argtypes = [vp, C.POINTER(LioParams)]
+        L.flb_vio_update_enqueue.argtypes = [vp, C.POINTER(VioParams)]
+        L.flb_state_reset_enqueue.argtypes = [vp]
+        L.flb_profile_start.argtypes = [vp]
+        L.flb_profile_stop.argtypes = [vp, vp, vp]
+        L.flb_launch_count.restype = C.c_int64
+        L.flb_launch_count.argtypes = [vp]
+        L.flb_comm_unique_id.argtypes = [vp]
+        L.flb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.flb_comm_destroy.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def lio_params(frame, max_iteration, early_stop=True) -> LioParams:
+    p = LioParams()
+    p.R_LI[:] = np.asarray(frame["R_LI"], np.float64).ravel()
+    p.t_LI[:] = np.asarray(frame["t_LI"], np.float64)
+    p.laser_point_cov = frame["cfg"].laser_point_cov
+    p.max_iteration = max_iteration
+    p.conv_rot_deg = 0.01 if early_stop else 0.0
+    p.conv_pos_cm = 0.015 if early_stop else 0.0
+    return p
+
+
+def vio_params(frame, max_iteration, early_stop=True, force_all_passes=False) -> VioParams:
+    p = VioParams()
+    p.Rcl[:] = np.asarray(frame["Rcl"], np.float64).ravel()
+    p.Pcl[:] = np.asarray(frame["Pcl"], np.float64)
+    p.R_LI[:] = np.asarray(frame["R_LI"], np.float64).ravel()
+    p.t_LI[:] = np.asarray(frame["t_LI"], np.float64)
+    p.img_point_cov = frame["cfg"].img_point_cov
+    p.max_iteration = max_iteration
+    p.conv_rot_deg = 0.001 if early_stop else 0.0
+    p.conv_pos_cm = 0.001 if early_stop else 0.0
+    p.force_all_passes = int(force_all_passes)
+    return p
+
+
+class Handle:
+    """Owns one flb_handle.  Method names follow the C ABI."""
+
+    def __init__(self, device=0, cell_size=0.6, knn_max_d2=5.0, plane_threshold=0.1, persistent=1):
+        self.L = lib()
+        cfg = Config()
+        cfg.device, cfg.cell_size, cfg.knn_max_d2, cfg.plane_threshold, cfg.persistent = \
+            device, cell_size, knn_max_d2, plane_threshold, persistent
+        self.h = C.c_void_p()
+        rc = self.L.flb_create(C.byref(cfg), C.byref(self.h))
+        if rc != FLB_OK:
+            raise FlbError(rc, self.L.flb_last_error(None).decode())
+        self.N = self.M = self.Pn = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.flb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != FLB_OK:
+            raise FlbError(rc, self.L.flb_last_error(self.h).decode())
+
+    # ---- uploads
+    def map_upload(self, xyz):
+        a = np.ascontiguousarray(xyz, np.float32)
+        self._ck(self.L.flb_map_upload(self.h, _p(a), a.shape[0], a.shape[1]))
+        self.M = a.shape[0]
+
+    def scan_upload(self, body_xyz):
+        a = np.ascontiguousarray(body_xyz, np.float32)
+        self._ck(self.L.flb_scan_upload(self.h, _p(a), a.shape[0], a.shape[1] if a.ndim == 2 else 3))
+        self.N = a.shape[0]
+
+    def image_upload(self, gray):
+        a = np.ascontiguousarray(gray, np.uint8)
+        self._ck(self.L.flb_image_upload(self.h, _p(a), a.shape[1], a.shape[0], a.shape[1]))
+
+    def patches_upload(self, pos, patch, level):
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        patch = np.ascontiguousarray(patch, np.float32).reshape(len(pos), 192)
+        level = np.ascontiguousarray(level, np.int32)
+        self._ck(self.L.flb_patches_upload(self.h, _p(pos), _p(patch), _p(level), len(pos)))
+        self.Pn = len(pos)
+
+    def camera_set(self, cam: dict):
+        c = Camera()
+        c.width, c.height = cam["width"], cam["height"]
+        c.fx, c.fy, c.cx, c.cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+        c.d[:] = cam["d"]
+        self._ck(self.L.flb_camera_set(self.h, C.byref(c)))
+
+    def load_frame(self, frame):
+        """Upload everything a synthetic frame holds."""
+        self.map_upload(frame["map_xyz"])
+        self.scan_upload(frame["scan_body"])
+        if len(frame["patch_pos"]):
+            self.camera_set(frame["cam"])
+            self.image_upload(frame["image"])
+            self.patches_upload(frame["patch_pos"], frame["patch_ref"], frame["patch_level"])
+
+    # ---- kNN
+    def knn(self, q_world):
+        q = np.ascontiguousarray(q_world, np.float32)
+        idx = np.empty((len(q), 5), np.int32)
+        d2 = np.empty((len(q), 5), np.float32)
+        self._ck(self.L.flb_knn(self.h, _p(q), len(q), _p(idx), _p(d2)))
+        return idx, d2
+
+    # ---- LIO
+    def lio_pass(self, prm: LioParams, R, p, rematch: bool, width=6, export=True):
+        R = np.ascontiguousarray(R, np.float64)
+        p = np.ascontiguousarray(p, np.float64)
+        eq = NormalEq()
+        self._ck(self.L.flb_lio_pass(self.h, C.byref(prm), _p(R), _p(p), int(rematch), width, C.byref(eq)))
+        out = dict(n=eq.n_eff, total_residual=eq.sum_abs_res,
+                   HTH=np.array(eq.HTH[:width * width]).reshape(width, width), HTh=np.array(eq.HTh[:width]))
+        if export:
+            N = self.N
+            world = np.empty((N, 3), np.float32)
+            nn_idx = np.empty((N, 5), np.int32)
+            nn_d2 = np.empty((N, 5), np.float32)
+            pabcd = np.empty((N, 4), np.float32)
+            pd2 = np.empty(N, np.float32)
+            sel = np.empty(N, np.uint8)
+            rows = np.empty((N, width))
+            meas = np.empty(N)
+            sel_idx = np.empty(N, np.int32)
+            n = C.c_int()
+            self._ck(self.L.flb_lio_export(self.h, _p(world), _p(nn_idx), _p(nn_d2), _p(pabcd), _p(pd2), _p(sel), _p(rows),
+                                           _p(meas), _p(sel_idx), C.byref(n)))
+            out.update(world=world, nn_idx=nn_idx, nn_d2=nn_d2, pabcd=pabcd, pd2=pd2, rowmask=sel,
+                       rows=rows[:n.value], meas=meas[:n.value], sel_idx=sel_idx[:n.value])
+        return out
+
+    def lio_update(self, prm: LioParams, x: State18, x_prop: State18) -> LioReport:
+        rep = LioReport()
+        self._ck(self.L.flb_lio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep)))
+        return rep
+
+    # ---- VIO
+    def vio_pass(self, prm: VioParams, R, p, level: int, export=True):
+        R = np.ascontiguousarray(R, np.float64)
+        p = np.ascontiguousarray(p, np.float64)
+        eq = VioEq()
+        self._ck(self.L.flb_vio_pass(self.h, C.byref(prm), _p(R), _p(p), level, C.byref(eq)))
+        out = dict(error=np.float32(eq.error), n_meas=eq.n_meas, skipped=eq.skipped,
+                   HTH6=np.array(eq.HTH[:]).reshape(6, 6), HTz6=np.array(eq.HTz[:]))
+        if export:
+            z = np.empty(self.Pn * 64)
+            H = np.empty((self.Pn * 64, 6))
+            err = np.empty(self.Pn, np.float32)
+            self._ck(self.L.flb_vio_export(self.h, _p(z), _p(H), _p(err)))
+            out.update(z=z, H_sub=H, errors=err)
+        return out
+
+    def vio_update(self, prm: VioParams, x: State18, x_prop: State18) -> VioReport:
+        rep = VioReport()
+        self._ck(self.L.flb_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep)))
+        return rep
+
+    # ---- device-resident loop
+    def state_upload(self, x: State18, x_prop: State18):
+        self._ck(self.L.flb_state_upload(self.h, C.byref(x), C.byref(x_prop)))
+
+    def state_download(self):
+        x, lr, vr = State18(), LioReport(), VioReport()
+        self._ck(self.L.flb_state_download(self.h, C.byref(x), C.byref(lr), C.byref(vr)))
+        return x, lr, vr
+
+    def lio_update_enqueue(self, prm):
+        self._ck(self.L.flb_lio_update_enqueue(self.h, C.byref(prm)))
+
+    def vio_update_enqueue(self, prm):
+        self._ck(self.L.flb_vio_update_enqueue(self.h, C.byref(prm)))
+
+    def state_reset_enqueue(self):
+        self._ck(self.L.flb_state_reset_enqueue(self.h))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.L.flb_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.L.flb_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.L.flb_launch_count(self.h))
+
+    def profile_start(self):
+        self._ck(self.L.flb_profile_start(self.h))
+
+    def profile_stop(self):
+        ms = np.zeros(4)
+        n = np.zeros(4, np.int64)
+        self._ck(self.L.flb_profile_stop(self.h, _p(ms), _p(n)))
+        return ms, n
+
+    # ---- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = lib().flb_comm_unique_id(buf)
+        if rc != FLB_OK:
+            raise FlbError(rc, lib().flb_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.L.flb_comm_init(self.h, buf, rank, world))

@@ -1,0 +1,1034 @@
+// flb_capi.cu -- the C ABI of include/fastlivo_b200.h over the sm_100a kernels.
+// Host side is plain C++ (no Eigen / PCL / torch); the handle owns device memory,
+// one stream, CUDA events and an optional NCCL communicator (dlopen'ed lazily).
+#include "../../include/fastlivo_b200.h"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flb_kernels.cuh"
+
+using namespace flb;
+
+static_assert(sizeof(flb_state18) == sizeof(State18), "flb_state18 and device State18 must match");
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(n, 16);
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---- NCCL through dlopen (no link-time dependency) ----------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        GetUniqueId = (int (*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+constexpr int kLioBlock = 128;
+constexpr int kVioBlock = 256;
+
+}  // namespace
+
+struct flb_handle {
+    int device = 0;
+    flb_config cfg{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // map
+    int M = 0;
+    GridDesc grid{};
+    int ncell = 0;
+    DevBuf<float> map_raw;
+    DevBuf<unsigned> keys, keys_sorted;
+    DevBuf<int> vals, vals_sorted;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<float4> map_pts;
+    DevBuf<int> cell_start;
+
+    // scan + per-point persistent
+    int N = 0;
+    DevBuf<float4> scan;
+    DevBuf<unsigned char> sel, plane_ok;
+    DevBuf<float4> plane;
+
+    // LIO exports (lazily allocated)
+    DevBuf<float> x_world, x_nn_d2, x_pd2;
+    DevBuf<int> x_nn_idx;
+    DevBuf<unsigned char> x_rowmask;
+    DevBuf<double> x_rows, x_meas;
+    int last_pass_width = 0;
+    bool last_pass_valid = false;
+
+    // reductions / solve
+    DevBuf<double> partials;     // max(nblocks_lio * 92, nblocks_vio * 29)
+    DevBuf<double> packed;       // 128
+    DevBuf<double> pose12;       // 12
+    DevBuf<double> Pinv;         // 324
+    DevBuf<double> G_last;       // 108
+    DevBuf<State18> states;      // [0]=x [1]=x_prop [2]=old_state(VIO) [3]=saved x [4]=saved x_prop
+    DevBuf<LioCtrl> lio_ctrl;
+    DevBuf<VioCtrl> vio_ctrl;
+    PinBuf pin;                  // staging for uploads
+    PinBuf pin_out;              // staging for downloads
+    bool state_valid = false;
+
+    // VIO inputs
+    int img_w = 0, img_h = 0;
+    DevBuf<unsigned char> img;
+    int Pn = 0;
+    DevBuf<double> patch_pos;
+    DevBuf<float> patch_ref;
+    DevBuf<int> patch_level;
+    DevBuf<float> errors;        // Pn (local shard)
+    DevBuf<float> errors_all;    // padded shard * world (multi-GPU)
+    DevBuf<double> x_z, x_H;
+    bool cam_set = false;
+    CamModel cam{};
+    bool last_vio_valid = false;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    int err_shard = 0;           // max patches per rank (equal-size ncclAllGather shards)
+
+    // profiling
+    bool profiling = false;
+    struct Ev { cudaEvent_t a, b; int fam; };
+    std::vector<Ev> evs;
+};
+
+namespace {
+
+int fail(flb_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define FLB_CUDA(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(h, FLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define FLB_CHECK_H(h)                                   \
+    do {                                                 \
+        if (!(h)) return FLB_ERR_INVALID;                \
+        cudaError_t _e = cudaSetDevice((h)->device);     \
+        if (_e != cudaSuccess) return fail(h, FLB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+// launch bookkeeping: count every kernel; when profiling, bracket it with an event pair
+struct LaunchScope {
+    flb_handle* h;
+    int fam;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(flb_handle* h_, int fam_) : h(h_), fam(fam_) {
+        h->launches++;
+        if (h->profiling) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, h->stream);
+        }
+    }
+    ~LaunchScope() {
+        if (h->profiling) {
+            cudaEventRecord(b, h->stream);
+            h->evs.push_back({a, b, fam});
+        }
+    }
+};
+enum { FAM_LIO_KNN = 0, FAM_LIO_PLAIN = 1, FAM_VIO = 2, FAM_SOLVE = 3, FAM_OTHER = 4 };
+
+void to_dev_params(const flb_lio_params* p, LioParamsDev& d) {
+    std::memcpy(d.R_LI, p->R_LI, sizeof(d.R_LI));
+    std::memcpy(d.t_LI, p->t_LI, sizeof(d.t_LI));
+    d.sigma = p->laser_point_cov;
+    d.max_iteration = p->max_iteration;
+    d.conv_rot_deg = p->conv_rot_deg;
+    d.conv_pos_cm = p->conv_pos_cm;
+}
+
+// LidarSelector::init() constants, src/lidar_selection.cpp:41-52 + set_extrinsic :35-39 (host, once per call)
+void to_dev_params(const flb_vio_params* p, VioParamsDev& d) {
+    double Rli[9], Pli[3], t[3];
+    m3_T(p->R_LI, Rli);
+    m3_vec(Rli, p->t_LI, t);
+    for (int i = 0; i < 3; ++i) Pli[i] = -t[i];
+    m3_mul(p->Rcl, Rli, d.Rci);
+    m3_vec(p->Rcl, Pli, t);
+    for (int i = 0; i < 3; ++i) d.Pci[i] = t[i] + p->Pcl[i];
+    d.sigma = p->img_point_cov;
+    d.max_iteration = p->max_iteration;
+    d.conv_rot_deg = p->conv_rot_deg;
+    d.conv_pos_cm = p->conv_pos_cm;
+    d.force_all_passes = p->force_all_passes;
+}
+
+int lio_nblocks(const flb_handle* h) { return (h->N + kLioBlock - 1) / kLioBlock; }
+int vio_nblocks(const flb_handle* h) { return (h->Pn + (kVioBlock / 32) - 1) / (kVioBlock / 32); }
+
+int ensure_common(flb_handle* h) {
+    FLB_CUDA(h, h->packed.reserve(128));
+    FLB_CUDA(h, h->pose12.reserve(12));
+    FLB_CUDA(h, h->Pinv.reserve(324));
+    FLB_CUDA(h, h->G_last.reserve(108));
+    FLB_CUDA(h, h->states.reserve(5));
+    FLB_CUDA(h, h->lio_ctrl.reserve(1));
+    FLB_CUDA(h, h->vio_ctrl.reserve(1));
+    FLB_CUDA(h, h->pin.reserve(1 << 16));
+    FLB_CUDA(h, h->pin_out.reserve(1 << 16));
+    return FLB_OK;
+}
+
+LioArgs make_lio_args(flb_handle* h, const LioParamsDev& prm, bool exports, int width) {
+    LioArgs a{};
+    a.scan = h->scan.p;
+    a.N = h->N;
+    a.grid = h->grid;
+    a.cell_start = h->cell_start.p;
+    a.map_pts = h->map_pts.p;
+    a.state = &h->states.p[0];
+    a.prm = prm;
+    a.plane_thr = (float)h->cfg.plane_threshold;
+    a.ctrl = h->lio_ctrl.p;
+    a.force_rematch = -1;
+    a.pose_override = nullptr;
+    a.sel = h->sel.p;
+    a.plane = h->plane.p;
+    a.plane_ok = h->plane_ok.p;
+    a.partials = h->partials.p;
+    if (exports) {
+        a.x_world = h->x_world.p;
+        a.x_nn_idx = h->x_nn_idx.p;
+        a.x_nn_d2 = h->x_nn_d2.p;
+        a.x_pd2 = h->x_pd2.p;
+        a.x_rowmask = h->x_rowmask.p;
+        a.x_rows = h->x_rows.p;
+        a.x_meas = h->x_meas.p;
+    }
+    (void)width;
+    return a;
+}
+
+int launch_lio_pass(flb_handle* h, const LioArgs& a, int width, bool knn_family) {
+    const int nb = lio_nblocks(h);
+    if (nb == 0) return FLB_OK;
+    LaunchScope ls(h, knn_family ? FAM_LIO_KNN : FAM_LIO_PLAIN);
+    if (width == 6) k_lio_pass<6, kLioBlock><<<nb, kLioBlock, 0, h->stream>>>(a);
+    else k_lio_pass<12, kLioBlock><<<nb, kLioBlock, 0, h->stream>>>(a);
+    FLB_CUDA(h, cudaGetLastError());
+    return FLB_OK;
+}
+
+// all-reduce of the packed sums (and all-gather of the per-patch errors) for multi-GPU
+int allreduce_packed(flb_handle* h, const double* partials, int nblocks, int K) {
+    {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_reduce_only<<<1, 32, 0, h->stream>>>(partials, nblocks, K, h->packed.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    int r = g_nccl.AllReduce(h->packed.p, h->packed.p, (size_t)K, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (r != 0) return fail(h, FLB_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    h->launches++;
+    return FLB_OK;
+}
+
+int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
+    if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_update: map and scan must be uploaded first");
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_lio_update: no device state (flb_state_upload)");
+    if (prm->max_iteration < 0) return fail(h, FLB_ERR_INVALID, "max_iteration < 0");
+    LioParamsDev d;
+    to_dev_params(prm, d);
+    LioSolveArgs s{};
+    s.state = &h->states.p[0];
+    s.state_prop = &h->states.p[1];
+    s.ctrl = h->lio_ctrl.p;
+    s.Pinv = h->Pinv.p;
+    s.partials = h->partials.p;
+    s.nblocks = lio_nblocks(h);
+    s.prm = d;
+    {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_lio_begin<<<1, 32, 0, h->stream>>>(s);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    LioArgs a = make_lio_args(h, d, false, 6);
+    const int T = prm->max_iteration;
+    for (int it = -1; it < T; ++it) {
+        // Statically known rematch schedule when early stop is disabled is NOT assumed here:
+        // the kernel reads ctrl->nearest_search_en / ctrl->stop on the device.
+        int rc = launch_lio_pass(h, a, 6, it == -1);
+        if (rc) return rc;
+        if (h->comm) {
+            rc = allreduce_packed(h, h->partials.p, lio_nblocks(h), lio_packed(6));
+            if (rc) return rc;
+            s.partials = h->packed.p;
+            s.nblocks = 1;
+        }
+        LaunchScope ls(h, FAM_SOLVE);
+        k_lio_finalize<<<1, 32, 0, h->stream>>>(s);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    h->last_pass_valid = false;
+    return FLB_OK;
+}
+
+int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
+    if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update: camera and image must be set first");
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_vio_update: no device state (flb_state_upload)");
+    VioParamsDev d;
+    to_dev_params(prm, d);
+    VioSolveArgs s{};
+    s.state = &h->states.p[0];
+    s.state_prop = &h->states.p[1];
+    s.old_state = &h->states.p[2];
+    s.ctrl = h->vio_ctrl.p;
+    s.Pinv = h->Pinv.p;
+    s.G_last = h->G_last.p;
+    s.partials = h->partials.p;
+    s.nblocks = vio_nblocks(h);
+    s.errors = h->errors.p;
+    s.Pn_total = h->Pn;
+    s.prm = d;
+    {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_vio_begin<<<1, 32, 0, h->stream>>>(s);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    VioArgs a{};
+    a.img = h->img.p;
+    a.cam = h->cam;
+    a.pos = h->patch_pos.p;
+    a.patch = h->patch_ref.p;
+    a.search_level = h->patch_level.p;
+    a.Pn = h->Pn;
+    a.state = &h->states.p[0];
+    a.pose_override = nullptr;
+    a.prm = d;
+    a.ctrl = h->vio_ctrl.p;
+    a.force_level = -1;
+    a.errors = h->errors.p;
+    a.partials = h->partials.p;
+    const int nb = vio_nblocks(h);
+    const int total = 3 * std::max(prm->max_iteration, 0);
+    for (int it = 0; it < total && h->Pn > 0; ++it) {
+        {
+            LaunchScope ls(h, FAM_VIO);
+            k_vio_pass<kVioBlock><<<nb, kVioBlock, 0, h->stream>>>(a);
+            FLB_CUDA(h, cudaGetLastError());
+        }
+        if (h->comm) {
+            int rc = allreduce_packed(h, h->partials.p, nb, kVioPacked);
+            if (rc) return rc;
+            s.partials = h->packed.p;
+            s.nblocks = 1;
+            // gather every rank's per-patch errors in patch order (shards padded to errors.cap/world)
+            const size_t shard = (size_t)h->err_shard;
+            int r = g_nccl.AllGather(h->errors.p, h->errors_all.p, shard, kNcclFloat32, h->comm, h->stream);
+            if (r != 0) return fail(h, FLB_ERR_COMM, "ncclAllGather failed");
+            h->launches++;
+            s.errors = h->errors_all.p;
+            s.Pn_total = (int)(shard * (size_t)h->world);
+        }
+        LaunchScope ls(h, FAM_SOLVE);
+        k_vio_finalize<<<1, 64, 0, h->stream>>>(s);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    h->last_vio_valid = false;
+    return FLB_OK;
+}
+
+void fill_lio_report(const LioCtrl& c, flb_lio_report* rep) {
+    rep->passes = c.passes;
+    rep->knn_passes = c.knn_passes;
+    rep->n_eff_last = c.n_eff_last;
+    rep->res_mean_last = c.res_mean_last;
+    rep->rows_total = c.rows_total;
+    rep->converged_last = c.converged_last;
+    rep->status = c.status;
+}
+void fill_vio_report(const VioCtrl& c, flb_vio_report* rep) {
+    for (int l = 0; l < 3; ++l) { rep->passes[l] = c.passes[l]; rep->last_error[l] = c.level_error[l]; }
+    rep->rows_total = c.rows_total;
+    rep->skipped_last = c.skipped_last;
+    rep->cov_updated = c.cov_updated;
+    rep->status = c.status;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flb_abi_version(void) { return FLB_ABI_VERSION; }
+
+const char* flb_last_error(const flb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int flb_create(const flb_config* cfg, flb_handle** out) {
+    if (!out) return FLB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FLB_ERR_NO_DEVICE,
+                    "no CUDA device (%s): fastlivo_b200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    flb_config c{};
+    if (cfg) c = *cfg;
+    if (c.device < 0 || c.device >= ndev) return fail(nullptr, FLB_ERR_INVALID, "device %d out of range [0,%d)", c.device, ndev);
+    if (!(c.cell_size > 0)) c.cell_size = 0.6;
+    if (!(c.knn_max_d2 > 0)) c.knn_max_d2 = 5.0;
+    if (!(c.plane_threshold > 0)) c.plane_threshold = 0.1;
+    e = cudaSetDevice(c.device);
+    if (e != cudaSuccess) return fail(nullptr, FLB_ERR_CUDA, "cudaSetDevice(%d): %s", c.device, cudaGetErrorString(e));
+    flb_handle* h = new flb_handle;
+    h->device = c.device;
+    h->cfg = c;
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(nullptr, FLB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    h->stream = h->own_stream;
+    int rc = ensure_common(h);
+    if (rc) {
+        g_create_error = h->err;
+        cudaStreamDestroy(h->own_stream);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return FLB_OK;
+}
+
+int flb_destroy(flb_handle* h) {
+    if (!h) return FLB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (auto& ev : h->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    h->map_raw.release(); h->keys.release(); h->keys_sorted.release(); h->vals.release(); h->vals_sorted.release();
+    h->cub_tmp.release(); h->map_pts.release(); h->cell_start.release(); h->scan.release(); h->sel.release();
+    h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
+    h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
+    h->packed.release(); h->pose12.release(); h->Pinv.release(); h->G_last.release(); h->states.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
+    h->pin.release(); h->pin_out.release();
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return FLB_OK;
+}
+
+int flb_set_stream(flb_handle* h, void* cuda_stream) {
+    FLB_CHECK_H(h);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return FLB_OK;
+}
+
+int flb_synchronize(flb_handle* h) {
+    FLB_CHECK_H(h);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+int64_t flb_launch_count(const flb_handle* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------
+int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
+    FLB_CHECK_H(h);
+    if (!xyz || M < 1 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_map_upload: bad arguments (M=%d stride=%d)", M, stride);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FLB_CUDA(h, h->pin.reserve((size_t)M * 3 * sizeof(float)));
+    float* st = static_cast<float*>(h->pin.p);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < M; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            const float v = xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_upload: non-finite coordinate at point %d", i);
+            st[3 * (size_t)i + k] = v;
+            lo[k] = std::min(lo[k], v);
+            hi[k] = std::max(hi[k], v);
+        }
+    }
+    // grid geometry; enlarge the cell if the dense grid would exceed 2^25 cells (still exact, just slower)
+    double cell = h->cfg.cell_size;
+    for (;;) {
+        const double nx = std::floor((hi[0] - lo[0]) / cell) + 1, ny = std::floor((hi[1] - lo[1]) / cell) + 1,
+                     nz = std::floor((hi[2] - lo[2]) / cell) + 1;
+        if (nx * ny * nz <= (double)(1 << 25)) break;
+        cell *= 1.26;
+    }
+    GridDesc g{};
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+    g.cell = (float)cell;
+    g.inv_cell = 1.0f / g.cell;
+    g.nx = (int)std::floor((hi[0] - lo[0]) / cell) + 1;
+    g.ny = (int)std::floor((hi[1] - lo[1]) / cell) + 1;
+    g.nz = (int)std::floor((hi[2] - lo[2]) / cell) + 1;
+    g.max_d2 = (float)h->cfg.knn_max_d2;
+    g.max_ring = (int)std::ceil(std::sqrt(h->cfg.knn_max_d2) / cell) + 1;
+    const int ncell = g.nx * g.ny * g.nz;
+    FLB_CUDA(h, h->map_raw.reserve((size_t)M * 3));
+    FLB_CUDA(h, h->keys.reserve(M));
+    FLB_CUDA(h, h->keys_sorted.reserve(M));
+    FLB_CUDA(h, h->vals.reserve(M));
+    FLB_CUDA(h, h->vals_sorted.reserve(M));
+    FLB_CUDA(h, h->map_pts.reserve(M));
+    FLB_CUDA(h, h->cell_start.reserve((size_t)ncell + 1));
+    FLB_CUDA(h, cudaMemcpyAsync(h->map_raw.p, st, (size_t)M * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const int nb = (M + 255) / 256;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_map_cell_ids<<<nb, 256, 0, h->stream>>>(h->map_raw.p, M, 3, g, h->keys.p, h->vals.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    int end_bit = 1;
+    while ((1u << end_bit) < (unsigned)ncell && end_bit < 32) ++end_bit;
+    size_t tmp_bytes = 0;
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->keys.p, h->keys_sorted.p, h->vals.p, h->vals_sorted.p, M,
+                                                0, end_bit, h->stream));
+    FLB_CUDA(h, h->cub_tmp.reserve(tmp_bytes));
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->keys.p, h->keys_sorted.p, h->vals.p,
+                                                h->vals_sorted.p, M, 0, end_bit, h->stream));
+    h->launches += 4;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_map_gather<<<nb, 256, 0, h->stream>>>(h->map_raw.p, M, 3, h->keys_sorted.p, h->vals_sorted.p, h->map_pts.p,
+                                                 h->cell_start.p, ncell);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->M = M;
+    h->grid = g;
+    h->ncell = ncell;
+    return FLB_OK;
+}
+
+int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
+    FLB_CHECK_H(h);
+    if (!body_xyz || N < 0 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: bad arguments");
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FLB_CUDA(h, h->pin.reserve((size_t)std::max(N, 1) * sizeof(float4)));
+    float4* st = static_cast<float4*>(h->pin.p);
+    for (int i = 0; i < N; ++i)
+        st[i] = make_float4(body_xyz[(size_t)i * stride], body_xyz[(size_t)i * stride + 1], body_xyz[(size_t)i * stride + 2], 0.f);
+    FLB_CUDA(h, h->scan.reserve(N));
+    FLB_CUDA(h, h->sel.reserve(N));
+    FLB_CUDA(h, h->plane_ok.reserve(N));
+    FLB_CUDA(h, h->plane.reserve(N));
+    const int nb = (N + kLioBlock - 1) / kLioBlock;
+    FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)nb * lio_packed(12), h->partials.cap)));
+    FLB_CUDA(h, cudaMemcpyAsync(h->scan.p, st, (size_t)N * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
+    FLB_CUDA(h, cudaMemsetAsync(h->sel.p, 1, std::max(N, 1), h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(h->plane_ok.p, 0, std::max(N, 1), h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->N = N;
+    h->last_pass_valid = false;
+    return FLB_OK;
+}
+
+int flb_knn(flb_handle* h, const float* q, int nq, int* idx, float* d2) {
+    FLB_CHECK_H(h);
+    if (h->M <= 0) return fail(h, FLB_ERR_STATE, "flb_knn: no map uploaded");
+    if (!q || !idx || !d2 || nq < 0) return fail(h, FLB_ERR_INVALID, "flb_knn: bad arguments");
+    if (nq == 0) return FLB_OK;
+    DevBuf<float> dq, dd;
+    DevBuf<int> di;
+    FLB_CUDA(h, dq.reserve((size_t)nq * 3));
+    FLB_CUDA(h, dd.reserve((size_t)nq * kMatch));
+    FLB_CUDA(h, di.reserve((size_t)nq * kMatch));
+    FLB_CUDA(h, cudaMemcpyAsync(dq.p, q, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, FAM_LIO_KNN);
+        k_knn<<<(nq + 127) / 128, 128, 0, h->stream>>>(h->grid, h->cell_start.p, h->map_pts.p, dq.p, nq, di.p, dd.p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx, di.p, (size_t)nq * kMatch * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d2, dd.p, (size_t)nq * kMatch * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    dq.release(); dd.release(); di.release();
+    if (e != cudaSuccess) return fail(h, FLB_ERR_CUDA, "flb_knn: %s", cudaGetErrorString(e));
+    return FLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int flb_lio_pass(flb_handle* h, const flb_lio_params* prm, const double R[9], const double p[3], int rematch, int width,
+                 flb_normal_eq* out) {
+    FLB_CHECK_H(h);
+    if (!prm || !R || !p || !out || (width != 6 && width != 12)) return fail(h, FLB_ERR_INVALID, "flb_lio_pass: bad arguments");
+    if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_pass: map and scan must be uploaded first");
+    const int N = h->N;
+    FLB_CUDA(h, h->x_world.reserve((size_t)N * 3));
+    FLB_CUDA(h, h->x_nn_idx.reserve((size_t)N * kMatch));
+    FLB_CUDA(h, h->x_nn_d2.reserve((size_t)N * kMatch));
+    FLB_CUDA(h, h->x_pd2.reserve(N));
+    FLB_CUDA(h, h->x_rowmask.reserve(N));
+    FLB_CUDA(h, h->x_rows.reserve((size_t)N * 12));
+    FLB_CUDA(h, h->x_meas.reserve(N));
+    LioParamsDev d;
+    to_dev_params(prm, d);
+    double* st = static_cast<double*>(h->pin.p);
+    std::memcpy(st, R, 9 * sizeof(double));
+    std::memcpy(st + 9, p, 3 * sizeof(double));
+    FLB_CUDA(h, cudaMemcpyAsync(h->pose12.p, st, 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LioArgs a = make_lio_args(h, d, true, width);
+    a.force_rematch = rematch ? 1 : 0;
+    a.pose_override = h->pose12.p;
+    int rc = launch_lio_pass(h, a, width, rematch != 0);
+    if (rc) return rc;
+    const int K = lio_packed(width);
+    if (h->comm) {
+        rc = allreduce_packed(h, h->partials.p, lio_nblocks(h), K);
+        if (rc) return rc;
+    } else {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_reduce_only<<<1, 32, 0, h->stream>>>(h->partials.p, lio_nblocks(h), K, h->packed.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    double* po = static_cast<double*>(h->pin_out.p);
+    FLB_CUDA(h, cudaMemcpyAsync(po, h->packed.p, K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memset(out, 0, sizeof(*out));
+    out->width = width;
+    int k = 0;
+    for (int r = 0; r < width; ++r)
+        for (int c = r; c < width; ++c) {
+            out->HTH[r * width + c] = po[k];
+            out->HTH[c * width + r] = po[k];
+            ++k;
+        }
+    for (int r = 0; r < width; ++r) out->HTh[r] = po[k + r];
+    out->n_eff = (int)po[K - 2];
+    out->sum_abs_res = po[K - 1];
+    h->last_pass_width = width;
+    h->last_pass_valid = true;
+    return FLB_OK;
+}
+
+int flb_lio_export(flb_handle* h, float* world_xyz, int* nn_idx, float* nn_d2, float* pabcd, float* pd2, uint8_t* selected,
+                   double* rows, double* meas, int* sel_idx, int* n_rows) {
+    FLB_CHECK_H(h);
+    if (!h->last_pass_valid) return fail(h, FLB_ERR_STATE, "flb_lio_export: no flb_lio_pass to export");
+    const int N = h->N, W = h->last_pass_width;
+    cudaStream_t s = h->stream;
+    if (world_xyz) FLB_CUDA(h, cudaMemcpyAsync(world_xyz, h->x_world.p, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (nn_idx) FLB_CUDA(h, cudaMemcpyAsync(nn_idx, h->x_nn_idx.p, (size_t)N * kMatch * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (nn_d2) FLB_CUDA(h, cudaMemcpyAsync(nn_d2, h->x_nn_d2.p, (size_t)N * kMatch * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (pabcd) FLB_CUDA(h, cudaMemcpyAsync(pabcd, h->plane.p, (size_t)N * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    if (pd2) FLB_CUDA(h, cudaMemcpyAsync(pd2, h->x_pd2.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    std::vector<unsigned char> mask(N);
+    FLB_CUDA(h, cudaMemcpyAsync(mask.data(), h->x_rowmask.p, N, cudaMemcpyDeviceToHost, s));
+    std::vector<double> hrows, hmeas;
+    if (rows || meas) {
+        hrows.resize((size_t)N * W);
+        hmeas.resize(N);
+        FLB_CUDA(h, cudaMemcpyAsync(hrows.data(), h->x_rows.p, (size_t)N * W * sizeof(double), cudaMemcpyDeviceToHost, s));
+        FLB_CUDA(h, cudaMemcpyAsync(hmeas.data(), h->x_meas.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    FLB_CUDA(h, cudaStreamSynchronize(s));
+    // order-preserving compaction == laserCloudOri / corr_normvect (src/laserMapping.cpp:1588-1600)
+    int n = 0;
+    for (int i = 0; i < N; ++i) {
+        if (selected) selected[i] = mask[i];
+        if (!mask[i]) continue;
+        if (rows) std::memcpy(rows + (size_t)n * W, hrows.data() + (size_t)i * W, W * sizeof(double));
+        if (meas) meas[n] = hmeas[i];
+        if (sel_idx) sel_idx[n] = i;
+        ++n;
+    }
+    if (n_rows) *n_rows = n;
+    return FLB_OK;
+}
+
+int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_prop) {
+    FLB_CHECK_H(h);
+    if (!x || !x_prop) return fail(h, FLB_ERR_INVALID, "flb_state_upload: null state");
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FLB_CUDA(h, h->pin.reserve(2 * sizeof(State18)));
+    State18* st = static_cast<State18*>(h->pin.p);
+    std::memcpy(&st[0], x, sizeof(State18));
+    std::memcpy(&st[1], x_prop, sizeof(State18));
+    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[0], st, 2 * sizeof(State18), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[3], &h->states.p[0], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    h->state_valid = true;
+    return FLB_OK;
+}
+
+int flb_state_reset_enqueue(flb_handle* h) {
+    FLB_CHECK_H(h);
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_reset_enqueue: no state uploaded");
+    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[0], &h->states.p[3], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    return FLB_OK;
+}
+
+int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio) {
+    FLB_CHECK_H(h);
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_download: no state uploaded");
+    char* po = static_cast<char*>(h->pin_out.p);
+    FLB_CUDA(h, cudaMemcpyAsync(po, &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18), h->lio_ctrl.p, sizeof(LioCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl), h->vio_ctrl.p, sizeof(VioCtrl), cudaMemcpyDeviceToHost,
+                                h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (x) std::memcpy(x, po, sizeof(State18));
+    if (lio) {
+        LioCtrl c;
+        std::memcpy(&c, po + sizeof(State18), sizeof(c));
+        fill_lio_report(c, lio);
+    }
+    if (vio) {
+        VioCtrl c;
+        std::memcpy(&c, po + sizeof(State18) + sizeof(LioCtrl), sizeof(c));
+        fill_vio_report(c, vio);
+    }
+    return FLB_OK;
+}
+
+int flb_lio_update_enqueue(flb_handle* h, const flb_lio_params* prm) {
+    FLB_CHECK_H(h);
+    if (!prm) return fail(h, FLB_ERR_INVALID, "null params");
+    return enqueue_lio_update(h, prm);
+}
+
+int flb_vio_update_enqueue(flb_handle* h, const flb_vio_params* prm) {
+    FLB_CHECK_H(h);
+    if (!prm) return fail(h, FLB_ERR_INVALID, "null params");
+    return enqueue_vio_update(h, prm);
+}
+
+int flb_lio_update(flb_handle* h, const flb_lio_params* prm, flb_state18* x, const flb_state18* x_prop, flb_lio_report* rep) {
+    FLB_CHECK_H(h);
+    if (!prm || !x || !x_prop) return fail(h, FLB_ERR_INVALID, "flb_lio_update: null argument");
+    int rc = flb_state_upload(h, x, x_prop);
+    if (rc) return rc;
+    rc = enqueue_lio_update(h, prm);
+    if (rc) return rc;
+    flb_lio_report r{};
+    rc = flb_state_download(h, x, &r, nullptr);
+    if (rc) return rc;
+    if (rep) *rep = r;
+    if (r.status != 0) return fail(h, r.status, "flb_lio_update: device reported status %d (singular normal matrix?)", r.status);
+    return FLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, int stride) {
+    FLB_CHECK_H(h);
+    if (!gray || width < 16 || height < 16 || stride < width) return fail(h, FLB_ERR_INVALID, "flb_image_upload: bad arguments");
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FLB_CUDA(h, h->img.reserve((size_t)width * height));
+    FLB_CUDA(h, h->pin.reserve((size_t)width * height));
+    unsigned char* st = static_cast<unsigned char*>(h->pin.p);
+    for (int r = 0; r < height; ++r) std::memcpy(st + (size_t)r * width, gray + (size_t)r * stride, width);
+    FLB_CUDA(h, cudaMemcpyAsync(h->img.p, st, (size_t)width * height, cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->img_w = width;
+    h->img_h = height;
+    h->last_vio_valid = false;
+    return FLB_OK;
+}
+
+int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, const int* search_level, int Pn) {
+    FLB_CHECK_H(h);
+    if (Pn < 0 || (Pn > 0 && (!pos || !patch || !search_level))) return fail(h, FLB_ERR_INVALID, "flb_patches_upload: bad arguments");
+    for (int i = 0; i < Pn; ++i)
+        if (search_level[i] < 0 || search_level[i] > 2) return fail(h, FLB_ERR_INVALID, "search_level[%d] = %d outside [0,2]", i, search_level[i]);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)std::max(Pn, 1);
+    FLB_CUDA(h, h->patch_pos.reserve(n * 3));
+    FLB_CUDA(h, h->patch_ref.reserve(n * 192));
+    FLB_CUDA(h, h->patch_level.reserve(n));
+    FLB_CUDA(h, h->errors.reserve(n));
+    const int nb = (Pn + 7) / 8;
+    FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)std::max(nb, 1) * kVioPacked, h->partials.cap)));
+    const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int));
+    FLB_CUDA(h, h->pin.reserve(bytes));
+    char* st = static_cast<char*>(h->pin.p);
+    if (Pn > 0) {
+        std::memcpy(st, pos, (size_t)Pn * 3 * sizeof(double));
+        char* st2 = st + (size_t)Pn * 3 * sizeof(double);
+        std::memcpy(st2, patch, (size_t)Pn * 192 * sizeof(float));
+        char* st3 = st2 + (size_t)Pn * 192 * sizeof(float);
+        std::memcpy(st3, search_level, (size_t)Pn * sizeof(int));
+        FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, st, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, st2, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, st3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h->comm) {
+        // agree on the largest shard so every rank contributes an equal-size block to ncclAllGather;
+        // the padding entries stay 0.0f, and adding 0.0f to the sequential float sum is exact.
+        int* dmax = reinterpret_cast<int*>(h->packed.p);
+        FLB_CUDA(h, cudaMemcpyAsync(dmax, &Pn, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        int r = g_nccl.AllReduce(dmax, dmax, 1, kNcclInt32, kNcclMax, h->comm, h->stream);
+        if (r != 0) return fail(h, FLB_ERR_COMM, "ncclAllReduce(max Pn) failed");
+        int shard = 0;
+        FLB_CUDA(h, cudaMemcpyAsync(&shard, dmax, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->err_shard = std::max(shard, 1);
+        FLB_CUDA(h, h->errors.reserve((size_t)h->err_shard));
+        FLB_CUDA(h, h->errors_all.reserve((size_t)h->err_shard * (size_t)h->world));
+    }
+    FLB_CUDA(h, cudaMemsetAsync(h->errors.p, 0, h->errors.cap * sizeof(float), h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->Pn = Pn;
+    h->last_vio_valid = false;
+    return FLB_OK;
+}
+
+int flb_camera_set(flb_handle* h, const flb_camera* cam) {
+    FLB_CHECK_H(h);
+    if (!cam || cam->width < 16 || cam->height < 16 || !(std::fabs(cam->fx) > 0) || !(std::fabs(cam->fy) > 0))
+        return fail(h, FLB_ERR_INVALID, "flb_camera_set: bad camera");
+    CamModel c{};
+    c.width = cam->width;
+    c.height = cam->height;
+    c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy;
+    for (int i = 0; i < 5; ++i) c.d[i] = cam->d[i];
+    // vikit PinholeCamera::errorMultiplier2() = |fx|, errorMultiplier() = |4 fx fy| (src/lidar_selection.cpp:58-59)
+    c.jfx = std::fabs(cam->fx);
+    c.jfy = std::fabs(4.0 * cam->fx * cam->fy) / (4. * c.jfx);
+    h->cam = c;
+    h->cam_set = true;
+    return FLB_OK;
+}
+
+int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], const double p[3], int level, flb_vio_eq* out) {
+    FLB_CHECK_H(h);
+    if (!prm || !R || !p || !out || level < 0 || level > 2) return fail(h, FLB_ERR_INVALID, "flb_vio_pass: bad arguments");
+    if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_pass: camera and image must be set first");
+    if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
+    std::memset(out, 0, sizeof(*out));
+    if (h->Pn == 0) return FLB_OK;
+    const size_t Pn = h->Pn;
+    FLB_CUDA(h, h->x_z.reserve(Pn * 64));
+    FLB_CUDA(h, h->x_H.reserve(Pn * 64 * 6));
+    VioParamsDev d;
+    to_dev_params(prm, d);
+    double* st = static_cast<double*>(h->pin.p);
+    std::memcpy(st, R, 9 * sizeof(double));
+    std::memcpy(st + 9, p, 3 * sizeof(double));
+    FLB_CUDA(h, cudaMemcpyAsync(h->pose12.p, st, 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    VioArgs a{};
+    a.img = h->img.p;
+    a.cam = h->cam;
+    a.pos = h->patch_pos.p;
+    a.patch = h->patch_ref.p;
+    a.search_level = h->patch_level.p;
+    a.Pn = h->Pn;
+    a.state = &h->states.p[0];
+    a.pose_override = h->pose12.p;
+    a.prm = d;
+    a.ctrl = h->vio_ctrl.p;
+    a.force_level = level;
+    a.errors = h->errors.p;
+    a.partials = h->partials.p;
+    a.x_z = h->x_z.p;
+    a.x_H = h->x_H.p;
+    const int nb = vio_nblocks(h);
+    {
+        LaunchScope ls(h, FAM_VIO);
+        k_vio_pass<kVioBlock><<<nb, kVioBlock, 0, h->stream>>>(a);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_reduce_only<<<1, 32, 0, h->stream>>>(h->partials.p, nb, kVioPacked, h->packed.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    FLB_CUDA(h, h->pin_out.reserve(kVioPacked * sizeof(double) + Pn * sizeof(float)));
+    double* po = static_cast<double*>(h->pin_out.p);
+    float* pe = reinterpret_cast<float*>(po + kVioPacked);
+    FLB_CUDA(h, cudaMemcpyAsync(po, h->packed.p, kVioPacked * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(pe, h->errors.p, Pn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    int k = 0;
+    for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c) {
+            out->HTH[r * 6 + c] = po[k];
+            out->HTH[c * 6 + r] = po[k];
+            ++k;
+        }
+    for (int r = 0; r < 6; ++r) out->HTz[r] = po[21 + r];
+    out->n_meas = (int64_t)po[27];
+    out->skipped = (int)po[28];
+    // error = sum_i errors[i] (float, patch order) / n_meas  (src/lidar_selection.cpp:852,857)
+    float e = 0.0f;
+    for (size_t i = 0; i < Pn; ++i) e = e + pe[i];
+    out->error = e / (float)(size_t)out->n_meas;
+    h->last_vio_valid = true;
+    return FLB_OK;
+}
+
+int flb_vio_export(flb_handle* h, double* z, double* H_sub, float* errors) {
+    FLB_CHECK_H(h);
+    if (!h->last_vio_valid) return fail(h, FLB_ERR_STATE, "flb_vio_export: no flb_vio_pass to export");
+    const size_t Pn = h->Pn;
+    if (z) FLB_CUDA(h, cudaMemcpyAsync(z, h->x_z.p, Pn * 64 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (H_sub) FLB_CUDA(h, cudaMemcpyAsync(H_sub, h->x_H.p, Pn * 64 * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (errors) FLB_CUDA(h, cudaMemcpyAsync(errors, h->errors.p, Pn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+int flb_vio_update(flb_handle* h, const flb_vio_params* prm, flb_state18* x, const flb_state18* x_prop, flb_vio_report* rep) {
+    FLB_CHECK_H(h);
+    if (!prm || !x || !x_prop) return fail(h, FLB_ERR_INVALID, "flb_vio_update: null argument");
+    if (h->cam_set && (h->cam.width != h->img_w || h->cam.height != h->img_h))
+        return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
+    int rc = flb_state_upload(h, x, x_prop);
+    if (rc) return rc;
+    rc = enqueue_vio_update(h, prm);
+    if (rc) return rc;
+    flb_vio_report r{};
+    rc = flb_state_download(h, x, nullptr, &r);
+    if (rc) return rc;
+    if (rep) *rep = r;
+    if (r.status != 0) return fail(h, r.status, "flb_vio_update: device reported status %d", r.status);
+    return FLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int flb_profile_start(flb_handle* h) {
+    FLB_CHECK_H(h);
+    for (auto& ev : h->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    h->evs.clear();
+    h->profiling = true;
+    return FLB_OK;
+}
+
+int flb_profile_stop(flb_handle* h, double ms[4], int64_t launches[4]) {
+    FLB_CHECK_H(h);
+    h->profiling = false;
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4; ++i) { if (ms) ms[i] = 0.0; if (launches) launches[i] = 0; }
+    for (auto& ev : h->evs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev.a, ev.b);
+        if (ev.fam < 4) {
+            if (ms) ms[ev.fam] += t;
+            if (launches) launches[ev.fam] += 1;
+        }
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+    }
+    h->evs.clear();
+    return FLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int flb_comm_unique_id(void* unique_id_128b) {
+    if (!unique_id_128b) return FLB_ERR_INVALID;
+    if (!g_nccl.load()) return fail(nullptr, FLB_ERR_COMM, "libnccl.so.2 not found");
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, FLB_ERR_COMM, "ncclGetUniqueId failed (%d)", r);
+    std::memcpy(unique_id_128b, &id, 128);
+    return FLB_OK;
+}
+
+int flb_comm_init(flb_handle* h, const void* unique_id_128b, int rank, int world_size) {
+    FLB_CHECK_H(h);
+    if (!unique_id_128b || world_size < 1 || rank < 0 || rank >= world_size) return fail(h, FLB_ERR_INVALID, "flb_comm_init: bad arguments");
+    if (!g_nccl.load()) return fail(h, FLB_ERR_COMM, "libnccl.so.2 not found");
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id_128b, 128);
+    int r = g_nccl.CommInitRank(&h->comm, world_size, id, rank);
+    if (r != 0) { h->comm = nullptr; return fail(h, FLB_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+    h->rank = rank;
+    h->world = world_size;
+    return FLB_OK;
+}
+
+int flb_comm_destroy(flb_handle* h) {
+    FLB_CHECK_H(h);
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    h->world = 1;
+    h->rank = 0;
+    return FLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,588 @@
+// flb_device.cuh -- per-thread device math of the FAST-LIVO hot path (sm_100a).
+//
+// Everything here is a pure function of its arguments, compiled with
+// -fmad=false so that every float/double expression rounds exactly as written
+// (the reference's x86-64 build has no FMA contraction either).  The functions are
+// FLB_HD so that tests/hostemu can compile the very same source with g++ and check
+// it against the oracle without a GPU; the product library only ever calls them
+// from __global__ kernels (kernels.cu).
+//
+// Reference citations are relative to hku-mars/FAST-LIVO @ dcebf84.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FLB_HD __host__ __device__ __forceinline__
+#define FLB_UNROLL _Pragma("unroll")
+#else
+#define FLB_HD inline
+#define FLB_UNROLL
+#endif
+
+namespace flb {
+
+constexpr int kMatch = 5;    // NUM_MATCH_POINTS, include/common_lib.h:39
+constexpr int kDim = 18;     // DIM_STATE,        include/common_lib.h:34
+constexpr int kPatch = 8;    // patch_size (every config), patch_size_total = 64
+
+// ------------------------------------------------------------------ 3x3 helpers
+FLB_HD void m3_mul(const double* A, const double* B, double* C) {
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        FLB_UNROLL
+        for (int j = 0; j < 3; ++j)
+            C[3 * i + j] = A[3 * i + 0] * B[0 + j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    }
+}
+FLB_HD void m3_T(const double* A, double* T) {
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        FLB_UNROLL
+        for (int j = 0; j < 3; ++j) T[3 * i + j] = A[3 * j + i];
+    }
+}
+FLB_HD void m3_vec(const double* A, const double* v, double* o) {
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) o[i] = A[3 * i + 0] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+// SKEW_SYM_MATRX, include/so3_math.h:9
+FLB_HD void skew3(const double* v, double* K) {
+    K[0] = 0.0;   K[1] = -v[2]; K[2] = v[1];
+    K[3] = v[2];  K[4] = 0.0;   K[5] = -v[0];
+    K[6] = -v[1]; K[7] = v[0];  K[8] = 0.0;
+}
+FLB_HD double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// include/so3_math.h:54-72  Exp(v1, v2, v3)
+FLB_HD void so3_exp(const double* v, double* R) {
+    const double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (nrm > 0.00001) {
+        const double r[3] = {v[0] / nrm, v[1] / nrm, v[2] / nrm};
+        double K[9], KK[9];
+        skew3(r, K);
+        m3_mul(K, K, KK);
+        const double s = sin(nrm), c1 = 1.0 - cos(nrm);
+        FLB_UNROLL
+        for (int i = 0; i < 9; ++i) R[i] = R[i] + s * K[i] + c1 * KK[i];
+    }
+}
+
+// include/so3_math.h:75-81  Log(R)
+FLB_HD void so3_log(const double* R, double* out) {
+    const double tr = R[0] + R[4] + R[8];
+    const double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
+    const double K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+    if (fabs(theta) < 0.001) {
+        FLB_UNROLL
+        for (int i = 0; i < 3; ++i) out[i] = 0.5 * K[i];
+    } else {
+        const double f = 0.5 * theta / sin(theta);
+        FLB_UNROLL
+        for (int i = 0; i < 3; ++i) out[i] = f * K[i];
+    }
+}
+
+// ------------------------------------------------------------------ plane fit
+// esti_plane<float>, include/common_lib.h:448-493: least squares A(5x3) x = -1 by
+// column-pivoted Householder QR in float32, then normalise and test the 5 points.
+// Operation order is the oracle's (oracle/flo_oracle.cpp: flo_esti_plane); with
+// -fmad=false this is bit-exact against it.  All array indices are compile-time
+// after unrolling so qr[][] lives in registers.
+FLB_HD bool plane_fit5(const float (&nb)[kMatch][3], float threshold, float (&pabcd)[4]) {
+    constexpr int rows = kMatch, cols = 3;
+    float qr[rows][cols];
+    FLB_UNROLL
+    for (int j = 0; j < rows; ++j) {
+        FLB_UNROLL
+        for (int c = 0; c < cols; ++c) qr[j][c] = nb[j][c];
+    }
+    float hcoef[cols];
+    int colidx[cols] = {0, 1, 2};
+    float nrmU[cols], nrmD[cols];
+    FLB_UNROLL
+    for (int c = 0; c < cols; ++c) {
+        float s = 0.f;
+        FLB_UNROLL
+        for (int j = 0; j < rows; ++j) s = s + qr[j][c] * qr[j][c];
+        nrmD[c] = nrmU[c] = sqrtf(s);
+    }
+    const float eps = 1.1920928955078125e-07f;  // FLT_EPSILON
+    float maxnorm = nrmU[0];
+    FLB_UNROLL
+    for (int c = 1; c < cols; ++c)
+        if (nrmU[c] > maxnorm) maxnorm = nrmU[c];
+    const float th0 = maxnorm * eps;
+    const float threshold_helper = (th0 * th0) / float(rows);
+    const float downdate_thr = sqrtf(eps);
+    int nonzero_pivots = cols;
+    FLB_UNROLL
+    for (int k = 0; k < cols; ++k) {
+        int big = k;
+        float bigv = nrmU[k];
+        FLB_UNROLL
+        for (int c = k + 1; c < cols; ++c)
+            if (nrmU[c] > bigv) { bigv = nrmU[c]; big = c; }
+        const float big_sq = bigv * bigv;
+        if (nonzero_pivots == cols && big_sq < threshold_helper * float(rows - k)) nonzero_pivots = k;
+        FLB_UNROLL
+        for (int c = k + 1; c < cols; ++c) {
+            if (c == big) {
+                FLB_UNROLL
+                for (int j = 0; j < rows; ++j) { const float t = qr[j][k]; qr[j][k] = qr[j][c]; qr[j][c] = t; }
+                float t = nrmU[k]; nrmU[k] = nrmU[c]; nrmU[c] = t;
+                t = nrmD[k]; nrmD[k] = nrmD[c]; nrmD[c] = t;
+                const int ti = colidx[k]; colidx[k] = colidx[c]; colidx[c] = ti;
+            }
+        }
+        float tailSq = 0.f;
+        FLB_UNROLL
+        for (int j = k + 1; j < rows; ++j) tailSq = tailSq + qr[j][k] * qr[j][k];
+        const float c0 = qr[k][k];
+        float beta, tau;
+        if (tailSq <= 1.17549435082228750797e-38f) {  // FLT_MIN
+            tau = 0.f;
+            beta = c0;
+            FLB_UNROLL
+            for (int j = k + 1; j < rows; ++j) qr[j][k] = 0.f;
+        } else {
+            beta = sqrtf(c0 * c0 + tailSq);
+            if (c0 >= 0.f) beta = -beta;
+            const float den = c0 - beta;
+            FLB_UNROLL
+            for (int j = k + 1; j < rows; ++j) qr[j][k] = qr[j][k] / den;
+            tau = (beta - c0) / beta;
+        }
+        qr[k][k] = beta;
+        hcoef[k] = tau;
+        if (tau != 0.f) {
+            FLB_UNROLL
+            for (int c = k + 1; c < cols; ++c) {
+                float tmp = 0.f;
+                FLB_UNROLL
+                for (int j = k + 1; j < rows; ++j) tmp = tmp + qr[j][k] * qr[j][c];
+                tmp = tmp + qr[k][c];
+                qr[k][c] = qr[k][c] - tau * tmp;
+                FLB_UNROLL
+                for (int j = k + 1; j < rows; ++j) qr[j][c] = qr[j][c] - (tau * qr[j][k]) * tmp;
+            }
+        }
+        FLB_UNROLL
+        for (int c = k + 1; c < cols; ++c) {
+            if (nrmU[c] != 0.f) {
+                float temp = fabsf(qr[k][c]) / nrmU[c];
+                temp = (1.f + temp) * (1.f - temp);
+                temp = temp < 0.f ? 0.f : temp;
+                const float ratio = nrmU[c] / nrmD[c];
+                const float temp2 = temp * (ratio * ratio);
+                if (temp2 <= downdate_thr) {
+                    float s = 0.f;
+                    FLB_UNROLL
+                    for (int j = k + 1; j < rows; ++j) s = s + qr[j][c] * qr[j][c];
+                    nrmD[c] = sqrtf(s);
+                    nrmU[c] = nrmD[c];
+                } else {
+                    nrmU[c] = nrmU[c] * sqrtf(temp);
+                }
+            }
+        }
+    }
+    float cv[rows];
+    FLB_UNROLL
+    for (int j = 0; j < rows; ++j) cv[j] = -1.0f;
+    float x[3] = {0.f, 0.f, 0.f};
+    FLB_UNROLL
+    for (int k = 0; k < cols; ++k) {
+        if (k < nonzero_pivots) {
+            const float tau = hcoef[k];
+            if (tau != 0.f) {
+                float tmp = 0.f;
+                FLB_UNROLL
+                for (int j = k + 1; j < rows; ++j) tmp = tmp + qr[j][k] * cv[j];
+                tmp = tmp + cv[k];
+                cv[k] = cv[k] - tau * tmp;
+                FLB_UNROLL
+                for (int j = k + 1; j < rows; ++j) cv[j] = cv[j] - (tau * qr[j][k]) * tmp;
+            }
+        }
+    }
+    FLB_UNROLL
+    for (int i = cols - 1; i >= 0; --i) {
+        if (i < nonzero_pivots) {
+            cv[i] = cv[i] / qr[i][i];
+            FLB_UNROLL
+            for (int r = 0; r < i; ++r) cv[r] = cv[r] - cv[i] * qr[r][i];
+        }
+    }
+    FLB_UNROLL
+    for (int i = 0; i < cols; ++i) {
+        if (i < nonzero_pivots) {
+            FLB_UNROLL
+            for (int c = 0; c < cols; ++c)
+                if (colidx[i] == c) x[c] = cv[i];
+        }
+    }
+    const float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    pabcd[0] = x[0] / n;
+    pabcd[1] = x[1] / n;
+    pabcd[2] = x[2] / n;
+    pabcd[3] = (float)(1.0 / (double)n);
+    bool ok = true;
+    FLB_UNROLL
+    for (int j = 0; j < rows; ++j) {
+        const float v = pabcd[0] * nb[j][0] + pabcd[1] * nb[j][1] + pabcd[2] * nb[j][2] + pabcd[3];
+        if (!(fabsf(v) <= threshold)) ok = false;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------ LIO per-point
+// Per-pass constants (uniform over the scan): pose, extrinsic and their transposes.
+struct LioPose {
+    double R[9], p[3];       // state.rot_end / pos_end
+    double R_LI[9], t_LI[3]; // Lidar_rot_to_IMU / Lidar_offset_to_IMU
+    double Rt[9], RLIt[9];   // transposes
+};
+
+// pointBodyToWorld, src/laserMapping.cpp:272-286: double math, float store.
+FLB_HD void lio_body_to_world(const LioPose& c, const float* pb, double* pI, float* pw) {
+    const double b[3] = {(double)pb[0], (double)pb[1], (double)pb[2]};
+    m3_vec(c.R_LI, b, pI);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) pI[k] = pI[k] + c.t_LI[k];
+    double w[3];
+    m3_vec(c.R, pI, w);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) pw[k] = (float)(w[k] + c.p[k]);
+}
+
+// Residual + gate, src/laserMapping.cpp:1573-1576.  Returns s > 0.9.
+FLB_HD bool lio_residual(const float* pabcd, const float* pw, const float* pb, float* pd2_out) {
+    const float pd2 = pabcd[0] * pw[0] + pabcd[1] * pw[1] + pabcd[2] * pw[2] + pabcd[3];
+    const double b[3] = {(double)pb[0], (double)pb[1], (double)pb[2]};
+    const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(norm3(b)));
+    *pd2_out = pd2;
+    return (double)s > 0.9;
+}
+
+// Live-layout row [A, n], A = [p_I]x * R^T * n   (src/laserMapping.cpp:1611-1625)
+FLB_HD void lio_row6(const LioPose& c, const double* pI, const float* pabcd, double* row) {
+    double cross[9], M1[9], A[3];
+    skew3(pI, cross);
+    const double nv[3] = {(double)pabcd[0], (double)pabcd[1], (double)pabcd[2]};
+    m3_mul(cross, c.Rt, M1);
+    m3_vec(M1, nv, A);
+    row[0] = A[0]; row[1] = A[1]; row[2] = A[2];
+    row[3] = nv[0]; row[4] = nv[1]; row[5] = nv[2];
+}
+
+// IKFoM-layout row [n, A, B, C]  (src/laserMapping.cpp:1063-1082):
+//   C = R^T n, A = [p_I]x C, B = [p_b]x R_LI^T C
+FLB_HD void lio_row12(const LioPose& c, const double* pI, const float* pb, const float* pabcd, double* row) {
+    const double nv[3] = {(double)pabcd[0], (double)pabcd[1], (double)pabcd[2]};
+    const double b[3] = {(double)pb[0], (double)pb[1], (double)pb[2]};
+    double C[3], A[3], B[3], cross[9], crossb[9], M2[9];
+    m3_vec(c.Rt, nv, C);
+    skew3(pI, cross);
+    m3_vec(cross, C, A);
+    skew3(b, crossb);
+    m3_mul(crossb, c.RLIt, M2);
+    m3_vec(M2, C, B);
+    row[0] = nv[0]; row[1] = nv[1]; row[2] = nv[2];
+    row[3] = A[0];  row[4] = A[1];  row[5] = A[2];
+    row[6] = B[0];  row[7] = B[1];  row[8] = B[2];
+    row[9] = C[0];  row[10] = C[1]; row[11] = C[2];
+}
+
+// ------------------------------------------------------------------ kNN over the uniform grid
+struct GridDesc {
+    float ox, oy, oz;     // origin (min corner)
+    float cell, inv_cell;
+    int nx, ny, nz;       // cells per axis; cell id = (z*ny + y)*nx + x  (x fastest)
+    float max_d2;         // 5.0
+    int max_ring;         // ceil(sqrt(max_d2)/cell) + 1
+};
+
+struct Top5 {
+    float d[kMatch];
+    int i[kMatch];
+};
+
+FLB_HD void top5_init(Top5& t) {
+    FLB_UNROLL
+    for (int j = 0; j < kMatch; ++j) { t.d[j] = INFINITY; t.i[j] = -1; }
+}
+
+// Strict-< insertion (first visited wins a tie: ikd_Tree.cpp:860), ascending order.
+FLB_HD void top5_insert(Top5& t, float d, int id) {
+    if (d < t.d[4]) {
+        if (d < t.d[3]) {
+            t.d[4] = t.d[3]; t.i[4] = t.i[3];
+            if (d < t.d[2]) {
+                t.d[3] = t.d[2]; t.i[3] = t.i[2];
+                if (d < t.d[1]) {
+                    t.d[2] = t.d[1]; t.i[2] = t.i[1];
+                    if (d < t.d[0]) {
+                        t.d[1] = t.d[0]; t.i[1] = t.i[0];
+                        t.d[0] = d; t.i[0] = id;
+                    } else { t.d[1] = d; t.i[1] = id; }
+                } else { t.d[2] = d; t.i[2] = id; }
+            } else { t.d[3] = d; t.i[3] = id; }
+        } else { t.d[4] = d; t.i[4] = id; }
+    }
+}
+
+// calc_dist, include/ikd-Tree/ikd_Tree.cpp:1291-1295: (dx*dx + dy*dy) + dz*dz in float32.
+FLB_HD float dist2f(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+#if defined(__CUDACC__)
+typedef float4 map_pt;
+#else
+struct map_pt { float x, y, z, w; };
+#endif
+#if defined(__CUDA_ARCH__)
+#define FLB_LDG4(ptr) __ldg(ptr)
+#define FLB_LDGI(ptr) __ldg(ptr)
+#else
+#define FLB_LDG4(ptr) (*(ptr))
+#define FLB_LDGI(ptr) (*(ptr))
+#endif
+
+// Scan one contiguous run of sorted map points [s, e).
+FLB_HD void knn_scan_run(const map_pt* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t) {
+    for (int m = s; m < e; ++m) {
+        const map_pt P = FLB_LDG4(pts + m);
+        top5_insert(t, dist2f(qx, qy, qz, P.x, P.y, P.z), m);
+    }
+}
+
+// Exact 5-NN restricted to d2 <= max_d2, by ring expansion over the sorted uniform grid.
+// After all cells within Chebyshev radius r of the query's cell are scanned, every
+// unscanned point is at least (r*cell + margin) away, margin = distance from the query
+// to the nearest face of its own cell.  Terminate when the 5th best is inside that
+// bound (minus a float slack that also covers points binned across a face by
+// rounding), or when the bound passes sqrt(max_d2).  Returns sorted positions in t.i.
+FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, const map_pt* __restrict__ pts,
+                      float qx, float qy, float qz, Top5& t) {
+    top5_init(t);
+    const float fx = (qx - g.ox) * g.inv_cell, fy = (qy - g.oy) * g.inv_cell, fz = (qz - g.oz) * g.inv_cell;
+    // far outside the grid: nothing within sqrt(max_d2)
+    const float lim = (float)(g.max_ring + 2);
+    if (!(fx > -lim && fy > -lim && fz > -lim && fx < (float)g.nx + lim && fy < (float)g.ny + lim &&
+          fz < (float)g.nz + lim))
+        return;
+    const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+    float mx = fminf(fx - (float)cx, (float)(cx + 1) - fx);
+    float my = fminf(fy - (float)cy, (float)(cy + 1) - fy);
+    float mz = fminf(fz - (float)cz, (float)(cz + 1) - fz);
+    const float margin = fmaxf(fminf(mx, fminf(my, mz)) * g.cell - 1e-3f * g.cell, 0.f);
+    for (int r = 0; r <= g.max_ring; ++r) {
+        const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
+        for (int z = (z0 < 0 ? 0 : z0); z <= (z1 >= g.nz ? g.nz - 1 : z1); ++z) {
+            const bool zface = (z == z0) || (z == z1);
+            for (int y = (y0 < 0 ? 0 : y0); y <= (y1 >= g.ny ? g.ny - 1 : y1); ++y) {
+                const int rowbase = (z * g.ny + y) * g.nx;
+                const int xa = x0 < 0 ? 0 : x0, xb = x1 >= g.nx ? g.nx - 1 : x1;
+                if (zface || y == y0 || y == y1 || r == 0) {
+                    if (xa <= xb) {
+                        const int s = FLB_LDGI(cell_start + rowbase + xa), e = FLB_LDGI(cell_start + rowbase + xb + 1);
+                        knn_scan_run(pts, s, e, qx, qy, qz, t);
+                    }
+                } else {
+                    if (x0 >= 0 && x0 < g.nx) {
+                        const int s = FLB_LDGI(cell_start + rowbase + x0), e = FLB_LDGI(cell_start + rowbase + x0 + 1);
+                        knn_scan_run(pts, s, e, qx, qy, qz, t);
+                    }
+                    if (x1 >= 0 && x1 < g.nx) {
+                        const int s = FLB_LDGI(cell_start + rowbase + x1), e = FLB_LDGI(cell_start + rowbase + x1 + 1);
+                        knn_scan_run(pts, s, e, qx, qy, qz, t);
+                    }
+                }
+            }
+        }
+        const float bound = (float)r * g.cell + margin;
+        const float b2 = bound * bound;
+        if (t.d[4] <= b2) break;        // 5th best is certainly final
+        if (b2 > g.max_d2 * 1.0001f) break;  // everything unscanned is beyond max_d2
+    }
+}
+
+// ------------------------------------------------------------------ VIO per-patch / per-pixel
+struct CamModel {
+    int width, height;
+    double fx, fy, cx, cy;   // projection (world2cam)
+    double d[5];
+    double jfx, jfy;         // dpi's fx, fy: |fx|, |4 fx fy| / (4 |fx|)  (src/lidar_selection.cpp:58-59)
+};
+
+// Per-pass constants of UpdateState, src/lidar_selection.cpp:776-782 + init() :41-52.
+struct VioPose {
+    double Rcw[9], Pcw[3];   // :780-781
+    double Jdp_dt[9];        // :782  (= Rci * Rwi^T)
+    double Jdphi_dR[9];      // = Rci
+    double Jdp_dR[9];        // = -Rci * [Pic]x
+};
+
+FLB_HD void vio_make_pose(const double* Rci, const double* Pci, const double* R, const double* p, VioPose& o) {
+    double Rt[9], t[3];
+    m3_T(R, Rt);
+    m3_mul(Rci, Rt, o.Rcw);
+    m3_vec(o.Rcw, p, t);
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) o.Pcw[i] = -t[i] + Pci[i];
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) { o.Jdp_dt[i] = o.Rcw[i]; o.Jdphi_dR[i] = Rci[i]; }
+    double RciT[9], Pic[3], sk[9], m[9];
+    m3_T(Rci, RciT);
+    m3_vec(RciT, Pci, Pic);
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) Pic[i] = -Pic[i];
+    skew3(Pic, sk);
+    m3_mul(Rci, sk, m);
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) o.Jdp_dR[i] = -m[i];
+}
+
+// vikit PinholeCamera::world2cam(Vector3d).
+FLB_HD void world2cam(const CamModel& cam, const double* pf, double* px) {
+    const double x = pf[0] / pf[2], y = pf[1] / pf[2];
+    if (!(fabs(cam.d[0]) > 0.0000001)) {
+        px[0] = cam.fx * x + cam.cx;
+        px[1] = cam.fy * y + cam.cy;
+    } else {
+        const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+        const double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+        const double cdist = 1 + cam.d[0] * r2 + cam.d[1] * r4 + cam.d[4] * r6;
+        const double xd = x * cdist + cam.d[2] * a1 + cam.d[3] * a2;
+        const double yd = y * cdist + cam.d[2] * a3 + cam.d[3] * a1;
+        px[0] = xd * cam.fx + cam.cx;
+        px[1] = yd * cam.fy + cam.cy;
+    }
+}
+
+// Patch-level quantities of src/lidar_selection.cpp:792-816.
+struct PatchGeom {
+    double Jdpi[6];      // dpi(pf), :92-103
+    double p_hat[9];     // skew(pf), :805
+    float w_tl, w_tr, w_bl, w_br;
+    int u_i, v_i;        // integer anchor
+    int scale;
+    bool valid;          // in front of the camera and tap footprint inside the image (our guard)
+};
+
+FLB_HD void vio_patch_geom(const CamModel& cam, const VioPose& vp, const double* pos, int level, int search_level,
+                           PatchGeom& g) {
+    const int scale = 1 << (level + search_level);
+    g.scale = scale;
+    g.valid = false;
+    double pf[3];
+    m3_vec(vp.Rcw, pos, pf);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) pf[k] = pf[k] + vp.Pcw[k];
+    if (!(pf[2] > 0.0)) return;
+    double pc[2];
+    world2cam(cam, pf, pc);
+    if (!(fabs(pc[0]) < 1e6) || !(fabs(pc[1]) < 1e6)) return;
+    {
+        const double x = pf[0], y = pf[1], z_inv = 1. / pf[2], z_inv_2 = z_inv * z_inv;
+        g.Jdpi[0] = cam.jfx * z_inv; g.Jdpi[1] = 0.0; g.Jdpi[2] = -cam.jfx * x * z_inv_2;
+        g.Jdpi[3] = 0.0; g.Jdpi[4] = cam.jfy * z_inv; g.Jdpi[5] = -cam.jfy * y * z_inv_2;
+    }
+    skew3(pf, g.p_hat);
+    const float u_ref = (float)pc[0];
+    const float v_ref = (float)pc[1];
+    const int u_i = (int)(floorf((float)(pc[0] / scale)) * (float)scale);   // :809
+    const int v_i = (int)(floorf((float)(pc[1] / scale)) * (float)scale);
+    if (u_i - 5 * scale < 0 || u_i + 5 * scale > cam.width - 1 || v_i - 5 * scale < 0 ||
+        v_i + 5 * scale > cam.height - 1)
+        return;
+    const float su = (u_ref - (float)u_i) / (float)scale;
+    const float sv = (v_ref - (float)v_i) / (float)scale;
+    g.w_tl = (float)((1.0 - (double)su) * (1.0 - (double)sv));    // :813-816 (double expressions -> float)
+    g.w_tr = (float)((double)su * (1.0 - (double)sv));
+    g.w_bl = (float)((1.0 - (double)su) * (double)sv);
+    g.w_br = su * sv;
+    g.u_i = u_i;
+    g.v_i = v_i;
+    g.valid = true;
+}
+
+// One pixel of the 8x8 loop, src/lidar_selection.cpp:819-847.
+// L is the patch's 11x11 tap lattice (stride `scale` pixels, centred on the anchor):
+//   L[r][c] = img[(v_i + (r-5)*scale) * W + u_i + (c-5)*scale]  as float.
+// Pixel (x = row, y = col) reads img_ptr[a*scale + b*scale*W] = L[x+1+b][y+1+a].
+template <typename Lat>
+FLB_HD void vio_pixel(const Lat& L, const PatchGeom& g, const VioPose& vp, int x, int y, float ref, double* row,
+                      double* res_out) {
+    const int r = x + 1, c = y + 1;
+    const float wtl = g.w_tl, wtr = g.w_tr, wbl = g.w_bl, wbr = g.w_br;
+    const float du = 0.5f * ((wtl * L(r, c + 1) + wtr * L(r, c + 2) + wbl * L(r + 1, c + 1) + wbr * L(r + 1, c + 2)) -
+                             (wtl * L(r, c - 1) + wtr * L(r, c) + wbl * L(r + 1, c - 1) + wbr * L(r + 1, c)));
+    const float dv = 0.5f * ((wtl * L(r + 1, c) + wtr * L(r + 1, c + 1) + wbl * L(r + 2, c) + wbr * L(r + 2, c + 1)) -
+                             (wtl * L(r - 1, c) + wtr * L(r - 1, c + 1) + wbl * L(r, c) + wbr * L(r, c + 1)));
+    const double inv_scale = (1.0 / g.scale);
+    const double J0 = (double)du * inv_scale, J1 = (double)dv * inv_scale;
+    double JJ[3], Jdphi[3], Jdp[3];
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) JJ[k] = J0 * g.Jdpi[k] + J1 * g.Jdpi[3 + k];
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) Jdphi[k] = JJ[0] * g.p_hat[k] + JJ[1] * g.p_hat[3 + k] + JJ[2] * g.p_hat[6 + k];
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) Jdp[k] = (-J0) * g.Jdpi[k] + (-J1) * g.Jdpi[3 + k];
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k)
+        row[k] = (Jdphi[0] * vp.Jdphi_dR[k] + Jdphi[1] * vp.Jdphi_dR[3 + k] + Jdphi[2] * vp.Jdphi_dR[6 + k]) +
+                 (Jdp[0] * vp.Jdp_dR[k] + Jdp[1] * vp.Jdp_dR[3 + k] + Jdp[2] * vp.Jdp_dR[6 + k]);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k)
+        row[3 + k] = Jdp[0] * vp.Jdp_dt[k] + Jdp[1] * vp.Jdp_dt[3 + k] + Jdp[2] * vp.Jdp_dt[6 + k];
+    const float resf = wtl * L(r, c) + wtr * L(r, c + 1) + wbl * L(r + 1, c) + wbr * L(r + 1, c + 1) - ref;  // :837
+    *res_out = (double)resf;
+}
+
+// ------------------------------------------------------------------ 18-DoF state algebra
+struct State18 {
+    double rot[9], pos[3], vel[3], bg[3], ba[3], grav[3];
+    double cov[kDim * kDim];
+};
+
+// StatesGroup::operator+=, include/common_lib.h:343-352
+FLB_HD void state_boxplus(State18& x, const double* d) {
+    double E[9], Rn[9];
+    so3_exp(d, E);
+    m3_mul(x.rot, E, Rn);
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) x.rot[i] = Rn[i];
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        x.pos[i] += d[3 + i];
+        x.vel[i] += d[6 + i];
+        x.bg[i] += d[9 + i];
+        x.ba[i] += d[12 + i];
+        x.grav[i] += d[15 + i];
+    }
+}
+
+// StatesGroup::operator- (a - b), include/common_lib.h:354-365
+FLB_HD void state_boxminus(const State18& a, const State18& b, double* out) {
+    double bT[9], rotd[9];
+    m3_T(b.rot, bT);
+    m3_mul(bT, a.rot, rotd);
+    so3_log(rotd, out);
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        out[3 + i] = a.pos[i] - b.pos[i];
+        out[6 + i] = a.vel[i] - b.vel[i];
+        out[9 + i] = a.bg[i] - b.bg[i];
+        out[12 + i] = a.ba[i] - b.ba[i];
+        out[15 + i] = a.grav[i] - b.grav[i];
+    }
+}
+
+}  // namespace flb

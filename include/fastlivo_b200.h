@@ -1,0 +1,236 @@
+/* fastlivo_b200 -- C ABI of the B200-native FAST-LIVO measurement/ESKF hot path.
+ *
+ * Plain C, plain pointers and sizes, no torch / Eigen / PCL types.  Every entry
+ * point cites the reference code it replaces (paths relative to the reference
+ * tree hku-mars/FAST-LIVO @ dcebf84).  INTEGRATION.md shows the bindings a
+ * maintainer of the reference adds on its side.
+ *
+ * Conventions
+ *   - all pointers are HOST pointers owned by the caller for the duration of
+ *     the call only; the library copies.  The opaque handle owns all device
+ *     memory, one CUDA stream and (optionally) one NCCL communicator.
+ *   - matrices are row-major doubles; rotations are 3x3 row-major.
+ *   - every function returns an int status: FLB_OK (0) or a negative FLB_ERR_*;
+ *     nothing throws or aborts.  flb_last_error() gives a message.
+ *   - a handle is single-caller; distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device flb_create() fails with
+ *     FLB_ERR_NO_DEVICE.
+ */
+#ifndef FASTLIVO_B200_H
+#define FASTLIVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLB_OK             0
+#define FLB_ERR_INVALID   -1  /* bad argument */
+#define FLB_ERR_CUDA      -2  /* CUDA runtime error (see flb_last_error) */
+#define FLB_ERR_NO_DEVICE -3  /* no usable CUDA device: the product path refuses to run */
+#define FLB_ERR_STATE     -4  /* call order: map / scan / image / patches not uploaded */
+#define FLB_ERR_NUMERIC   -5  /* singular normal matrix or non-finite state */
+#define FLB_ERR_COMM      -6  /* NCCL not available / communicator error */
+#define FLB_ERR_TIMEOUT   -7  /* device-side barrier watchdog tripped */
+
+#define FLB_ABI_VERSION 1
+
+typedef struct flb_handle flb_handle;
+
+typedef struct flb_config {
+    int    device;           /* CUDA ordinal */
+    double cell_size;        /* uniform-grid cell for the device map; <=0 -> 0.6 (2 x filter_size_map) */
+    double knn_max_d2;       /* neighbours farther than this never select a point: 5.0,
+                                src/laserMapping.cpp:1549; <=0 -> 5.0 */
+    double plane_threshold;  /* esti_plane threshold 0.1f, src/laserMapping.cpp:1571; <=0 -> 0.1 */
+    int    persistent;       /* 1: one persistent kernel per update (default); 0: kernel-per-pass */
+    int    reserved[7];
+} flb_config;
+
+/* 18-DoF state == StatesGroup, include/common_lib.h:296-381.
+ * cov order [rot, pos, vel, bias_g, bias_a, gravity]. */
+typedef struct flb_state18 {
+    double rot[9];
+    double pos[3];
+    double vel[3];
+    double bg[3];
+    double ba[3];
+    double grav[3];
+    double cov[324];
+} flb_state18;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int         flb_abi_version(void);
+int         flb_create(const flb_config* cfg, flb_handle** out);
+int         flb_destroy(flb_handle* h);
+const char* flb_last_error(const flb_handle* h);   /* h may be NULL: last create error */
+/* Run all subsequent work of this handle on an existing CUDA stream (cudaStream_t
+ * passed as void*), e.g. torch's current stream.  NULL restores the handle's own. */
+int         flb_set_stream(flb_handle* h, void* cuda_stream);
+int         flb_synchronize(flb_handle* h);
+
+/* ---- map: the query half of ikd-Tree -------------------------------------------
+ * Replaces KD_TREE::Build (include/ikd-Tree/ikd_Tree.cpp:337-348, called at
+ * src/laserMapping.cpp:1411-1419): uploads M map points (float xyz, stride in
+ * floats: 3 for packed, 4 for float4, 12 for pcl::PointXYZINormal) and builds the
+ * device-resident sorted uniform grid the kNN kernel walks. */
+int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride_floats);
+
+/* ---- scan ------------------------------------------------------------------------
+ * feats_down_body (src/laserMapping.cpp:1398-1399): N already-downsampled points in
+ * the LiDAR body frame. */
+int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride_floats);
+
+/* Exact 5-NN of nq WORLD-frame float queries, KD_TREE::Nearest_Search semantics
+ * (include/ikd-Tree/ikd_Tree.cpp:350-380, 843-986, 1291-1295): float32
+ * (dx*dx+dy*dy)+dz*dz, ascending order.  idx: nq x 5 indices into the uploaded map,
+ * d2: nq x 5.  A query whose 5th neighbour is farther than knn_max_d2 gets
+ * idx = -1 / d2 = +inf for the entries beyond knn_max_d2 (the reference rejects such
+ * points at src/laserMapping.cpp:1549, so the bounded search is behaviourally identical). */
+int flb_knn(flb_handle* h, const float* q_world, int nq, int* idx, float* d2);
+
+/* ---- LIO -------------------------------------------------------------------------- */
+typedef struct flb_lio_params {
+    double R_LI[9];          /* Lidar_rot_to_IMU     src/laserMapping.cpp:104-105 */
+    double t_LI[3];          /* Lidar_offset_to_IMU */
+    double laser_point_cov;  /* LASER_POINT_COV      src/laserMapping.cpp:1109 */
+    int    max_iteration;    /* NUM_MAX_ITERATIONS: the loop runs iterCount = -1..T-1 (:1506) */
+    double conv_rot_deg;     /* 0.01  (:1688); 0 disables the convergence test */
+    double conv_pos_cm;      /* 0.015 (:1688) */
+} flb_lio_params;
+
+typedef struct flb_lio_report {
+    int     passes;
+    int     knn_passes;
+    int     n_eff_last;      /* effct_feat_num */
+    double  res_mean_last;   /* src/laserMapping.cpp:1602 */
+    int64_t rows_total;      /* point-to-plane rows assembled over all passes */
+    int     converged_last;
+    int     status;          /* FLB_OK or FLB_ERR_NUMERIC / FLB_ERR_TIMEOUT raised on device */
+} flb_lio_report;
+
+/* Packed normal equations of one pass.  width = 6: live layout [rot, pos]
+ * (Hsub, src/laserMapping.cpp:1608-1629); width = 12: IKFoM layout
+ * [pos, rot, offset_R_L_I, offset_T_L_I] (h_x, src/laserMapping.cpp:1059-1089). */
+typedef struct flb_normal_eq {
+    int    width;
+    int    n_eff;
+    double sum_abs_res;      /* total_residual, :1597 */
+    double HTH[144];         /* width x width row-major in the leading entries */
+    double HTh[12];
+} flb_normal_eq;
+
+/* One pass of the matching loop body src/laserMapping.cpp:1508-1630 at pose (R,p):
+ * pointBodyToWorld (:272-286), [kNN (:1543) + esti_plane (common_lib.h:448-493) when
+ * rematch], residual + gates (:1573-1584), compaction (:1588-1602), rows (:1608-1629),
+ * H^T H / H^T z (:1664-1666).  Also the measurement half of h_share_model (:960-1094)
+ * when width = 12 (rematch == ekfom_data.converge, :994). */
+int flb_lio_pass(flb_handle* h, const flb_lio_params* prm, const double R[9], const double p[3],
+                 int rematch, int width, flb_normal_eq* out);
+
+/* Per-point / per-row products of the LAST flb_lio_pass (any pointer may be NULL):
+ *   world_xyz N x 3 float (feats_down_world); nn_idx N x 5 (Nearest_Points as map
+ *   indices, -1 = none); nn_d2 N x 5; pabcd N x 4 (cached plane); pd2 N;
+ *   selected N (point_selected_surf && res_last<=2, i.e. the row mask);
+ *   rows n x width doubles row-major (Hsub or h_x); meas n (meas_vec / h);
+ *   sel_idx n (scan index of each compacted row, the order of laserCloudOri). */
+int flb_lio_export(flb_handle* h, float* world_xyz, int* nn_idx, float* nn_d2, float* pabcd, float* pd2,
+                   uint8_t* selected, double* rows, double* meas, int* sel_idx, int* n_rows);
+
+/* The whole iterated update src/laserMapping.cpp:1504-1733 (control flow: SURVEY.md
+ * Appendix A), run on the device without a host round trip per pass.  x: in = state
+ * before the update (normally == x_prop), out = updated state and covariance. */
+int flb_lio_update(flb_handle* h, const flb_lio_params* prm, flb_state18* x, const flb_state18* x_prop,
+                   flb_lio_report* rep);
+
+/* ---- VIO --------------------------------------------------------------------------- */
+typedef struct flb_camera {
+    int    width, height;
+    double fx, fy, cx, cy;   /* vikit PinholeCamera (config/camera_pinhole.yaml) */
+    double d[5];             /* radtan; enabled iff |d0| > 1e-7 */
+} flb_camera;
+
+typedef struct flb_vio_params {
+    double Rcl[9], Pcl[3];   /* camera<-lidar extrinsic, src/laserMapping.cpp:1206 (set_camera2lidar) */
+    double R_LI[9], t_LI[3]; /* LidarSelector::set_extrinsic, src/lidar_selection.cpp:35-39 */
+    double img_point_cov;    /* src/lidar_selection.cpp:873 */
+    int    max_iteration;    /* LidarSelector::NUM_MAX_ITERATIONS */
+    float  conv_rot_deg;     /* 0.001f (:883); 0 disables */
+    float  conv_pos_cm;      /* 0.001f */
+    int    force_all_passes; /* benchmark mode: fixed pass count (no error test, no EKF_end) */
+} flb_vio_params;
+
+typedef struct flb_vio_report {
+    int     passes[3];       /* index = pyramid level */
+    float   last_error[3];
+    int64_t rows_total;      /* photometric rows (pixels) assembled over all passes */
+    int     skipped_last;    /* patches dropped by the bounds / depth guard in the last pass */
+    int     cov_updated;
+    int     status;
+} flb_vio_report;
+
+typedef struct flb_vio_eq {
+    double  HTH[36];
+    double  HTz[6];
+    float   error;           /* mean squared photometric error, :857 */
+    int64_t n_meas;
+    int     skipped;
+} flb_vio_eq;
+
+/* cv::Mat img of LidarSelector::detect (src/lidar_selection.cpp:1027-1037): gray uint8. */
+int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, int stride_bytes);
+/* SubSparseMap (include/common_lib.h:263-292) flattened: pos Pn x 3 (Point::pos_),
+ * patch Pn x 3 x 64 floats (warpAffine layout, src/lidar_selection.cpp:279-295),
+ * search_level Pn. */
+int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, const int* search_level, int Pn);
+int flb_camera_set(flb_handle* h, const flb_camera* cam);
+
+/* One measurement pass of LidarSelector::UpdateState (src/lidar_selection.cpp:772-857)
+ * at pose (R,p) and pyramid level `level`. */
+int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], const double p[3], int level,
+                 flb_vio_eq* out);
+/* Rows of the LAST flb_vio_pass: z Pn*64 doubles, H_sub Pn*64 x 6 row-major,
+ * errors Pn floats (sub_sparse_map->errors). */
+int flb_vio_export(flb_handle* h, double* z, double* H_sub, float* errors);
+
+/* LidarSelector::ComputeJ (src/lidar_selection.cpp:967-983): UpdateState (:743-902)
+ * for level = 2,1,0, then cov -= G*cov, all on the device. */
+int flb_vio_update(flb_handle* h, const flb_vio_params* prm, flb_state18* x, const flb_state18* x_prop,
+                   flb_vio_report* rep);
+
+/* ---- device-resident frame loop (benchmark / pipeline use) ---------------------------
+ * Enqueue-only variants: state stays on the device between calls, nothing is copied
+ * back until flb_state_download.  flb_frame_enqueue = one LIO update followed by one
+ * VIO update whose prior is the LIO posterior (zero-motion propagation). */
+int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_prop);
+int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio);
+int flb_lio_update_enqueue(flb_handle* h, const flb_lio_params* prm);
+int flb_vio_update_enqueue(flb_handle* h, const flb_vio_params* prm);
+/* restore x := x_prop := the state given to the last flb_state_upload (device-side copy) */
+int flb_state_reset_enqueue(flb_handle* h);
+
+/* Per-kernel-family device time of the work enqueued between start and stop,
+ * measured with CUDA events on the handle's stream (adds one event pair per launch:
+ * use for profiling runs, not for headline timing).  ms[0] = LIO rematch passes,
+ * ms[1] = LIO plain passes, ms[2] = VIO passes, ms[3] = solves/finalize; launches[i]
+ * the matching launch counts. */
+int flb_profile_start(flb_handle* h);
+int flb_profile_stop(flb_handle* h, double ms[4], int64_t launches[4]);
+/* kernels launched by this handle since creation */
+int64_t flb_launch_count(const flb_handle* h);
+
+/* ---- multi-GPU -------------------------------------------------------
+ * One process per GPU.  Each rank uploads ITS contiguous shard of the scan points and
+ * patches, the full map and image, and identical states; every pass all-reduces the
+ * packed normal equations (ncclAllReduce, ncclDouble, ncclSum) and every rank runs
+ * the identical solve.  unique_id is the 128-byte ncclUniqueId produced by
+ * flb_comm_unique_id on rank 0 and distributed by the caller (e.g. torch.distributed). */
+int flb_comm_unique_id(void* unique_id_128b);
+int flb_comm_init(flb_handle* h, const void* unique_id_128b, int rank, int world_size);
+int flb_comm_destroy(flb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTLIVO_B200_H */
