@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- ESKF frames/s and residuals/s of the FAST-LIVO measurement + iterated-ESKF hot
+path on B200 (BASELINE.json metric), with the reference-equivalent CPU path timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl reference]
+
+A *step* is one frame: one full LIO update (all passes, kNN on the rematch passes) followed by
+one full VIO update (ComputeJ: 3 pyramid levels) whose prior is the LIO posterior, on one
+synthetic Avia-shaped frame (fast-livo_b200/synth.py).  Pass counts are fixed (early stop
+disabled) so that the GPU and CPU arms do identical work.
+
+  value : frames/s with all inputs resident in HBM (state reset on the device each step)
+  e2e   : frames/s through the C ABI with HOST buffers: per step the scan, image, patch list
+          and both states go host->device and the updated state + reports come back
+  roofline / cpu_baseline : see DESIGN.md §5.
+
+N > 1 (torchrun, one rank per GPU): the scan points and patches are block-sharded, map / image /
+state replicated, packed normal equations all-reduced with NCCL every pass (BASELINE.json
+config 5) -- total work is fixed, so scaling is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import fastlivo_loader  # noqa: E402
+
+METRIC = "eskf_frames_per_sec"
+UNIT = "frames/s"
+
+# Algorithmic bytes per unit (SURVEY.md §8d / DESIGN.md §4)
+B_LIO_KNN, B_LIO_PLAIN, B_VIO = 132, 33, 405
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pass_counts(cfg):
+    """Fixed pass schedule with early stop disabled: K LIO passes with
+    kNN on the first and the last, K VIO passes on each of 3 levels."""
+    k = cfg.lio_passes
+    knn = min(k, 2) if k >= 2 else 1
+    return dict(lio_T=k - 1, lio_knn=knn, lio_plain=k - knn, vio_T=cfg.vio_passes, vio_passes=3 * cfg.vio_passes)
+
+
+def cpu_frame_runner(po, frame, nthreads):
+    """The CPU arm: oracle restatement + the reference's own ikd-Tree (oracle/_ref) when present."""
+    cfg = frame["cfg"]
+    pc = pass_counts(cfg)
+    tree = po.IkdTreeRef(frame["map_xyz"]) if po.ref_lib() is not None else None
+    lio = po.Lio(frame["map_xyz"], frame["scan_body"], tree)
+    vio = po.Vio(frame["image"], frame["patch_pos"], frame["patch_ref"], frame["patch_level"], frame["cam"]) if cfg.n_patch else None
+    lprm = po.lio_params(frame, pc["lio_T"], nthreads=nthreads, early_stop=False)
+    vprm = po.vio_params(frame, pc["vio_T"], early_stop=False, force_all_passes=True) if vio else None
+
+    def run():
+        x = po.state_from_frame(frame)
+        lrep = lio.update(lprm, x, x.copy())
+        rows = lrep.rows_total
+        if vio:
+            vrep = vio.update(vprm, x, x.copy())
+            rows += vrep.rows_total
+        return x, rows
+    kind = "reference kNN (ikd_Tree.cpp via oracle/_ref) + line-cited C++ port of the rest" if tree else "port (brute-force kNN)"
+    return run, kind
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    flb = fastlivo_loader.load()
+    po = fastlivo_loader.oracle()
+    cfg = flb.synth.CONFIGS[args.workload]
+    frame = flb.synth.make_frame(cfg)
+    cores = os.cpu_count() or 1
+    run, kind = cpu_frame_runner(po, frame, cores)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    rows = 0
+    for _ in range(args.steps):
+        _, r = run()
+        rows += r
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": workload_config(cfg, args.gpus, "n/a"),
+        "residuals_per_sec": rows / dt,
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} frames of {cfg.name}; {kind}; OpenMP over scan points "
+                                   f"({cores} threads), VIO serial as in the reference"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, gpus, l2):
+    pc = pass_counts(cfg)
+    return {"workload": f"{cfg.name}: {cfg.n_scan} scan pts vs {cfg.n_map}-pt map, {cfg.img_w}x{cfg.img_h} image, "
+                        f"{cfg.n_patch} 8x8 patches; {cfg.lio_passes} LIO passes ({pc['lio_knn']} with kNN) + "
+                        f"3x{cfg.vio_passes} VIO passes per frame, early stop disabled",
+            "parallelism": "single GPU" if gpus == 1 else f"scan/patch block-sharded over {gpus} GPUs, NCCL all-reduce of the normal equations per pass",
+            "l2": l2, "seed": cfg.seed}
+
+
+def shard(n, rank, world):
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "T0", "T1"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded cpu_baseline sample")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 30:
+            args.steps = 30           # bounded sample: the CPU arm needs ~0.1-1 s per frame
+        return run_reference(args)
+
+    import torch
+    flb = fastlivo_loader.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    cfg = flb.synth.CONFIGS[args.workload]
+    frame = flb.synth.make_frame(cfg)
+    pc = pass_counts(cfg)
+    h = flb.Handle(device=local, cell_size=cfg.cell_size)
+    stream = torch.cuda.current_stream(dev)
+    h.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+    s0, s1 = shard(cfg.n_scan, rank, world)
+    p0, p1 = shard(cfg.n_patch, rank, world)
+    scan = frame["scan_body"][s0:s1]
+    ppos, pref, plev = frame["patch_pos"][p0:p1], frame["patch_ref"][p0:p1], frame["patch_level"][p0:p1]
+    h.map_upload(frame["map_xyz"])
+    h.scan_upload(scan)
+    has_vio = cfg.n_patch > 0
+    if has_vio:
+        h.camera_set(frame["cam"])
+        h.image_upload(frame["image"])
+        h.patches_upload(ppos, pref, plev)
+    lprm = flb.capi.lio_params(frame, pc["lio_T"], early_stop=False)
+    vprm = flb.capi.vio_params(frame, pc["vio_T"], early_stop=False, force_all_passes=True)
+    x0 = flb.capi.State18.from_frame(frame)
+    h.state_upload(x0, x0.copy())
+
+    def enqueue_frame():
+        # x := x_prop := prior ; LIO update ; x_prop := x (zero-motion propagation) ; VIO update
+        h.state_reset_enqueue()
+        h.lio_update_enqueue(lprm)
+        if has_vio:
+            h.state_set_prior_enqueue()
+            h.vio_update_enqueue(vprm)
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        enqueue_frame()
+    barrier()
+    xw, lrep, vrep = h.state_download()
+    rows_per_frame = lrep.rows_total + (vrep.rows_total if has_vio else 0)
+    if world > 1:
+        pass  # rows are already global: the reduced n_eff / n_meas come out of the all-reduce
+
+    # ---- timed region: value (inputs resident)
+    sampler = ClockSampler(local) if rank == 0 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    l0 = h.launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        starts[i].record(stream)
+        enqueue_frame()
+        ends[i].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = h.launch_count() - l0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    total_ms = float(step_ms.sum())
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    fps = args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the blocking C ABI, H2D + D2H inside the timed region
+    e2e_steps = max(min(args.steps, 50), 3)
+    img = frame["image"]
+
+    def e2e_frame():
+        h.scan_upload(scan)
+        x = x0.copy()
+        h.lio_update(lprm, x, x0)
+        if has_vio:
+            h.image_upload(img)
+            h.patches_upload(ppos, pref, plev)
+            xp = x.copy()
+            h.vio_update(vprm, x, xp)
+        return x
+    for _ in range(3):
+        xe = e2e_frame()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        if flush is not None:
+            flush.zero_()
+        xe = e2e_frame()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    if flush is not None:   # subtract the flush cost measured separately (it is not part of the step)
+        barrier()
+        tf = time.perf_counter()
+        for _ in range(e2e_steps):
+            flush.zero_()
+        barrier()
+        e2e_dt -= time.perf_counter() - tf
+    if dist is not None:
+        t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_fps = e2e_steps / e2e_dt
+    state_b = 2736
+    h2d = len(scan) * 12 + 2 * state_b + ((img.size + len(ppos) * (24 + 768 + 4) + 2 * state_b) if has_vio else 0)
+    d2h = (state_b + 64) * (2 if has_vio else 1)
+
+    # ---- per-kernel-family device time (separate profiled run: one event pair per launch)
+    prof_steps = max(min(args.steps, 20), 3)
+    h.profile_start()
+    for _ in range(prof_steps):
+        if flush is not None:
+            flush.zero_()
+        enqueue_frame()
+    fam_ms, fam_n = h.profile_stop()
+    barrier()
+    hbm, peak_src = peaks()
+    n_loc, pn_loc = len(scan), len(ppos)
+    fam_bytes = [B_LIO_KNN * n_loc, B_LIO_PLAIN * n_loc, B_VIO * pn_loc, 0]
+    fam_names = ["k_lio_pass(kNN+plane+residual)", "k_lio_pass(cached plane)", "k_vio_pass", "k_*_finalize/begin(solve)"]
+    fams = []
+    for i in range(4):
+        if fam_n[i] == 0:
+            continue
+        avg_us = 1e3 * fam_ms[i] / fam_n[i]
+        gbs = fam_bytes[i] / (avg_us * 1e-6) / 1e9 if fam_bytes[i] else 0.0
+        fams.append({"kernel": fam_names[i], "launches_per_frame": int(fam_n[i] // prof_steps), "avg_us": avg_us,
+                     "share_of_frame": float(fam_ms[i] / max(fam_ms.sum(), 1e-12)), "algorithmic_bytes": fam_bytes[i],
+                     "achieved_gbs": gbs})
+    dom = max((f for f in fams if f["algorithmic_bytes"] > 0), key=lambda f: f["share_of_frame"], default=None)
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                    "frac": dom["achieved_gbs"] / hbm, "traffic": None, "peak_source": peak_src,
+                    "note": "working set is L2-resident and the kernel is latency-bound at this size (SURVEY.md §7 H2)"}
+
+    # ---- cpu_baseline (rank 0, N == 1 only): bounded sample on the host cores
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1:
+        po = fastlivo_loader.oracle()
+        cores = os.cpu_count() or 1
+        run4, kind = cpu_frame_runner(po, frame, min(4, cores))
+        runall, _ = cpu_frame_runner(po, frame, cores)
+        xo, _ = run4()
+        xo2, _ = runall()
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_frames):
+            run4()
+        dt4 = (time.perf_counter() - t0) / args.cpu_frames
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_frames):
+            runall()
+        dtall = (time.perf_counter() - t0) / args.cpu_frames
+        best = min(dt4, dtall)
+        cpu = {"value": 1.0 / best, "unit": UNIT, "cores": cores if dtall <= dt4 else min(4, cores), "kind": "port",
+               "sample": f"{args.cpu_frames} frames of {cfg.name} per thread setting; {kind}",
+               "fps_4_threads": 1.0 / dt4, "fps_all_cores": 1.0 / dtall, "host_cores": cores}
+        ve, vo = xe.vector(), xo.vector()
+        parity = {"state_rel_err_vs_cpu": float(np.abs(ve - vo).max() / np.abs(vo).max()),
+                  "state_rel_err_resident_vs_cpu": float(np.abs(xw.vector() - vo).max() / np.abs(vo).max())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": workload_config(cfg, world, "inputs resident; L2 flushed (256 MiB write) between timed steps"
+                                      if flush is not None else "inputs resident; L2 NOT flushed (working set < L2)"),
+            "residuals_per_sec": rows_per_frame * fps, "rows_per_frame": int(rows_per_frame),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "residuals_per_sec": rows_per_frame * e2e_fps},
+            "roofline": roofline, "kernels": fams, "cpu_baseline": cpu, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,7 +117,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_map_upload", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update",
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
-           "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_profile_start", "flb_profile_stop",
+           "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
            "flb_launch_count", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy"]
 
 
@@ -170,6 +170,7 @@ def lib():
         L.flb_lio_update_enqueue.argtypes = [vp, C.POINTER(LioParams)]
         L.flb_vio_update_enqueue.argtypes = [vp, C.POINTER(VioParams)]
         L.flb_state_reset_enqueue.argtypes = [vp]
+        L.flb_state_set_prior_enqueue.argtypes = [vp]
         L.flb_profile_start.argtypes = [vp]
         L.flb_profile_stop.argtypes = [vp, vp, vp]
         L.flb_launch_count.restype = C.c_int64
@@ -354,6 +355,9 @@ class Handle:
 
     def state_reset_enqueue(self):
         self._ck(self.L.flb_state_reset_enqueue(self.h))
+
+    def state_set_prior_enqueue(self):
+        self._ck(self.L.flb_state_set_prior_enqueue(self.h))
 
     def set_stream(self, stream_ptr):
         self._ck(self.L.flb_set_stream(self.h, C.c_void_p(stream_ptr)))

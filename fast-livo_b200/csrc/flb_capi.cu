@@ -744,6 +744,13 @@ int flb_state_reset_enqueue(flb_handle* h) {
     return FLB_OK;
 }
 
+int flb_state_set_prior_enqueue(flb_handle* h) {
+    FLB_CHECK_H(h);
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_set_prior_enqueue: no state uploaded");
+    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[1], &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    return FLB_OK;
+}
+
 int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio) {
     FLB_CHECK_H(h);
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_download: no state uploaded");

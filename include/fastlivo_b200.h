@@ -209,6 +209,9 @@ int flb_lio_update_enqueue(flb_handle* h, const flb_lio_params* prm);
 int flb_vio_update_enqueue(flb_handle* h, const flb_vio_params* prm);
 /* restore x := x_prop := the state given to the last flb_state_upload (device-side copy) */
 int flb_state_reset_enqueue(flb_handle* h);
+/* x_prop := x on the device: `state_propagat = state` (src/laserMapping.cpp:1292) with a
+ * zero-motion IMU propagation between the LIO and the VIO update */
+int flb_state_set_prior_enqueue(flb_handle* h);
 
 /* Per-kernel-family device time of the work enqueued between start and stop,
  * measured with CUDA events on the handle's stream (adds one event pair per launch:
