@@ -177,3 +177,32 @@ def test_call_order_and_argument_errors(flb):
         h.map_upload(np.full((8, 3), np.nan, np.float32))
     assert e.value.code == -1
     h.close()
+
+
+def test_gpu_matches_committed_golden(flb, handle):
+    """The CUDA path against tests/golden/T0_golden.npz (no generator, no oracle at run time)."""
+    from golden_util import load_golden
+    frame, g = load_golden()
+    handle.load_frame(frame)
+    o = handle.lio_pass(flb.capi.lio_params(frame, 3), frame["R_prop"], frame["p_prop"], True, width=12)
+    assert (bits(o["world"]) == bits(g["lio_world"])).all()
+    ok = g["lio_nn_d2"][:, 4] <= 5.0
+    assert (o["nn_idx"][ok] == g["lio_nn_idx"][ok]).all()
+    sel = g["lio_sel_idx"]
+    assert (o["sel_idx"] == sel).all()
+    assert (bits(o["pabcd"][sel]) == bits(g["lio_pabcd"][sel])).all()
+    assert (bits(o["pd2"][sel]) == bits(g["lio_pd2"][sel])).all()
+    np.testing.assert_allclose(o["rows"], g["lio_h_x"], rtol=1e-12)
+    assert rel(o["HTH"], g["lio_HTH12"]) < 1e-11
+    x = flb.capi.State18.from_frame(frame)
+    rep = handle.lio_update(flb.capi.lio_params(frame, 4), x, x.copy())
+    assert [rep.passes, rep.knn_passes, rep.n_eff_last, rep.rows_total] == list(g["lio_report"])
+    assert rel(x.vector(), g["lio_state"]) < STATE_RTOL
+    for level in (2, 0):
+        v = handle.vio_pass(flb.capi.vio_params(frame, 3), frame["R_prop"], frame["p_prop"], level)
+        assert (bits(v["z"]) == bits(g[f"vio{level}_z"])).all()
+        assert (bits(v["errors"]) == bits(g[f"vio{level}_errors"])).all()
+    xv = x.copy()
+    vrep = handle.vio_update(flb.capi.vio_params(frame, 4), xv, x.copy())
+    assert [*vrep.passes, vrep.rows_total, vrep.cov_updated] == list(g["vio_report"])
+    assert rel(xv.vector(), g["vio_state"]) < STATE_RTOL
