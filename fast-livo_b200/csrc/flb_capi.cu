@@ -143,6 +143,9 @@ struct flb_handle {
     DevBuf<State18> states;      // [0]=x [1]=x_prop [2]=old_state(VIO) [3]=saved x [4]=saved x_prop
     DevBuf<LioCtrl> lio_ctrl;
     DevBuf<VioCtrl> vio_ctrl;
+    DevBuf<GridBarrier> barrier; // grid barrier of the persistent kernels
+    int num_sms = 0;
+    int occ_lio = 0, occ_vio = 0;
     PinBuf pin;                  // staging for uploads
     PinBuf pin_out;              // staging for downloads
     bool state_valid = false;
@@ -257,6 +260,13 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, h->states.reserve(5));
     FLB_CUDA(h, h->lio_ctrl.reserve(1));
     FLB_CUDA(h, h->vio_ctrl.reserve(1));
+    FLB_CUDA(h, h->barrier.reserve(1));
+    FLB_CUDA(h, cudaMemset(h->barrier.p, 0, sizeof(GridBarrier)));
+    FLB_CUDA(h, cudaMemset(h->lio_ctrl.p, 0, sizeof(LioCtrl)));
+    FLB_CUDA(h, cudaMemset(h->vio_ctrl.p, 0, sizeof(VioCtrl)));
+    FLB_CUDA(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_lio, k_lio_update_persistent<kLioBlock>, kLioBlock, 0));
+    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioBlock>, kVioBlock, 0));
     FLB_CUDA(h, h->pin.reserve(1 << 16));
     FLB_CUDA(h, h->pin_out.reserve(1 << 16));
     return FLB_OK;
@@ -329,12 +339,28 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     s.partials = h->partials.p;
     s.nblocks = lio_nblocks(h);
     s.prm = d;
+    LioArgs a = make_lio_args(h, d, false, 6);
+    if (h->cfg.persistent && !h->comm) {
+        // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
+        const int cap = std::max(1, h->occ_lio * h->num_sms);
+        const int grid = std::max(1, std::min(lio_nblocks(h), cap));
+        FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * lio_packed(12), h->partials.cap)));
+        a.partials = h->partials.p;
+        s.partials = h->partials.p;
+        s.nblocks = grid;
+        GridBarrier* bar = h->barrier.p;
+        void* args[] = {&a, &s, &bar};
+        LaunchScope ls(h, FAM_LIO_KNN);
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,
+                                                h->stream));
+        h->last_pass_valid = false;
+        return FLB_OK;
+    }
     {
         LaunchScope ls(h, FAM_SOLVE);
         k_lio_begin<<<1, 32, 0, h->stream>>>(s);
         FLB_CUDA(h, cudaGetLastError());
     }
-    LioArgs a = make_lio_args(h, d, false, 6);
     const int T = prm->max_iteration;
     for (int it = -1; it < T; ++it) {
         // Statically known rematch schedule when early stop is disabled is NOT assumed here:
@@ -372,7 +398,8 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     s.errors = h->errors.p;
     s.Pn_total = h->Pn;
     s.prm = d;
-    {
+    const bool persistent = h->cfg.persistent && !h->comm && h->Pn > 0 && prm->max_iteration > 0;
+    if (!persistent) {
         LaunchScope ls(h, FAM_SOLVE);
         k_vio_begin<<<1, 32, 0, h->stream>>>(s);
         FLB_CUDA(h, cudaGetLastError());
@@ -392,6 +419,18 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     a.errors = h->errors.p;
     a.partials = h->partials.p;
     const int nb = vio_nblocks(h);
+    if (persistent) {
+        const int cap = std::max(1, h->occ_vio * h->num_sms);
+        const int grid = std::max(1, std::min(nb, cap));
+        s.nblocks = grid;
+        GridBarrier* bar = h->barrier.p;
+        void* args[] = {&a, &s, &bar};
+        LaunchScope ls(h, FAM_VIO);
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioBlock>, dim3(grid), dim3(kVioBlock), args, 0,
+                                                h->stream));
+        h->last_vio_valid = false;
+        return FLB_OK;
+    }
     const int total = 3 * std::max(prm->max_iteration, 0);
     for (int it = 0; it < total && h->Pn > 0; ++it) {
         {
@@ -454,6 +493,7 @@ int flb_create(const flb_config* cfg, flb_handle** out) {
         return fail(nullptr, FLB_ERR_NO_DEVICE,
                     "no CUDA device (%s): fastlivo_b200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
     flb_config c{};
+    c.persistent = 1;
     if (cfg) c = *cfg;
     if (c.device < 0 || c.device >= ndev) return fail(nullptr, FLB_ERR_INVALID, "device %d out of range [0,%d)", c.device, ndev);
     if (!(c.cell_size > 0)) c.cell_size = 0.6;
@@ -492,7 +532,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->Pinv.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->barrier.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->pin.release(); h->pin_out.release();
     cudaStreamDestroy(h->own_stream);
@@ -759,7 +799,17 @@ int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_v
     FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18), h->lio_ctrl.p, sizeof(LioCtrl), cudaMemcpyDeviceToHost, h->stream));
     FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl), h->vio_ctrl.p, sizeof(VioCtrl), cudaMemcpyDeviceToHost,
                                 h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl), h->barrier.p, sizeof(GridBarrier),
+                                cudaMemcpyDeviceToHost, h->stream));
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    {
+        GridBarrier b;
+        std::memcpy(&b, po + sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl), sizeof(b));
+        if (b.timeout) {
+            cudaMemset(h->barrier.p, 0, sizeof(GridBarrier));
+            return fail(h, FLB_ERR_TIMEOUT, "device-side grid barrier watchdog tripped");
+        }
+    }
     if (x) std::memcpy(x, po, sizeof(State18));
     if (lio) {
         LioCtrl c;

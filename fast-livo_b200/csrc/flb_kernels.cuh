@@ -790,3 +790,553 @@ __global__ void __launch_bounds__(64) k_vio_finalize(VioSolveArgs a) {
 }
 
 }  // namespace flb
+
+// =======================================================================================
+// Persistent (one launch per update) kernels
+// =======================================================================================
+// All blocks are co-resident (cooperative launch, grid <= SMs x occupancy).  Every pass ends
+// in a grid barrier whose LAST ARRIVER becomes the leader: it reduces the block partials in
+// fixed order, runs the 18-DoF solve with the whole block, publishes state + control through
+// L2, and releases the other blocks.  There is no host round trip, no empty launch and no
+// cross-block floating-point atomic; the result is bit-identical to the kernel-per-pass path.
+namespace flb {
+
+struct GridBarrier {
+    unsigned int count;
+    unsigned int gen;
+    int timeout;
+    int pad;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Arrive; returns true (to every thread of the block) when this block is the last arriver.
+__device__ __forceinline__ bool grid_arrive(GridBarrier* b, unsigned nblocks, unsigned* s_scratch /*2 words smem*/) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned g = ld_acquire_u32(&b->gen);
+        __threadfence();
+        const unsigned ticket = atomicAdd(&b->count, 1u);
+        __threadfence();
+        s_scratch[0] = (ticket == nblocks - 1) ? 1u : 0u;
+        s_scratch[1] = g;
+    }
+    __syncthreads();
+    return s_scratch[0] != 0;
+}
+// Leader: open the barrier.  Call with the whole block.
+__device__ __forceinline__ void grid_release(GridBarrier* b, const unsigned* s_scratch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        b->count = 0;
+        __threadfence();
+        st_release_u32(&b->gen, s_scratch[1] + 1u);
+    }
+    __syncthreads();
+}
+// Non-leader: wait.  A watchdog (~seconds) turns a would-be hang into FLB_ERR_TIMEOUT.
+__device__ __forceinline__ bool grid_wait(GridBarrier* b, const unsigned* s_scratch) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        unsigned long long spins = 0;
+        while (ld_acquire_u32(&b->gen) == s_scratch[1]) {
+            __nanosleep(40);
+            if (++spins > 3000000ull) { ok = 0; b->timeout = 1; break; }
+            if ((spins & 0xffff) == 0 && *((volatile int*)&b->timeout)) { ok = 0; break; }
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Block-parallel Gauss-Jordan on S[N x (N+M)], row stride LD (odd: conflict-free), executed by
+// the first `nt` threads of the block (all of them must call; they sync on named barrier 1).
+// Same arithmetic as warp_gauss_jordan: scale the pivot row by 1/pivot, then eliminate.
+template <int N, int M, int LD, int NT>
+__device__ __forceinline__ bool block_gauss_jordan(double* S, int tid) {
+    constexpr int COLS = N + M;
+    constexpr int E = N * COLS;
+    constexpr int PER = (E + NT - 1) / NT;   // elements per thread
+    bool ok = true;
+    for (int k = 0; k < N; ++k) {
+        const double piv = S[k * LD + k];
+        if (!(fabs(piv) > 1e-300) || !isfinite(piv)) ok = false;
+        const double inv = 1.0 / piv;
+        double v[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * NT;
+            if (e < E) {
+                const int i = e / COLS, j = e - i * COLS;
+                const double rkj = S[k * LD + j] * inv;
+                v[q] = (i == k) ? rkj : S[i * LD + j] - S[i * LD + k] * rkj;
+            }
+        }
+        named_sync(1, NT);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * NT;
+            if (e < E) {
+                const int i = e / COLS, j = e - i * COLS;
+                S[i * LD + j] = v[q];
+            }
+        }
+        named_sync(1, NT);
+    }
+    return ok;
+}
+
+struct LeaderSmem {
+    State18 x, xp;                       // L2 copies of state / prior
+    double S[kDim * 37];                 // GJ workspace (LD = 37 for 18x36, LD = 25 for 18x24)
+    double Pinv[kDim * kDim];
+    double HTH[36], HTz[6];
+    double vec[kDim], sol[kDim], Gc[kDim * 6];
+    double top[6 * kDim];
+    double packed[32];
+    double part[4][32];
+    int flags[4];
+};
+
+__device__ __forceinline__ void load_state_l2(State18* dst, const State18* src, int tid, int nt) {
+    const double* s = reinterpret_cast<const double*>(src);
+    double* d = reinterpret_cast<double*>(dst);
+    for (int e = tid; e < (int)(sizeof(State18) / sizeof(double)); e += nt) d[e] = __ldcg(s + e);
+}
+__device__ __forceinline__ void store_state(State18* dst, const State18* src, int tid, int nt, bool with_cov) {
+    const double* s = reinterpret_cast<const double*>(src);
+    double* d = reinterpret_cast<double*>(dst);
+    const int n = with_cov ? (int)(sizeof(State18) / sizeof(double)) : 24;
+    for (int e = tid; e < n; e += nt) d[e] = s[e];
+}
+
+// Fixed-order reduction of the block partials by the leader: 4 contiguous quarters per entry,
+// combined ((q0+q1)+q2)+q3.  (Different association than the kernel-per-pass path's single
+// sequential sum: both are deterministic; they agree to ~1e-16 relative.)
+template <int K>
+__device__ __forceinline__ void leader_reduce(const double* partials, int nblocks, LeaderSmem& sm, int tid) {
+    const int q = tid & 31, part = tid >> 5;
+    if (part < 4 && q < K) {
+        const int per = (nblocks + 3) / 4;
+        const int b0 = part * per, b1 = min(nblocks, b0 + per);
+        double s = 0.0;
+        for (int b = b0; b < b1; ++b) s += __ldcg(partials + (size_t)b * K + q);
+        sm.part[part][q] = s;
+    }
+    __syncthreads();
+    if (tid < K) sm.packed[tid] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
+    __syncthreads();
+}
+
+// Solve with the whole block (nt_gj threads run the elimination).  Requires sm.x / sm.xp /
+// sm.HTH / sm.HTz loaded; `first` computes the prior information from sm.x.cov and stores it
+// to global Pinv, otherwise loads it from L2.
+template <int NT>
+__device__ __forceinline__ bool leader_solve(LeaderSmem& sm, double* Pinv_g, double sigma, double sign, bool first, int tid) {
+    constexpr int nt_gj = NT;
+    bool ok = true;
+    if (tid == nt_gj) state_boxminus(sm.xp, sm.x, sm.vec);      // a thread outside the GJ team
+    if (first) {
+        constexpr int LD = 37;
+        if (tid < nt_gj) {
+            for (int e = tid; e < kDim * 2 * kDim; e += nt_gj) {
+                const int i = e / (2 * kDim), j = e - i * 2 * kDim;
+                sm.S[i * LD + j] = (j < kDim) ? sm.x.cov[i * kDim + j] / sigma : ((j - kDim == i) ? 1.0 : 0.0);
+            }
+            named_sync(1, nt_gj);
+            ok = block_gauss_jordan<kDim, kDim, LD, NT>(sm.S, tid);
+            for (int e = tid; e < kDim * kDim; e += nt_gj) {
+                const int i = e / kDim, j = e - i * kDim;
+                const double v = sm.S[i * LD + kDim + j];
+                sm.Pinv[e] = v;
+                Pinv_g[e] = v;
+            }
+        }
+    } else {
+        for (int e = tid; e < kDim * kDim; e += blockDim.x) sm.Pinv[e] = __ldcg(Pinv_g + e);
+    }
+    __syncthreads();
+    constexpr int LD2 = 25;
+    if (tid < nt_gj) {
+        for (int e = tid; e < kDim * (kDim + 6); e += nt_gj) {
+            const int i = e / (kDim + 6), j = e - i * (kDim + 6);
+            double v;
+            if (j < kDim) {
+                v = sm.Pinv[i * kDim + j];
+                if (i < 6 && j < 6) v = sm.HTH[i * 6 + j] + v;
+            } else {
+                v = (j - kDim == i) ? 1.0 : 0.0;
+            }
+            sm.S[i * LD2 + j] = v;
+        }
+        named_sync(1, nt_gj);
+        ok = block_gauss_jordan<kDim, 6, LD2, NT>(sm.S, tid) && ok;
+    }
+    __syncthreads();
+    if (tid < kDim * 6) {
+        const int i = tid / 6, j = tid - i * 6;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += sm.S[i * LD2 + kDim + k] * sm.HTH[k * 6 + j];
+        sm.Gc[tid] = s;
+    }
+    __syncthreads();
+    if (tid < kDim) {
+        double kz = 0.0, gv = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            kz += sm.S[tid * LD2 + kDim + k] * sm.HTz[k];
+            gv += sm.Gc[tid * 6 + k] * sm.vec[k];
+        }
+        sm.sol[tid] = sign * kz + sm.vec[tid] - gv;
+    }
+    __syncthreads();
+    return ok;
+}
+
+// cov (smem state) <- cov - Gc * cov[:6,:]
+__device__ __forceinline__ void leader_cov_update(LeaderSmem& sm, const double* Gc, int tid, int nt) {
+    for (int e = tid; e < 6 * kDim; e += nt) sm.top[e] = sm.x.cov[e];
+    __syncthreads();
+    for (int e = tid; e < kDim * kDim; e += nt) {
+        const int i = e / kDim, j = e - i * kDim;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += Gc[i * 6 + k] * sm.top[k * kDim + j];
+        sm.x.cov[e] = sm.x.cov[e] - s;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// LIO: whole iterated update in one launch
+// ---------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar) {
+    constexpr int K = lio_packed(6);
+    constexpr int NW = BLOCK / 32;
+    __shared__ LioPose s_pose;
+    __shared__ double s_acc[NW][K];
+    __shared__ unsigned s_bar[2];
+    __shared__ LeaderSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = s.prm.max_iteration;
+    // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
+    int iterCount = -1, rematch_num = 0, nearest = 1;
+    bool first = true;
+    for (;;) {
+        if (tid == 0) {
+            LioPose& pose = s_pose;
+            for (int i = 0; i < 9; ++i) { pose.R[i] = __ldcg(&a.state->rot[i]); pose.R_LI[i] = a.prm.R_LI[i]; }
+            for (int i = 0; i < 3; ++i) { pose.p[i] = __ldcg(&a.state->pos[i]); pose.t_LI[i] = a.prm.t_LI[i]; }
+            m3_T(pose.R, pose.Rt);
+            m3_T(pose.R_LI, pose.RLIt);
+        }
+        __syncthreads();
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        const int stride = gridDim.x * BLOCK;
+        for (int i = blockIdx.x * BLOCK + tid; i < a.N; i += stride) {
+            bool active;
+            double row[6], z, absres;
+            lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres);
+            if (active) {
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int c = r; c < 6; ++c) { acc[k] += row[r] * row[c]; ++k; }
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[21 + r] += row[r] * z;
+                acc[27] += 1.0;
+                acc[28] += absres;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double v = warp_sum(acc[k]);
+            if (lane == 0) s_acc[warp][k] = v;
+        }
+        __syncthreads();
+        for (int q = tid; q < K; q += BLOCK) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += s_acc[w][q];
+            a.partials[(size_t)blockIdx.x * K + q] = v;
+        }
+        const bool leader = grid_arrive(bar, gridDim.x, s_bar);
+        if (leader) {
+            load_state_l2(&sm.x, s.state, tid, BLOCK);
+            load_state_l2(&sm.xp, s.state_prop, tid, BLOCK);
+            leader_reduce<K>(a.partials, gridDim.x, sm, tid);
+            if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
+            __syncthreads();
+            const bool ok = leader_solve<BLOCK - 32>(sm, s.Pinv, s.prm.sigma, +1.0, first, tid);
+            if (tid == 0) {
+                LioCtrl c;
+                if (first) {
+                    c.passes = c.knn_passes = 0;
+                    c.rows_total = 0;
+                    c.status = 0;
+                } else {
+                    c.passes = __ldcg(&s.ctrl->passes);
+                    c.knn_passes = __ldcg(&s.ctrl->knn_passes);
+                    c.rows_total = __ldcg(&s.ctrl->rows_total);
+                    c.status = __ldcg(&s.ctrl->status);
+                }
+                const int n_eff = (int)sm.packed[K - 2];
+                c.passes += 1;
+                c.knn_passes += nearest ? 1 : 0;
+                c.n_eff_last = n_eff;
+                c.res_mean_last = sm.packed[K - 1] / (double)n_eff;
+                c.rows_total += n_eff;
+                state_boxplus(sm.x, sm.sol);                                                   // :1683
+                bool converged = false;
+                if ((norm3(sm.sol) * 57.3 < s.prm.conv_rot_deg) && (norm3(sm.sol + 3) * 100 < s.prm.conv_pos_cm))
+                    converged = true;                                                          // :1688
+                int nn = 0, rn = rematch_num;
+                if (converged || ((rn == 0) && (iterCount == (T - 2)))) { nn = 1; rn++; }       // :1700-1705
+                int stop = 0;
+                if (rn >= 2 || (iterCount == T - 1)) stop = 1;                                  // :1708
+                if (!ok) { stop = 1; c.status = -5; }
+                c.converged_last = converged ? 1 : 0;
+                c.iterCount = iterCount + 1;
+                c.rematch_num = rn;
+                c.nearest_search_en = nn;
+                c.stop = stop;
+                *s.ctrl = c;
+                sm.flags[0] = stop;
+                sm.flags[1] = ok ? 1 : 0;
+            }
+            __syncthreads();
+            const bool do_cov = sm.flags[0] && sm.flags[1];
+            if (do_cov) leader_cov_update(sm, sm.Gc, tid, BLOCK);                               // :1715
+            store_state(s.state, &sm.x, tid, BLOCK, do_cov);
+            __threadfence();
+            grid_release(bar, s_bar);
+        } else {
+            if (!grid_wait(bar, s_bar)) return;
+        }
+        // every block: pick up the published control through L2
+        const int stop = __ldcg(&s.ctrl->stop);
+        nearest = __ldcg(&s.ctrl->nearest_search_en);
+        rematch_num = __ldcg(&s.ctrl->rematch_num);
+        iterCount = __ldcg(&s.ctrl->iterCount);
+        first = false;
+        if (stop) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// VIO: ComputeJ (3 levels x up to T passes) in one launch
+// ---------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar) {
+    constexpr int NW = BLOCK / 32;
+    __shared__ VioPose s_pose;
+    __shared__ float s_lat[NW][128];
+    __shared__ double s_res[NW][64];
+    __shared__ double s_acc[NW][kVioPacked];
+    __shared__ unsigned s_bar[2];
+    __shared__ LeaderSmem sm;
+    __shared__ float s_error;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.Pn <= 0) return;                                     // :969-970 (host also short-circuits)
+    int level = 2;
+    bool first = true;
+    for (;;) {
+        if (tid == 0) {
+            double R[9], p[3];
+            for (int i = 0; i < 9; ++i) R[i] = __ldcg(&a.state->rot[i]);
+            for (int i = 0; i < 3; ++i) p[i] = __ldcg(&a.state->pos[i]);
+            vio_make_pose(a.prm.Rci, a.prm.Pci, R, p, s_pose);
+        }
+        __syncthreads();
+        double acc[27];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+        double n_meas = 0.0, skipped = 0.0;
+        for (int i = blockIdx.x * NW + warp; i < a.Pn; i += gridDim.x * NW) {
+            PatchGeom g;
+            const double pos[3] = {a.pos[3 * (size_t)i], a.pos[3 * (size_t)i + 1], a.pos[3 * (size_t)i + 2]};
+            vio_patch_geom(a.cam, s_pose, pos, level, a.search_level[i], g);
+            if (g.valid) {
+                const int W = a.cam.width;
+                const unsigned char* base = a.img + (size_t)(g.v_i - 5 * g.scale) * W + (g.u_i - 5 * g.scale);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = lane + 32 * q;
+                    if (e < 121) {
+                        const int r = e / 11, c = e - r * 11;
+                        s_lat[warp][e] = (float)__ldg(base + (size_t)r * g.scale * W + c * g.scale);
+                    }
+                }
+                __syncwarp();
+                LatView L{s_lat[warp]};
+                const int x = lane >> 2, y0 = (lane & 3) * 2;
+                const float* P = a.patch + (size_t)i * 192 + 64 * level;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int y = y0 + q;
+                    double row[6], res;
+                    vio_pixel(L, g, s_pose, x, y, __ldg(P + x * 8 + y), row, &res);
+                    s_res[warp][x * 8 + y] = res;
+                    int k = 0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = r; c < 6; ++c) { acc[k] += row[r] * row[c]; ++k; }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) acc[21 + r] += row[r] * res;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    float pe = 0.0f;
+                    for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[warp][e] * s_res[warp][e]);   // :843
+                    a.errors[i] = pe;                                                                          // :851
+                    n_meas += 64.0;
+                }
+                __syncwarp();
+            } else if (lane == 0) {
+                a.errors[i] = 0.0f;
+                skipped += 1.0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const double v = warp_sum(acc[k]);
+            if (lane == 0) s_acc[warp][k] = v;
+        }
+        if (lane == 0) { s_acc[warp][27] = n_meas; s_acc[warp][28] = skipped; }
+        __syncthreads();
+        for (int q = tid; q < kVioPacked; q += BLOCK) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += s_acc[w][q];
+            a.partials[(size_t)blockIdx.x * kVioPacked + q] = v;
+        }
+        const bool leader = grid_arrive(bar, gridDim.x, s_bar);
+        if (leader) {
+            load_state_l2(&sm.x, s.state, tid, BLOCK);
+            load_state_l2(&sm.xp, s.state_prop, tid, BLOCK);
+            if (first) {
+                // old_state = *state (:747)
+                store_state(s.old_state, &sm.x, tid, BLOCK, true);
+            }
+            leader_reduce<kVioPacked>(a.partials, gridDim.x, sm, tid);
+            if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
+            __syncthreads();
+            // the last warp forms the exact sequential float sum of the per-patch errors (:852)
+            // while the others run the speculative solve
+            if (tid == BLOCK - 1) {
+                float e = 0.0f;
+                const float* er = s.errors;
+                int i = 0;
+                for (; i + 8 <= s.Pn_total; i += 8) {
+                    const float e0 = __ldcg(er + i), e1 = __ldcg(er + i + 1), e2 = __ldcg(er + i + 2), e3 = __ldcg(er + i + 3),
+                                e4 = __ldcg(er + i + 4), e5 = __ldcg(er + i + 5), e6 = __ldcg(er + i + 6), e7 = __ldcg(er + i + 7);
+                    e = e + e0; e = e + e1; e = e + e2; e = e + e3; e = e + e4; e = e + e5; e = e + e6; e = e + e7;
+                }
+                for (; i < s.Pn_total; ++i) e = e + __ldcg(er + i);
+                s_error = e;
+            }
+            const bool ok = leader_solve<BLOCK - 64>(sm, s.Pinv, s.prm.sigma, -1.0, first, tid);
+            if (tid == 0) {
+                VioCtrl c;
+                if (first) {
+                    c.level = 2; c.iteration = 0; c.stop = 0;
+                    c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;
+                    for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
+                    c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
+                } else {
+                    const int* src = reinterpret_cast<const int*>(s.ctrl);
+                    int* dst = reinterpret_cast<int*>(&c);
+                    for (int e = 0; e < (int)(sizeof(VioCtrl) / sizeof(int)); ++e) dst[e] = __ldcg(src + e);
+                }
+                const long long nm = (long long)sm.packed[27];
+                const float error = s_error / (float)(unsigned long long)nm;                       // :857
+                c.passes[level] += 1;
+                c.rows_total += nm;
+                c.skipped_last = (int)sm.packed[28];
+                bool EKF_end = false;
+                int accept = 0;
+                if (s.prm.force_all_passes || error <= c.last_error) {                             // :861
+                    accept = 1;
+                    c.last_error = error;
+                    if (!s.prm.force_all_passes && (norm3(sm.sol) * 57.3f < s.prm.conv_rot_deg) &&
+                        (norm3(sm.sol + 3) * 100.0f < s.prm.conv_pos_cm))
+                        EKF_end = true;                                                            // :883
+                    c.any_solved = 1;
+                } else {
+                    EKF_end = true;                                                                // :890
+                }
+                if (!ok) { EKF_end = true; c.status = -5; }
+                c.iteration += 1;
+                int docov = 0, newlevel = 0;
+                if (EKF_end || c.iteration >= s.prm.max_iteration) {
+                    c.level_error[level] = c.last_error;
+                    c.now_error = c.last_error;
+                    c.level = level - 1;
+                    c.iteration = 0;
+                    c.last_error = 1e10f;
+                    newlevel = 1;
+                    if (c.level < 0 || !ok) {
+                        c.stop = 1;
+                        if (c.now_error < 1e10f && ok) { docov = 1; c.cov_updated = 1; }           // :978-981
+                    }
+                }
+                *s.ctrl = c;
+                sm.flags[0] = accept;
+                sm.flags[1] = docov;
+                sm.flags[2] = newlevel;
+            }
+            __syncthreads();
+            const int accept = sm.flags[0], docov = sm.flags[1], newlevel = sm.flags[2];
+            if (accept) {
+                store_state(s.old_state, &sm.x, tid, BLOCK, true);                                 // old_state = *state (:863)
+                for (int e = tid; e < kDim * 6; e += BLOCK) s.G_last[e] = sm.Gc[e];
+                __syncthreads();
+                if (tid == 0) state_boxplus(sm.x, sm.sol);                                         // :879
+                __syncthreads();
+            } else {
+                load_state_l2(&sm.x, s.old_state, tid, BLOCK);                                     // *state = old_state (:890)
+                __syncthreads();
+            }
+            if (docov) {
+                if (!accept) {
+                    for (int e = tid; e < kDim * 6; e += BLOCK) sm.Gc[e] = __ldcg(s.G_last + e);
+                    __syncthreads();
+                }
+                leader_cov_update(sm, sm.Gc, tid, BLOCK);                                          // :980
+            }
+            store_state(s.state, &sm.x, tid, BLOCK, true);
+            if (newlevel) store_state(s.old_state, &sm.x, tid, BLOCK, true);                       // :747 of the next level
+            __threadfence();
+            grid_release(bar, s_bar);
+        } else {
+            if (!grid_wait(bar, s_bar)) return;
+        }
+        const int stop = __ldcg(&s.ctrl->stop);
+        level = __ldcg(&s.ctrl->level);
+        first = false;
+        if (stop) break;
+    }
+}
+
+}  // namespace flb

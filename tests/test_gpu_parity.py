@@ -12,9 +12,11 @@ pytestmark = pytest.mark.gpu
 STATE_RTOL = 1e-9     # bar is 1e-5 (north_star); measured ~1e-12
 
 
-@pytest.fixture(scope="module")
-def handle(flb):
-    h = flb.Handle(device=0)
+@pytest.fixture(scope="module", params=[1, 0], ids=["persistent", "kernel-per-pass"])
+def handle(flb, request):
+    """Both execution modes of the update: one cooperative persistent kernel per update (default)
+    and the kernel-per-pass path; they must agree with the oracle (and hence with each other)."""
+    h = flb.Handle(device=0, persistent=request.param)
     yield h
     h.close()
 
