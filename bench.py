@@ -214,7 +214,11 @@ def main():
     frame = flb.synth.make_frame(cfg)
     pc = pass_counts(cfg)
     h = flb.Handle(device=local, cell_size=cfg.cell_size)
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) torch stream: the library's kernels, the L2 flush and the timing events
+    # must all be on the SAME stream, and flb_set_stream(NULL) would mean "the handle's own stream"
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
     if world > 1:
         uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
@@ -287,10 +291,27 @@ def main():
     fps = args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host buffers through the blocking C ABI, H2D + D2H inside the timed region
+    trace = None
+    if world == 1:
+        # device-side per-pass trace of the persistent kernels (one extra frame, outside the timed region)
+        h.trace_enable(True)
+        if flush is not None:
+            flush.zero_()
+        enqueue_frame()
+        barrier()
+        tl, tv = h.trace_download(0), h.trace_download(1)
+        h.trace_enable(False)
+
+        def split(t):
+            t = np.concatenate([[0.0], t])
+            return {"pass_us": [round(float(t[i + 1] - t[i]), 2) for i in range(0, len(t) - 1, 2)],
+                    "solve_us": [round(float(t[i + 2] - t[i + 1]), 2) for i in range(0, len(t) - 2, 2)]}
+        trace = {"lio": split(tl), "vio": split(tv),
+                 "note": "per pass: time until every block reached the barrier / leader reduce+solve+publish (globaltimer)"}
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": fps, "unit": UNIT, "ms_per_step": total_ms / args.steps,
-                              "gpu_launches": int(launches), "quick": True}), flush=True)
+                              "gpu_launches": int(launches), "quick": True, "trace": trace}), flush=True)
         h.close()
         return
     e2e_steps = max(min(args.steps, 50), 3)
@@ -399,7 +420,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "residuals_per_sec": rows_per_frame * e2e_fps},
-            "roofline": roofline, "kernels": fams, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "kernels": fams, "pass_trace": trace, "cpu_baseline": cpu, "parity": parity,
         }
         print(json.dumps(line), flush=True)
     h.close()

@@ -118,7 +118,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
-           "flb_launch_count", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy"]
+           "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy"]
 
 
 def lib_path() -> str:
@@ -173,6 +173,8 @@ def lib():
         L.flb_state_set_prior_enqueue.argtypes = [vp]
         L.flb_profile_start.argtypes = [vp]
         L.flb_profile_stop.argtypes = [vp, vp, vp]
+        L.flb_trace_enable.argtypes = [vp, C.c_int]
+        L.flb_trace_download.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
         L.flb_launch_count.restype = C.c_int64
         L.flb_launch_count.argtypes = [vp]
         L.flb_comm_unique_id.argtypes = [vp]
@@ -376,6 +378,15 @@ class Handle:
         n = np.zeros(4, np.int64)
         self._ck(self.L.flb_profile_stop(self.h, _p(ms), _p(n)))
         return ms, n
+
+    def trace_enable(self, on=True):
+        self._ck(self.L.flb_trace_enable(self.h, int(on)))
+
+    def trace_download(self, which):
+        us = np.zeros(128)
+        n = C.c_int()
+        self._ck(self.L.flb_trace_download(self.h, which, _p(us), 128, C.byref(n)))
+        return us[:n.value]
 
     # ---- multi-GPU
     @staticmethod

@@ -144,6 +144,8 @@ struct flb_handle {
     DevBuf<LioCtrl> lio_ctrl;
     DevBuf<VioCtrl> vio_ctrl;
     DevBuf<GridBarrier> barrier; // grid barrier of the persistent kernels
+    DevBuf<unsigned long long> trace;  // [0..kTraceLen) LIO, [kTraceLen..2*kTraceLen) VIO
+    bool tracing = false;
     int num_sms = 0;
     int occ_lio = 0, occ_vio = 0;
     PinBuf pin;                  // staging for uploads
@@ -261,6 +263,8 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, h->lio_ctrl.reserve(1));
     FLB_CUDA(h, h->vio_ctrl.reserve(1));
     FLB_CUDA(h, h->barrier.reserve(1));
+    FLB_CUDA(h, h->trace.reserve(2 * kTraceLen));
+    FLB_CUDA(h, cudaMemset(h->trace.p, 0, 2 * kTraceLen * sizeof(unsigned long long)));
     FLB_CUDA(h, cudaMemset(h->barrier.p, 0, sizeof(GridBarrier)));
     FLB_CUDA(h, cudaMemset(h->lio_ctrl.p, 0, sizeof(LioCtrl)));
     FLB_CUDA(h, cudaMemset(h->vio_ctrl.p, 0, sizeof(VioCtrl)));
@@ -349,7 +353,8 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         s.partials = h->partials.p;
         s.nblocks = grid;
         GridBarrier* bar = h->barrier.p;
-        void* args[] = {&a, &s, &bar};
+        unsigned long long* trace = h->tracing ? h->trace.p : nullptr;
+        void* args[] = {&a, &s, &bar, &trace};
         LaunchScope ls(h, FAM_LIO_KNN);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,
                                                 h->stream));
@@ -424,7 +429,8 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         const int grid = std::max(1, std::min(nb, cap));
         s.nblocks = grid;
         GridBarrier* bar = h->barrier.p;
-        void* args[] = {&a, &s, &bar};
+        unsigned long long* trace = h->tracing ? h->trace.p + kTraceLen : nullptr;
+        void* args[] = {&a, &s, &bar, &trace};
         LaunchScope ls(h, FAM_VIO);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioBlock>, dim3(grid), dim3(kVioBlock), args, 0,
                                                 h->stream));
@@ -532,7 +538,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->Pinv.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->barrier.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->barrier.release(); h->trace.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->pin.release(); h->pin_out.release();
     cudaStreamDestroy(h->own_stream);
@@ -1052,6 +1058,28 @@ int flb_profile_stop(flb_handle* h, double ms[4], int64_t launches[4]) {
         cudaEventDestroy(ev.b);
     }
     h->evs.clear();
+    return FLB_OK;
+}
+
+int flb_trace_enable(flb_handle* h, int on) {
+    FLB_CHECK_H(h);
+    h->tracing = on != 0;
+    FLB_CUDA(h, cudaMemsetAsync(h->trace.p, 0, 2 * kTraceLen * sizeof(unsigned long long), h->stream));
+    return FLB_OK;
+}
+
+int flb_trace_download(flb_handle* h, int which, double* us, int max_entries, int* n_entries) {
+    FLB_CHECK_H(h);
+    if (!us || !n_entries || (which != 0 && which != 1)) return fail(h, FLB_ERR_INVALID, "flb_trace_download: bad arguments");
+    unsigned long long t[kTraceLen];
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FLB_CUDA(h, cudaMemcpy(t, h->trace.p + which * kTraceLen, sizeof(t), cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int i = 1; i < kTraceLen && i - 1 < max_entries; ++i) {
+        if (t[i] == 0) break;
+        us[n++] = (double)(t[i] - t[0]) * 1e-3;
+    }
+    *n_entries = n;
     return FLB_OK;
 }
 

@@ -808,6 +808,15 @@ struct GridBarrier {
     int pad;
 };
 
+// Optional device-side pass trace (profiling aid): %globaltimer (ns) at kernel entry [0], then for
+// pass k: [1+2k] = all blocks arrived (leader elected), [2+2k] = leader released the barrier.
+constexpr int kTraceLen = 128;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1025,7 +1034,8 @@ __device__ __forceinline__ void leader_cov_update(LeaderSmem& sm, const double* 
 // LIO: whole iterated update in one launch
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar) {
+__global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar,
+                                                                 unsigned long long* trace) {
     constexpr int K = lio_packed(6);
     constexpr int NW = BLOCK / 32;
     __shared__ LioPose s_pose;
@@ -1037,6 +1047,8 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
     // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
     int iterCount = -1, rematch_num = 0, nearest = 1;
     bool first = true;
+    int pass_no = 0;
+    if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
     for (;;) {
         if (tid == 0) {
             LioPose& pose = s_pose;
@@ -1081,6 +1093,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         }
         const bool leader = grid_arrive(bar, gridDim.x, s_bar);
         if (leader) {
+            if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             load_state_l2(&sm.x, s.state, tid, BLOCK);
             load_state_l2(&sm.xp, s.state_prop, tid, BLOCK);
             leader_reduce<K>(a.partials, gridDim.x, sm, tid);
@@ -1127,6 +1140,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
             const bool do_cov = sm.flags[0] && sm.flags[1];
             if (do_cov) leader_cov_update(sm, sm.Gc, tid, BLOCK);                               // :1715
             store_state(s.state, &sm.x, tid, BLOCK, do_cov);
+            if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             __threadfence();
             grid_release(bar, s_bar);
         } else {
@@ -1138,6 +1152,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         rematch_num = __ldcg(&s.ctrl->rematch_num);
         iterCount = __ldcg(&s.ctrl->iterCount);
         first = false;
+        ++pass_no;
         if (stop) break;
     }
 }
@@ -1146,7 +1161,8 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
 // VIO: ComputeJ (3 levels x up to T passes) in one launch
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar) {
+__global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
+                                                                 unsigned long long* trace) {
     constexpr int NW = BLOCK / 32;
     __shared__ VioPose s_pose;
     __shared__ float s_lat[NW][128];
@@ -1155,10 +1171,14 @@ __global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioS
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
     __shared__ float s_error;
+    constexpr int kErrChunk = 2048;
+    __shared__ float s_err[kErrChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (a.Pn <= 0) return;                                     // :969-970 (host also short-circuits)
     int level = 2;
     bool first = true;
+    int pass_no = 0;
+    if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
     for (;;) {
         if (tid == 0) {
             double R[9], p[3];
@@ -1233,6 +1253,7 @@ __global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioS
         }
         const bool leader = grid_arrive(bar, gridDim.x, s_bar);
         if (leader) {
+            if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             load_state_l2(&sm.x, s.state, tid, BLOCK);
             load_state_l2(&sm.xp, s.state_prop, tid, BLOCK);
             if (first) {
@@ -1242,19 +1263,27 @@ __global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioS
             leader_reduce<kVioPacked>(a.partials, gridDim.x, sm, tid);
             if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
             __syncthreads();
-            // the last warp forms the exact sequential float sum of the per-patch errors (:852)
-            // while the others run the speculative solve
-            if (tid == BLOCK - 1) {
-                float e = 0.0f;
-                const float* er = s.errors;
-                int i = 0;
-                for (; i + 8 <= s.Pn_total; i += 8) {
-                    const float e0 = __ldcg(er + i), e1 = __ldcg(er + i + 1), e2 = __ldcg(er + i + 2), e3 = __ldcg(er + i + 3),
-                                e4 = __ldcg(er + i + 4), e5 = __ldcg(er + i + 5), e6 = __ldcg(er + i + 6), e7 = __ldcg(er + i + 7);
-                    e = e + e0; e = e + e1; e = e + e2; e = e + e3; e = e + e4; e = e + e5; e = e + e6; e = e + e7;
+            // One thread forms the exact sequential float sum of the per-patch errors (:852) while the
+            // others run the speculative solve.  The errors are first staged into shared memory by the
+            // whole block (coalesced L2 reads), so the serial chain costs one FADD latency per patch
+            // instead of one L2 round trip per batch.
+            float e_run = 0.0f;
+            for (int base = 0; base < s.Pn_total; base += kErrChunk) {
+                const int nchunk = min(kErrChunk, s.Pn_total - base);
+                for (int e = tid; e < nchunk; e += BLOCK) s_err[e] = __ldcg(s.errors + base + e);
+                __syncthreads();
+                if (tid == BLOCK - 1) {
+                    float e = e_run;
+                    int i = 0;
+                    for (; i + 8 <= nchunk; i += 8) {
+                        e = e + s_err[i]; e = e + s_err[i + 1]; e = e + s_err[i + 2]; e = e + s_err[i + 3];
+                        e = e + s_err[i + 4]; e = e + s_err[i + 5]; e = e + s_err[i + 6]; e = e + s_err[i + 7];
+                    }
+                    for (; i < nchunk; ++i) e = e + s_err[i];
+                    e_run = e;
+                    if (base + kErrChunk >= s.Pn_total) s_error = e;
                 }
-                for (; i < s.Pn_total; ++i) e = e + __ldcg(er + i);
-                s_error = e;
+                if (base + kErrChunk < s.Pn_total) __syncthreads();
             }
             const bool ok = leader_solve<BLOCK - 64>(sm, s.Pinv, s.prm.sigma, -1.0, first, tid);
             if (tid == 0) {
@@ -1327,6 +1356,7 @@ __global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioS
             }
             store_state(s.state, &sm.x, tid, BLOCK, true);
             if (newlevel) store_state(s.old_state, &sm.x, tid, BLOCK, true);                       // :747 of the next level
+            if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             __threadfence();
             grid_release(bar, s_bar);
         } else {
@@ -1335,6 +1365,7 @@ __global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioS
         const int stop = __ldcg(&s.ctrl->stop);
         level = __ldcg(&s.ctrl->level);
         first = false;
+        ++pass_no;
         if (stop) break;
     }
 }

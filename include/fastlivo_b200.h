@@ -220,6 +220,11 @@ int flb_state_set_prior_enqueue(flb_handle* h);
  * the matching launch counts. */
 int flb_profile_start(flb_handle* h);
 int flb_profile_stop(flb_handle* h, double ms[4], int64_t launches[4]);
+/* Device-side pass trace of the persistent kernels (profiling aid; %globaltimer).  After an update,
+ * flb_trace_download(which = 0 LIO / 1 VIO) returns microseconds since kernel entry, two per pass:
+ * [2k] all blocks arrived at the pass barrier, [2k+1] the leader finished the solve and released. */
+int flb_trace_enable(flb_handle* h, int on);
+int flb_trace_download(flb_handle* h, int which, double* us, int max_entries, int* n_entries);
 /* kernels launched by this handle since creation */
 int64_t flb_launch_count(const flb_handle* h);
 
