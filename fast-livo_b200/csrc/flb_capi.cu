@@ -251,7 +251,7 @@ void to_dev_params(const flb_vio_params* p, VioParamsDev& d) {
     d.force_all_passes = p->force_all_passes;
 }
 
-int lio_nblocks(const flb_handle* h) { return (h->N + kLioBlock - 1) / kLioBlock; }
+int lio_nblocks(const flb_handle* h) { return (int)(((size_t)h->N * kGroup + kLioBlock - 1) / kLioBlock); }
 int vio_nblocks(const flb_handle* h) { return (h->Pn + (kVioBlock / 32) - 1) / (kVioBlock / 32); }
 
 int ensure_common(flb_handle* h) {
@@ -644,8 +644,8 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CUDA(h, h->sel.reserve(N));
     FLB_CUDA(h, h->plane_ok.reserve(N));
     FLB_CUDA(h, h->plane.reserve(N));
-    const int nb = (N + kLioBlock - 1) / kLioBlock;
-    FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)nb * lio_packed(12), h->partials.cap)));
+    const size_t nb = ((size_t)N * kGroup + kLioBlock - 1) / kLioBlock;
+    FLB_CUDA(h, h->partials.reserve(std::max<size_t>(nb * lio_packed(12), h->partials.cap)));
     FLB_CUDA(h, cudaMemcpyAsync(h->scan.p, st, (size_t)N * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
     FLB_CUDA(h, cudaMemsetAsync(h->sel.p, 1, std::max(N, 1), h->stream));
@@ -669,7 +669,7 @@ int flb_knn(flb_handle* h, const float* q, int nq, int* idx, float* d2) {
     FLB_CUDA(h, cudaMemcpyAsync(dq.p, q, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     {
         LaunchScope ls(h, FAM_LIO_KNN);
-        k_knn<<<(nq + 127) / 128, 128, 0, h->stream>>>(h->grid, h->cell_start.p, h->map_pts.p, dq.p, nq, di.p, dd.p);
+        k_knn<<<(int)(((size_t)nq * kGroup + 127) / 128), 128, 0, h->stream>>>(h->grid, h->cell_start.p, h->map_pts.p, dq.p, nq, di.p, dd.p);
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx, di.p, (size_t)nq * kMatch * sizeof(int), cudaMemcpyDeviceToHost, h->stream);

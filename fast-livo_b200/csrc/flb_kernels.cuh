@@ -118,14 +118,117 @@ __global__ void k_map_gather(const float* __restrict__ xyz, int M, int stride, c
 }
 
 // ---------------------------------------------------------------------------------------
-// standalone kNN (flb_knn): thread per query
+// Group-cooperative exact 5-NN: kGroup consecutive lanes share one query.  The (z,y) cell rows of
+// each Chebyshev ring are dealt round-robin to the lanes (a row's x-range is one contiguous run of
+// the sorted map), every lane keeps a private sorted top-5, and the group merges them with
+// shuffles after each ring.  Same termination rule and same strict-< semantics as knn5_grid
+// (flb_device.cuh); 8x more threads in flight and an ~8x shorter dependent-load chain per query.
+// Must be called by all kGroup lanes of the group with identical (qx,qy,qz); every lane returns
+// the merged result (sorted map positions).
+// ---------------------------------------------------------------------------------------
+constexpr int kGroup = 8;
+
+__device__ __forceinline__ void knn5_group_merge(Top5& loc, Top5& G, int sub, unsigned gmask) {
+#pragma unroll
+    for (int j = 0; j < kMatch; ++j) {
+        float md = loc.d[0];
+        int mi = loc.i[0];
+        int ml = sub;
+#pragma unroll
+        for (int off = kGroup / 2; off > 0; off >>= 1) {
+            const float od = __shfl_xor_sync(gmask, md, off);
+            const int oi = __shfl_xor_sync(gmask, mi, off);
+            const int ol = __shfl_xor_sync(gmask, ml, off);
+            if (od < md || (od == md && ol < ml)) { md = od; mi = oi; ml = ol; }
+        }
+        G.d[j] = md;
+        G.i[j] = mi;
+        if (ml == sub && mi >= 0) {   // this lane's head won: pop it
+#pragma unroll
+            for (int q = 0; q < kMatch - 1; ++q) { loc.d[q] = loc.d[q + 1]; loc.i[q] = loc.i[q + 1]; }
+            loc.d[kMatch - 1] = INFINITY;
+            loc.i[kMatch - 1] = -1;
+        }
+    }
+}
+
+__device__ __forceinline__ void knn_scan_run_thr(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
+                                                 float thr, Top5& t) {
+    for (int m = s; m < e; ++m) {
+        const float4 P = __ldg(pts + m);
+        const float d = dist2f(qx, qy, qz, P.x, P.y, P.z);
+        if (d < thr) top5_insert(t, d, m);
+    }
+}
+
+__device__ __forceinline__ void knn5_grid_group(const GridDesc& g, const int* __restrict__ cell_start,
+                                                const float4* __restrict__ pts, float qx, float qy, float qz, Top5& G,
+                                                int sub, unsigned gmask) {
+    top5_init(G);
+    const float fx = (qx - g.ox) * g.inv_cell, fy = (qy - g.oy) * g.inv_cell, fz = (qz - g.oz) * g.inv_cell;
+    const float lim = (float)(g.max_ring + 2);
+    if (!(fx > -lim && fy > -lim && fz > -lim && fx < (float)g.nx + lim && fy < (float)g.ny + lim &&
+          fz < (float)g.nz + lim))
+        return;
+    const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+    const float mx = fminf(fx - (float)cx, (float)(cx + 1) - fx);
+    const float my = fminf(fy - (float)cy, (float)(cy + 1) - fy);
+    const float mz = fminf(fz - (float)cz, (float)(cz + 1) - fz);
+    const float margin = fmaxf(fminf(mx, fminf(my, mz)) * g.cell - 1e-3f * g.cell, 0.f);
+    Top5 loc;
+    top5_init(loc);
+    float thr = INFINITY;   // current global 5th-best distance
+    // rings 0 and 1 are scanned together (a 3x3 block of 3-cell x-rows); then one shell per round
+    for (int r = 1; r <= g.max_ring; ++r) {
+        const int side = 2 * r + 1;
+        const int ntask = side * side;
+        const int x0 = cx - r, x1 = cx + r;
+        const int xa = x0 < 0 ? 0 : x0, xb = x1 >= g.nx ? g.nx - 1 : x1;
+        for (int t = sub; t < ntask; t += kGroup) {
+            const int dz = t / side - r, dy = t - (t / side) * side - r;
+            const int z = cz + dz, y = cy + dy;
+            if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+            const int rowbase = (z * g.ny + y) * g.nx;
+            const bool face = (r == 1) || dz == -r || dz == r || dy == -r || dy == r;
+            if (face) {
+                if (xa <= xb) {
+                    const int s = __ldg(cell_start + rowbase + xa), e = __ldg(cell_start + rowbase + xb + 1);
+                    knn_scan_run_thr(pts, s, e, qx, qy, qz, thr, loc);
+                }
+            } else {
+                if (x0 >= 0 && x0 < g.nx) {
+                    const int s = __ldg(cell_start + rowbase + x0), e = __ldg(cell_start + rowbase + x0 + 1);
+                    knn_scan_run_thr(pts, s, e, qx, qy, qz, thr, loc);
+                }
+                if (x1 >= 0 && x1 < g.nx) {
+                    const int s = __ldg(cell_start + rowbase + x1), e = __ldg(cell_start + rowbase + x1 + 1);
+                    knn_scan_run_thr(pts, s, e, qx, qy, qz, thr, loc);
+                }
+            }
+        }
+        knn5_group_merge(loc, G, sub, gmask);
+        // lane 0 carries the merged list forward, the others restart empty below the global threshold
+        thr = G.d[kMatch - 1];
+        if (sub == 0) loc = G; else top5_init(loc);
+        const float bound = (float)r * g.cell + margin;
+        const float b2 = bound * bound;
+        if (G.d[kMatch - 1] <= b2) break;
+        if (b2 > g.max_d2 * 1.0001f) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// standalone kNN (flb_knn): kGroup lanes per query
 // ---------------------------------------------------------------------------------------
 __global__ void k_knn(GridDesc g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
                       const float* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gid / kGroup, sub = threadIdx.x & (kGroup - 1);
+    if (i >= nq) return;   // group-uniform
+    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) & ~(kGroup - 1));
     Top5 t;
-    knn5_grid(g, cell_start, pts, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], t);
+    knn5_grid_group(g, cell_start, pts, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], t, sub, gmask);
+    if (sub != 0) return;
 #pragma unroll
     for (int j = 0; j < kMatch; ++j) {
         const bool ok = (t.i[j] >= 0) && !(t.d[j] > g.max_d2);
@@ -167,9 +270,11 @@ struct LioArgs {
     double* x_meas;              // N
 };
 
+// One scan point.  Rematch passes: called by all kGroup lanes of a group (cooperative kNN), lane
+// sub == 0 carries on with the plane fit / residual / row; plain passes: one thread per point (sub = 0).
 template <int W>
-__device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose, bool rematch, int i, bool& active,
-                                          double (&row)[W], double& z, double& absres) {
+__device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose, bool rematch, int i, int sub, unsigned gmask,
+                                          bool& active, double (&row)[W], double& z, double& absres) {
     active = false;
     z = 0.0;
     absres = 0.0;
@@ -183,7 +288,8 @@ __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose,
     float pabcd[4];
     if (rematch) {
         Top5 t;
-        knn5_grid(a.grid, a.cell_start, a.map_pts, pw[0], pw[1], pw[2], t);
+        knn5_grid_group(a.grid, a.cell_start, a.map_pts, pw[0], pw[1], pw[2], t, sub, gmask);
+        if (sub != 0) return;
         const bool five = t.i[kMatch - 1] >= 0;
         sel = five && !(t.d[kMatch - 1] > a.grid.max_d2);     // src/laserMapping.cpp:1549 (+ :1567 size check)
         pok = false;
@@ -213,9 +319,10 @@ __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose,
             }
         }
     } else {
-        sel = a.sel[i] != 0;
-        pok = a.plane_ok[i] != 0;
-        const float4 pl = a.plane[i];
+        // through L2: in the persistent kernel these were written by another SM in an earlier pass
+        sel = __ldcg(a.sel + i) != 0;
+        pok = __ldcg(a.plane_ok + i) != 0;
+        const float4 pl = __ldcg(a.plane + i);
         pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w;
     }
     float pd2 = 0.f;
@@ -254,7 +361,8 @@ __device__ __forceinline__ void lio_make_pose(const LioArgs& a, LioPose& pose) {
     m3_T(pose.R_LI, pose.RLIt);
 }
 
-// One thread per scan point; block partial sums written to partials[blockIdx.x][*].
+// kGroup lanes per scan point (cooperative kNN on rematch passes; lanes sub != 0 idle on plain passes);
+// block partial sums written to partials[blockIdx.x][*].
 template <int W, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) {
     constexpr int K = lio_packed(W);
@@ -270,12 +378,13 @@ __global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) {
     }
     if (threadIdx.x == 0) lio_make_pose(a, s_pose);
     __syncthreads();
-    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const int i = (blockIdx.x * BLOCK + threadIdx.x) / kGroup, sub = threadIdx.x & (kGroup - 1);
+    const unsigned gmask = ((1u << kGroup) - 1u) << ((threadIdx.x & 31) & ~(kGroup - 1));
     bool active = false;
     double row[W], z = 0.0, absres = 0.0;
 #pragma unroll
     for (int k = 0; k < W; ++k) row[k] = 0.0;
-    if (i < a.N) lio_point<W>(a, s_pose, rematch != 0, i, active, row, z, absres);
+    if (i < a.N && (rematch || sub == 0)) lio_point<W>(a, s_pose, rematch != 0, i, sub, gmask, active, row, z, absres);
     // warp-level reduction of the packed products, then across warps in fixed order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int k = 0;
@@ -457,7 +566,15 @@ template <int K>
 __device__ __forceinline__ void reduce_partials(const double* partials, int nblocks, double* out /*smem K*/, int lane) {
     for (int q = lane; q < K; q += 32) {
         double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * K + q];
+        int b = 0;
+        for (; b + 8 <= nblocks; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = partials[(size_t)(b + u) * K + q];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; b < nblocks; ++b) s += partials[(size_t)b * K + q];
         out[q] = s;
     }
     __syncwarp();
@@ -466,7 +583,15 @@ __device__ __forceinline__ void reduce_partials(const double* partials, int nblo
 __global__ void __launch_bounds__(32) k_reduce_only(const double* partials, int nblocks, int K, double* out) {
     for (int q = threadIdx.x; q < K; q += 32) {
         double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * K + q];
+        int b = 0;
+        for (; b + 8 <= nblocks; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = partials[(size_t)(b + u) * K + q];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; b < nblocks; ++b) s += partials[(size_t)b * K + q];
         out[q] = s;
     }
 }
@@ -942,7 +1067,17 @@ __device__ __forceinline__ void leader_reduce(const double* partials, int nblock
         const int per = (nblocks + 3) / 4;
         const int b0 = part * per, b1 = min(nblocks, b0 + per);
         double s = 0.0;
-        for (int b = b0; b < b1; ++b) s += __ldcg(partials + (size_t)b * K + q);
+        // batches of 8 independent L2 loads, then the adds in block order: the chain costs one L2
+        // round trip per 8 blocks instead of one per block
+        int b = b0;
+        for (; b + 8 <= b1; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + (size_t)(b + u) * K + q);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; b < b1; ++b) s += __ldcg(partials + (size_t)b * K + q);
         sm.part[part][q] = s;
     }
     __syncthreads();
@@ -1061,11 +1196,15 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
-        const int stride = gridDim.x * BLOCK;
-        for (int i = blockIdx.x * BLOCK + tid; i < a.N; i += stride) {
+        // rematch passes: kGroup lanes per point (cooperative kNN); plain passes: one thread per point
+        const int gthreads = gridDim.x * BLOCK, gtid = blockIdx.x * BLOCK + tid;
+        const int per = nearest ? kGroup : 1;
+        const int sub = nearest ? (tid & (kGroup - 1)) : 0;
+        const unsigned gmask = ((1u << kGroup) - 1u) << (lane & ~(kGroup - 1));
+        for (int i = gtid / per; i < a.N; i += gthreads / per) {
             bool active;
             double row[6], z, absres;
-            lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres);
+            lio_point<6>(a, s_pose, nearest != 0, i, sub, gmask, active, row, z, absres);
             if (active) {
                 int k = 0;
 #pragma unroll
@@ -1161,7 +1300,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
 // VIO: ComputeJ (3 levels x up to T passes) in one launch
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
+__global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
                                                                  unsigned long long* trace) {
     constexpr int NW = BLOCK / 32;
     __shared__ VioPose s_pose;
