@@ -96,9 +96,6 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclInt32 = 2, kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
-constexpr int kLioBlock = 128;
-constexpr int kVioBlock = 256;
-
 }  // namespace
 
 struct flb_handle {
@@ -122,12 +119,15 @@ struct flb_handle {
 
     // scan + per-point persistent
     int N = 0;
+    DevBuf<float> scan_raw;
+    DevBuf<unsigned> skeys, skeys_sorted;
+    DevBuf<int> svals, svals_sorted;
     DevBuf<float4> scan;
     DevBuf<unsigned char> sel, plane_ok;
     DevBuf<float4> plane;
 
     // LIO exports (lazily allocated)
-    DevBuf<float> x_world, x_nn_d2, x_pd2;
+    DevBuf<float> x_world, x_nn_d2, x_pd2, x_pabcd;
     DevBuf<int> x_nn_idx;
     DevBuf<unsigned char> x_rowmask;
     DevBuf<double> x_rows, x_meas;
@@ -138,7 +138,7 @@ struct flb_handle {
     DevBuf<double> partials;     // max(nblocks_lio * 92, nblocks_vio * 29)
     DevBuf<double> packed;       // 128
     DevBuf<double> pose12;       // 12
-    DevBuf<double> Pinv;         // 324
+    DevBuf<PriorBlock> prior;    // P11^-1 and P21*P11^-1 of the running update
     DevBuf<double> G_last;       // 108
     DevBuf<State18> states;      // [0]=x [1]=x_prop [2]=old_state(VIO) [3]=saved x [4]=saved x_prop
     DevBuf<LioCtrl> lio_ctrl;
@@ -251,13 +251,13 @@ void to_dev_params(const flb_vio_params* p, VioParamsDev& d) {
     d.force_all_passes = p->force_all_passes;
 }
 
-int lio_nblocks(const flb_handle* h) { return (int)(((size_t)h->N * kGroup + kLioBlock - 1) / kLioBlock); }
+int lio_nblocks(const flb_handle* h) { return (h->N + kLioBlock - 1) / kLioBlock; }
 int vio_nblocks(const flb_handle* h) { return (h->Pn + (kVioBlock / 32) - 1) / (kVioBlock / 32); }
 
 int ensure_common(flb_handle* h) {
     FLB_CUDA(h, h->packed.reserve(128));
     FLB_CUDA(h, h->pose12.reserve(12));
-    FLB_CUDA(h, h->Pinv.reserve(324));
+    FLB_CUDA(h, h->prior.reserve(1));
     FLB_CUDA(h, h->G_last.reserve(108));
     FLB_CUDA(h, h->states.reserve(5));
     FLB_CUDA(h, h->lio_ctrl.reserve(1));
@@ -297,6 +297,7 @@ LioArgs make_lio_args(flb_handle* h, const LioParamsDev& prm, bool exports, int 
         a.x_world = h->x_world.p;
         a.x_nn_idx = h->x_nn_idx.p;
         a.x_nn_d2 = h->x_nn_d2.p;
+        a.x_pabcd = h->x_pabcd.p;
         a.x_pd2 = h->x_pd2.p;
         a.x_rowmask = h->x_rowmask.p;
         a.x_rows = h->x_rows.p;
@@ -339,7 +340,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     s.state = &h->states.p[0];
     s.state_prop = &h->states.p[1];
     s.ctrl = h->lio_ctrl.p;
-    s.Pinv = h->Pinv.p;
+    s.prior = h->prior.p;
     s.partials = h->partials.p;
     s.nblocks = lio_nblocks(h);
     s.prm = d;
@@ -363,7 +364,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     }
     {
         LaunchScope ls(h, FAM_SOLVE);
-        k_lio_begin<<<1, 32, 0, h->stream>>>(s);
+        k_lio_begin<<<1, 32, 0, h->stream>>>(h->lio_ctrl.p);
         FLB_CUDA(h, cudaGetLastError());
     }
     const int T = prm->max_iteration;
@@ -379,7 +380,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
             s.nblocks = 1;
         }
         LaunchScope ls(h, FAM_SOLVE);
-        k_lio_finalize<<<1, 32, 0, h->stream>>>(s);
+        k_lio_finalize<<<1, kLeaderBlock, 0, h->stream>>>(s);
         FLB_CUDA(h, cudaGetLastError());
     }
     h->last_pass_valid = false;
@@ -396,7 +397,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     s.state_prop = &h->states.p[1];
     s.old_state = &h->states.p[2];
     s.ctrl = h->vio_ctrl.p;
-    s.Pinv = h->Pinv.p;
+    s.prior = h->prior.p;
     s.G_last = h->G_last.p;
     s.partials = h->partials.p;
     s.nblocks = vio_nblocks(h);
@@ -406,7 +407,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     const bool persistent = h->cfg.persistent && !h->comm && h->Pn > 0 && prm->max_iteration > 0;
     if (!persistent) {
         LaunchScope ls(h, FAM_SOLVE);
-        k_vio_begin<<<1, 32, 0, h->stream>>>(s);
+        k_vio_begin<<<1, 32, 0, h->stream>>>(h->vio_ctrl.p, h->Pn);
         FLB_CUDA(h, cudaGetLastError());
     }
     VioArgs a{};
@@ -458,7 +459,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
             s.Pn_total = (int)(shard * (size_t)h->world);
         }
         LaunchScope ls(h, FAM_SOLVE);
-        k_vio_finalize<<<1, 64, 0, h->stream>>>(s);
+        k_vio_finalize<<<1, kLeaderBlock, 0, h->stream>>>(s);
         FLB_CUDA(h, cudaGetLastError());
     }
     h->last_vio_valid = false;
@@ -537,7 +538,7 @@ int flb_destroy(flb_handle* h) {
     h->cub_tmp.release(); h->map_pts.release(); h->cell_start.release(); h->scan.release(); h->sel.release();
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
-    h->packed.release(); h->pose12.release(); h->Pinv.release(); h->G_last.release(); h->states.release();
+    h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
     h->lio_ctrl.release(); h->vio_ctrl.release(); h->barrier.release(); h->trace.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->pin.release(); h->pin_out.release();
@@ -636,20 +637,54 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CHECK_H(h);
     if (!body_xyz || N < 0 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: bad arguments");
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    FLB_CUDA(h, h->pin.reserve((size_t)std::max(N, 1) * sizeof(float4)));
-    float4* st = static_cast<float4*>(h->pin.p);
+    const size_t n1 = (size_t)std::max(N, 1);
+    FLB_CUDA(h, h->pin.reserve(n1 * 3 * sizeof(float)));
+    float* st = static_cast<float*>(h->pin.p);
+    float lo[3] = {INFINITY, INFINITY, INFINITY};
     for (int i = 0; i < N; ++i)
-        st[i] = make_float4(body_xyz[(size_t)i * stride], body_xyz[(size_t)i * stride + 1], body_xyz[(size_t)i * stride + 2], 0.f);
-    FLB_CUDA(h, h->scan.reserve(N));
-    FLB_CUDA(h, h->sel.reserve(N));
-    FLB_CUDA(h, h->plane_ok.reserve(N));
-    FLB_CUDA(h, h->plane.reserve(N));
-    const size_t nb = ((size_t)N * kGroup + kLioBlock - 1) / kLioBlock;
+        for (int k = 0; k < 3; ++k) {
+            const float v = body_xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: non-finite coordinate at point %d", i);
+            st[3 * (size_t)i + k] = v;
+            lo[k] = std::min(lo[k], v);
+        }
+    FLB_CUDA(h, h->scan_raw.reserve(n1 * 3));
+    FLB_CUDA(h, h->skeys.reserve(n1));
+    FLB_CUDA(h, h->skeys_sorted.reserve(n1));
+    FLB_CUDA(h, h->svals.reserve(n1));
+    FLB_CUDA(h, h->svals_sorted.reserve(n1));
+    FLB_CUDA(h, h->scan.reserve(n1));
+    FLB_CUDA(h, h->sel.reserve(n1));
+    FLB_CUDA(h, h->plane_ok.reserve(n1));
+    FLB_CUDA(h, h->plane.reserve(n1));
+    const size_t nb = (n1 + kLioBlock - 1) / kLioBlock;
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>(nb * lio_packed(12), h->partials.cap)));
-    FLB_CUDA(h, cudaMemcpyAsync(h->scan.p, st, (size_t)N * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    if (N > 0) {
+        FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        // Morton order in the body frame (cell = the map grid's cell): spatially coherent warps at any pose
+        const float inv_cell = 1.0f / (float)h->cfg.cell_size;
+        const int g = (N + 255) / 256;
+        {
+            LaunchScope ls(h, FAM_OTHER);
+            k_scan_keys<<<g, 256, 0, h->stream>>>(h->scan_raw.p, N, lo[0], lo[1], lo[2], inv_cell, h->skeys.p, h->svals.p);
+            FLB_CUDA(h, cudaGetLastError());
+        }
+        size_t tmp_bytes = 0;
+        FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
+                                                    h->svals_sorted.p, N, 0, 30, h->stream));
+        FLB_CUDA(h, h->cub_tmp.reserve(tmp_bytes));
+        FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
+                                                    h->svals_sorted.p, N, 0, 30, h->stream));
+        h->launches += 3;
+        {
+            LaunchScope ls(h, FAM_OTHER);
+            k_scan_gather<<<g, 256, 0, h->stream>>>(h->scan_raw.p, N, h->svals_sorted.p, h->scan.p);
+            FLB_CUDA(h, cudaGetLastError());
+        }
+    }
     // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
-    FLB_CUDA(h, cudaMemsetAsync(h->sel.p, 1, std::max(N, 1), h->stream));
-    FLB_CUDA(h, cudaMemsetAsync(h->plane_ok.p, 0, std::max(N, 1), h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(h->sel.p, 1, n1, h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(h->plane_ok.p, 0, n1, h->stream));
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->N = N;
     h->last_pass_valid = false;
@@ -669,7 +704,7 @@ int flb_knn(flb_handle* h, const float* q, int nq, int* idx, float* d2) {
     FLB_CUDA(h, cudaMemcpyAsync(dq.p, q, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     {
         LaunchScope ls(h, FAM_LIO_KNN);
-        k_knn<<<(int)(((size_t)nq * kGroup + 127) / 128), 128, 0, h->stream>>>(h->grid, h->cell_start.p, h->map_pts.p, dq.p, nq, di.p, dd.p);
+        k_knn<<<(nq + 127) / 128, 128, 0, h->stream>>>(h->grid, h->cell_start.p, h->map_pts.p, dq.p, nq, di.p, dd.p);
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx, di.p, (size_t)nq * kMatch * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
@@ -691,6 +726,7 @@ int flb_lio_pass(flb_handle* h, const flb_lio_params* prm, const double R[9], co
     FLB_CUDA(h, h->x_nn_idx.reserve((size_t)N * kMatch));
     FLB_CUDA(h, h->x_nn_d2.reserve((size_t)N * kMatch));
     FLB_CUDA(h, h->x_pd2.reserve(N));
+    FLB_CUDA(h, h->x_pabcd.reserve((size_t)N * 4));
     FLB_CUDA(h, h->x_rowmask.reserve(N));
     FLB_CUDA(h, h->x_rows.reserve((size_t)N * 12));
     FLB_CUDA(h, h->x_meas.reserve(N));
@@ -743,7 +779,7 @@ int flb_lio_export(flb_handle* h, float* world_xyz, int* nn_idx, float* nn_d2, f
     if (world_xyz) FLB_CUDA(h, cudaMemcpyAsync(world_xyz, h->x_world.p, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (nn_idx) FLB_CUDA(h, cudaMemcpyAsync(nn_idx, h->x_nn_idx.p, (size_t)N * kMatch * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (nn_d2) FLB_CUDA(h, cudaMemcpyAsync(nn_d2, h->x_nn_d2.p, (size_t)N * kMatch * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (pabcd) FLB_CUDA(h, cudaMemcpyAsync(pabcd, h->plane.p, (size_t)N * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    if (pabcd) FLB_CUDA(h, cudaMemcpyAsync(pabcd, h->x_pabcd.p, (size_t)N * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (pd2) FLB_CUDA(h, cudaMemcpyAsync(pd2, h->x_pd2.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, s));
     std::vector<unsigned char> mask(N);
     FLB_CUDA(h, cudaMemcpyAsync(mask.data(), h->x_rowmask.p, N, cudaMemcpyDeviceToHost, s));
