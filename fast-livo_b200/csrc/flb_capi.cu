@@ -1112,8 +1112,8 @@ int flb_trace_download(flb_handle* h, int which, double* us, int max_entries, in
     FLB_CUDA(h, cudaMemcpy(t, h->trace.p + which * kTraceLen, sizeof(t), cudaMemcpyDeviceToHost));
     int n = 0;
     for (int i = 1; i < kTraceLen && i - 1 < max_entries; ++i) {
-        if (t[i] == 0) break;
-        us[n++] = (double)(t[i] - t[0]) * 1e-3;
+        if (t[i] == 0 && i < 64) { if (max_entries < kTraceLen - 1) break; us[n++] = 0.0; continue; }
+        us[n++] = t[i] ? (double)(t[i] - t[0]) * 1e-3 : 0.0;
     }
     *n_entries = n;
     return FLB_OK;

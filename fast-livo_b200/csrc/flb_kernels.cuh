@@ -71,6 +71,15 @@ constexpr int kLioBlock = 128;
 constexpr int kVioBlock = 256;
 constexpr int kLeaderBlock = 256;       // block size of the kernel-per-pass finalize kernels
 
+// Optional device-side pass trace (profiling aid): %globaltimer (ns) at kernel entry [0], then for
+// pass k: [1+2k] = all blocks arrived (leader elected), [2+2k] = leader released the barrier.
+constexpr int kTraceLen = 128;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -546,10 +555,26 @@ struct LeaderSmem {
     float error;
 };
 
-__device__ __forceinline__ void load_state_l2(State18* dst, const State18* src, int tid, int nt) {
-    const double* s = reinterpret_cast<const double*>(src);
-    double* d = reinterpret_cast<double*>(dst);
-    for (int e = tid; e < (int)(sizeof(State18) / sizeof(double)); e += nt) d[e] = __ldcg(s + e);
+// The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
+__device__ __forceinline__ void load_poses_l2(State18* x, const State18* xg, State18* xp, const State18* xpg, int tid) {
+    if (tid < 24) reinterpret_cast<double*>(x)[tid] = __ldcg(reinterpret_cast<const double*>(xg) + tid);
+    else if (tid < 48) reinterpret_cast<double*>(xp)[tid - 24] = __ldcg(reinterpret_cast<const double*>(xpg) + tid - 24);
+}
+// The covariance only (needed for the prior block on the first pass and for the update on the last).
+template <int NT>
+__device__ __forceinline__ void load_cov_l2(State18* dst, const State18* src, int tid) {
+    constexpr int PER = (kDim * kDim + NT - 1) / NT;
+    double v[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int e = tid + u * NT;
+        v[u] = (e < kDim * kDim) ? __ldcg(src->cov + e) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int e = tid + u * NT;
+        if (e < kDim * kDim) dst->cov[e] = v[u];
+    }
 }
 __device__ __forceinline__ void store_state(State18* dst, const State18* src, int tid, int nt, bool with_cov) {
     const double* s = reinterpret_cast<const double*>(src);
@@ -569,14 +594,15 @@ __device__ __forceinline__ void leader_reduce(const double* partials, int nblock
         const int b0 = part * per, b1 = min(nblocks, b0 + per);
         double s = 0.0;
         int b = b0;
-        for (; b + 16 <= b1; b += 16) {
+        for (; b < b1; b += 16) {
+            // 16 independent L2 loads in flight (guarded at the tail: adding +0.0 is exact), then the
+            // adds in block order
             double v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = __ldcg(partials + (size_t)(b + u) * K + q);
+            for (int u = 0; u < 16; ++u) v[u] = (b + u < b1) ? __ldcg(partials + (size_t)(b + u) * K + q) : 0.0;
 #pragma unroll
             for (int u = 0; u < 16; ++u) s += v[u];
         }
-        for (; b < b1; ++b) s += __ldcg(partials + (size_t)b * K + q);
         sm.part[part][q] = s;
     }
     __syncthreads();
@@ -729,20 +755,25 @@ struct LioSolveArgs {
 
 // One LIO leader step (whole block, NT threads).  `first`: first pass of this update.  Loop state
 // comes in by value (block-local mirrors in the persistent kernel, ctrl in the per-pass path).
+#define FLB_STAMP(k) do { if (fine && threadIdx.x == 0) fine[k] = global_ns(); } while (0)
 template <int NT>
 __device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm, bool first, int iterCount, int rematch_num,
-                                           int nearest) {
+                                           int nearest, unsigned long long* fine = nullptr) {
     constexpr int K = lio_packed(6);
     const int tid = threadIdx.x;
     const int T = s.prm.max_iteration;
-    load_state_l2(&sm.x, s.state, tid, NT);
-    load_state_l2(&sm.xp, s.state_prop, tid, NT);
+    load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
+    if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
+    __syncthreads();
+    FLB_STAMP(0);
     leader_reduce<K>(s.partials, s.nblocks, sm, tid);
+    FLB_STAMP(1);
     if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
     __syncthreads();
     leader_step<Team<NT, false>>(sm, s.prior, first, s.prm.sigma, +1.0, tid);
     const bool ok = sm.flags[3] == 0;
     __syncthreads();
+    FLB_STAMP(2);
     if (tid == 0) {
         LioCtrl c;
         if (first) {
@@ -780,9 +811,14 @@ __device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm
         sm.flags[1] = ok ? 1 : 0;
     }
     __syncthreads();
+    FLB_STAMP(3);
     const bool do_cov = sm.flags[0] && sm.flags[1];
-    if (do_cov) leader_cov_update(sm, sm.Gc, tid, NT);                                  // :1715
+    if (do_cov) {
+        if (!first) { load_cov_l2<NT>(&sm.x, s.state, tid); __syncthreads(); }
+        leader_cov_update(sm, sm.Gc, tid, NT);                                          // :1715
+    }
     store_state(s.state, &sm.x, tid, NT, do_cov);
+    FLB_STAMP(4);
 }
 
 __global__ void __launch_bounds__(32) k_lio_begin(LioCtrl* ctrl) {
@@ -829,9 +865,12 @@ constexpr int kErrChunk = 2048;
 template <int NT>
 __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm, float* s_err, bool first, int level) {
     const int tid = threadIdx.x;
-    load_state_l2(&sm.x, s.state, tid, NT);
-    load_state_l2(&sm.xp, s.state_prop, tid, NT);
-    if (first) store_state(s.old_state, &sm.x, tid, NT, true);                           // old_state = *state (:747)
+    // The covariance is constant during ComputeJ (only :980 changes it, on the last pass), so old_state
+    // carries the 24 pose/bias doubles only.
+    load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
+    if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
+    __syncthreads();
+    if (first) store_state(s.old_state, &sm.x, tid, NT, false);                          // old_state = *state (:747)
     leader_reduce<kVioPacked>(s.partials, s.nblocks, sm, tid);
     if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
     // stage the first chunk of per-patch errors with the whole block (coalesced L2 reads)
@@ -922,24 +961,25 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
     __syncthreads();
     const int accept = sm.flags[0], docov = sm.flags[1], newlevel = sm.flags[2];
     if (accept) {
-        store_state(s.old_state, &sm.x, tid, NT, true);                                    // old_state = *state (:863)
+        store_state(s.old_state, &sm.x, tid, NT, false);                                   // old_state = *state (:863)
         for (int e = tid; e < kDim * 6; e += NT) s.G_last[e] = sm.Gc[e];
         __syncthreads();
         if (tid == 0) state_boxplus(sm.x, sm.sol);                                         // :879
         __syncthreads();
     } else {
-        load_state_l2(&sm.x, s.old_state, tid, NT);                                        // *state = old_state (:890)
-        __syncthreads();
+        if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(reinterpret_cast<const double*>(s.old_state) + tid);
+        __syncthreads();                                                                   // *state = old_state (:890)
     }
     if (docov) {
         if (!accept) {
             for (int e = tid; e < kDim * 6; e += NT) sm.Gc[e] = __ldcg(s.G_last + e);
             __syncthreads();
         }
+        if (!first) { load_cov_l2<NT>(&sm.x, s.state, tid); __syncthreads(); }
         leader_cov_update(sm, sm.Gc, tid, NT);                                             // :980
     }
-    store_state(s.state, &sm.x, tid, NT, true);
-    if (newlevel) store_state(s.old_state, &sm.x, tid, NT, true);                          // :747 of the next level
+    store_state(s.state, &sm.x, tid, NT, docov != 0);
+    if (newlevel) store_state(s.old_state, &sm.x, tid, NT, false);                         // :747 of the next level
 }
 
 __global__ void __launch_bounds__(32) k_vio_begin(VioCtrl* ctrl, int Pn_total) {
@@ -983,15 +1023,6 @@ struct GridBarrier {
     int timeout;
     int pad;
 };
-
-// Optional device-side pass trace (profiling aid): %globaltimer (ns) at kernel entry [0], then for
-// pass k: [1+2k] = all blocks arrived (leader elected), [2+2k] = leader released the barrier.
-constexpr int kTraceLen = 128;
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -1077,7 +1108,8 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         const bool leader = grid_arrive(bar, gridDim.x, s_bar);
         if (leader) {
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
-            lio_leader<BLOCK>(s, sm, first, iterCount, rematch_num, nearest);
+            lio_leader<BLOCK>(s, sm, first, iterCount, rematch_num, nearest,
+                              (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             grid_release(bar, s_bar);
         } else {
