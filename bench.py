@@ -364,23 +364,32 @@ def main():
     barrier()
     hbm, peak_src = peaks()
     n_loc, pn_loc = len(scan), len(ppos)
-    fam_bytes = [B_LIO_KNN * n_loc, B_LIO_PLAIN * n_loc, B_VIO * pn_loc, 0]
-    fam_names = ["k_lio_pass(kNN+plane+residual)", "k_lio_pass(cached plane)", "k_vio_pass", "k_*_finalize/begin(solve)"]
+    persistent = world == 1          # the NCCL path runs kernel-per-pass
+    if persistent:
+        # one cooperative kernel per update: its algorithmic bytes are the sum over its passes
+        fam_bytes = [(B_LIO_KNN * pc["lio_knn"] + B_LIO_PLAIN * pc["lio_plain"]) * n_loc, 0, B_VIO * pc["vio_passes"] * pn_loc, 0]
+        fam_names = [f"k_lio_update_persistent ({pc['lio_knn']} kNN + {pc['lio_plain']} plain passes + solves)", "-",
+                     f"k_vio_update_persistent ({pc['vio_passes']} passes + solves)", "-"]
+    else:
+        fam_bytes = [B_LIO_KNN * n_loc, B_LIO_PLAIN * n_loc, B_VIO * pn_loc, 0]
+        fam_names = ["k_lio_pass(kNN+plane+residual)", "k_lio_pass(cached plane)", "k_vio_pass", "k_*_finalize/begin(solve)"]
     fams = []
     for i in range(4):
         if fam_n[i] == 0:
             continue
         avg_us = 1e3 * fam_ms[i] / fam_n[i]
         gbs = fam_bytes[i] / (avg_us * 1e-6) / 1e9 if fam_bytes[i] else 0.0
-        fams.append({"kernel": fam_names[i], "launches_per_frame": int(fam_n[i] // prof_steps), "avg_us": avg_us,
-                     "share_of_frame": float(fam_ms[i] / max(fam_ms.sum(), 1e-12)), "algorithmic_bytes": fam_bytes[i],
+        fams.append({"kernel": fam_names[i], "launches_per_frame": float(fam_n[i]) / prof_steps, "avg_us": avg_us,
+                     "share_of_frame": float(fam_ms[i] / max(fam_ms.sum(), 1e-12)), "algorithmic_bytes": int(fam_bytes[i]),
                      "achieved_gbs": gbs})
     dom = max((f for f in fams if f["algorithmic_bytes"] > 0), key=lambda f: f["share_of_frame"], default=None)
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                     "frac": dom["achieved_gbs"] / hbm, "traffic": None, "peak_source": peak_src,
-                    "note": "working set is L2-resident and the kernel is latency-bound at this size (SURVEY.md §7 H2)"}
+                    "avg_launch_us": dom["avg_us"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+                    "note": "the whole working set (~8 MB) is L2-resident and every pass is a dependent step: the kernel is "
+                            "latency-bound, not bandwidth-bound, at this size (SURVEY.md section 7 H2; DESIGN.md section 4)"}
 
     # ---- cpu_baseline (rank 0, N == 1 only): bounded sample on the host cores
     cpu = None
