@@ -347,8 +347,10 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     LioArgs a = make_lio_args(h, d, false, 6);
     if (h->cfg.persistent && !h->comm) {
         // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
+        // whole multiples of the SM count (<= co-resident capacity): chunks are dealt round-robin to blocks
         const int cap = std::max(1, h->occ_lio * h->num_sms);
-        const int grid = std::max(1, std::min(lio_nblocks(h), cap));
+        const int want = std::min(cap, std::max(h->num_sms, std::min(2, h->occ_lio) * h->num_sms));
+        const int grid = std::max(1, std::min((h->N + 31) / 32, want));
         FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * lio_packed(12), h->partials.cap)));
         a.partials = h->partials.p;
         s.partials = h->partials.p;
@@ -427,7 +429,11 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     const int nb = vio_nblocks(h);
     if (persistent) {
         const int cap = std::max(1, h->occ_vio * h->num_sms);
-        const int grid = std::max(1, std::min(nb, cap));
+        // patches are dealt warp-round-robin: use every co-resident block so all SMs carry equal load
+        const int grid = std::max(1, std::min(h->Pn, cap));
+        FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * kVioPacked, h->partials.cap)));
+        a.partials = h->partials.p;
+        s.partials = h->partials.p;
         s.nblocks = grid;
         GridBarrier* bar = h->barrier.p;
         unsigned long long* trace = h->tracing ? h->trace.p + kTraceLen : nullptr;

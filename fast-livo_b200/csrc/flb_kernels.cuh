@@ -1098,11 +1098,17 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
-        for (int i = blockIdx.x * BLOCK + tid; i < a.N; i += gridDim.x * BLOCK) {
-            bool active;
-            double row[6], z, absres;
-            lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres);
-            if (active) lio_accumulate<6>(acc, row, z, absres);
+        // 32-point (Morton-contiguous) chunks dealt round-robin to the blocks, so that every SM gets the
+        // same number of warps' worth of work whatever N is; the chunk -> thread map is the same in
+        // every pass, so each thread re-reads only its own per-point cache entries.
+        for (int c = (tid >> 5) * gridDim.x + blockIdx.x; c * 32 < a.N; c += (BLOCK / 32) * gridDim.x) {
+            const int i = c * 32 + (tid & 31);
+            if (i < a.N) {
+                bool active;
+                double row[6], z, absres;
+                lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres);
+                if (active) lio_accumulate<6>(acc, row, z, absres);
+            }
         }
         block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
         const bool leader = grid_arrive(bar, gridDim.x, s_bar);
