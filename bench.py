@@ -303,6 +303,8 @@ def main():
         h.trace_enable(False)
 
         def split(t):
+            t = t[:63]
+            t = t[:int(np.argmax(t == 0))] if (t == 0).any() else t     # entries 64.. are the fine leader stamps
             t = np.concatenate([[0.0], t])
             return {"pass_us": [round(float(t[i + 1] - t[i]), 2) for i in range(0, len(t) - 1, 2)],
                     "solve_us": [round(float(t[i + 2] - t[i + 1]), 2) for i in range(0, len(t) - 2, 2)]}

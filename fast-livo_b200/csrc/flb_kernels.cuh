@@ -550,7 +550,7 @@ struct LeaderSmem {
     double vec[kDim], sol[kDim], Gc[kDim * 6];
     double top[6 * kDim];
     double packed[32];
-    double part[4][32];
+    double part[8][32];
     int flags[4];
     float error;
 };
@@ -583,20 +583,19 @@ __device__ __forceinline__ void store_state(State18* dst, const State18* src, in
     for (int e = tid; e < n; e += nt) d[e] = s[e];
 }
 
-// Fixed-order reduction of the block partials: 4 contiguous quarters per entry (one warp each),
-// every quarter summed in block order from batches of 16 independent L2 loads, then
-// ((q0+q1)+q2)+q3.  Needs >= 128 threads.
-template <int K>
+// Fixed-order reduction of the block partials: PARTS = NT/32 contiguous slices per entry (one warp
+// each), every slice summed in block order from batches of 16 independent L2 loads (guarded at the
+// tail: adding +0.0 is exact), then the slices combined left to right.
+template <int K, int NT>
 __device__ __forceinline__ void leader_reduce(const double* partials, int nblocks, LeaderSmem& sm, int tid) {
+    constexpr int PARTS = NT / 32;
+    static_assert(PARTS <= 8 && K <= 32, "LeaderSmem::part is [8][32]");
     const int q = tid & 31, part = tid >> 5;
-    if (part < 4 && q < K) {
-        const int per = (nblocks + 3) / 4;
+    if (q < K) {
+        const int per = (nblocks + PARTS - 1) / PARTS;
         const int b0 = part * per, b1 = min(nblocks, b0 + per);
         double s = 0.0;
-        int b = b0;
-        for (; b < b1; b += 16) {
-            // 16 independent L2 loads in flight (guarded at the tail: adding +0.0 is exact), then the
-            // adds in block order
+        for (int b = b0; b < b1; b += 16) {
             double v[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) v[u] = (b + u < b1) ? __ldcg(partials + (size_t)(b + u) * K + q) : 0.0;
@@ -606,8 +605,41 @@ __device__ __forceinline__ void leader_reduce(const double* partials, int nblock
         sm.part[part][q] = s;
     }
     __syncthreads();
-    if (tid < K) sm.packed[tid] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
+    if (tid < K) {
+        double s = sm.part[0][tid];
+#pragma unroll
+        for (int p = 1; p < PARTS; ++p) s += sm.part[p][tid];
+        sm.packed[tid] = s;
+    }
     __syncthreads();
+}
+
+template <int K, int NT, class TeamT>
+__device__ __forceinline__ void team_reduce(const double* partials, int nblocks, LeaderSmem& sm, int tid) {
+    constexpr int PARTS = NT / 32;
+    static_assert(PARTS <= 8 && K <= 32, "LeaderSmem::part is [8][32]");
+    const int q = tid & 31, part = tid >> 5;
+    if (q < K) {
+        const int per = (nblocks + PARTS - 1) / PARTS;
+        const int b0 = part * per, b1 = min(nblocks, b0 + per);
+        double s = 0.0;
+        for (int b = b0; b < b1; b += 16) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (b + u < b1) ? __ldcg(partials + (size_t)(b + u) * K + q) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s += v[u];
+        }
+        sm.part[part][q] = s;
+    }
+    TeamT::sync();
+    if (tid < K) {
+        double s = sm.part[0][tid];
+#pragma unroll
+        for (int p = 1; p < PARTS; ++p) s += sm.part[p][tid];
+        sm.packed[tid] = s;
+    }
+    TeamT::sync();
 }
 
 __device__ __forceinline__ void unpack_sym6(const double* packed, double* HTH, double* HTz) {
@@ -766,7 +798,7 @@ __device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm
     if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
     __syncthreads();
     FLB_STAMP(0);
-    leader_reduce<K>(s.partials, s.nblocks, sm, tid);
+    leader_reduce<K, NT>(s.partials, s.nblocks, sm, tid);
     FLB_STAMP(1);
     if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
     __syncthreads();
@@ -865,22 +897,13 @@ constexpr int kErrChunk = 2048;
 template <int NT>
 __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm, float* s_err, bool first, int level) {
     const int tid = threadIdx.x;
-    // The covariance is constant during ComputeJ (only :980 changes it, on the last pass), so old_state
-    // carries the 24 pose/bias doubles only.
-    load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
-    if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
-    __syncthreads();
-    if (first) store_state(s.old_state, &sm.x, tid, NT, false);                          // old_state = *state (:747)
-    leader_reduce<kVioPacked>(s.partials, s.nblocks, sm, tid);
-    if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
-    // stage the first chunk of per-patch errors with the whole block (coalesced L2 reads)
+    // Stage the (first chunk of) per-patch errors with the whole block -- one coalesced L2 round trip.
     for (int e = tid; e < min(kErrChunk, s.Pn_total); e += NT) s_err[e] = __ldcg(s.errors + e);
     __syncthreads();
-    // The last warp forms the exact sequential float sum of the per-patch errors (:852) -- a serial
-    // chain of one FADD latency per patch over errors staged in shared memory (coalesced L2 reads) --
-    // while the other NT-32 threads run the (speculative) solve on a named barrier.
     static_assert(NT - 32 >= kDim * 6, "solve team too small");
     if (tid >= NT - 32) {
+        // The last warp forms the exact sequential float sum of the per-patch errors (:852): a serial
+        // chain of one FADD latency per patch, hidden behind the other warps' reduce + solve.
         const int lane = tid - (NT - 32);
         float e_run = 0.0f;
         for (int base = 0; base < s.Pn_total; base += kErrChunk) {
@@ -904,7 +927,17 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
         }
         if (lane == 0) sm.error = e_run;
     } else {
-        leader_step<Team<NT - 32, true>>(sm, s.prior, first, s.prm.sigma, -1.0, tid);     // :871-878 (sign: :878)
+        // Solve team (first NT-32 threads, named barrier 1).  The covariance is constant during ComputeJ
+        // (only :980 changes it, on the last pass), so old_state carries the 24 pose/bias doubles only.
+        using T = Team<NT - 32, true>;
+        load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
+        if (first) load_cov_l2<NT - 32>(&sm.x, s.state, tid);
+        T::sync();
+        if (first) store_state(s.old_state, &sm.x, tid, NT - 32, false);                 // old_state = *state (:747)
+        team_reduce<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
+        if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
+        T::sync();
+        leader_step<T>(sm, s.prior, first, s.prm.sigma, -1.0, tid);                       // :871-878 (sign: :878)
     }
     __syncthreads();
     const bool ok = sm.flags[3] == 0;
@@ -918,6 +951,7 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
         } else {
             const int* src = reinterpret_cast<const int*>(s.ctrl);
             int* dst = reinterpret_cast<int*>(&c);
+#pragma unroll
             for (int e = 0; e < (int)(sizeof(VioCtrl) / sizeof(int)); ++e) dst[e] = __ldcg(src + e);
         }
         const long long nm = (long long)sm.packed[27];
