@@ -386,9 +386,17 @@ def main():
                      "achieved_gbs": gbs})
     dom = max((f for f in fams if f["algorithmic_bytes"] > 0), key=lambda f: f["share_of_frame"], default=None)
     roofline = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if dom and persistent and args.workload == "C2" and os.path.exists(tpath):
+        with open(tpath) as tf:
+            tj = json.load(tf)
+        traffic = tj.get(dom["kernel"].split(" ")[0])
     if dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                    "frac": dom["achieved_gbs"] / hbm, "traffic": None, "peak_source": peak_src,
+                    "frac": dom["achieved_gbs"] / hbm, "traffic": traffic,
+                    "traffic_source": "ncu --set full capture, profiles/r01_traffic.json" if traffic else None,
+                    "peak_source": peak_src,
                     "avg_launch_us": dom["avg_us"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
                     "note": "the whole working set (~8 MB) is L2-resident and every pass is a dependent step: the kernel is "
                             "latency-bound, not bandwidth-bound, at this size (SURVEY.md section 7 H2; DESIGN.md section 4)"}
