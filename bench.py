@@ -320,12 +320,15 @@ def main():
     img = frame["image"]
 
     def e2e_frame():
+        # All of this frame's host inputs go in first (uploads are enqueue-only: the library packs them into
+        # pinned staging and returns), then the two blocking updates.  The map stays resident.
         h.scan_upload(scan)
-        x = x0.copy()
-        h.lio_update(lprm, x, x0)
         if has_vio:
             h.image_upload(img)
             h.patches_upload(ppos, pref, plev)
+        x = x0.copy()
+        h.lio_update(lprm, x, x0)
+        if has_vio:
             xp = x.copy()
             h.vio_update(vprm, x, xp)
         return x

@@ -65,6 +65,40 @@ struct PinBuf {
     }
 };
 
+// Pinned staging area for host->device uploads.  An upload packs the caller's data into it and
+// enqueues the copy; `done` marks that copy, and the next user of the same area waits on it (normally
+// long complete), so uploads never block on the stream and the caller's buffer is free on return.
+struct Staging {
+    PinBuf buf;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+    cudaError_t acquire(size_t bytes, void** out) {
+        if (pending) {
+            cudaError_t e = cudaEventSynchronize(done);
+            if (e != cudaSuccess) return e;
+            pending = false;
+        }
+        cudaError_t e = buf.reserve(bytes);
+        if (e != cudaSuccess) return e;
+        if (!done) {
+            e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        *out = buf.p;
+        return cudaSuccess;
+    }
+    cudaError_t mark(cudaStream_t s) {
+        cudaError_t e = cudaEventRecord(done, s);
+        pending = (e == cudaSuccess);
+        return e;
+    }
+    void release() {
+        if (done) cudaEventDestroy(done);
+        done = nullptr;
+        buf.release();
+    }
+};
+
 // ---- NCCL through dlopen (no link-time dependency) ----------------------------------
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -148,7 +182,7 @@ struct flb_handle {
     bool tracing = false;
     int num_sms = 0;
     int occ_lio = 0, occ_vio = 0;
-    PinBuf pin;                  // staging for uploads
+    Staging st_map, st_scan, st_img, st_patch, st_state, st_misc;   // per-kind upload staging
     PinBuf pin_out;              // staging for downloads
     bool state_valid = false;
 
@@ -271,7 +305,6 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_lio, k_lio_update_persistent<kLioBlock>, kLioBlock, 0));
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioBlock>, kVioBlock, 0));
-    FLB_CUDA(h, h->pin.reserve(1 << 16));
     FLB_CUDA(h, h->pin_out.reserve(1 << 16));
     return FLB_OK;
 }
@@ -547,7 +580,8 @@ int flb_destroy(flb_handle* h) {
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
     h->lio_ctrl.release(); h->vio_ctrl.release(); h->barrier.release(); h->trace.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
-    h->pin.release(); h->pin_out.release();
+    h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
+    h->st_misc.release(); h->pin_out.release();
     cudaStreamDestroy(h->own_stream);
     delete h;
     return FLB_OK;
@@ -573,8 +607,9 @@ int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
     FLB_CHECK_H(h);
     if (!xyz || M < 1 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_map_upload: bad arguments (M=%d stride=%d)", M, stride);
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    FLB_CUDA(h, h->pin.reserve((size_t)M * 3 * sizeof(float)));
-    float* st = static_cast<float*>(h->pin.p);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_map.acquire((size_t)M * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < M; ++i) {
         for (int k = 0; k < 3; ++k) {
@@ -642,10 +677,10 @@ int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
 int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CHECK_H(h);
     if (!body_xyz || N < 0 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: bad arguments");
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     const size_t n1 = (size_t)std::max(N, 1);
-    FLB_CUDA(h, h->pin.reserve(n1 * 3 * sizeof(float)));
-    float* st = static_cast<float*>(h->pin.p);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_scan.acquire(n1 * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
     float lo[3] = {INFINITY, INFINITY, INFINITY};
     for (int i = 0; i < N; ++i)
         for (int k = 0; k < 3; ++k) {
@@ -667,6 +702,7 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>(nb * lio_packed(12), h->partials.cap)));
     if (N > 0) {
         FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        FLB_CUDA(h, h->st_scan.mark(h->stream));
         // Morton order in the body frame (cell = the map grid's cell): spatially coherent warps at any pose
         const float inv_cell = 1.0f / (float)h->cfg.cell_size;
         const int g = (N + 255) / 256;
@@ -691,8 +727,7 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
     FLB_CUDA(h, cudaMemsetAsync(h->sel.p, 1, n1, h->stream));
     FLB_CUDA(h, cudaMemsetAsync(h->plane_ok.p, 0, n1, h->stream));
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->N = N;
+    h->N = N;     // enqueue-only: everything later on this handle's stream is ordered after the upload
     h->last_pass_valid = false;
     return FLB_OK;
 }
@@ -738,10 +773,13 @@ int flb_lio_pass(flb_handle* h, const flb_lio_params* prm, const double R[9], co
     FLB_CUDA(h, h->x_meas.reserve(N));
     LioParamsDev d;
     to_dev_params(prm, d);
-    double* st = static_cast<double*>(h->pin.p);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_misc.acquire(12 * sizeof(double), &stv));
+    double* st = static_cast<double*>(stv);
     std::memcpy(st, R, 9 * sizeof(double));
     std::memcpy(st + 9, p, 3 * sizeof(double));
     FLB_CUDA(h, cudaMemcpyAsync(h->pose12.p, st, 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_misc.mark(h->stream));
     LioArgs a = make_lio_args(h, d, true, width);
     a.force_rematch = rematch ? 1 : 0;
     a.pose_override = h->pose12.p;
@@ -814,12 +852,13 @@ int flb_lio_export(flb_handle* h, float* world_xyz, int* nn_idx, float* nn_d2, f
 int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_prop) {
     FLB_CHECK_H(h);
     if (!x || !x_prop) return fail(h, FLB_ERR_INVALID, "flb_state_upload: null state");
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    FLB_CUDA(h, h->pin.reserve(2 * sizeof(State18)));
-    State18* st = static_cast<State18*>(h->pin.p);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_state.acquire(2 * sizeof(State18), &stv));
+    State18* st = static_cast<State18*>(stv);
     std::memcpy(&st[0], x, sizeof(State18));
     std::memcpy(&st[1], x_prop, sizeof(State18));
     FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[0], st, 2 * sizeof(State18), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_state.mark(h->stream));
     FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[3], &h->states.p[0], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
     h->state_valid = true;
     return FLB_OK;
@@ -903,13 +942,14 @@ int flb_lio_update(flb_handle* h, const flb_lio_params* prm, flb_state18* x, con
 int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, int stride) {
     FLB_CHECK_H(h);
     if (!gray || width < 16 || height < 16 || stride < width) return fail(h, FLB_ERR_INVALID, "flb_image_upload: bad arguments");
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     FLB_CUDA(h, h->img.reserve((size_t)width * height));
-    FLB_CUDA(h, h->pin.reserve((size_t)width * height));
-    unsigned char* st = static_cast<unsigned char*>(h->pin.p);
-    for (int r = 0; r < height; ++r) std::memcpy(st + (size_t)r * width, gray + (size_t)r * stride, width);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_img.acquire((size_t)width * height, &stv));
+    unsigned char* st = static_cast<unsigned char*>(stv);
+    if (stride == width) std::memcpy(st, gray, (size_t)width * height);
+    else for (int r = 0; r < height; ++r) std::memcpy(st + (size_t)r * width, gray + (size_t)r * stride, width);
     FLB_CUDA(h, cudaMemcpyAsync(h->img.p, st, (size_t)width * height, cudaMemcpyHostToDevice, h->stream));
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    FLB_CUDA(h, h->st_img.mark(h->stream));
     h->img_w = width;
     h->img_h = height;
     h->last_vio_valid = false;
@@ -921,7 +961,6 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     if (Pn < 0 || (Pn > 0 && (!pos || !patch || !search_level))) return fail(h, FLB_ERR_INVALID, "flb_patches_upload: bad arguments");
     for (int i = 0; i < Pn; ++i)
         if (search_level[i] < 0 || search_level[i] > 2) return fail(h, FLB_ERR_INVALID, "search_level[%d] = %d outside [0,2]", i, search_level[i]);
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     const size_t n = (size_t)std::max(Pn, 1);
     FLB_CUDA(h, h->patch_pos.reserve(n * 3));
     FLB_CUDA(h, h->patch_ref.reserve(n * 192));
@@ -930,8 +969,9 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     const int nb = (Pn + 7) / 8;
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)std::max(nb, 1) * kVioPacked, h->partials.cap)));
     const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int));
-    FLB_CUDA(h, h->pin.reserve(bytes));
-    char* st = static_cast<char*>(h->pin.p);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_patch.acquire(bytes, &stv));
+    char* st = static_cast<char*>(stv);
     if (Pn > 0) {
         std::memcpy(st, pos, (size_t)Pn * 3 * sizeof(double));
         char* st2 = st + (size_t)Pn * 3 * sizeof(double);
@@ -941,6 +981,7 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
         FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, st, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, st2, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, st3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        FLB_CUDA(h, h->st_patch.mark(h->stream));
     }
     if (h->comm) {
         // agree on the largest shard so every rank contributes an equal-size block to ncclAllGather;
@@ -957,7 +998,6 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
         FLB_CUDA(h, h->errors_all.reserve((size_t)h->err_shard * (size_t)h->world));
     }
     FLB_CUDA(h, cudaMemsetAsync(h->errors.p, 0, h->errors.cap * sizeof(float), h->stream));
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->Pn = Pn;
     h->last_vio_valid = false;
     return FLB_OK;
@@ -992,10 +1032,13 @@ int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], co
     FLB_CUDA(h, h->x_H.reserve(Pn * 64 * 6));
     VioParamsDev d;
     to_dev_params(prm, d);
-    double* st = static_cast<double*>(h->pin.p);
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_misc.acquire(12 * sizeof(double), &stv));
+    double* st = static_cast<double*>(stv);
     std::memcpy(st, R, 9 * sizeof(double));
     std::memcpy(st + 9, p, 3 * sizeof(double));
     FLB_CUDA(h, cudaMemcpyAsync(h->pose12.p, st, 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_misc.mark(h->stream));
     VioArgs a{};
     a.img = h->img.p;
     a.cam = h->cam;
