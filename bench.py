@@ -56,7 +56,7 @@ class ClockSampler:
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -182,7 +182,7 @@ def shard(n, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "T0", "T1"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -256,7 +256,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: the timed region may be shorter than one nvidia-smi period)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         enqueue_frame()
     barrier()
@@ -266,7 +267,6 @@ def main():
         pass  # rows are already global: the reduced n_eff / n_meas come out of the all-reduce
 
     # ---- timed region: value (inputs resident)
-    sampler = ClockSampler(local) if rank == 0 else None
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     l0 = h.launch_count()

@@ -184,7 +184,20 @@ class IkdTreeRef:
             raise RuntimeError("oracle/_ref/libikdtree_ref.so missing (built only where /root/reference exists)")
         self._R = R
         m = f32(map_xyz)
-        self.handle = R.ikdref_build(_p(m), len(m), 3)
+        # the reference's KD_TREE constructor printf()s "Multi thread started" (ikd_Tree.cpp:170); keep
+        # the caller's stdout clean (bench.py prints exactly one JSON line)
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        try:
+            os.dup2(devnull, 1)
+            self.handle = R.ikdref_build(_p(m), len(m), 3)
+            C.CDLL(None).fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
 
     def knn(self, q, k=5, nthreads=4):
         q = f32(q)
