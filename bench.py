@@ -164,12 +164,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(cfg, gpus, l2):
+def workload_config(cfg, gpus, l2, coll="fused NVLink peer-memory exchange (in-kernel)"):
     pc = pass_counts(cfg)
     return {"workload": f"{cfg.name}: {cfg.n_scan} scan pts vs {cfg.n_map}-pt map, {cfg.img_w}x{cfg.img_h} image, "
                         f"{cfg.n_patch} 8x8 patches; {cfg.lio_passes} LIO passes ({pc['lio_knn']} with kNN) + "
                         f"3x{cfg.vio_passes} VIO passes per frame, early stop disabled",
-            "parallelism": "single GPU" if gpus == 1 else f"scan/patch block-sharded over {gpus} GPUs, NCCL all-reduce of the normal equations per pass",
+            "parallelism": "single GPU" if gpus == 1 else f"scan/patch block-sharded over {gpus} GPUs, {coll} of the normal equations per pass",
             "l2": l2, "seed": cfg.seed}
 
 
@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded cpu_baseline sample")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: fused NVLink exchange inside the persistent kernels (default) or NCCL between per-pass kernels")
     ap.add_argument("--quick", action="store_true", help="profiling aid: skip the e2e / profile / cpu_baseline legs")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -220,10 +222,14 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
-    if world > 1:
+    if world > 1 and args.collective == "nccl":
         uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         h.comm_init(uid[0], rank, world)
+    elif world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, h.p2p_export())
+        h.p2p_attach(rank, world, handles)
     s0, s1 = shard(cfg.n_scan, rank, world)
     p0, p1 = shard(cfg.n_patch, rank, world)
     scan = frame["scan_body"][s0:s1]
@@ -369,7 +375,7 @@ def main():
     barrier()
     hbm, peak_src = peaks()
     n_loc, pn_loc = len(scan), len(ppos)
-    persistent = world == 1          # the NCCL path runs kernel-per-pass
+    persistent = world == 1 or args.collective == "p2p"   # the NCCL path runs kernel-per-pass
     if persistent:
         # one cooperative kernel per update: its algorithmic bytes are the sum over its passes
         fam_bytes = [(B_LIO_KNN * pc["lio_knn"] + B_LIO_PLAIN * pc["lio_plain"]) * n_loc, 0, B_VIO * pc["vio_passes"] * pn_loc, 0]
@@ -436,7 +442,8 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
             "config": workload_config(cfg, world, "inputs resident; L2 flushed (256 MiB write) between timed steps"
-                                      if flush is not None else "inputs resident; L2 NOT flushed (working set < L2)"),
+                                      if flush is not None else "inputs resident; L2 NOT flushed (working set < L2)",
+                                      "NCCL all-reduce" if args.collective == "nccl" else "fused NVLink peer-memory exchange (in-kernel)"),
             "residuals_per_sec": rows_per_frame * fps, "rows_per_frame": int(rows_per_frame),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "gpu_launches": int(launches), "clocks": clocks,

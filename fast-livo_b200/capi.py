@@ -118,7 +118,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
-           "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy"]
+           "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach"]
 
 
 def lib_path() -> str:
@@ -180,6 +180,9 @@ def lib():
         L.flb_comm_unique_id.argtypes = [vp]
         L.flb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
         L.flb_comm_destroy.argtypes = [vp]
+        L.flb_p2p_export.argtypes = [vp, vp]
+        L.flb_p2p_attach.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.flb_p2p_detach.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -396,6 +399,17 @@ class Handle:
         if rc != FLB_OK:
             raise FlbError(rc, lib().flb_last_error(None).decode())
         return buf.raw
+
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.flb_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, rank: int, world: int, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.L.flb_p2p_attach(self.h, rank, world, buf))
 
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, 128)

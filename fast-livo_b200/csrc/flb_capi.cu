@@ -204,6 +204,11 @@ struct flb_handle {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     int err_shard = 0;           // max patches per rank (equal-size ncclAllGather shards)
+    // fused NVLink exchange (persistent kernels, no NCCL in the data path)
+    DevBuf<P2PMailbox> mailbox;
+    DevBuf<unsigned long long> p2p_seq;
+    P2PArgs p2p{};               // world <= 1: not attached
+    void* p2p_peer_ptr[kP2PMaxWorld] = {nullptr};
 
     // profiling
     bool profiling = false;
@@ -367,6 +372,8 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_update: map and scan must be uploaded first");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_lio_update: no device state (flb_state_upload)");
     if (prm->max_iteration < 0) return fail(h, FLB_ERR_INVALID, "max_iteration < 0");
+    if (h->p2p.world > 1 && !h->cfg.persistent)
+        return fail(h, FLB_ERR_STATE, "the fused NVLink exchange lives in the persistent kernels (flb_config.persistent = 1)");
     LioParamsDev d;
     to_dev_params(prm, d);
     LioSolveArgs s{};
@@ -377,8 +384,10 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     s.partials = h->partials.p;
     s.nblocks = lio_nblocks(h);
     s.prm = d;
+    s.p2p = h->p2p;
+    s.timeout_flag = &h->barrier.p->timeout;
     LioArgs a = make_lio_args(h, d, false, 6);
-    if (h->cfg.persistent && !h->comm) {
+    if (h->cfg.persistent && (!h->comm || h->p2p.world > 1)) {
         // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
         // whole multiples of the SM count (<= co-resident capacity): chunks are dealt round-robin to blocks
         const int cap = std::max(1, h->occ_lio * h->num_sms);
@@ -439,7 +448,13 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     s.errors = h->errors.p;
     s.Pn_total = h->Pn;
     s.prm = d;
-    const bool persistent = h->cfg.persistent && !h->comm && h->Pn > 0 && prm->max_iteration > 0;
+    s.p2p = h->p2p;
+    s.timeout_flag = &h->barrier.p->timeout;
+    const bool fused = h->p2p.world > 1;
+    if (fused && !h->cfg.persistent)
+        return fail(h, FLB_ERR_STATE, "the fused NVLink exchange lives in the persistent kernels (flb_config.persistent = 1)");
+    if (fused && h->Pn > kP2PErrCap) return fail(h, FLB_ERR_INVALID, "fused multi-GPU mode: at most %d patches per rank", kP2PErrCap);
+    const bool persistent = h->cfg.persistent && (fused || (!h->comm && h->Pn > 0)) && prm->max_iteration > 0;
     if (!persistent) {
         LaunchScope ls(h, FAM_SOLVE);
         k_vio_begin<<<1, 32, 0, h->stream>>>(h->vio_ctrl.p, h->Pn);
@@ -463,7 +478,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (persistent) {
         const int cap = std::max(1, h->occ_vio * h->num_sms);
         // patches are dealt warp-round-robin: use every co-resident block so all SMs carry equal load
-        const int grid = std::max(1, std::min(h->Pn, cap));
+        const int grid = std::max(1, std::min(std::max(h->Pn, 1), cap));
         FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * kVioPacked, h->partials.cap)));
         a.partials = h->partials.p;
         s.partials = h->partials.p;
@@ -572,6 +587,10 @@ int flb_destroy(flb_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+        if (h->p2p_peer_ptr[r]) cudaIpcCloseMemHandle(h->p2p_peer_ptr[r]);
+    h->mailbox.release();
+    h->p2p_seq.release();
     for (auto& ev : h->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     h->map_raw.release(); h->keys.release(); h->keys_sorted.release(); h->vals.release(); h->vals_sorted.release();
     h->cub_tmp.release(); h->map_pts.release(); h->cell_start.release(); h->scan.release(); h->sel.release();
@@ -1190,6 +1209,55 @@ int flb_comm_init(flb_handle* h, const void* unique_id_128b, int rank, int world
     if (r != 0) { h->comm = nullptr; return fail(h, FLB_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
     h->rank = rank;
     h->world = world_size;
+    return FLB_OK;
+}
+
+// ---- fused NVLink exchange -------------------------------------------------------------------
+int flb_p2p_export(flb_handle* h, void* handle_64b) {
+    FLB_CHECK_H(h);
+    if (!handle_64b) return fail(h, FLB_ERR_INVALID, "flb_p2p_export: null handle buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    FLB_CUDA(h, h->mailbox.reserve(1));
+    FLB_CUDA(h, h->p2p_seq.reserve(1));
+    FLB_CUDA(h, cudaMemset(h->mailbox.p, 0, sizeof(P2PMailbox)));
+    FLB_CUDA(h, cudaMemset(h->p2p_seq.p, 0, sizeof(unsigned long long)));
+    cudaIpcMemHandle_t ih;
+    FLB_CUDA(h, cudaIpcGetMemHandle(&ih, h->mailbox.p));
+    std::memcpy(handle_64b, &ih, 64);
+    return FLB_OK;
+}
+
+int flb_p2p_attach(flb_handle* h, int rank, int world_size, const void* handles) {
+    FLB_CHECK_H(h);
+    if (!handles || world_size < 1 || world_size > kP2PMaxWorld || rank < 0 || rank >= world_size)
+        return fail(h, FLB_ERR_INVALID, "flb_p2p_attach: bad arguments (world <= %d)", kP2PMaxWorld);
+    if (!h->mailbox.p) return fail(h, FLB_ERR_STATE, "flb_p2p_attach: call flb_p2p_export first");
+    P2PArgs a{};
+    a.world = world_size;
+    a.rank = rank;
+    a.seq = h->p2p_seq.p;
+    for (int r = 0; r < world_size; ++r) {
+        if (r == rank) { a.mail[r] = h->mailbox.p; continue; }
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, static_cast<const char*>(handles) + 64 * (size_t)r, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(h, FLB_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        h->p2p_peer_ptr[r] = ptr;
+        a.mail[r] = static_cast<P2PMailbox*>(ptr);
+    }
+    h->p2p = a;
+    h->rank = rank;
+    h->world = world_size;
+    return FLB_OK;
+}
+
+int flb_p2p_detach(flb_handle* h) {
+    FLB_CHECK_H(h);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+        if (h->p2p_peer_ptr[r]) { cudaIpcCloseMemHandle(h->p2p_peer_ptr[r]); h->p2p_peer_ptr[r] = nullptr; }
+    h->p2p = P2PArgs{};
     return FLB_OK;
 }
 

@@ -553,6 +553,7 @@ struct LeaderSmem {
     double part[8][32];
     int flags[4];
     float error;
+    int p2p_par;
 };
 
 // The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
@@ -775,6 +776,84 @@ __device__ __forceinline__ void leader_cov_update(LeaderSmem& sm, const double* 
     __syncthreads();
 }
 
+// =======================================================================================
+// Fused NVLink exchange (multi-GPU): no NCCL in the data path
+// =======================================================================================
+// Every rank owns a mailbox in its device memory; peers map it (CUDA IPC) and the LEADER BLOCK of
+// each rank writes its packed normal-equation sums (and, for VIO, its shard of per-patch errors)
+// straight into every rank's mailbox over NVLink, publishes a sequence number with a
+// system-scope release store, and waits for the other ranks' sequence numbers in its OWN memory.
+// All ranks then add the contributions in rank order: bit-identical sums everywhere, so the
+// replicated solve yields bit-identical states with no broadcast.  Slots are double-buffered by
+// sequence parity: a rank can only be one exchange ahead of the slowest rank.
+constexpr int kP2PMaxWorld = 8;
+constexpr int kP2PErrCap = 16384;        // per-rank patch shard capacity of the error gather
+struct P2PSlot {
+    unsigned long long seq;
+    double data[32];                     // packed sums; data[31] = number of error entries sent
+};
+struct P2PMailbox {
+    P2PSlot slot[2][kP2PMaxWorld];
+    float errs[2][kP2PMaxWorld][kP2PErrCap];
+};
+struct P2PArgs {
+    int world, rank;
+    P2PMailbox* mail[kP2PMaxWorld];      // mail[rank] is the local one; others are peer mappings
+    unsigned long long* seq;             // device-resident exchange counter (same value on every rank)
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All-reduce sm.packed[0..K) across ranks in rank order, executed by a team of threads (TeamT).
+// If errs_local != nullptr the team also pushes n_err floats to every rank's gather area.
+// Returns the sequence parity used (the gather area of this exchange is mail[rank]->errs[par]).
+template <int K, class TeamT>
+__device__ __forceinline__ int p2p_exchange(const P2PArgs& pp, LeaderSmem& sm, const float* errs_local, int n_err, int tid,
+                                            int* timeout_flag) {
+    __shared__ unsigned long long s_seq;
+    if (tid == 0) {
+        const unsigned long long q = __ldcg(pp.seq) + 1ull;
+        *pp.seq = q;
+        s_seq = q;
+    }
+    TeamT::sync();
+    const unsigned long long seq = s_seq;
+    const int par = (int)(seq & 1ull);
+    for (int r = 0; r < pp.world; ++r) {
+        P2PMailbox* m = pp.mail[r];
+        if (tid < K) m->slot[par][pp.rank].data[tid] = sm.packed[tid];
+        if (tid == K) m->slot[par][pp.rank].data[31] = (double)n_err;
+        if (errs_local)
+            for (int e = tid; e < n_err; e += TeamT::size) m->errs[par][pp.rank][e] = __ldcg(errs_local + e);
+    }
+    __threadfence_system();
+    TeamT::sync();
+    if (tid < pp.world) st_release_sys_u64(&pp.mail[tid]->slot[par][pp.rank].seq, seq);
+    if (tid < pp.world) {
+        const unsigned long long* f = &pp.mail[pp.rank]->slot[par][tid].seq;
+        unsigned long long spins = 0;
+        while (ld_acquire_sys_u64(f) != seq) {
+            __nanosleep(50);
+            if (++spins > 60000000ull) { *timeout_flag = 1; break; }   // ~5 s: ranks may start far apart
+        }
+    }
+    TeamT::sync();
+    if (tid < K) {
+        double s = 0.0;
+        for (int r = 0; r < pp.world; ++r) s += __ldcv(&pp.mail[pp.rank]->slot[par][r].data[tid]);
+        sm.packed[tid] = s;
+    }
+    TeamT::sync();
+    return par;
+}
+
 struct LioSolveArgs {
     State18* state;
     const State18* state_prop;
@@ -783,6 +862,8 @@ struct LioSolveArgs {
     const double* partials;  // nblocks * lio_packed(6)   (or 1 x packed after an all-reduce)
     int nblocks;
     LioParamsDev prm;
+    P2PArgs p2p;             // world <= 1: single GPU
+    int* timeout_flag;       // GridBarrier::timeout
 };
 
 // One LIO leader step (whole block, NT threads).  `first`: first pass of this update.  Loop state
@@ -799,6 +880,7 @@ __device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm
     __syncthreads();
     FLB_STAMP(0);
     leader_reduce<K, NT>(s.partials, s.nblocks, sm, tid);
+    if (s.p2p.world > 1) p2p_exchange<K, Team<NT, false>>(s.p2p, sm, nullptr, 0, tid, s.timeout_flag);
     FLB_STAMP(1);
     if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
     __syncthreads();
@@ -886,9 +968,11 @@ struct VioSolveArgs {
     double* G_last;          // 18x6, the G of the last accepted solve (:874, used at :980)
     const double* partials;
     int nblocks;
-    const float* errors;     // all patches, patch order
+    const float* errors;     // all patches, patch order (local shard in the fused multi-GPU mode)
     int Pn_total;
     VioParamsDev prm;
+    P2PArgs p2p;             // world <= 1: single GPU
+    int* timeout_flag;
 };
 
 constexpr int kErrChunk = 2048;
@@ -897,8 +981,11 @@ constexpr int kErrChunk = 2048;
 template <int NT>
 __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm, float* s_err, bool first, int level) {
     const int tid = threadIdx.x;
+    const bool multi = s.p2p.world > 1;
     // Stage the (first chunk of) per-patch errors with the whole block -- one coalesced L2 round trip.
-    for (int e = tid; e < min(kErrChunk, s.Pn_total); e += NT) s_err[e] = __ldcg(s.errors + e);
+    // (Fused multi-GPU mode: the errors of ALL ranks arrive with the exchange instead.)
+    if (!multi)
+        for (int e = tid; e < min(kErrChunk, s.Pn_total); e += NT) s_err[e] = __ldcg(s.errors + e);
     __syncthreads();
     static_assert(NT - 32 >= kDim * 6, "solve team too small");
     if (tid >= NT - 32) {
@@ -906,24 +993,31 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
         // chain of one FADD latency per patch, hidden behind the other warps' reduce + solve.
         const int lane = tid - (NT - 32);
         float e_run = 0.0f;
-        for (int base = 0; base < s.Pn_total; base += kErrChunk) {
-            const int nchunk = min(kErrChunk, s.Pn_total - base);
-            if (base > 0) {   // later chunks (Pn > kErrChunk): staged by this warp alone
+        if (multi) asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");   // wait for the exchange
+        const int nsrc = multi ? s.p2p.world : 1;
+        for (int r = 0; r < nsrc; ++r) {
+            // patch order = rank 0's shard, then rank 1's, ... (contiguous block partition)
+            const float* src = multi ? s.p2p.mail[s.p2p.rank]->errs[sm.p2p_par][r] : s.errors;
+            const int n_r = multi ? (int)__ldcv(&s.p2p.mail[s.p2p.rank]->slot[sm.p2p_par][r].data[31]) : s.Pn_total;
+            for (int base = 0; base < n_r; base += kErrChunk) {
+                const int nchunk = min(kErrChunk, n_r - base);
+                if (multi || base > 0) {   // staged by this warp alone (single GPU: only for Pn > kErrChunk)
 #pragma unroll 8
-                for (int e = lane; e < nchunk; e += 32) s_err[e] = __ldcg(s.errors + base + e);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                float e = e_run;
-                int i = 0;
-                for (; i + 8 <= nchunk; i += 8) {
-                    e = e + s_err[i]; e = e + s_err[i + 1]; e = e + s_err[i + 2]; e = e + s_err[i + 3];
-                    e = e + s_err[i + 4]; e = e + s_err[i + 5]; e = e + s_err[i + 6]; e = e + s_err[i + 7];
+                    for (int e = lane; e < nchunk; e += 32) s_err[e] = __ldcv(src + base + e);
                 }
-                for (; i < nchunk; ++i) e = e + s_err[i];
-                e_run = e;
+                __syncwarp();
+                if (lane == 0) {
+                    float e = e_run;
+                    int i = 0;
+                    for (; i + 8 <= nchunk; i += 8) {
+                        e = e + s_err[i]; e = e + s_err[i + 1]; e = e + s_err[i + 2]; e = e + s_err[i + 3];
+                        e = e + s_err[i + 4]; e = e + s_err[i + 5]; e = e + s_err[i + 6]; e = e + s_err[i + 7];
+                    }
+                    for (; i < nchunk; ++i) e = e + s_err[i];
+                    e_run = e;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         if (lane == 0) sm.error = e_run;
     } else {
@@ -935,6 +1029,11 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
         T::sync();
         if (first) store_state(s.old_state, &sm.x, tid, NT - 32, false);                 // old_state = *state (:747)
         team_reduce<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
+        if (multi) {
+            const int par = p2p_exchange<kVioPacked, T>(s.p2p, sm, s.errors, s.Pn_total, tid, s.timeout_flag);
+            if (tid == 0) sm.p2p_par = par;
+            asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");              // release the error-sum warp
+        }
         if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
         T::sync();
         leader_step<T>(sm, s.prior, first, s.prm.sigma, -1.0, tid);                       // :871-878 (sign: :878)
@@ -1181,7 +1280,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, V
     __shared__ LeaderSmem sm;
     __shared__ float s_err[kErrChunk];
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (a.Pn <= 0) return;                                     // :969-970 (host also short-circuits)
+    if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
     int level = 2;
     bool first = true;
     int pass_no = 0;

@@ -238,6 +238,16 @@ int flb_comm_unique_id(void* unique_id_128b);
 int flb_comm_init(flb_handle* h, const void* unique_id_128b, int rank, int world_size);
 int flb_comm_destroy(flb_handle* h);
 
+/* Fused NVLink exchange: the B200-idiomatic alternative to the NCCL path.  The persistent update
+ * kernel's leader block writes its packed sums (and VIO per-patch errors) straight into every rank's
+ * mailbox over NVLink peer memory and waits on sequence flags -- one kernel per update, no NCCL call,
+ * bit-identical results on every rank and to the single-GPU run up to the summation order.
+ * Each rank: flb_p2p_export() -> 64-byte CUDA IPC handle; gather all handles (rank order) with any host
+ * transport; flb_p2p_attach().  One process per GPU, all GPUs NVLink peers; <= 8 ranks. */
+int flb_p2p_export(flb_handle* h, void* handle_64b);
+int flb_p2p_attach(flb_handle* h, int rank, int world_size, const void* handles_world_x_64b);
+int flb_p2p_detach(flb_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,7 +87,7 @@ def test_shard_partition_properties():
             assert max(b - a for a, b in cuts) <= (n + w - 1) // w
 
 
-def _gpu_worker(rank, world, port, out):
+def _gpu_worker(rank, world, port, out, mode="nccl"):
     import torch
     import torch.distributed as dist
     import fastlivo_loader
@@ -96,9 +96,14 @@ def _gpu_worker(rank, world, port, out):
     flb = fastlivo_loader.load()
     f = flb.synth.make_frame("T1")
     h = flb.Handle(device=rank)
-    uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    h.comm_init(uid[0], rank, world)
+    if mode == "nccl":
+        uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+    else:   # fused NVLink exchange inside the persistent kernels
+        handles = [None] * world
+        dist.all_gather_object(handles, h.p2p_export())
+        h.p2p_attach(rank, world, handles)
     s0, s1 = shard(len(f["scan_body"]), rank, world)
     p0, p1 = shard(len(f["patch_pos"]), rank, world)
     h.map_upload(f["map_xyz"])
@@ -119,14 +124,17 @@ def _gpu_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_nccl_sharded_update_matches_oracle(flb, po, frames, tmp_path):
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_sharded_update_matches_oracle(flb, po, frames, tmp_path, mode):
+    """Both collectives: NCCL all-reduce between per-pass kernels, and the fused NVLink exchange inside
+    the persistent kernel's leader block."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     out = str(tmp_path / "gpu.npz")
     world = 2
-    mp.spawn(_gpu_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_gpu_worker, args=(world, _free_port(), out, mode), nprocs=world, join=True)
     r = np.load(out)
     f = frames("T1")
     lio = po.Lio(f["map_xyz"], f["scan_body"])
