@@ -91,6 +91,30 @@ class NormalEq(C.Structure):
                 ("HTH", C.c_double * 144), ("HTh", C.c_double * 12)]
 
 
+class StateIkfom(C.Structure):
+    """flb_state_ikfom == state_ikfom (reference include/use-ikfom.hpp:12-21); quaternions (x, y, z, w)."""
+    _fields_ = [("pos", C.c_double * 3), ("rot", C.c_double * 4), ("offset_R_L_I", C.c_double * 4),
+                ("offset_T_L_I", C.c_double * 3), ("vel", C.c_double * 3), ("bg", C.c_double * 3),
+                ("ba", C.c_double * 3), ("grav", C.c_double * 3), ("P", C.c_double * 529)]
+
+    def vector(self):
+        return np.concatenate([self.pos[:], self.rot[:], self.offset_R_L_I[:], self.offset_T_L_I[:], self.vel[:],
+                               self.bg[:], self.ba[:], self.grav[:]])
+
+    @property
+    def cov(self):
+        return np.array(self.P[:]).reshape(23, 23)
+
+
+class IkfomParams(C.Structure):
+    _fields_ = [("laser_point_cov", C.c_double), ("max_iteration", C.c_int), ("limit", C.c_double * 23)]
+
+
+class IkfomReport(C.Structure):
+    _fields_ = [("passes", C.c_int), ("knn_passes", C.c_int), ("n_eff_last", C.c_int), ("converged_last", C.c_int),
+                ("res_mean_last", C.c_double), ("rows_total", C.c_int64), ("status", C.c_int)]
+
+
 class Camera(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
                 ("cx", C.c_double), ("cy", C.c_double), ("d", C.c_double * 5)]
@@ -114,7 +138,7 @@ class VioEq(C.Structure):
 
 # every symbol include/fastlivo_b200.h declares (checked by the CPU-only test tier)
 SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "flb_set_stream", "flb_synchronize",
-           "flb_map_upload", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update",
+           "flb_map_upload", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update", "flb_lio_update_ikfom",
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
@@ -159,6 +183,7 @@ def lib():
         L.flb_lio_pass.argtypes = [vp, C.POINTER(LioParams), vp, vp, C.c_int, C.c_int, C.POINTER(NormalEq)]
         L.flb_lio_export.argtypes = [vp] + [vp] * 9 + [C.POINTER(C.c_int)]
         L.flb_lio_update.argtypes = [vp, C.POINTER(LioParams), C.POINTER(State18), C.POINTER(State18), C.POINTER(LioReport)]
+        L.flb_lio_update_ikfom.argtypes = [vp, C.POINTER(IkfomParams), C.POINTER(StateIkfom), C.POINTER(IkfomReport)]
         L.flb_image_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.flb_patches_upload.argtypes = [vp, vp, vp, vp, C.c_int]
         L.flb_camera_set.argtypes = [vp, C.POINTER(Camera)]
@@ -320,6 +345,11 @@ class Handle:
     def lio_update(self, prm: LioParams, x: State18, x_prop: State18) -> LioReport:
         rep = LioReport()
         self._ck(self.L.flb_lio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep)))
+        return rep
+
+    def lio_update_ikfom(self, prm: IkfomParams, x: StateIkfom) -> IkfomReport:
+        rep = IkfomReport()
+        self._ck(self.L.flb_lio_update_ikfom(self.h, C.byref(prm), C.byref(x), C.byref(rep)))
         return rep
 
     # ---- VIO

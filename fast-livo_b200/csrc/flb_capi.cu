@@ -20,6 +20,7 @@
 using namespace flb;
 
 static_assert(sizeof(flb_state18) == sizeof(State18), "flb_state18 and device State18 must match");
+static_assert(sizeof(flb_state_ikfom) == sizeof(StateIkfom), "flb_state_ikfom and device StateIkfom must match");
 
 namespace {
 
@@ -175,6 +176,9 @@ struct flb_handle {
     DevBuf<PriorBlock> prior;    // P11^-1 and P21*P11^-1 of the running update
     DevBuf<double> G_last;       // 108
     DevBuf<State18> states;      // [0]=x [1]=x_prop [2]=old_state(VIO) [3]=saved x [4]=saved x_prop
+    DevBuf<StateIkfom> ik_states;   // [0] = x_/P_, [1] = x_propagated/P_propagated
+    DevBuf<IkfomCtrl> ik_ctrl;
+    int occ_ik = 0;
     DevBuf<LioCtrl> lio_ctrl;
     DevBuf<VioCtrl> vio_ctrl;
     DevBuf<GridBarrier> barrier; // grid barrier of the persistent kernels
@@ -309,6 +313,9 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, cudaMemset(h->vio_ctrl.p, 0, sizeof(VioCtrl)));
     FLB_CUDA(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_lio, k_lio_update_persistent<kLioBlock>, kLioBlock, 0));
+    FLB_CUDA(h, h->ik_states.reserve(2));
+    FLB_CUDA(h, h->ik_ctrl.reserve(1));
+    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_ik, k_lio_update_ikfom_persistent<kLioBlock>, kLioBlock, 0));
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioBlock>, kVioBlock, 0));
     FLB_CUDA(h, h->pin_out.reserve(1 << 16));
     return FLB_OK;
@@ -597,7 +604,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->barrier.release(); h->trace.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->trace.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
@@ -954,6 +961,68 @@ int flb_lio_update(flb_handle* h, const flb_lio_params* prm, flb_state18* x, con
     if (rc) return rc;
     if (rep) *rep = r;
     if (r.status != 0) return fail(h, r.status, "flb_lio_update: device reported status %d (singular normal matrix?)", r.status);
+    return FLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int flb_lio_update_ikfom(flb_handle* h, const flb_ikfom_params* prm, flb_state_ikfom* x, flb_ikfom_report* rep) {
+    FLB_CHECK_H(h);
+    if (!prm || !x) return fail(h, FLB_ERR_INVALID, "flb_lio_update_ikfom: null argument");
+    if (prm->max_iteration < 0) return fail(h, FLB_ERR_INVALID, "max_iteration < 0");
+    if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_update_ikfom: map and scan must be uploaded first");
+    if (h->comm || h->p2p.world > 1) return fail(h, FLB_ERR_STATE, "flb_lio_update_ikfom: single-GPU only");
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_state.acquire(sizeof(StateIkfom), &stv));
+    std::memcpy(stv, x, sizeof(StateIkfom));
+    FLB_CUDA(h, cudaMemcpyAsync(&h->ik_states.p[0], stv, sizeof(StateIkfom), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_state.mark(h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(&h->ik_states.p[1], &h->ik_states.p[0], sizeof(StateIkfom), cudaMemcpyDeviceToDevice, h->stream));
+    LioParamsDev d{};            // the extrinsic comes from the state every pass; only plane_thr / grid matter here
+    LioArgs a = make_lio_args(h, d, false, 12);
+    IkfomSolveArgs s{};
+    s.state = &h->ik_states.p[0];
+    s.state_prop = &h->ik_states.p[1];
+    s.ctrl = h->ik_ctrl.p;
+    s.prm.R = prm->laser_point_cov;
+    s.prm.max_iteration = prm->max_iteration;
+    std::memcpy(s.prm.limit, prm->limit, sizeof(s.prm.limit));
+    const int cap = std::max(1, h->occ_ik * h->num_sms);
+    const int want = std::min(cap, std::max(h->num_sms, std::min(2, h->occ_ik) * h->num_sms));
+    const int grid = std::max(1, std::min((h->N + 31) / 32, want));
+    FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * lio_packed(12), h->partials.cap)));
+    a.partials = h->partials.p;
+    s.partials = h->partials.p;
+    s.nblocks = grid;
+    GridBarrier* bar = h->barrier.p;
+    void* args[] = {&a, &s, &bar};
+    {
+        LaunchScope ls(h, FAM_LIO_KNN);
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_ikfom_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,
+                                                h->stream));
+    }
+    h->last_pass_valid = false;
+    FLB_CUDA(h, h->pin_out.reserve(sizeof(StateIkfom) + sizeof(IkfomCtrl) + sizeof(GridBarrier)));
+    char* po = static_cast<char*>(h->pin_out.p);
+    FLB_CUDA(h, cudaMemcpyAsync(po, &h->ik_states.p[0], sizeof(StateIkfom), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(StateIkfom), h->ik_ctrl.p, sizeof(IkfomCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(StateIkfom) + sizeof(IkfomCtrl), h->barrier.p, sizeof(GridBarrier), cudaMemcpyDeviceToHost,
+                                h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    GridBarrier b;
+    std::memcpy(&b, po + sizeof(StateIkfom) + sizeof(IkfomCtrl), sizeof(b));
+    if (b.timeout) {
+        cudaMemset(h->barrier.p, 0, sizeof(GridBarrier));
+        return fail(h, FLB_ERR_TIMEOUT, "device-side grid barrier watchdog tripped");
+    }
+    std::memcpy(x, po, sizeof(StateIkfom));
+    IkfomCtrl c;
+    std::memcpy(&c, po + sizeof(StateIkfom), sizeof(c));
+    if (rep) {
+        rep->passes = c.passes; rep->knn_passes = c.knn_passes; rep->n_eff_last = c.n_eff_last;
+        rep->converged_last = c.converged_last; rep->res_mean_last = c.res_mean_last; rep->rows_total = c.rows_total;
+        rep->status = c.status;
+    }
+    if (c.status != 0) return fail(h, c.status, "flb_lio_update_ikfom: device reported status %d", c.status);
     return FLB_OK;
 }
 

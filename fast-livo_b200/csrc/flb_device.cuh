@@ -617,4 +617,224 @@ FLB_HD void state_boxminus(const State18& a, const State18& b, double* out) {
     }
 }
 
+
+// ------------------------------------------------------------------ IKFoM manifold algebra (row a8)
+// state_ikfom = pos, rot(SO3), offset_R_L_I(SO3), offset_T_L_I, vel, bg, ba, grav(S2, |g| = 9.8090)
+// (include/use-ikfom.hpp:12-21; DOF 23).  Quaternions are (x, y, z, w) like Eigen's coeffs().
+// MTK primitives restated from include/IKFoM_toolkit/mtk/{src/mtkmath.hpp, types/SOn.hpp, types/S2.hpp}.
+constexpr int kIk = 23;
+constexpr double kMtkTol = 1e-11;                 // MTK::tolerance<double>()
+constexpr double kGravLen = 98090.0 / 10000.0;    // S2<double, 98090, 10000, 1>::length
+
+struct StateIkfom {
+    double pos[3], rot[4], offset_R_L_I[4], offset_T_L_I[3], vel[3], bg[3], ba[3], grav[3];
+    double P[kIk * kIk];
+};
+constexpr int kIkHead = 26;   // doubles before P
+
+FLB_HD void mm_small(const double* A, int ra, int ca, const double* B, int cb, double* C) {
+    for (int i = 0; i < ra; ++i)
+        for (int j = 0; j < cb; ++j) {
+            double s = 0;
+            for (int k = 0; k < ca; ++k) s += A[i * ca + k] * B[k * cb + j];
+            C[i * cb + j] = s;
+        }
+}
+FLB_HD void transpose_small(const double* A, int r, int c, double* T) {
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < c; ++j) T[j * r + i] = A[i * c + j];
+}
+
+// mtkmath.hpp:141-171
+FLB_HD void mtk_cos_sinc_sqrt(double x2, double* c, double* sc) {
+    const double taylor_0 = 2.220446049250313e-16;
+    const double taylor_2 = sqrt(taylor_0);
+    const double taylor_n = sqrt(taylor_2);
+    if (x2 >= taylor_n) {
+        const double x = sqrt(x2);
+        *c = cos(x);
+        *sc = sin(x) / x;
+        return;
+    }
+    const double inv[7] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
+    double cosi = 1., sinc = 1;
+    double term = -1 / 2. * x2;
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        cosi += term;
+        term *= inv[2 * i];
+        sinc += term;
+        term *= -inv[2 * i + 1] * x2;
+    }
+    *c = cosi;
+    *sc = sinc;
+}
+// SO3::exp(vec, scale) (SOn.hpp:282-286, mtkmath.hpp:249-256)
+FLB_HD void quat_exp(const double* v, double scale, double* q) {
+    const double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    double c, sc;
+    mtk_cos_sinc_sqrt(scale * scale * n2, &c, &sc);
+    const double mult = sc * scale;
+    q[0] = mult * v[0]; q[1] = mult * v[1]; q[2] = mult * v[2];
+    q[3] = c;
+}
+FLB_HD void quat_mul(const double* a, const double* b, double* o) {
+    const double ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+    o[3] = aw * bw - ax * bx - ay * by - az * bz;
+    o[0] = aw * bx + ax * bw + ay * bz - az * by;
+    o[1] = aw * by + ay * bw + az * bx - ax * bz;
+    o[2] = aw * bz + az * bw + ax * by - ay * bx;
+}
+FLB_HD void quat_to_R(const double* q, double* R) {   // Eigen::Quaternion::toRotationMatrix
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y,
+                 tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+// SO3::log (SOn.hpp:291-295, mtkmath.hpp:269-289 with plus_minus_periodicity = true)
+FLB_HD void quat_log(const double* q, double* out) {
+    double nv = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (nv < kMtkTol) nv = kMtkTol;
+    const double s = 2.0 / nv * atan(nv / q[3]);
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) out[i] = s * q[i];
+}
+// MTK::A_matrix, mtkmath.hpp:235-247
+FLB_HD void mtk_A_matrix(const double* v, double* A) {
+    const double sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double nrm = sqrt(sq);
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) A[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (nrm < kMtkTol) return;
+    double K[9], KK[9];
+    skew3(v, K);
+    mm_small(K, 3, 3, K, 3, KK);
+    const double a = (1 - cos(nrm)) / sq, b = (1 - sin(nrm) / nrm) / sq;
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) A[i] = A[i] + a * K[i] + b * KK[i];
+}
+// S2 (S2_typ = 1), S2.hpp:206-231
+FLB_HD void s2_Bx(const double* vec, double* Bx /*3x2*/) {
+    if (vec[0] + kGravLen > kMtkTol) {
+        const double d = kGravLen + vec[0];
+        Bx[0] = -vec[1];                        Bx[1] = -vec[2];
+        Bx[2] = kGravLen - vec[1] * vec[1] / d; Bx[3] = -vec[2] * vec[1] / d;
+        Bx[4] = -vec[2] * vec[1] / d;           Bx[5] = kGravLen - vec[2] * vec[2] / d;
+        FLB_UNROLL
+        for (int i = 0; i < 6; ++i) Bx[i] /= kGravLen;
+    } else {
+        FLB_UNROLL
+        for (int i = 0; i < 6; ++i) Bx[i] = 0;
+        Bx[3] = -1;
+        Bx[4] = 1;
+    }
+}
+FLB_HD void s2_boxplus(double* vec, const double* delta) {   // S2.hpp:112-118
+    double Bx[6], Bu[3], q[4], R[9], o[3];
+    s2_Bx(vec, Bx);
+    mm_small(Bx, 3, 2, delta, 1, Bu);
+    quat_exp(Bu, 0.5, q);
+    quat_to_R(q, R);
+    mm_small(R, 3, 3, vec, 1, o);
+    vec[0] = o[0]; vec[1] = o[1]; vec[2] = o[2];
+}
+FLB_HD void s2_boxminus(const double* vec, const double* other, double* res) {   // S2.hpp:120-144
+    double K[9], t[3];
+    skew3(vec, K);
+    mm_small(K, 3, 3, other, 1, t);
+    const double v_sin = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    const double v_cos = vec[0] * other[0] + vec[1] * other[1] + vec[2] * other[2];
+    const double theta = atan2(v_sin, v_cos);
+    if (v_sin < kMtkTol) {
+        if (fabs(theta) > kMtkTol) { res[0] = 3.1415926; res[1] = 0; }
+        else { res[0] = 0; res[1] = 0; }
+    } else {
+        double Bx[6], BxT[6], Ko[9], u[3], r2[2];
+        s2_Bx(other, Bx);
+        transpose_small(Bx, 3, 2, BxT);
+        skew3(other, Ko);
+        mm_small(Ko, 3, 3, vec, 1, u);
+        mm_small(BxT, 2, 3, u, 1, r2);
+        res[0] = theta / v_sin * r2[0];
+        res[1] = theta / v_sin * r2[1];
+    }
+}
+FLB_HD void s2_Nx_yy(const double* vec, double* Nx /*2x3*/) {   // S2.hpp:262-267
+    double Bx[6], BxT[6], K[9];
+    s2_Bx(vec, Bx);
+    transpose_small(Bx, 3, 2, BxT);
+    skew3(vec, K);
+    mm_small(BxT, 2, 3, K, 3, Nx);
+    FLB_UNROLL
+    for (int i = 0; i < 6; ++i) Nx[i] = 1 / kGravLen / kGravLen * Nx[i];
+}
+FLB_HD void s2_Mx(const double* vec, const double* delta, double* Mx /*3x2*/) {   // S2.hpp:269-283
+    double Bx[6], K[9];
+    s2_Bx(vec, Bx);
+    skew3(vec, K);
+    if (sqrt(delta[0] * delta[0] + delta[1] * delta[1]) < kMtkTol) {
+        mm_small(K, 3, 3, Bx, 2, Mx);
+        FLB_UNROLL
+        for (int i = 0; i < 6; ++i) Mx[i] = -Mx[i];
+    } else {
+        // the reference passes scalar(1/2) == 0 (integer division) to MTK::exp here (S2.hpp:280):
+        // exp_delta is the identity rotation.  Mirrored.
+        double Bu[3], q[4], R[9], A[9], AT[9], t1[9], t2[9];
+        mm_small(Bx, 3, 2, delta, 1, Bu);
+        quat_exp(Bu, 0.0, q);
+        quat_to_R(q, R);
+        mtk_A_matrix(Bu, A);
+        transpose_small(A, 3, 3, AT);
+        mm_small(R, 3, 3, K, 3, t1);
+        mm_small(t1, 3, 3, AT, 3, t2);
+        mm_small(t2, 3, 3, Bx, 2, Mx);
+        FLB_UNROLL
+        for (int i = 0; i < 6; ++i) Mx[i] = -Mx[i];
+    }
+}
+// state_ikfom::boxplus / boxminus (build_manifold.hpp:192-202)
+FLB_HD void ikfom_boxplus(StateIkfom& x, const double* d) {
+    double q[4], o[4];
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) x.pos[i] += d[i];
+    quat_exp(d + 3, 0.5, q);
+    quat_mul(x.rot, q, o);
+    FLB_UNROLL
+    for (int i = 0; i < 4; ++i) x.rot[i] = o[i];
+    quat_exp(d + 6, 0.5, q);
+    quat_mul(x.offset_R_L_I, q, o);
+    FLB_UNROLL
+    for (int i = 0; i < 4; ++i) x.offset_R_L_I[i] = o[i];
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        x.offset_T_L_I[i] += d[9 + i];
+        x.vel[i] += d[12 + i];
+        x.bg[i] += d[15 + i];
+        x.ba[i] += d[18 + i];
+    }
+    s2_boxplus(x.grav, d + 21);
+}
+FLB_HD void ikfom_boxminus(const StateIkfom& a, const StateIkfom& b, double* res) {   // a [-] b
+    double c[4], q[4];
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) res[i] = a.pos[i] - b.pos[i];
+    c[0] = -b.rot[0]; c[1] = -b.rot[1]; c[2] = -b.rot[2]; c[3] = b.rot[3];
+    quat_mul(c, a.rot, q);
+    quat_log(q, res + 3);
+    c[0] = -b.offset_R_L_I[0]; c[1] = -b.offset_R_L_I[1]; c[2] = -b.offset_R_L_I[2]; c[3] = b.offset_R_L_I[3];
+    quat_mul(c, a.offset_R_L_I, q);
+    quat_log(q, res + 6);
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        res[9 + i] = a.offset_T_L_I[i] - b.offset_T_L_I[i];
+        res[12 + i] = a.vel[i] - b.vel[i];
+        res[15 + i] = a.bg[i] - b.bg[i];
+        res[18 + i] = a.ba[i] - b.ba[i];
+    }
+    s2_boxminus(a.grav, b.grav, res + 21);
+}
+
 }  // namespace flb

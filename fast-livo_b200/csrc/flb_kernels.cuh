@@ -1313,3 +1313,375 @@ __global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, V
 }
 
 }  // namespace flb
+
+// =======================================================================================
+// IKFoM-typed update: esekfom update_iterated_dyn_share_modified
+// (include/IKFoM_toolkit/esekfom/esekfom.hpp:1619-1928) driven by h_share_model
+// (src/laserMapping.cpp:960-1094), 23-DoF state_ikfom, all on the device in one launch.
+// =======================================================================================
+namespace flb {
+
+struct IkfomCtrl {
+    int i;            // loop index of esekfom.hpp:1633 (starts at -1)
+    int t;            // convergence counter (:1824)
+    int converge;     // dyn_share.converge: the NEXT pass redoes the kNN (:994 of laserMapping.cpp)
+    int stop;
+    int passes, knn_passes, n_eff_last, converged_last, status;
+    double res_mean_last;
+    long long rows_total;
+};
+
+struct IkfomParamsDev {
+    double R;
+    int max_iteration;
+    double limit[kIk];
+};
+
+struct IkfomSolveArgs {
+    StateIkfom* state;             // x_ and P_ (in / out)
+    const StateIkfom* state_prop;  // x_propagated and P_propagated
+    IkfomCtrl* ctrl;
+    const double* partials;        // nblocks * lio_packed(12)
+    int nblocks;
+    IkfomParamsDev prm;
+};
+
+struct IkLeaderSmem {
+    StateIkfom x;                  // head = x_, P = the working P_
+    double xp_head[kIkHead];
+    double L[kIk * kIk];
+    double Kx[kIk * 12];
+    double K[kIk * 12];            // P_inv[:, :12]
+    double HTH[144], HTh[12];
+    double S[12 * 25];             // 12 x 24 Gauss-Jordan workspace, row stride 25
+    double P11inv[144];
+    double B[11 * 12];
+    double dx[kIk], dx_new[kIk], dxo[kIk], Kh[kIk];
+    double AT[2][9], T2[4];
+    double packed[96];
+    int flags[4];
+};
+
+// Gauss-Jordan of an N x 2N system (row stride LD) by the whole block, no pivoting (SPD).
+template <int N, int LD, int NT>
+__device__ __forceinline__ void gj_block(double* S, int* bad, int tid) {
+    constexpr int COLS = 2 * N, E = N * COLS, PER = (E + NT - 1) / NT;
+    for (int k = 0; k < N; ++k) {
+        const double piv = S[k * LD + k];
+        if (!(fabs(piv) > 1e-300) || !isfinite(piv)) *bad = 1;
+        const double inv = __drcp_rn(piv);
+        double v[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * NT;
+            if (e < E) {
+                const int i = e / COLS, j = e - i * COLS;
+                const double rkj = S[k * LD + j] * inv;
+                v[q] = (i == k) ? rkj : S[i * LD + j] - S[i * LD + k] * rkj;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * NT;
+            if (e < E) {
+                const int i = e / COLS, j = e - i * COLS;
+                S[i * LD + j] = v[q];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// M[idx.., c] = T * src[idx.., c] for every column c (T is KxK); threads c < cols.
+template <int KD>
+__device__ __forceinline__ void ik_rows_apply(double* M, int ldm, int cols, int idx, const double* T, const double* src,
+                                              int lds, int tid) {
+    if (tid < cols) {
+        double v[KD];
+#pragma unroll
+        for (int i = 0; i < KD; ++i) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < KD; ++k) s += T[i * KD + k] * src[(idx + k) * lds + tid];
+            v[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < KD; ++i) M[(idx + i) * ldm + tid] = v[i];
+    }
+}
+// M[r, idx..] = M[r, idx..] * T^T for every row r; threads r < kIk.
+template <int KD>
+__device__ __forceinline__ void ik_cols_apply_T(double* M, int idx, const double* T, int tid) {
+    if (tid < kIk) {
+        double v[KD];
+#pragma unroll
+        for (int j = 0; j < KD; ++j) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < KD; ++k) s += M[tid * kIk + idx + k] * T[j * KD + k];
+            v[j] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < KD; ++j) M[tid * kIk + idx + j] = v[j];
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void ikfom_leader(const IkfomSolveArgs& s, IkLeaderSmem& sm, bool first, int it, int tcount,
+                                             int converge_in) {
+    constexpr int K = lio_packed(12);
+    const int tid = threadIdx.x;
+    // ---- loads: x_ head, x_propagated head, P_ = P_propagated (:1654)
+    {
+        const double* xs = reinterpret_cast<const double*>(s.state);
+        const double* ps = reinterpret_cast<const double*>(s.state_prop);
+        if (tid < kIkHead) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(xs + tid);
+        else if (tid < 2 * kIkHead) sm.xp_head[tid - kIkHead] = __ldcg(ps + tid - kIkHead);
+        constexpr int PER = (kIk * kIk + NT - 1) / NT;
+        double v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { const int e = tid + u * NT; v[u] = e < kIk * kIk ? __ldcg(ps + kIkHead + e) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { const int e = tid + u * NT; if (e < kIk * kIk) sm.x.P[e] = v[u]; }
+    }
+    // ---- fixed-order reduction of the block partials (block order, 16 loads in flight)
+    if (tid < K) {
+        double acc = 0.0;
+        for (int b = 0; b < s.nblocks; b += 16) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (b + u < s.nblocks) ? __ldcg(s.partials + (size_t)(b + u) * K + tid) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc += v[u];
+        }
+        sm.packed[tid] = acc;
+    }
+    if (tid == 0) sm.flags[3] = 0;
+    __syncthreads();
+    if (tid == 0) {   // HTH (12x12 symmetric) and h_x^T h
+        int k = 0;
+        for (int r = 0; r < 12; ++r)
+            for (int c = r; c < 12; ++c) { sm.HTH[r * 12 + c] = sm.packed[k]; sm.HTH[c * 12 + r] = sm.packed[k]; ++k; }
+        for (int r = 0; r < 12; ++r) sm.HTh[r] = sm.packed[78 + r];
+    }
+    if (tid == 32) {  // dx = x_ [-] x_propagated (:1646) and the projection matrices (:1656-1696)
+        StateIkfom* xp = reinterpret_cast<StateIkfom*>(sm.xp_head);   // head only
+        ikfom_boxminus(sm.x, *xp, sm.dx);
+        for (int a = 0; a < kIk; ++a) sm.dx_new[a] = sm.dx[a];
+        for (int q = 0; q < 2; ++q) {
+            const int idx = 3 + 3 * q;
+            double A[9], v[3];
+            mtk_A_matrix(sm.dx + idx, A);
+            transpose_small(A, 3, 3, sm.AT[q]);
+            mm_small(sm.AT[q], 3, 3, sm.dx_new + idx, 1, v);
+            for (int a = 0; a < 3; ++a) sm.dx_new[idx + a] = v[a];
+        }
+        double Nx[6], Mx[6], v2[2];
+        s2_Nx_yy(sm.x.grav, Nx);
+        s2_Mx(xp->grav, sm.dx + 21, Mx);
+        mm_small(Nx, 2, 3, Mx, 2, sm.T2);
+        mm_small(sm.T2, 2, 2, sm.dx_new + 21, 1, v2);
+        sm.dx_new[21] = v2[0];
+        sm.dx_new[22] = v2[1];
+    }
+    __syncthreads();
+    double* P = sm.x.P;
+    for (int q = 0; q < 2; ++q) {
+        ik_rows_apply<3>(P, kIk, kIk, 3 + 3 * q, sm.AT[q], P, kIk, tid);
+        __syncthreads();
+        ik_cols_apply_T<3>(P, 3 + 3 * q, sm.AT[q], tid);
+        __syncthreads();
+    }
+    ik_rows_apply<2>(P, kIk, kIk, 21, sm.T2, P, kIk, tid);
+    __syncthreads();
+    ik_cols_apply_T<2>(P, 21, sm.T2, tid);
+    __syncthreads();
+    // ---- P_inv[:, :12] by the Schur complement (see the 18-DoF leader): P11 = P_[:12, :12]
+    for (int e = tid; e < 12 * 24; e += NT) {
+        const int i = e / 24, j = e - i * 24;
+        sm.S[i * 25 + j] = (j < 12) ? P[i * kIk + j] : ((j - 12 == i) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    gj_block<12, 25, NT>(sm.S, &sm.flags[3], tid);
+    for (int e = tid; e < 144; e += NT) sm.P11inv[e] = sm.S[(e / 12) * 25 + 12 + (e % 12)];
+    __syncthreads();
+    for (int e = tid; e < 11 * 12; e += NT) {   // B = P21 * P11^-1
+        const int i = e / 12, j = e - i * 12;
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc += P[(12 + i) * kIk + k] * sm.P11inv[k * 12 + j];
+        sm.B[e] = acc;
+    }
+    for (int e = tid; e < 12 * 24; e += NT) {
+        const int i = e / 24, j = e - i * 24;
+        sm.S[i * 25 + j] = (j < 12) ? sm.HTH[i * 12 + j] + s.prm.R * sm.P11inv[i * 12 + j] : ((j - 12 == i) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    gj_block<12, 25, NT>(sm.S, &sm.flags[3], tid);
+    for (int e = tid; e < 144; e += NT) sm.K[e] = sm.S[(e / 12) * 25 + 12 + (e % 12)];   // Kt
+    __syncthreads();
+    for (int e = tid; e < 11 * 12; e += NT) {   // Kb = B * Kt
+        const int i = e / 12, j = e - i * 12;
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc += sm.B[i * 12 + k] * sm.K[k * 12 + j];
+        sm.K[144 + e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < kIk * 12; e += NT) {  // K_x[:, :12] = P_inv[:, :12] * HTH   (:1806)
+        const int i = e / 12, j = e - i * 12;
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc += sm.K[i * 12 + k] * sm.HTH[k * 12 + j];
+        sm.Kx[e] = acc;
+    }
+    if (tid < kIk) {                            // K_h = P_inv[:, :12] * h_x^T h       (:1801)
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc += sm.K[tid * 12 + k] * sm.HTh[k];
+        sm.Kh[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < kIk) {                            // dx_ = K_h + (K_x - I) * dx_new      (:1812)
+        double acc = sm.Kh[tid];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc += sm.Kx[tid * 12 + k] * sm.dx_new[k];
+        sm.dxo[tid] = acc - sm.dx_new[tid];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        IkfomCtrl c;
+        if (first) {
+            c.passes = c.knn_passes = 0;
+            c.rows_total = 0;
+            c.status = 0;
+        } else {
+            c.passes = __ldcg(&s.ctrl->passes);
+            c.knn_passes = __ldcg(&s.ctrl->knn_passes);
+            c.rows_total = __ldcg(&s.ctrl->rows_total);
+            c.status = __ldcg(&s.ctrl->status);
+        }
+        const bool ok = sm.flags[3] == 0;
+        const int n_eff = (int)sm.packed[K - 2];
+        c.passes += 1;
+        c.knn_passes += converge_in ? 1 : 0;
+        c.n_eff_last = n_eff;
+        c.res_mean_last = sm.packed[K - 1] / (double)n_eff;
+        c.rows_total += n_eff;
+        ikfom_boxplus(sm.x, sm.dxo);                                   // :1814
+        int conv = 1;
+        for (int a = 0; a < kIk; ++a)
+            if (fabs(sm.dxo[a]) > s.prm.limit[a]) { conv = 0; break; } // :1816-1823
+        int t = tcount;
+        if (conv) t++;
+        if (!t && it == s.prm.max_iteration - 2) conv = 1;             // :1826-1829
+        int fin = (t > 1 || it == s.prm.max_iteration - 1) ? 1 : 0;    // :1831
+        if (!ok) { fin = 1; c.status = -5; }
+        c.converged_last = conv;
+        c.i = it + 1;
+        c.t = t;
+        c.converge = conv;
+        c.stop = fin;
+        *s.ctrl = c;
+        sm.flags[0] = fin && ok;
+        if (fin && ok) {                                               // projections with dx_ (:1836-1893)
+            for (int q = 0; q < 2; ++q) {
+                double A[9];
+                mtk_A_matrix(sm.dxo + 3 + 3 * q, A);
+                transpose_small(A, 3, 3, sm.AT[q]);
+            }
+            double Nx[6], Mx[6];
+            s2_Nx_yy(sm.x.grav, Nx);
+            s2_Mx(reinterpret_cast<StateIkfom*>(sm.xp_head)->grav, sm.dxo + 21, Mx);
+            mm_small(Nx, 2, 3, Mx, 2, sm.T2);
+        }
+    }
+    __syncthreads();
+    if (sm.flags[0]) {
+        for (int e = tid; e < kIk * kIk; e += NT) sm.L[e] = P[e];      // L_ = P_ (:1833)
+        __syncthreads();
+        for (int q = 0; q < 2; ++q) {
+            const int idx = 3 + 3 * q;
+            ik_rows_apply<3>(sm.L, kIk, kIk, idx, sm.AT[q], P, kIk, tid);        // L_ rows from P_ rows
+            if (tid >= 32 && tid < 44) ik_rows_apply<3>(sm.Kx, 12, 12, idx, sm.AT[q], sm.Kx, 12, tid - 32);
+            __syncthreads();
+            ik_cols_apply_T<3>(sm.L, idx, sm.AT[q], tid);
+            if (tid >= 32 && tid < 32 + kIk) ik_cols_apply_T<3>(P, idx, sm.AT[q], tid - 32);
+            __syncthreads();
+        }
+        ik_rows_apply<2>(sm.L, kIk, kIk, 21, sm.T2, P, kIk, tid);
+        if (tid >= 32 && tid < 44) ik_rows_apply<2>(sm.Kx, 12, 12, 21, sm.T2, sm.Kx, 12, tid - 32);
+        __syncthreads();
+        ik_cols_apply_T<2>(sm.L, 21, sm.T2, tid);
+        if (tid >= 32 && tid < 32 + kIk) ik_cols_apply_T<2>(P, 21, sm.T2, tid - 32);
+        __syncthreads();
+        // P_ = L_ - K_x[:, :12] * P_[:12, :]   (:1918)
+        double* Pg = s.state->P;
+        for (int e = tid; e < kIk * kIk; e += NT) {
+            const int i = e / kIk, j = e - i * kIk;
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc += sm.Kx[i * 12 + k] * P[k * kIk + j];
+            Pg[e] = sm.L[e] - acc;
+        }
+    }
+    if (tid < kIkHead) reinterpret_cast<double*>(s.state)[tid] = reinterpret_cast<const double*>(&sm.x)[tid];
+}
+
+// Pose of a pass from state_ikfom: R = rot.toRotationMatrix(), extrinsic from offset_R_L_I / offset_T_L_I
+__device__ __forceinline__ void ikfom_make_pose(const StateIkfom* st, LioPose& pose) {
+    double head[kIkHead];
+    const double* g = reinterpret_cast<const double*>(st);
+    for (int i = 0; i < kIkHead; ++i) head[i] = __ldcg(g + i);
+    const StateIkfom* x = reinterpret_cast<const StateIkfom*>(head);
+    quat_to_R(x->rot, pose.R);
+    quat_to_R(x->offset_R_L_I, pose.R_LI);
+    for (int i = 0; i < 3; ++i) { pose.p[i] = x->pos[i]; pose.t_LI[i] = x->offset_T_L_I[i]; }
+    m3_T(pose.R, pose.Rt);
+    m3_T(pose.R_LI, pose.RLIt);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_lio_update_ikfom_persistent(LioArgs a, IkfomSolveArgs s, GridBarrier* bar) {
+    constexpr int K = lio_packed(12);
+    __shared__ LioPose s_pose;
+    __shared__ double s_acc[BLOCK / 32][K];
+    __shared__ unsigned s_bar[2];
+    __shared__ IkLeaderSmem sm;
+    const int tid = threadIdx.x;
+    int it = -1, tcount = 0, converge = 1;     // esekfom.hpp:1622-1624, :1633
+    bool first = true;
+    for (;;) {
+        if (tid == 0) ikfom_make_pose(s.state, s_pose);
+        __syncthreads();
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int c = (tid >> 5) * gridDim.x + blockIdx.x; c * 32 < a.N; c += (BLOCK / 32) * gridDim.x) {
+            const int i = c * 32 + (tid & 31);
+            if (i < a.N) {
+                bool active;
+                double row[12], z, absres;
+                lio_point<12>(a, s_pose, converge != 0, i, active, row, z, absres);   // converge => redo kNN (:994)
+                if (active) lio_accumulate<12>(acc, row, z, absres);
+            }
+        }
+        block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
+        const bool leader = grid_arrive(bar, gridDim.x, s_bar);
+        if (leader) {
+            ikfom_leader<BLOCK>(s, sm, first, it, tcount, converge);
+            grid_release(bar, s_bar);
+        } else {
+            if (!grid_wait(bar, s_bar)) return;
+        }
+        const int stop = __ldcg(&s.ctrl->stop);
+        converge = __ldcg(&s.ctrl->converge);
+        tcount = __ldcg(&s.ctrl->t);
+        it = __ldcg(&s.ctrl->i);
+        first = false;
+        if (stop) break;
+    }
+}
+
+}  // namespace flb

@@ -144,6 +144,42 @@ int flb_lio_export(flb_handle* h, float* world_xyz, int* nn_idx, float* nn_d2, f
 int flb_lio_update(flb_handle* h, const flb_lio_params* prm, flb_state18* x, const flb_state18* x_prop,
                    flb_lio_report* rep);
 
+/* ---- IKFoM-typed LIO update (the `#define USE_IKFOM` estimator) -------------------------
+ * state_ikfom (include/use-ikfom.hpp:12-21): pos, rot, offset_R_L_I, offset_T_L_I, vel, bg, ba, grav(S2,
+ * |g| = 9.8090).  Quaternions are (x, y, z, w) like Eigen's coeffs(); P is the 23x23 covariance, row-major,
+ * in the sub-manifold order above (DOF 23). */
+typedef struct flb_state_ikfom {
+    double pos[3];
+    double rot[4];
+    double offset_R_L_I[4];
+    double offset_T_L_I[3];
+    double vel[3], bg[3], ba[3];
+    double grav[3];
+    double P[529];
+} flb_state_ikfom;
+
+typedef struct flb_ikfom_params {
+    double laser_point_cov;  /* R in kf.update_iterated_dyn_share_modified(LASER_POINT_COV, ...), laserMapping.cpp:1484 */
+    int    max_iteration;    /* maximum_iter of kf.init_dyn_share(..., NUM_MAX_ITERATIONS, epsi), :1235 */
+    double limit[23];        /* epsi (0.001 each, :1233-1234) */
+} flb_ikfom_params;
+
+typedef struct flb_ikfom_report {
+    int     passes, knn_passes, n_eff_last, converged_last;
+    double  res_mean_last;
+    int64_t rows_total;
+    int     status;
+} flb_ikfom_report;
+
+/* esekfom::esekf<state_ikfom,12,input_ikfom>::update_iterated_dyn_share_modified
+ * (include/IKFoM_toolkit/esekfom/esekfom.hpp:1619-1928) with h_dyn_share = h_share_model
+ * (src/laserMapping.cpp:960-1094), i.e. the block src/laserMapping.cpp:1482-1494, in one device launch:
+ * per pass the 12-column rows [n, A, B, C] and h_x^T h_x / h_x^T h, the SO3/S2 re-projection of P, the
+ * information-form gain, x [+] dx, the per-component convergence test and, on the last pass, the
+ * covariance update.  x: in = x_ (== the propagated state) and P_; out = updated.  Needs the map and the
+ * scan uploaded; single GPU, persistent mode. */
+int flb_lio_update_ikfom(flb_handle* h, const flb_ikfom_params* prm, flb_state_ikfom* x, flb_ikfom_report* rep);
+
 /* ---- VIO --------------------------------------------------------------------------- */
 typedef struct flb_camera {
     int    width, height;

@@ -398,6 +398,11 @@ flo_lio* flo_lio_create(const float* map_xyz, int M, const float* scan_body_xyz,
     return L;
 }
 
+void flo_lio_reset(flo_lio* L) {
+    std::fill(L->selected.begin(), L->selected.end(), 1);
+    std::fill(L->res_last.begin(), L->res_last.end(), 1000.0);
+}
+
 void flo_lio_destroy(flo_lio* L) {
     if (!L) return;
     if (L->own_ctx) flo_free(L->own_ctx);

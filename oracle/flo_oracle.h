@@ -106,6 +106,41 @@ int flo_lio_pass(flo_lio*, const flo_lio_params*, const double R[9], const doubl
 int flo_lio_update(flo_lio*, const flo_lio_params*, flo_state18* x, const flo_state18* x_prop,
                    flo_lio_report* rep);
 
+/* fresh frame: point_selected_surf = true, res_last = 1000 (src/laserMapping.cpp:1441,1469) */
+void flo_lio_reset(flo_lio*);
+
+/* ---- IKFoM-typed estimator (oracle/flo_ikfom.cpp) ---------------------
+ * state_ikfom, include/use-ikfom.hpp:12-21.  Quaternions are (x, y, z, w) like Eigen's coeffs();
+ * P is the 23x23 covariance, row-major, order [pos, rot, offset_R_L_I, offset_T_L_I, vel, bg, ba, grav(2)]. */
+typedef struct flo_state_ikfom {
+    double pos[3];
+    double rot[4];
+    double offset_R_L_I[4];
+    double offset_T_L_I[3];
+    double vel[3], bg[3], ba[3];
+    double grav[3];
+    double P[529];
+} flo_state_ikfom;
+
+typedef struct flo_ikfom_params {
+    double laser_point_cov;   /* R of update_iterated_dyn_share_modified(R, ...) (laserMapping.cpp:1484) */
+    int    max_iteration;     /* maximum_iter (init_dyn_share, laserMapping.cpp:1235) */
+    double limit[23];         /* epsi = 0.001 each (laserMapping.cpp:1233-1234) */
+    int    nthreads;
+} flo_ikfom_params;
+
+typedef struct flo_ikfom_report {
+    int passes, knn_passes, n_eff_last, converged_last;
+    double res_mean_last;
+    int64_t rows_total;
+} flo_ikfom_report;
+
+void flo_ikfom_boxplus(flo_state_ikfom* x, const double* d23);
+void flo_ikfom_boxminus(const flo_state_ikfom* a, const flo_state_ikfom* b, double* res23);   /* a [-] b */
+void flo_quat_to_R(const double* q_xyzw, double* R9);
+/* esekfom.hpp:1619-1928 driven by h_share_model (laserMapping.cpp:960-1094) */
+int  flo_ikfom_update(flo_lio*, const flo_ikfom_params*, flo_state_ikfom* x, flo_ikfom_report* rep);
+
 /* ---- VIO ---------------------------------------------------------------------- */
 typedef struct flo_vio flo_vio;
 

@@ -83,13 +83,88 @@ class VioReport(C.Structure):
                 ("skipped_last", C.c_int), ("cov_updated", C.c_int)]
 
 
+class StateIkfom(C.Structure):
+    """flo_state_ikfom == state_ikfom (include/use-ikfom.hpp:12-21); quaternions (x, y, z, w)."""
+    _fields_ = [("pos", C.c_double * 3), ("rot", C.c_double * 4), ("offset_R_L_I", C.c_double * 4),
+                ("offset_T_L_I", C.c_double * 3), ("vel", C.c_double * 3), ("bg", C.c_double * 3),
+                ("ba", C.c_double * 3), ("grav", C.c_double * 3), ("P", C.c_double * 529)]
+
+    def copy(self):
+        o = StateIkfom()
+        C.memmove(C.byref(o), C.byref(self), C.sizeof(StateIkfom))
+        return o
+
+    def vector(self):
+        return np.concatenate([self.pos[:], self.rot[:], self.offset_R_L_I[:], self.offset_T_L_I[:], self.vel[:],
+                               self.bg[:], self.ba[:], self.grav[:]])
+
+    @property
+    def cov(self):
+        return np.array(self.P[:]).reshape(23, 23)
+
+
+class IkfomParams(C.Structure):
+    _fields_ = [("laser_point_cov", C.c_double), ("max_iteration", C.c_int), ("limit", C.c_double * 23),
+                ("nthreads", C.c_int)]
+
+
+class IkfomReport(C.Structure):
+    _fields_ = [("passes", C.c_int), ("knn_passes", C.c_int), ("n_eff_last", C.c_int), ("converged_last", C.c_int),
+                ("res_mean_last", C.c_double), ("rows_total", C.c_int64)]
+
+
+def quat_from_R(R):
+    """Rotation matrix -> quaternion (x, y, z, w), w >= 0."""
+    R = np.asarray(R, np.float64)
+    w = np.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    if w > 1e-6:
+        q = np.array([(R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w), w])
+    else:   # 180 degree case: pick the largest diagonal
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(1 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = np.zeros(4)
+        q[i] = s / 4
+        q[j] = (R[j, i] + R[i, j]) / s
+        q[k] = (R[k, i] + R[i, k]) / s
+        q[3] = (R[k, j] - R[j, k]) / s
+    return q / np.linalg.norm(q)
+
+
+def state_ikfom_from_frame(frame, P=None):
+    """state_ikfom at the propagated prior of a synthetic frame (gravity along -z, |g| = 9.8090)."""
+    s = StateIkfom()
+    s.pos[:] = frame["p_prop"]
+    s.rot[:] = quat_from_R(frame["R_prop"])
+    s.offset_R_L_I[:] = quat_from_R(frame["R_LI"])
+    s.offset_T_L_I[:] = frame["t_LI"]
+    s.vel[:] = frame["vel"]
+    s.bg[:] = frame["bg"]
+    s.ba[:] = frame["ba"]
+    s.grav[:] = [0.0, 0.0, -9.8090]
+    if P is None:
+        P = np.diag(np.concatenate([np.full(3, 1e-3), np.full(3, 1e-4), np.full(3, 1e-6), np.full(3, 1e-6),
+                                    np.full(3, 1e-2), np.full(3, 1e-4), np.full(3, 1e-3), np.full(2, 1e-5)]))
+    s.P[:] = np.asarray(P, np.float64).ravel()
+    return s
+
+
+def ikfom_params(frame, max_iteration, nthreads=4, limit=0.001):
+    p = IkfomParams()
+    p.laser_point_cov = frame["cfg"].laser_point_cov
+    p.max_iteration = max_iteration
+    p.limit[:] = [limit] * 23
+    p.nthreads = nthreads
+    return p
+
+
 KNN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 
 
 def build(force: bool = False) -> None:
     """Compile the checker (and, when /root/reference is present, the reference ikd-Tree)."""
     need = force or not os.path.exists(_LIB) or \
-        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_oracle.h"))
+        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_ikfom.cpp", "flo_oracle.h"))
     if need:
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     if os.path.isdir("/root/reference/include/ikd-Tree") and (force or not os.path.exists(_REF)):
@@ -131,6 +206,11 @@ def lib():
         L.flo_state_boxplus.argtypes = [C.POINTER(State18), C.c_void_p]
         L.flo_state_boxminus.argtypes = [C.POINTER(State18), C.POINTER(State18), C.c_void_p]
         L.flo_inverse.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.flo_lio_reset.argtypes = [C.c_void_p]
+        L.flo_ikfom_boxplus.argtypes = [C.POINTER(StateIkfom), C.c_void_p]
+        L.flo_ikfom_boxminus.argtypes = [C.POINTER(StateIkfom), C.POINTER(StateIkfom), C.c_void_p]
+        L.flo_quat_to_R.argtypes = [C.c_void_p, C.c_void_p]
+        L.flo_ikfom_update.argtypes = [C.c_void_p, C.POINTER(IkfomParams), C.POINTER(StateIkfom), C.POINTER(IkfomReport)]
         _lib = L
     return _lib
 
@@ -273,6 +353,14 @@ class Lio:
     def update(self, prm: LioParams, x: State18, x_prop: State18):
         rep = LioReport()
         self.L.flo_lio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep))
+        return rep
+
+    def update_ikfom(self, prm: "IkfomParams", x: "StateIkfom"):
+        """esekfom update_iterated_dyn_share_modified on state_ikfom (oracle/flo_ikfom.cpp)."""
+        rep = IkfomReport()
+        rc = self.L.flo_ikfom_update(self.h, C.byref(prm), C.byref(x), C.byref(rep))
+        if rc != 0:
+            raise RuntimeError(f"flo_ikfom_update failed ({rc})")
         return rep
 
 

@@ -106,3 +106,27 @@ void emu_exp3(const double* v, double* R) { so3_exp(v, R); }
 void emu_log3(const double* R, double* o) { so3_log(R, o); }
 
 }  // extern "C"
+
+// ---- IKFoM manifold algebra (row a8) ----------------------------------------------------------
+extern "C" {
+void emu_ikfom_boxplus(double* state26, const double* d23) {
+    StateIkfom x;
+    std::memcpy(&x, state26, 26 * sizeof(double));
+    ikfom_boxplus(x, d23);
+    std::memcpy(state26, &x, 26 * sizeof(double));
+}
+void emu_ikfom_boxminus(const double* a26, const double* b26, double* res23) {
+    StateIkfom a, b;
+    std::memcpy(&a, a26, 26 * sizeof(double));
+    std::memcpy(&b, b26, 26 * sizeof(double));
+    ikfom_boxminus(a, b, res23);
+}
+void emu_ikfom_proj(const double* grav_x, const double* grav_prop, const double* seg2, const double* seg3, double* T2, double* AT) {
+    double Nx[6], Mx[6], A[9];
+    s2_Nx_yy(grav_x, Nx);
+    s2_Mx(grav_prop, seg2, Mx);
+    mm_small(Nx, 2, 3, Mx, 2, T2);
+    mtk_A_matrix(seg3, A);
+    transpose_small(A, 3, 3, AT);
+}
+}
