@@ -138,7 +138,7 @@ class VioEq(C.Structure):
 
 # every symbol include/fastlivo_b200.h declares (checked by the CPU-only test tier)
 SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "flb_set_stream", "flb_synchronize",
-           "flb_map_upload", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update", "flb_lio_update_ikfom",
+           "flb_map_upload", "flb_map_add_points", "flb_map_delete_boxes", "flb_map_size", "flb_map_download", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update", "flb_lio_update_ikfom",
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
@@ -179,6 +179,10 @@ def lib():
         L.flb_synchronize.argtypes = [vp]
         L.flb_map_upload.argtypes = [vp, vp, C.c_int, C.c_int]
         L.flb_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.flb_map_add_points.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float]
+        L.flb_map_delete_boxes.argtypes = [vp, vp, C.c_int]
+        L.flb_map_size.argtypes = [vp]
+        L.flb_map_download.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int)]
         L.flb_knn.argtypes = [vp, vp, C.c_int, vp, vp]
         L.flb_lio_pass.argtypes = [vp, C.POINTER(LioParams), vp, vp, C.c_int, C.c_int, C.POINTER(NormalEq)]
         L.flb_lio_export.argtypes = [vp] + [vp] * 9 + [C.POINTER(C.c_int)]
@@ -275,6 +279,23 @@ class Handle:
         a = np.ascontiguousarray(xyz, np.float32)
         self._ck(self.L.flb_map_upload(self.h, _p(a), a.shape[0], a.shape[1]))
         self.M = a.shape[0]
+
+    def map_add_points(self, world_xyz, downsample_size):
+        a = np.ascontiguousarray(world_xyz, np.float32)
+        self._ck(self.L.flb_map_add_points(self.h, _p(a), a.shape[0], a.shape[1], C.c_float(downsample_size)))
+        self.M = self.L.flb_map_size(self.h)
+
+    def map_delete_boxes(self, boxes):
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+        self._ck(self.L.flb_map_delete_boxes(self.h, _p(b), len(b)))
+        self.M = self.L.flb_map_size(self.h)
+
+    def map_download(self):
+        n = self.L.flb_map_size(self.h)
+        out = np.empty((n, 3), np.float32)
+        m = C.c_int()
+        self._ck(self.L.flb_map_download(self.h, _p(out), n, C.byref(m)))
+        return out
 
     def scan_upload(self, body_xyz):
         a = np.ascontiguousarray(body_xyz, np.float32)

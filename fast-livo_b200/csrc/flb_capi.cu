@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -151,6 +152,12 @@ struct flb_handle {
     DevBuf<unsigned char> cub_tmp;
     DevBuf<float4> map_pts;
     DevBuf<int> cell_start;
+    float map_lo[3] = {0, 0, 0}, map_hi[3] = {0, 0, 0};   // bounding box of everything ever in the map
+    // map maintenance scratch
+    DevBuf<float> map_comb, boxes;
+    DevBuf<unsigned long long> vkeys, vkeys_sorted;
+    DevBuf<unsigned char> keep;
+    DevBuf<int> sel_idx;
 
     // scan + per-point persistent
     int N = 0;
@@ -600,6 +607,7 @@ int flb_destroy(flb_handle* h) {
     h->p2p_seq.release();
     for (auto& ev : h->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     h->map_raw.release(); h->keys.release(); h->keys_sorted.release(); h->vals.release(); h->vals_sorted.release();
+    h->map_comb.release(); h->boxes.release(); h->vkeys.release(); h->vkeys_sorted.release(); h->keep.release(); h->sel_idx.release();
     h->cub_tmp.release(); h->map_pts.release(); h->cell_start.release(); h->scan.release(); h->sel.release();
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
@@ -629,23 +637,10 @@ int flb_synchronize(flb_handle* h) {
 int64_t flb_launch_count(const flb_handle* h) { return h ? h->launches : 0; }
 
 // ---------------------------------------------------------------------------------------
-int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
-    FLB_CHECK_H(h);
-    if (!xyz || M < 1 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_map_upload: bad arguments (M=%d stride=%d)", M, stride);
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    void* stv = nullptr;
-    FLB_CUDA(h, h->st_map.acquire((size_t)M * 3 * sizeof(float), &stv));
-    float* st = static_cast<float*>(stv);
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = 0; i < M; ++i) {
-        for (int k = 0; k < 3; ++k) {
-            const float v = xyz[(size_t)i * stride + k];
-            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_upload: non-finite coordinate at point %d", i);
-            st[3 * (size_t)i + k] = v;
-            lo[k] = std::min(lo[k], v);
-            hi[k] = std::max(hi[k], v);
-        }
-    }
+// Build the sorted uniform kNN grid over h->map_raw[0..M) with the bounding box h->map_lo/hi.
+static int rebuild_grid(flb_handle* h, int M) {
+    const float* lo = h->map_lo;
+    const float* hi = h->map_hi;
     // grid geometry; enlarge the cell if the dense grid would exceed 2^25 cells (still exact, just slower)
     double cell = h->cfg.cell_size;
     for (;;) {
@@ -664,14 +659,12 @@ int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
     g.max_d2 = (float)h->cfg.knn_max_d2;
     g.max_ring = (int)std::ceil(std::sqrt(h->cfg.knn_max_d2) / cell) + 1;
     const int ncell = g.nx * g.ny * g.nz;
-    FLB_CUDA(h, h->map_raw.reserve((size_t)M * 3));
     FLB_CUDA(h, h->keys.reserve(M));
     FLB_CUDA(h, h->keys_sorted.reserve(M));
     FLB_CUDA(h, h->vals.reserve(M));
     FLB_CUDA(h, h->vals_sorted.reserve(M));
     FLB_CUDA(h, h->map_pts.reserve(M));
     FLB_CUDA(h, h->cell_start.reserve((size_t)ncell + 1));
-    FLB_CUDA(h, cudaMemcpyAsync(h->map_raw.p, st, (size_t)M * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     const int nb = (M + 255) / 256;
     {
         LaunchScope ls(h, FAM_OTHER);
@@ -693,10 +686,143 @@ int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
                                                  h->cell_start.p, ncell);
         FLB_CUDA(h, cudaGetLastError());
     }
-    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->M = M;
     h->grid = g;
     h->ncell = ncell;
+    return FLB_OK;
+}
+
+int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride) {
+    FLB_CHECK_H(h);
+    if (!xyz || M < 1 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_map_upload: bad arguments (M=%d stride=%d)", M, stride);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_map.acquire((size_t)M * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < M; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            const float v = xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_upload: non-finite coordinate at point %d", i);
+            st[3 * (size_t)i + k] = v;
+            lo[k] = std::min(lo[k], v);
+            hi[k] = std::max(hi[k], v);
+        }
+    }
+    for (int k = 0; k < 3; ++k) { h->map_lo[k] = lo[k]; h->map_hi[k] = hi[k]; }
+    FLB_CUDA(h, h->map_raw.reserve((size_t)M * 3));
+    FLB_CUDA(h, cudaMemcpyAsync(h->map_raw.p, st, (size_t)M * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int rc = rebuild_grid(h, M);
+    if (rc) return rc;
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+// ---- device-resident map maintenance -----------------------------------
+// Compact h->map_comb by h->keep flags (positions given by idx_in) into map_raw, then rebuild the grid.
+static int compact_and_rebuild(flb_handle* h, const int* idx_in, int total) {
+    FLB_CUDA(h, h->sel_idx.reserve((size_t)total + 1));
+    size_t tmp_bytes = 0;
+    int* d_count = h->sel_idx.p + total;
+    FLB_CUDA(h, cub::DeviceSelect::Flagged(nullptr, tmp_bytes, idx_in, h->keep.p, h->sel_idx.p, d_count, total, h->stream));
+    FLB_CUDA(h, h->cub_tmp.reserve(tmp_bytes));
+    FLB_CUDA(h, cub::DeviceSelect::Flagged(h->cub_tmp.p, tmp_bytes, idx_in, h->keep.p, h->sel_idx.p, d_count, total, h->stream));
+    h->launches += 2;
+    int count = 0;
+    FLB_CUDA(h, cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (count < 1) return fail(h, FLB_ERR_STATE, "map maintenance would leave an empty map");
+    FLB_CUDA(h, h->map_raw.reserve((size_t)count * 3));   // never shrinks; grows only if count > capacity
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_gather_xyz<<<(count + 255) / 256, 256, 0, h->stream>>>(h->map_comb.p, h->sel_idx.p, count, h->map_raw.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    return rebuild_grid(h, count);
+}
+
+int flb_map_add_points(flb_handle* h, const float* world_xyz, int n, int stride, float downsample_size) {
+    FLB_CHECK_H(h);
+    if (h->M <= 0) return fail(h, FLB_ERR_STATE, "flb_map_add_points: no map uploaded");
+    if (!world_xyz || n < 0 || stride < 3 || !(downsample_size > 0)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: bad arguments");
+    if (n == 0) return FLB_OK;
+    const int M = h->M, total = M + n;
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_map.acquire((size_t)n * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = world_xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: non-finite coordinate at point %d", i);
+            if (std::fabs(v / downsample_size) > 1.0e6f) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: coordinate / downsample_size exceeds 2^20 voxels");
+            st[3 * (size_t)i + k] = v;
+            h->map_lo[k] = std::min(h->map_lo[k], v);
+            h->map_hi[k] = std::max(h->map_hi[k], v);
+        }
+    FLB_CUDA(h, h->map_comb.reserve((size_t)total * 3));
+    FLB_CUDA(h, h->vkeys.reserve(total));
+    FLB_CUDA(h, h->vkeys_sorted.reserve(total));
+    FLB_CUDA(h, h->vals.reserve(total));
+    FLB_CUDA(h, h->vals_sorted.reserve(total));
+    FLB_CUDA(h, h->keep.reserve(total));
+    FLB_CUDA(h, cudaMemcpyAsync(h->map_comb.p, h->map_raw.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(h->map_comb.p + (size_t)M * 3, st, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_map.mark(h->stream));
+    const int nb = (total + 255) / 256;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vox_keys<<<nb, 256, 0, h->stream>>>(h->map_comb.p, total, downsample_size, h->vkeys.p, h->vals.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    size_t tmp_bytes = 0;
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->vkeys.p, h->vkeys_sorted.p, h->vals.p, h->vals_sorted.p, total,
+                                                0, 63, h->stream));
+    FLB_CUDA(h, h->cub_tmp.reserve(tmp_bytes));
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->vkeys.p, h->vkeys_sorted.p, h->vals.p, h->vals_sorted.p,
+                                                total, 0, 63, h->stream));
+    h->launches += 4;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vox_resolve<<<nb, 256, 0, h->stream>>>(h->vkeys_sorted.p, h->vals_sorted.p, h->map_comb.p, total, M, downsample_size,
+                                                  h->keep.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    return compact_and_rebuild(h, h->vals_sorted.p, total);
+}
+
+int flb_map_delete_boxes(flb_handle* h, const float* boxes, int nb) {
+    FLB_CHECK_H(h);
+    if (h->M <= 0) return fail(h, FLB_ERR_STATE, "flb_map_delete_boxes: no map uploaded");
+    if (nb < 0 || (nb > 0 && !boxes)) return fail(h, FLB_ERR_INVALID, "flb_map_delete_boxes: bad arguments");
+    if (nb == 0) return FLB_OK;
+    const int M = h->M;
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_misc.acquire((size_t)nb * 6 * sizeof(float), &stv));
+    std::memcpy(stv, boxes, (size_t)nb * 6 * sizeof(float));
+    FLB_CUDA(h, h->boxes.reserve((size_t)nb * 6));
+    FLB_CUDA(h, cudaMemcpyAsync(h->boxes.p, stv, (size_t)nb * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_misc.mark(h->stream));
+    FLB_CUDA(h, h->map_comb.reserve((size_t)M * 3));
+    FLB_CUDA(h, h->vals.reserve(M));
+    FLB_CUDA(h, h->keep.reserve(M));
+    FLB_CUDA(h, cudaMemcpyAsync(h->map_comb.p, h->map_raw.p, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_box_flags<<<(M + 255) / 256, 256, 0, h->stream>>>(h->map_comb.p, M, h->boxes.p, nb, h->keep.p, h->vals.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    return compact_and_rebuild(h, h->vals.p, M);
+}
+
+int flb_map_size(const flb_handle* h) { return h ? h->M : 0; }
+
+int flb_map_download(flb_handle* h, float* xyz, int capacity, int* M_out) {
+    FLB_CHECK_H(h);
+    if (M_out) *M_out = h->M;
+    if (!xyz || capacity <= 0) return FLB_OK;
+    const int n = std::min(capacity, h->M);
+    FLB_CUDA(h, cudaMemcpyAsync(xyz, h->map_raw.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     return FLB_OK;
 }
 

@@ -129,6 +129,119 @@ __global__ void k_map_gather(const float* __restrict__ xyz, int M, int stride, c
 }
 
 // ---------------------------------------------------------------------------------------
+// map maintenance: KD_TREE::Add_Points(points, downsample = true)
+// (include/ikd-Tree/ikd_Tree.cpp:382-457) and Delete_Point_Boxes (:501-521) on the device map.
+//
+// Add_Points processes the new points one by one: box = the downsample voxel of the point,
+// Downsample_Storage = live points in the box, result = the one closest to the voxel centre (strict <,
+// starting from the new point); if the box held more than one point, or the new point won, the box is
+// emptied and `result` put back.  Its net effect per voxel is order-independent up to ties, so the
+// device version sorts (existing + new) points by voxel and lets one thread replay that sequential
+// rule over each voxel's handful of points.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long vox_key(float x, float y, float z, float ds) {
+    // floor(p / downsample_size) per axis (ikd_Tree.cpp:392-396), biased into 21 bits each
+    const long long ix = (long long)floorf(x / ds) + (1ll << 20), iy = (long long)floorf(y / ds) + (1ll << 20),
+                    iz = (long long)floorf(z / ds) + (1ll << 20);
+    return ((unsigned long long)(iz & 0x1fffff) << 42) | ((unsigned long long)(iy & 0x1fffff) << 21) |
+           (unsigned long long)(ix & 0x1fffff);
+}
+
+__global__ void k_vox_keys(const float* __restrict__ xyz, int total, float ds, unsigned long long* __restrict__ keys,
+                           int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    keys[i] = vox_key(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], ds);
+    vals[i] = i;
+}
+
+// keys/vals sorted by voxel (stable: ascending index inside a voxel, so existing points [idx < M] come
+// first and new points keep their submission order).  One thread per voxel segment.
+__global__ void k_vox_resolve(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                              const float* __restrict__ xyz, int total, int M, float ds, unsigned char* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const unsigned long long k = keys[i];
+    if (i > 0 && keys[i - 1] == k) return;          // not a segment head
+    int end = i;
+    while (end < total && keys[end] == k) ++end;
+    int first_new = end;
+    for (int j = i; j < end; ++j)
+        if (vals[j] >= M) { first_new = j; break; }
+    if (first_new == end) {                         // voxel untouched by this batch: keep everything
+        for (int j = i; j < end; ++j) keep[j] = 1;
+        return;
+    }
+    // box and centre from the first new point (ikd_Tree.cpp:392-400), float arithmetic as written there
+    const int v0 = vals[first_new];
+    float mn[3], mx[3], mid[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = floorf(xyz[3 * (size_t)v0 + a] / ds) * ds;
+        mx[a] = mn[a] + ds;
+        mid[a] = (float)((double)mn[a] + (double)(mx[a] - mn[a]) / 2.0);
+    }
+    // content of the box: existing points that pass the half-open box test (:1001)
+    int c = 0, best = -1;
+    float best_d = INFINITY;
+    for (int j = i; j < first_new; ++j) {
+        const float* p = xyz + 3 * (size_t)vals[j];
+        const bool in = mn[0] <= p[0] && mx[0] > p[0] && mn[1] <= p[1] && mx[1] > p[1] && mn[2] <= p[2] && mx[2] > p[2];
+        keep[j] = in ? 0 : 1;                       // (a point just outside its own float box is never touched)
+        if (in) {
+            ++c;
+            const float d = dist2f(p[0], p[1], p[2], mid[0], mid[1], mid[2]);
+            if (d < best_d) { best_d = d; best = j; }
+        }
+    }
+    const int c0 = c, best0 = best;
+    bool replaced = false;
+    for (int j = first_new; j < end; ++j) {
+        keep[j] = 0;
+        const float* p = xyz + 3 * (size_t)vals[j];
+        const float d = dist2f(p[0], p[1], p[2], mid[0], mid[1], mid[2]);
+        const bool p_wins = !(best_d < d);          // tmp_dist < min_dist, strict (:405)
+        if (c > 1 || p_wins) {                      // :412
+            if (p_wins) { best = j; best_d = d; }
+            c = 1;
+            replaced = true;
+        }
+    }
+    if (replaced) {
+        keep[best] = 1;
+    } else if (c0 > 0) {
+        // the single existing point beat every new one: nothing changes (:412 false every time)
+        for (int j = i; j < first_new; ++j)
+            if (!keep[j]) keep[j] = 1;
+        (void)best0;
+    }
+}
+
+// keep = not inside any box (half-open test of Delete_by_range, ikd_Tree.cpp:650); vals = iota
+__global__ void k_box_flags(const float* __restrict__ xyz, int M, const float* __restrict__ boxes, int nb,
+                            unsigned char* __restrict__ keep, int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+    bool del = false;
+    for (int b = 0; b < nb; ++b) {
+        const float* q = boxes + 6 * b;
+        if (q[0] <= x && q[3] > x && q[1] <= y && q[4] > y && q[2] <= z && q[5] > z) del = true;
+    }
+    keep[i] = del ? 0 : 1;
+    vals[i] = i;
+}
+
+__global__ void k_gather_xyz(const float* __restrict__ src, const int* __restrict__ idx, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = idx[i];
+    dst[3 * (size_t)i] = src[3 * (size_t)s];
+    dst[3 * (size_t)i + 1] = src[3 * (size_t)s + 1];
+    dst[3 * (size_t)i + 2] = src[3 * (size_t)s + 2];
+}
+
+// ---------------------------------------------------------------------------------------
 // scan preparation: Morton order in the BODY frame.  A rigid transform preserves spatial
 // neighbourhoods, so the lanes of a warp query neighbouring map cells at every pose: similar trip
 // counts (less divergence) and shared cache lines.  w carries the original scan index.

@@ -77,6 +77,22 @@ int         flb_synchronize(flb_handle* h);
  * device-resident sorted uniform grid the kNN kernel walks. */
 int flb_map_upload(flb_handle* h, const float* xyz, int M, int stride_floats);
 
+/* Device-resident map maintenance: the map follows the reference's ikd-Tree
+ * without a per-frame re-upload.
+ *   flb_map_add_points  == ikdtree.Add_Points(PointToAdd, true) with downsample_size = filter_size_map
+ *                          (map_incremental, src/laserMapping.cpp:692-706; ikd_Tree.cpp:382-457): per
+ *                          downsample voxel touched by a new point, only the point closest to the voxel
+ *                          centre survives (existing or new); untouched voxels are left alone.
+ *   flb_map_delete_boxes == ikdtree.Delete_Point_Boxes(cub_needrm) (lasermap_fov_segment,
+ *                          src/laserMapping.cpp:363-421; ikd_Tree.cpp:501-521): boxes nb x 6 floats
+ *                          (min xyz, max xyz), half-open containment min <= p < max.
+ * After either call map indices (flb_knn / flb_lio_export nn_idx) refer to the order flb_map_download
+ * returns.  |coordinate / downsample_size| must stay below 2^20. */
+int flb_map_add_points(flb_handle* h, const float* world_xyz, int n, int stride_floats, float downsample_size);
+int flb_map_delete_boxes(flb_handle* h, const float* boxes, int nb);
+int flb_map_size(const flb_handle* h);
+int flb_map_download(flb_handle* h, float* xyz, int capacity_points, int* M_out);
+
 /* ---- scan ------------------------------------------------------------------------
  * feats_down_body (src/laserMapping.cpp:1398-1399): N already-downsampled points in
  * the LiDAR body frame. */

@@ -71,4 +71,42 @@ int ikdref_knn(void* t, const float* q, int nq, int k, int* idx, float* d2, int 
     return 0;
 }
 
+// --- map maintenance -------------------------------------------------
+// KD_TREE::Add_Points(PointToAdd, downsample_on = true)  (ikd_Tree.cpp:382-457; called from
+// map_incremental, src/laserMapping.cpp:692-706), with set_downsample_param(filter_size_map).
+int ikdref_add_points(void* t, const float* xyz, int n, float downsample_size) {
+    KD_TREE* tree = static_cast<KD_TREE*>(t);
+    tree->set_downsample_param(downsample_size);
+    PointVector pts((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        PointType p;
+        p.x = xyz[3 * (size_t)i]; p.y = xyz[3 * (size_t)i + 1]; p.z = xyz[3 * (size_t)i + 2];
+        int32_t idx = -1 - i;
+        std::memcpy(&p.curvature, &idx, 4);
+        pts[i] = p;
+    }
+    return tree->Add_Points(pts, true);
+}
+
+// KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:501-521; lasermap_fov_segment, src/laserMapping.cpp:363-421).
+// boxes: nb x 6 floats (min xyz, max xyz).
+int ikdref_delete_boxes(void* t, const float* boxes, int nb) {
+    KD_TREE* tree = static_cast<KD_TREE*>(t);
+    std::vector<BoxPointType> v((size_t)nb);
+    for (int i = 0; i < nb; ++i)
+        for (int k = 0; k < 3; ++k) { v[i].vertex_min[k] = boxes[6 * i + k]; v[i].vertex_max[k] = boxes[6 * i + 3 + k]; }
+    return tree->Delete_Point_Boxes(v);
+}
+
+// All live points of the tree (KD_TREE::flatten, ikd_Tree.cpp:1247-1273).  Returns the count; fills at
+// most `capacity` points.
+int ikdref_flatten(void* t, float* xyz, int capacity) {
+    KD_TREE* tree = static_cast<KD_TREE*>(t);
+    PointVector st;
+    tree->flatten(tree->Root_Node, st, NOT_RECORD);
+    const int n = (int)st.size();
+    for (int i = 0; i < n && i < capacity; ++i) { xyz[3 * (size_t)i] = st[i].x; xyz[3 * (size_t)i + 1] = st[i].y; xyz[3 * (size_t)i + 2] = st[i].z; }
+    return n;
+}
+
 }  // extern "C"

@@ -227,6 +227,9 @@ def ref_lib():
         R.ikdref_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
         R.ikdref_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         R.ikdref_size.argtypes = [C.c_void_p]
+        R.ikdref_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float]
+        R.ikdref_delete_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        R.ikdref_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _ref = R
     return _ref
 
@@ -285,6 +288,21 @@ class IkdTreeRef:
         d2 = np.empty((len(q), k), np.float32)
         self._R.ikdref_knn(self.handle, _p(q), len(q), k, _p(idx), _p(d2), nthreads)
         return idx, d2
+
+    def add_points(self, xyz, downsample_size):
+        """ikdtree.Add_Points(points, true) with downsample_size = filter_size_map (laserMapping.cpp:692-706)."""
+        a = f32(xyz)
+        return self._R.ikdref_add_points(self.handle, _p(a), len(a), C.c_float(downsample_size))
+
+    def delete_boxes(self, boxes):
+        b = f32(boxes).reshape(-1, 6)
+        return self._R.ikdref_delete_boxes(self.handle, _p(b), len(b))
+
+    def points(self):
+        n = self._R.ikdref_flatten(self.handle, None, 0)
+        out = np.empty((n, 3), np.float32)
+        self._R.ikdref_flatten(self.handle, _p(out), n)
+        return out
 
     @property
     def fn_ptr(self):
