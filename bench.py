@@ -442,6 +442,8 @@ def main():
     if rank == 0 and world == 1:
         Rw, pw = frame["R_true"], frame["p_true"]
         world_pts = ((Rw @ (frame["R_LI"] @ frame["scan_body"].T.astype(np.float64) + frame["t_LI"][:, None])).T + pw).astype(np.float32)
+        h.map_add_points(world_pts, cfg.pitch)       # first call allocates the scratch buffers
+        h.map_upload(frame["map_xyz"])
         barrier()
         t0 = time.perf_counter()
         h.map_add_points(world_pts, cfg.pitch)
