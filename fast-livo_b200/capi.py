@@ -137,7 +137,7 @@ class VioEq(C.Structure):
 
 
 # every symbol include/fastlivo_b200.h declares (checked by the CPU-only test tier)
-SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "flb_set_stream", "flb_synchronize",
+SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "flb_set_stream", "flb_synchronize", "flb_host_alloc", "flb_host_free",
            "flb_map_upload", "flb_map_add_points", "flb_map_delete_boxes", "flb_map_size", "flb_map_download", "flb_scan_upload", "flb_knn", "flb_lio_pass", "flb_lio_export", "flb_lio_update", "flb_lio_update_ikfom",
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
@@ -177,6 +177,8 @@ def lib():
         L.flb_destroy.argtypes = [vp]
         L.flb_set_stream.argtypes = [vp, vp]
         L.flb_synchronize.argtypes = [vp]
+        L.flb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.flb_host_free.argtypes = [vp, vp]
         L.flb_map_upload.argtypes = [vp, vp, C.c_int, C.c_int]
         L.flb_scan_upload.argtypes = [vp, vp, C.c_int, C.c_int]
         L.flb_map_add_points.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float]
@@ -261,6 +263,10 @@ class Handle:
 
     def close(self):
         if getattr(self, "h", None):
+            self.L.flb_synchronize(self.h)
+            for ptr in getattr(self, "_pinned", []):
+                self.L.flb_host_free(self.h, ptr)
+            self._pinned = []
             self.L.flb_destroy(self.h)
             self.h = None
 
@@ -414,6 +420,18 @@ class Handle:
 
     def state_set_prior_enqueue(self):
         self._ck(self.L.flb_state_set_prior_enqueue(self.h))
+
+    def pinned_like(self, a):
+        """A page-locked copy of numpy array `a` (flb_host_alloc); freed with the handle."""
+        a = np.ascontiguousarray(a)
+        ptr = C.c_void_p()
+        self._ck(self.L.flb_host_alloc(self.h, max(a.nbytes, 1), C.byref(ptr)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_ubyte * max(a.nbytes, 1)).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+        out[...] = a
+        return out
 
     def set_stream(self, stream_ptr):
         self._ck(self.L.flb_set_stream(self.h, C.c_void_p(stream_ptr)))

@@ -139,6 +139,12 @@ struct flb_handle {
     flb_config cfg{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // The VIO inputs (image, patch list) are copied on a second stream so that their H2D transfer
+    // overlaps the LIO kernel running on `stream`; two events order them against the VIO kernels.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_vio_inputs = nullptr;   // recorded on copy_stream after the last image / patch copy
+    cudaEvent_t ev_vio_done = nullptr;     // recorded on `stream` after the last kernel that reads them
+    bool vio_inputs_pending = false, vio_done_pending = false;
     std::string err;
     int64_t launches = 0;
 
@@ -382,6 +388,41 @@ int allreduce_packed(flb_handle* h, const double* partials, int nblocks, int K) 
     return FLB_OK;
 }
 
+// true when p is page-locked host memory (flb_host_alloc / cudaHostAlloc / cudaHostRegister): the copy engine
+// can read it directly, so the staging memcpy is skipped
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// copy_stream must not overwrite the image / patches while a VIO kernel on `stream` still reads them
+int vio_copy_begin(flb_handle* h) {
+    if (h->vio_done_pending) {
+        FLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_vio_done, 0));
+        h->vio_done_pending = false;
+    }
+    return FLB_OK;
+}
+int vio_copy_end(flb_handle* h) {
+    FLB_CUDA(h, cudaEventRecord(h->ev_vio_inputs, h->copy_stream));
+    h->vio_inputs_pending = true;
+    return FLB_OK;
+}
+// a kernel on `stream` is about to read the image / patches
+int vio_inputs_acquire(flb_handle* h) {
+    if (h->vio_inputs_pending) {
+        FLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_vio_inputs, 0));
+        h->vio_inputs_pending = false;
+    }
+    return FLB_OK;
+}
+int vio_inputs_release(flb_handle* h) {
+    FLB_CUDA(h, cudaEventRecord(h->ev_vio_done, h->stream));
+    h->vio_done_pending = true;
+    return FLB_OK;
+}
+
 int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_update: map and scan must be uploaded first");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_lio_update: no device state (flb_state_upload)");
@@ -464,6 +505,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     s.prm = d;
     s.p2p = h->p2p;
     s.timeout_flag = &h->barrier.p->timeout;
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
     const bool fused = h->p2p.world > 1;
     if (fused && !h->cfg.persistent)
         return fail(h, FLB_ERR_STATE, "the fused NVLink exchange lives in the persistent kernels (flb_config.persistent = 1)");
@@ -504,7 +546,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioBlock>, dim3(grid), dim3(kVioBlock), args, 0,
                                                 h->stream));
         h->last_vio_valid = false;
-        return FLB_OK;
+        return vio_inputs_release(h);
     }
     const int total = 3 * std::max(prm->max_iteration, 0);
     for (int it = 0; it < total && h->Pn > 0; ++it) {
@@ -531,7 +573,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         FLB_CUDA(h, cudaGetLastError());
     }
     h->last_vio_valid = false;
-    return FLB_OK;
+    return vio_inputs_release(h);
 }
 
 void fill_lio_report(const LioCtrl& c, flb_lio_report* rep) {
@@ -585,6 +627,13 @@ int flb_create(const flb_config* cfg, flb_handle** out) {
         return fail(nullptr, FLB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     h->stream = h->own_stream;
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_vio_inputs, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_vio_done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(h->own_stream);
+        delete h;
+        return fail(nullptr, FLB_ERR_CUDA, "copy stream / event creation failed");
+    }
     int rc = ensure_common(h);
     if (rc) {
         g_create_error = h->err;
@@ -616,6 +665,10 @@ int flb_destroy(flb_handle* h) {
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
+    cudaStreamSynchronize(h->copy_stream);
+    cudaEventDestroy(h->ev_vio_inputs);
+    cudaEventDestroy(h->ev_vio_done);
+    cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->own_stream);
     delete h;
     return FLB_OK;
@@ -630,7 +683,21 @@ int flb_set_stream(flb_handle* h, void* cuda_stream) {
 
 int flb_synchronize(flb_handle* h) {
     FLB_CHECK_H(h);
+    FLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+int flb_host_alloc(flb_handle* h, size_t bytes, void** out) {
+    FLB_CHECK_H(h);
+    if (!out || bytes == 0) return fail(h, FLB_ERR_INVALID, "flb_host_alloc: bad arguments");
+    FLB_CUDA(h, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return FLB_OK;
+}
+
+int flb_host_free(flb_handle* h, void* p) {
+    FLB_CHECK_H(h);
+    if (p) FLB_CUDA(h, cudaFreeHost(p));
     return FLB_OK;
 }
 
@@ -1157,13 +1224,20 @@ int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, 
     FLB_CHECK_H(h);
     if (!gray || width < 16 || height < 16 || stride < width) return fail(h, FLB_ERR_INVALID, "flb_image_upload: bad arguments");
     FLB_CUDA(h, h->img.reserve((size_t)width * height));
-    void* stv = nullptr;
-    FLB_CUDA(h, h->st_img.acquire((size_t)width * height, &stv));
-    unsigned char* st = static_cast<unsigned char*>(stv);
-    if (stride == width) std::memcpy(st, gray, (size_t)width * height);
-    else for (int r = 0; r < height; ++r) std::memcpy(st + (size_t)r * width, gray + (size_t)r * stride, width);
-    FLB_CUDA(h, cudaMemcpyAsync(h->img.p, st, (size_t)width * height, cudaMemcpyHostToDevice, h->stream));
-    FLB_CUDA(h, h->st_img.mark(h->stream));
+    const unsigned char* src = gray;
+    const bool direct = (stride == width) && is_pinned(gray);     // page-locked caller buffer: no staging copy
+    if (!direct) {
+        void* stv = nullptr;
+        FLB_CUDA(h, h->st_img.acquire((size_t)width * height, &stv));
+        unsigned char* st = static_cast<unsigned char*>(stv);
+        if (stride == width) std::memcpy(st, gray, (size_t)width * height);
+        else for (int r = 0; r < height; ++r) std::memcpy(st + (size_t)r * width, gray + (size_t)r * stride, width);
+        src = st;
+    }
+    { int rcq = vio_copy_begin(h); if (rcq) return rcq; }
+    FLB_CUDA(h, cudaMemcpyAsync(h->img.p, src, (size_t)width * height, cudaMemcpyHostToDevice, h->copy_stream));
+    if (!direct) FLB_CUDA(h, h->st_img.mark(h->copy_stream));
+    { int rcq = vio_copy_end(h); if (rcq) return rcq; }
     h->img_w = width;
     h->img_h = height;
     h->last_vio_valid = false;
@@ -1183,19 +1257,26 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     const int nb = (Pn + 7) / 8;
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)std::max(nb, 1) * kVioPacked, h->partials.cap)));
     const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int));
-    void* stv = nullptr;
-    FLB_CUDA(h, h->st_patch.acquire(bytes, &stv));
-    char* st = static_cast<char*>(stv);
     if (Pn > 0) {
-        std::memcpy(st, pos, (size_t)Pn * 3 * sizeof(double));
-        char* st2 = st + (size_t)Pn * 3 * sizeof(double);
-        std::memcpy(st2, patch, (size_t)Pn * 192 * sizeof(float));
-        char* st3 = st2 + (size_t)Pn * 192 * sizeof(float);
-        std::memcpy(st3, search_level, (size_t)Pn * sizeof(int));
-        FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, st, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, st2, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, st3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        FLB_CUDA(h, h->st_patch.mark(h->stream));
+        const void *st = pos, *st2 = patch, *st3 = search_level;
+        const bool direct = is_pinned(pos) && is_pinned(patch) && is_pinned(search_level);
+        if (!direct) {
+            void* stv = nullptr;
+            FLB_CUDA(h, h->st_patch.acquire(bytes, &stv));
+            char* b = static_cast<char*>(stv);
+            std::memcpy(b, pos, (size_t)Pn * 3 * sizeof(double));
+            char* b2 = b + (size_t)Pn * 3 * sizeof(double);
+            std::memcpy(b2, patch, (size_t)Pn * 192 * sizeof(float));
+            char* b3 = b2 + (size_t)Pn * 192 * sizeof(float);
+            std::memcpy(b3, search_level, (size_t)Pn * sizeof(int));
+            st = b; st2 = b2; st3 = b3;
+        }
+        { int rcq = vio_copy_begin(h); if (rcq) return rcq; }
+        FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, st, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, st2, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+        FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, st3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+        if (!direct) FLB_CUDA(h, h->st_patch.mark(h->copy_stream));
+        { int rcq = vio_copy_end(h); if (rcq) return rcq; }
     }
     if (h->comm) {
         // agree on the largest shard so every rank contributes an equal-size block to ncclAllGather;
@@ -1241,6 +1322,7 @@ int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], co
     if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
     std::memset(out, 0, sizeof(*out));
     if (h->Pn == 0) return FLB_OK;
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
     const size_t Pn = h->Pn;
     FLB_CUDA(h, h->x_z.reserve(Pn * 64));
     FLB_CUDA(h, h->x_H.reserve(Pn * 64 * 6));
@@ -1280,6 +1362,7 @@ int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], co
         k_reduce_only<<<1, 32, 0, h->stream>>>(h->partials.p, nb, kVioPacked, h->packed.p);
         FLB_CUDA(h, cudaGetLastError());
     }
+    { int rcq = vio_inputs_release(h); if (rcq) return rcq; }
     FLB_CUDA(h, h->pin_out.reserve(kVioPacked * sizeof(double) + Pn * sizeof(float)));
     double* po = static_cast<double*>(h->pin_out.p);
     float* pe = reinterpret_cast<float*>(po + kVioPacked);

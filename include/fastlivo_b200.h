@@ -19,6 +19,7 @@
 #ifndef FASTLIVO_B200_H
 #define FASTLIVO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -69,6 +70,13 @@ const char* flb_last_error(const flb_handle* h);   /* h may be NULL: last create
  * passed as void*), e.g. torch's current stream.  NULL restores the handle's own. */
 int         flb_set_stream(flb_handle* h, void* cuda_stream);
 int         flb_synchronize(flb_handle* h);
+/* Optional page-locked host buffers.  Upload calls detect page-locked sources (these, cudaHostAlloc or
+ * cudaHostRegister memory) and let the copy engine read them directly instead of staging through the
+ * handle's own pinned area; such a buffer must then stay unmodified until the next blocking call on the
+ * handle (flb_*_update, flb_*_pass, flb_synchronize) returns.  Pageable buffers keep the plain contract:
+ * free to reuse as soon as the upload call returns. */
+int         flb_host_alloc(flb_handle* h, size_t bytes, void** out);
+int         flb_host_free(flb_handle* h, void* p);
 
 /* ---- map: the query half of ikd-Tree -------------------------------------------
  * Replaces KD_TREE::Build (include/ikd-Tree/ikd_Tree.cpp:337-348, called at
