@@ -300,6 +300,7 @@ void to_dev_params(const flb_vio_params* p, VioParamsDev& d) {
     m3_mul(p->Rcl, Rli, d.Rci);
     m3_vec(p->Rcl, Pli, t);
     for (int i = 0; i < 3; ++i) d.Pci[i] = t[i] + p->Pcl[i];
+    vio_pose_constants(d.Rci, d.Pci, d.Jdphi_dR, d.Jdp_dR);
     d.sigma = p->img_point_cov;
     d.max_iteration = p->max_iteration;
     d.conv_rot_deg = p->conv_rot_deg;
@@ -454,6 +455,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         s.nblocks = grid;
         GridBarrier* bar = h->barrier.p;
         unsigned long long* trace = h->tracing ? h->trace.p : nullptr;
+        a.probe = h->tracing ? h->trace.p + 112 : nullptr;
         void* args[] = {&a, &s, &bar, &trace};
         LaunchScope ls(h, FAM_LIO_KNN);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,

@@ -461,15 +461,11 @@ struct VioPose {
     double Jdp_dR[9];        // = -Rci * [Pic]x
 };
 
-FLB_HD void vio_make_pose(const double* Rci, const double* Pci, const double* R, const double* p, VioPose& o) {
-    double Rt[9], t[3];
-    m3_T(R, Rt);
-    m3_mul(Rci, Rt, o.Rcw);
-    m3_vec(o.Rcw, p, t);
+// State-independent part (LidarSelector::init(), src/lidar_selection.cpp:44-52): Jdphi_dR = Rci,
+// Jdp_dR = -Rci * [Pic]x with Pic = -Rci^T * Pci.  Computed once per update on the host.
+FLB_HD void vio_pose_constants(const double* Rci, const double* Pci, double* Jdphi_dR, double* Jdp_dR) {
     FLB_UNROLL
-    for (int i = 0; i < 3; ++i) o.Pcw[i] = -t[i] + Pci[i];
-    FLB_UNROLL
-    for (int i = 0; i < 9; ++i) { o.Jdp_dt[i] = o.Rcw[i]; o.Jdphi_dR[i] = Rci[i]; }
+    for (int i = 0; i < 9; ++i) Jdphi_dR[i] = Rci[i];
     double RciT[9], Pic[3], sk[9], m[9];
     m3_T(Rci, RciT);
     m3_vec(RciT, Pci, Pic);
@@ -478,7 +474,20 @@ FLB_HD void vio_make_pose(const double* Rci, const double* Pci, const double* R,
     skew3(Pic, sk);
     m3_mul(Rci, sk, m);
     FLB_UNROLL
-    for (int i = 0; i < 9; ++i) o.Jdp_dR[i] = -m[i];
+    for (int i = 0; i < 9; ++i) Jdp_dR[i] = -m[i];
+}
+
+// State-dependent part, once per pass (src/lidar_selection.cpp:780-782).
+FLB_HD void vio_make_pose(const double* Rci, const double* Pci, const double* Jdphi_dR, const double* Jdp_dR, const double* R,
+                          const double* p, VioPose& o) {
+    double Rt[9], t[3];
+    m3_T(R, Rt);
+    m3_mul(Rci, Rt, o.Rcw);
+    m3_vec(o.Rcw, p, t);
+    FLB_UNROLL
+    for (int i = 0; i < 3; ++i) o.Pcw[i] = -t[i] + Pci[i];
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) { o.Jdp_dt[i] = o.Rcw[i]; o.Jdphi_dR[i] = Jdphi_dR[i]; o.Jdp_dR[i] = Jdp_dR[i]; }
 }
 
 // vikit PinholeCamera::world2cam(Vector3d).

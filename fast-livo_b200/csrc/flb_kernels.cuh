@@ -57,6 +57,7 @@ struct LioParamsDev {
 
 struct VioParamsDev {
     double Rci[9], Pci[3];
+    double Jdphi_dR[9], Jdp_dR[9];   // state-independent Jacobian factors (LidarSelector::init)
     double sigma;
     int max_iteration;
     float conv_rot_deg, conv_pos_cm;
@@ -84,6 +85,37 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Transposing butterfly reduction of up to 32 per-lane accumulators: after 5 exchange steps lane l holds
+// the warp-wide total of accumulator l.  31 double shuffles instead of 5 per accumulator (K = 29: 145);
+// fixed tree => deterministic.
+template <int N, int S>
+struct ButterflyStep {
+    static __device__ __forceinline__ void run(double (&v)[32], int lane) {
+        constexpr int H = N / 2;
+        const bool up = (lane & S) != 0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const double keep = up ? v[j + H] : v[j];
+            const double send = up ? v[j] : v[j + H];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+        }
+        ButterflyStep<H, S / 2>::run(v, lane);
+    }
+};
+template <int N>
+struct ButterflyStep<N, 0> {
+    static __device__ __forceinline__ void run(double (&)[32], int) {}
+};
+template <int K>
+__device__ __forceinline__ double warp_transpose_reduce(const double (&acc)[K]) {
+    static_assert(K <= 32, "at most 32 accumulators");
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (i < K) ? acc[i] : 0.0;
+    ButterflyStep<32, 16>::run(v, threadIdx.x & 31);
+    return v[0];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -323,6 +355,7 @@ struct LioArgs {
     unsigned char* x_rowmask;    // N
     double* x_rows;              // N*W
     double* x_meas;              // N
+    unsigned long long* probe;   // profiling aid: stage timestamps of one thread (or null)
 };
 
 template <int W>
@@ -340,9 +373,12 @@ __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose,
     bool sel;
     bool pok;
     float pabcd[4];
+    const bool probe = a.probe && i == a.N / 2;
+    if (probe) a.probe[0] = global_ns();
     if (rematch) {
         Top5 t;
         knn5_grid(a.grid, a.cell_start, a.map_pts, pw[0], pw[1], pw[2], t);
+        if (probe) a.probe[1] = global_ns();
         const bool five = t.i[kMatch - 1] >= 0;
         sel = five && !(t.d[kMatch - 1] > a.grid.max_d2);     // src/laserMapping.cpp:1549 (+ :1567 size check)
         pok = false;
@@ -361,6 +397,7 @@ __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose,
         }
         pabcd[0] = pabcd[1] = pabcd[2] = pabcd[3] = 0.f;
         if (sel) pok = plane_fit5(nb, a.plane_thr, pabcd);     // :1571
+        if (probe) a.probe[2] = global_ns();
         a.plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
         a.plane_ok[i] = pok ? 1 : 0;
         if (a.x_nn_idx) {
@@ -392,6 +429,7 @@ __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose,
         z = -(double)pd2;                                      // :1628
         absres = (double)fabsf(pd2);
     }
+    if (probe) a.probe[3] = global_ns();
     if (a.x_world) {
         a.x_world[3 * (size_t)oi] = pw[0]; a.x_world[3 * (size_t)oi + 1] = pw[1]; a.x_world[3 * (size_t)oi + 2] = pw[2];
 #pragma unroll
@@ -420,10 +458,15 @@ template <int K, int BLOCK>
 __device__ __forceinline__ void block_reduce_store(const double (&acc)[K], double (*s_acc)[K], double* partials) {
     constexpr int NW = BLOCK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (K <= 32) {
+        const double v = warp_transpose_reduce<K>(acc);
+        if (lane < K) s_acc[warp][lane] = v;
+    } else {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) s_acc[warp][k] = v;
+        for (int k = 0; k < K; ++k) {
+            const double v = warp_sum(acc[k]);
+            if (lane == 0) s_acc[warp][k] = v;
+        }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < K; q += BLOCK) {
@@ -588,7 +631,7 @@ __device__ __forceinline__ void vio_make_pose_from(const VioArgs& a, VioPose& po
     double R[9], p[3];
     for (int i = 0; i < 9; ++i) R[i] = through_l2 ? __ldcg(Rg + i) : Rg[i];
     for (int i = 0; i < 3; ++i) p[i] = through_l2 ? __ldcg(pg + i) : pg[i];
-    vio_make_pose(a.prm.Rci, a.prm.Pci, R, p, pose);
+    vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, R, p, pose);
 }
 
 template <int BLOCK>
@@ -596,12 +639,9 @@ __device__ __forceinline__ void vio_block_reduce_store(const double (&acc)[27], 
                                                        double (*s_acc)[kVioPacked], double* partials) {
     constexpr int NW = BLOCK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) s_acc[warp][k] = v;
-    }
-    if (lane == 0) { s_acc[warp][27] = n_meas; s_acc[warp][28] = skipped; }
+    const double v = warp_transpose_reduce<27>(acc);
+    if (lane < 27) s_acc[warp][lane] = v;
+    if (lane == 0) { s_acc[warp][27] = n_meas; s_acc[warp][28] = skipped; }   // only lane 0 counts patches
     __syncthreads();
     for (int q = threadIdx.x; q < kVioPacked; q += BLOCK) {
         double s = 0.0;

@@ -73,7 +73,9 @@ void emu_vio(const double* camv, const double* Rci, const double* Pci, const dou
     cam.jfx = fabs(cam.fx);
     cam.jfy = fabs(4.0 * cam.fx * cam.fy) / (4. * cam.jfx);
     VioPose vp;
-    vio_make_pose(Rci, Pci, R, p, vp);
+    double Jdphi_dR[9], Jdp_dR[9];
+    vio_pose_constants(Rci, Pci, Jdphi_dR, Jdp_dR);
+    vio_make_pose(Rci, Pci, Jdphi_dR, Jdp_dR, R, p, vp);
     for (int i = 0; i < Pn; ++i) {
         PatchGeom g;
         vio_patch_geom(cam, vp, pos + 3 * i, level, search_level[i], g);
