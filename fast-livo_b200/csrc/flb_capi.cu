@@ -196,6 +196,7 @@ struct flb_handle {
     DevBuf<VioCtrl> vio_ctrl;
     DevBuf<GridBarrier> barrier; // grid barrier of the persistent kernels
     DevBuf<unsigned long long> trace;  // [0..kTraceLen) LIO, [kTraceLen..2*kTraceLen) VIO
+    DevBuf<unsigned long long> dbg;    // per-block stage stamps of the last LIO pass (tracing only)
     bool tracing = false;
     int num_sms = 0;
     int occ_lio = 0, occ_vio = 0;
@@ -456,7 +457,12 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         GridBarrier* bar = h->barrier.p;
         unsigned long long* trace = h->tracing ? h->trace.p : nullptr;
         a.probe = h->tracing ? h->trace.p + 112 : nullptr;
-        void* args[] = {&a, &s, &bar, &trace};
+        unsigned long long* dbg = nullptr;
+        if (h->tracing) {
+            FLB_CUDA(h, h->dbg.reserve((size_t)grid * 8));
+            dbg = h->dbg.p;
+        }
+        void* args[] = {&a, &s, &bar, &trace, &dbg};
         LaunchScope ls(h, FAM_LIO_KNN);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,
                                                 h->stream));
@@ -663,7 +669,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->trace.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->trace.release(); h->dbg.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
@@ -1449,6 +1455,15 @@ int flb_trace_enable(flb_handle* h, int on) {
     FLB_CHECK_H(h);
     h->tracing = on != 0;
     FLB_CUDA(h, cudaMemsetAsync(h->trace.p, 0, 2 * kTraceLen * sizeof(unsigned long long), h->stream));
+    return FLB_OK;
+}
+
+int flb_debug_block_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks) {
+    FLB_CHECK_H(h);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int n = (int)std::min<size_t>(h->dbg.cap / 8, (size_t)max_blocks);
+    if (n > 0) FLB_CUDA(h, cudaMemcpy(out, h->dbg.p, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *nblocks = n;
     return FLB_OK;
 }
 

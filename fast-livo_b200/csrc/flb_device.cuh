@@ -382,7 +382,9 @@ FLB_HD void knn_scan_run(const map_pt* __restrict__ pts, int s, int e, float qx,
 // x-rows whose 18 cell-table entries are fetched up front (independent loads: one memory round
 // trip instead of nine dependent ones); farther rings use the generic shell walk.
 FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, const map_pt* __restrict__ pts,
-                      float qx, float qy, float qz, Top5& t) {
+                      float qx, float qy, float qz, Top5& t, int* rows, int rstride) {
+    // rows: per-thread scratch for 18 ints, element k at rows[k * rstride] (shared memory on the device,
+    // one column per thread, so a warp's accesses are conflict-free)
     top5_init(t);
     const float fx = (qx - g.ox) * g.inv_cell, fy = (qy - g.oy) * g.inv_cell, fz = (qz - g.oz) * g.inv_cell;
     // far outside the grid: nothing within sqrt(max_d2)
@@ -396,19 +398,39 @@ FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, con
     float mz = fminf(fz - (float)cz, (float)(cz + 1) - fz);
     const float margin = fmaxf(fminf(mx, fminf(my, mz)) * g.cell - 1e-3f * g.cell, 0.f);
     {
-        // rings 0+1: rows (dz, dy) in {-1,0,1}^2, x-range [cx-1, cx+1] clipped to the grid
+        // rings 0+1: rows (dz, dy) in {-1,0,1}^2, x-range [cx-1, cx+1] clipped to the grid.  All 18
+        // cell-table entries are fetched up front (independent loads).
         const int xa = cx - 1 < 0 ? 0 : cx - 1, xb = cx + 1 >= g.nx ? g.nx - 1 : cx + 1;
-        int rs[9], re[9];
         FLB_UNROLL
         for (int k = 0; k < 9; ++k) {
             const int z = cz + k / 3 - 1, y = cy + k % 3 - 1;
             const bool in = (z >= 0 && z < g.nz && y >= 0 && y < g.ny && xa <= xb);
             const int rowbase = in ? (z * g.ny + y) * g.nx : 0;
-            rs[k] = in ? FLB_LDGI(cell_start + rowbase + xa) : 0;
-            re[k] = in ? FLB_LDGI(cell_start + rowbase + xb + 1) : 0;
+            rows[k * rstride] = in ? FLB_LDGI(cell_start + rowbase + xa) : 0;
+            rows[(9 + k) * rstride] = in ? FLB_LDGI(cell_start + rowbase + xb + 1) : 0;
         }
-        FLB_UNROLL
-        for (int k = 0; k < 9; ++k) knn_scan_run(pts, rs[k], re[k], qx, qy, qz, t);
+        // Walk the nine runs as ONE sequence, up to four points (independent 16-B loads) per step, in
+        // row order then index order.  A lane's trip count is its own candidate count / 4, so lanes whose
+        // non-empty rows differ (sparse, far-range chunks) no longer wait on each other row by row.
+        int k = -1, m = 0, e = 0;
+        for (;;) {
+            while (m >= e) {
+                if (++k >= 9) break;
+                m = rows[k * rstride];
+                e = rows[(9 + k) * rstride];
+            }
+            if (k >= 9) break;
+            const int n = e - m;
+            const map_pt P0 = FLB_LDG4(pts + m);
+            const map_pt P1 = FLB_LDG4(pts + (n > 1 ? m + 1 : m));
+            const map_pt P2 = FLB_LDG4(pts + (n > 2 ? m + 2 : m));
+            const map_pt P3 = FLB_LDG4(pts + (n > 3 ? m + 3 : m));
+            top5_insert(t, dist2f(qx, qy, qz, P0.x, P0.y, P0.z), m);
+            if (n > 1) top5_insert(t, dist2f(qx, qy, qz, P1.x, P1.y, P1.z), m + 1);
+            if (n > 2) top5_insert(t, dist2f(qx, qy, qz, P2.x, P2.y, P2.z), m + 2);
+            if (n > 3) top5_insert(t, dist2f(qx, qy, qz, P3.x, P3.y, P3.z), m + 3);
+            m += (n > 4 ? 4 : n);
+        }
         const float bound = g.cell + margin;
         const float b2 = bound * bound;
         if (t.d[4] <= b2) return;                 // 5th best is certainly final

@@ -311,10 +311,11 @@ __global__ void k_scan_gather(const float* __restrict__ xyz, int N, const int* _
 // ---------------------------------------------------------------------------------------
 __global__ void k_knn(GridDesc g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
                       const float* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+    __shared__ int s_rows[18][128];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     Top5 t;
-    knn5_grid(g, cell_start, pts, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], t);
+    knn5_grid(g, cell_start, pts, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], t, &s_rows[0][threadIdx.x], 128);
 #pragma unroll
     for (int j = 0; j < kMatch; ++j) {
         const bool ok = (t.i[j] >= 0) && !(t.d[j] > g.max_d2);
@@ -360,7 +361,7 @@ struct LioArgs {
 
 template <int W>
 __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose, bool rematch, int i, bool& active,
-                                          double (&row)[W], double& z, double& absres) {
+                                          double (&row)[W], double& z, double& absres, int* rows, int rstride) {
     active = false;
     z = 0.0;
     absres = 0.0;
@@ -377,7 +378,7 @@ __device__ __forceinline__ void lio_point(const LioArgs& a, const LioPose& pose,
     if (probe) a.probe[0] = global_ns();
     if (rematch) {
         Top5 t;
-        knn5_grid(a.grid, a.cell_start, a.map_pts, pw[0], pw[1], pw[2], t);
+        knn5_grid(a.grid, a.cell_start, a.map_pts, pw[0], pw[1], pw[2], t, rows, rstride);
         if (probe) a.probe[1] = global_ns();
         const bool five = t.i[kMatch - 1] >= 0;
         sel = five && !(t.d[kMatch - 1] > a.grid.max_d2);     // src/laserMapping.cpp:1549 (+ :1567 size check)
@@ -497,6 +498,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) {
     constexpr int K = lio_packed(W);
     __shared__ LioPose s_pose;
     __shared__ double s_acc[BLOCK / 32][K];
+    __shared__ int s_rows[18][BLOCK];
     int rematch;
     if (a.force_rematch >= 0) {
         rematch = a.force_rematch;
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) {
     if (i < a.N) {
         bool active;
         double row[W], z, absres;
-        lio_point<W>(a, s_pose, rematch != 0, i, active, row, z, absres);
+        lio_point<W>(a, s_pose, rematch != 0, i, active, row, z, absres, &s_rows[0][threadIdx.x], BLOCK);
         if (active) lio_accumulate<W>(acc, row, z, absres);
     }
     block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
@@ -1366,12 +1368,13 @@ __device__ __forceinline__ bool grid_wait(GridBarrier* b, const unsigned* s_scra
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar,
-                                                                 unsigned long long* trace) {
+                                                                 unsigned long long* trace, unsigned long long* dbg) {
     constexpr int K = lio_packed(6);
     __shared__ LioPose s_pose;
     __shared__ double s_acc[BLOCK / 32][K];
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
+    __shared__ int s_rows[18][BLOCK];
     const int tid = threadIdx.x;
     // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
     int iterCount = -1, rematch_num = 0, nearest = 1;
@@ -1379,8 +1382,10 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
     for (;;) {
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = global_ns();
         if (tid == 0) lio_make_pose(a, s_pose, true);
         __syncthreads();
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 1] = global_ns();
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
@@ -1392,12 +1397,15 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
             if (i < a.N) {
                 bool active;
                 double row[6], z, absres;
-                lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres);
+                lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres, &s_rows[0][tid], BLOCK);
                 if (active) lio_accumulate<6>(acc, row, z, absres);
             }
         }
+        if (dbg && (tid & 31) == 0) dbg[blockIdx.x * 8 + 4 + (tid >> 5)] = global_ns();   // per warp: compute done
         block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 2] = global_ns();
         const bool leader = grid_arrive(bar, gridDim.x, s_bar);
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 3] = global_ns();
         if (leader) {
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             lio_leader<BLOCK>(s, sm, first, iterCount, rematch_num, nearest,
@@ -1802,6 +1810,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_ikfom_persistent(LioArgs a
     __shared__ double s_acc[BLOCK / 32][K];
     __shared__ unsigned s_bar[2];
     __shared__ IkLeaderSmem sm;
+    __shared__ int s_rows[18][BLOCK];
     const int tid = threadIdx.x;
     int it = -1, tcount = 0, converge = 1;     // esekfom.hpp:1622-1624, :1633
     bool first = true;
@@ -1816,7 +1825,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_ikfom_persistent(LioArgs a
             if (i < a.N) {
                 bool active;
                 double row[12], z, absres;
-                lio_point<12>(a, s_pose, converge != 0, i, active, row, z, absres);   // converge => redo kNN (:994)
+                lio_point<12>(a, s_pose, converge != 0, i, active, row, z, absres, &s_rows[0][tid], BLOCK);   // converge => redo kNN (:994)
                 if (active) lio_accumulate<12>(acc, row, z, absres);
             }
         }

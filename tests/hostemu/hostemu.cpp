@@ -52,7 +52,8 @@ void emu_knn(const float* gridf /*ox,oy,oz,cell,inv_cell,max_d2*/, const int* gr
     const map_pt* pts = reinterpret_cast<const map_pt*>(pts4);
     for (int i = 0; i < nq; ++i) {
         Top5 t;
-        knn5_grid(g, cell_start, pts, q[3 * i], q[3 * i + 1], q[3 * i + 2], t);
+        int rows[18];
+        knn5_grid(g, cell_start, pts, q[3 * i], q[3 * i + 1], q[3 * i + 2], t, rows, 1);
         for (int j = 0; j < kMatch; ++j) { pos[5 * i + j] = t.i[j]; d2[5 * i + j] = t.d[j]; }
     }
 }
