@@ -195,6 +195,8 @@ struct flb_handle {
     DevBuf<LioCtrl> lio_ctrl;
     DevBuf<VioCtrl> vio_ctrl;
     DevBuf<GridBarrier> barrier; // grid barrier of the persistent kernels
+    DevBuf<unsigned long long> pkt;    // pose packet of the persistent kernels (kPktUnits flagged words)
+    unsigned pkt_epoch = 0;            // flag base of the next launch (flags are never reused, see next_epoch)
     DevBuf<unsigned long long> trace;  // [0..kTraceLen) LIO, [kTraceLen..2*kTraceLen) VIO
     DevBuf<unsigned long long> dbg;    // per-block stage stamps of the last LIO pass (tracing only)
     bool tracing = false;
@@ -324,6 +326,8 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, h->trace.reserve(2 * kTraceLen));
     FLB_CUDA(h, cudaMemset(h->trace.p, 0, 2 * kTraceLen * sizeof(unsigned long long)));
     FLB_CUDA(h, cudaMemset(h->barrier.p, 0, sizeof(GridBarrier)));
+    FLB_CUDA(h, h->pkt.reserve(kPktUnits));
+    FLB_CUDA(h, cudaMemset(h->pkt.p, 0, kPktUnits * sizeof(unsigned long long)));
     FLB_CUDA(h, cudaMemset(h->lio_ctrl.p, 0, sizeof(LioCtrl)));
     FLB_CUDA(h, cudaMemset(h->vio_ctrl.p, 0, sizeof(VioCtrl)));
     FLB_CUDA(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -425,10 +429,22 @@ int vio_inputs_release(flb_handle* h) {
     return FLB_OK;
 }
 
+// Flag base for one persistent launch: flags epoch+1 .. epoch+4095 belong to it alone.  On wrap-around the
+// packet is cleared (stream-ordered) so that no stale unit can ever match.
+int next_epoch(flb_handle* h, unsigned* epoch) {
+    if (h->pkt_epoch >= 0xFFFF0000u || h->pkt_epoch == 0) {
+        if (h->pkt_epoch) FLB_CUDA(h, cudaMemsetAsync(h->pkt.p, 0, kPktUnits * sizeof(unsigned long long), h->stream));
+        h->pkt_epoch = 4096;
+    }
+    *epoch = h->pkt_epoch;
+    h->pkt_epoch += 4096;
+    return FLB_OK;
+}
+
 int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_update: map and scan must be uploaded first");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_lio_update: no device state (flb_state_upload)");
-    if (prm->max_iteration < 0) return fail(h, FLB_ERR_INVALID, "max_iteration < 0");
+    if (prm->max_iteration < 0 || prm->max_iteration > 1000) return fail(h, FLB_ERR_INVALID, "max_iteration outside [0, 1000]");
     if (h->p2p.world > 1 && !h->cfg.persistent)
         return fail(h, FLB_ERR_STATE, "the fused NVLink exchange lives in the persistent kernels (flb_config.persistent = 1)");
     LioParamsDev d;
@@ -462,7 +478,10 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
             FLB_CUDA(h, h->dbg.reserve((size_t)grid * 8));
             dbg = h->dbg.p;
         }
-        void* args[] = {&a, &s, &bar, &trace, &dbg};
+        unsigned long long* pkt = h->pkt.p;
+        unsigned epoch = 0;
+        { int rce = next_epoch(h, &epoch); if (rce) return rce; }
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg};
         LaunchScope ls(h, FAM_LIO_KNN);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,
                                                 h->stream));
@@ -497,6 +516,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
 int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update: camera and image must be set first");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_vio_update: no device state (flb_state_upload)");
+    if (prm->max_iteration > 1000) return fail(h, FLB_ERR_INVALID, "max_iteration outside [0, 1000]");
     VioParamsDev d;
     to_dev_params(prm, d);
     VioSolveArgs s{};
@@ -549,7 +569,10 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         s.nblocks = grid;
         GridBarrier* bar = h->barrier.p;
         unsigned long long* trace = h->tracing ? h->trace.p + kTraceLen : nullptr;
-        void* args[] = {&a, &s, &bar, &trace};
+        unsigned long long* pkt = h->pkt.p;
+        unsigned epoch = 0;
+        { int rce = next_epoch(h, &epoch); if (rce) return rce; }
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace};
         LaunchScope ls(h, FAM_VIO);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioBlock>, dim3(grid), dim3(kVioBlock), args, 0,
                                                 h->stream));
@@ -669,7 +692,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->trace.release(); h->dbg.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();

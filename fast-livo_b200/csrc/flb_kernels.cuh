@@ -703,6 +703,7 @@ struct LeaderSmem {
     double HTH[36], HTz[6];
     double K[kDim * 6];       // K1[:, :6]
     double vec[kDim], sol[kDim], Gc[kDim * 6];
+    double xold[24];          // VIO: the pose/bias block before the accepted step (old_state, :863)
     double top[6 * kDim];
     double packed[32];
     double part[8][32];
@@ -863,23 +864,26 @@ __device__ __forceinline__ void leader_prior(LeaderSmem& sm, PriorBlock* out, in
     for (int e = tid; e < (int)(sizeof(PriorBlock) / sizeof(double)); e += TeamT::size) dst[e] = src[e];
 }
 
-template <class TeamT>
-__device__ __forceinline__ void leader_load_prior(LeaderSmem& sm, const PriorBlock* in, int tid) {
-    const double* src = reinterpret_cast<const double*>(in);
-    double* dst = reinterpret_cast<double*>(&sm.prior);
-    for (int e = tid; e < (int)(sizeof(PriorBlock) / sizeof(double)); e += TeamT::size) dst[e] = __ldcg(src + e);
+// Later leaders: fetch the prior block (one double per thread, tid < 108) into a register early and
+// commit it to shared memory once the reduction is done, so the L2 round trip hides behind it.
+constexpr int kPriorDoubles = (int)(sizeof(PriorBlock) / sizeof(double));
+__device__ __forceinline__ double prior_prefetch(const PriorBlock* in, int tid) {
+    return (tid < kPriorDoubles) ? __ldcg(reinterpret_cast<const double*>(in) + tid) : 0.0;
+}
+__device__ __forceinline__ void prior_commit(LeaderSmem& sm, double v, int tid) {
+    if (tid < kPriorDoubles) reinterpret_cast<double*>(&sm.prior)[tid] = v;
 }
 
 // The per-pass step, executed by the team (tid < TeamT::size).  Requires sm.x, sm.xp, sm.HTH,
-// sm.HTz; computes / loads the prior block, then sm.K, sm.Gc, sm.sol.  sm.flags[3] != 0 afterwards
+// sm.HTz and, when !first, sm.prior (prior_prefetch/prior_commit); computes sm.K, sm.Gc, sm.sol.  sm.flags[3] != 0 afterwards
 // means a singular system.
 template <class TeamT>
 __device__ __forceinline__ void leader_step(LeaderSmem& sm, PriorBlock* prior_g, bool first, double sigma, double sign,
                                             int tid) {
     if (tid == TeamT::size - 1) state_boxminus(sm.xp, sm.x, sm.vec);  // vec = state_propagat - state
     if (tid == 0) sm.flags[3] = 0;
+    static_assert(TeamT::size >= kPriorDoubles, "team too small for the prior prefetch");
     if (first) leader_prior<TeamT>(sm, prior_g, tid);
-    else leader_load_prior<TeamT>(sm, prior_g, tid);
     TeamT::sync();
     if (tid < 72) {
         const int i = tid / 12, j = tid - i * 12;
@@ -1021,20 +1025,24 @@ struct LioSolveArgs {
     int* timeout_flag;       // GridBarrier::timeout
 };
 
-// One LIO leader step (whole block, NT threads).  `first`: first pass of this update.  Loop state
-// comes in by value (block-local mirrors in the persistent kernel, ctrl in the per-pass path).
+// One LIO leader step (whole block, NT threads), in two halves so that the persistent kernel can
+// publish the new pose between them.  Requires the 24 pose/bias doubles of sm.x and sm.xp and the
+// control block `c` (shared memory) to be current; `first`: first pass of this update.
+//   lio_leader_solve : reduce -> [exchange] -> solve -> state (+)= solution -> loop control (c)
+//   lio_leader_finish: covariance update on the stopping pass; stores what later launches / the host need
 #define FLB_STAMP(k) do { if (fine && threadIdx.x == 0) fine[k] = global_ns(); } while (0)
 template <int NT>
-__device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm, bool first, int iterCount, int rematch_num,
-                                           int nearest, unsigned long long* fine = nullptr) {
+__device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSmem& sm, LioCtrl& c, bool first,
+                                                 unsigned long long* fine = nullptr) {
     constexpr int K = lio_packed(6);
     const int tid = threadIdx.x;
     const int T = s.prm.max_iteration;
-    load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
-    __syncthreads();
+    // later leaders fetch the prior block while the partials are being reduced
+    const double pri = first ? 0.0 : prior_prefetch(s.prior, tid);
     FLB_STAMP(0);
     leader_reduce<K, NT>(s.partials, s.nblocks, sm, tid);
+    if (!first) prior_commit(sm, pri, tid);
     if (s.p2p.world > 1) p2p_exchange<K, Team<NT, false>>(s.p2p, sm, nullptr, 0, tid, s.timeout_flag);
     FLB_STAMP(1);
     if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
@@ -1044,16 +1052,11 @@ __device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm
     __syncthreads();
     FLB_STAMP(2);
     if (tid == 0) {
-        LioCtrl c;
+        const int iterCount = c.iterCount, rematch_num = c.rematch_num, nearest = c.nearest_search_en;
         if (first) {
             c.passes = c.knn_passes = 0;
             c.rows_total = 0;
             c.status = 0;
-        } else {
-            c.passes = __ldcg(&s.ctrl->passes);
-            c.knn_passes = __ldcg(&s.ctrl->knn_passes);
-            c.rows_total = __ldcg(&s.ctrl->rows_total);
-            c.status = __ldcg(&s.ctrl->status);
         }
         const int n_eff = (int)sm.packed[K - 2];
         c.passes += 1;
@@ -1075,18 +1078,28 @@ __device__ __forceinline__ void lio_leader(const LioSolveArgs& s, LeaderSmem& sm
         c.rematch_num = rn;
         c.nearest_search_en = nn;
         c.stop = stop;
-        *s.ctrl = c;
         sm.flags[0] = stop;
         sm.flags[1] = ok ? 1 : 0;
     }
     __syncthreads();
     FLB_STAMP(3);
-    const bool do_cov = sm.flags[0] && sm.flags[1];
+}
+
+// `store_always`: kernel-per-pass path (state and control live in global memory between launches).
+template <int NT>
+__device__ __forceinline__ void lio_leader_finish(const LioSolveArgs& s, LeaderSmem& sm, const LioCtrl& c, bool first,
+                                                  bool store_always, unsigned long long* fine = nullptr) {
+    const int tid = threadIdx.x;
+    const bool stop = sm.flags[0] != 0;
+    const bool do_cov = stop && sm.flags[1];
     if (do_cov) {
         if (!first) { load_cov_l2<NT>(&sm.x, s.state, tid); __syncthreads(); }
         leader_cov_update(sm, sm.Gc, tid, NT);                                          // :1715
     }
-    store_state(s.state, &sm.x, tid, NT, do_cov);
+    if (stop || store_always) {
+        store_state(s.state, &sm.x, tid, NT, do_cov);
+        if (tid == 0) *s.ctrl = c;
+    }
     FLB_STAMP(4);
 }
 
@@ -1107,11 +1120,15 @@ __global__ void __launch_bounds__(32) k_lio_begin(LioCtrl* ctrl) {
 
 __global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize(LioSolveArgs s) {
     __shared__ LeaderSmem sm;
+    __shared__ LioCtrl c;
     if (s.ctrl->stop) return;
-    const int passes = s.ctrl->passes, iterCount = s.ctrl->iterCount, rematch_num = s.ctrl->rematch_num,
-              nearest = s.ctrl->nearest_search_en;
+    const int tid = threadIdx.x;
+    if (tid == 0) c = *s.ctrl;
+    load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     __syncthreads();
-    lio_leader<kLeaderBlock>(s, sm, passes == 0, iterCount, rematch_num, nearest);
+    const bool first = c.passes == 0;
+    lio_leader_solve<kLeaderBlock>(s, sm, c, first);
+    lio_leader_finish<kLeaderBlock>(s, sm, c, first, true);
 }
 
 struct VioSolveArgs {
@@ -1132,11 +1149,14 @@ struct VioSolveArgs {
 
 constexpr int kErrChunk = 2048;
 
-// One VIO leader step (whole block, NT threads); `level` = pyramid level of the pass just done.
+// One VIO leader step (whole block, NT threads), in two halves like the LIO one.  Requires the 24
+// pose/bias doubles of sm.x / sm.xp and the control block `c` (shared memory); c.level is the pyramid
+// level of the pass just done.
 template <int NT>
-__device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm, float* s_err, bool first, int level) {
+__device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first) {
     const int tid = threadIdx.x;
     const bool multi = s.p2p.world > 1;
+    const int level = c.level;
     // Stage the (first chunk of) per-patch errors with the whole block -- one coalesced L2 round trip.
     // (Fused multi-GPU mode: the errors of ALL ranks arrive with the exchange instead.)
     if (!multi)
@@ -1179,11 +1199,11 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
         // Solve team (first NT-32 threads, named barrier 1).  The covariance is constant during ComputeJ
         // (only :980 changes it, on the last pass), so old_state carries the 24 pose/bias doubles only.
         using T = Team<NT - 32, true>;
-        load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
         if (first) load_cov_l2<NT - 32>(&sm.x, s.state, tid);
-        T::sync();
+        const double pri = first ? 0.0 : prior_prefetch(s.prior, tid);
         if (first) store_state(s.old_state, &sm.x, tid, NT - 32, false);                 // old_state = *state (:747)
         team_reduce<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
+        if (!first) prior_commit(sm, pri, tid);
         if (multi) {
             const int par = p2p_exchange<kVioPacked, T>(s.p2p, sm, s.errors, s.Pn_total, tid, s.timeout_flag);
             if (tid == 0) sm.p2p_par = par;
@@ -1196,17 +1216,11 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
     __syncthreads();
     const bool ok = sm.flags[3] == 0;
     if (tid == 0) {
-        VioCtrl c;
         if (first) {
             c.level = 2; c.iteration = 0; c.stop = 0;
             c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;                   // :971
             for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
             c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
-        } else {
-            const int* src = reinterpret_cast<const int*>(s.ctrl);
-            int* dst = reinterpret_cast<int*>(&c);
-#pragma unroll
-            for (int e = 0; e < (int)(sizeof(VioCtrl) / sizeof(int)); ++e) dst[e] = __ldcg(src + e);
         }
         const long long nm = (long long)sm.packed[27];
         const float error = sm.error / (float)(unsigned long long)nm;                      // :857
@@ -1241,22 +1255,29 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
                 if (c.now_error < 1e10f && ok) { docov = 1; c.cov_updated = 1; }           // :978-981
             }
         }
-        *s.ctrl = c;
         sm.flags[0] = accept;
         sm.flags[1] = docov;
         sm.flags[2] = newlevel;
     }
     __syncthreads();
-    const int accept = sm.flags[0], docov = sm.flags[1], newlevel = sm.flags[2];
-    if (accept) {
-        store_state(s.old_state, &sm.x, tid, NT, false);                                   // old_state = *state (:863)
-        for (int e = tid; e < kDim * 6; e += NT) s.G_last[e] = sm.Gc[e];
+    if (sm.flags[0]) {
+        if (tid < 24) sm.xold[tid] = reinterpret_cast<const double*>(&sm.x)[tid];          // old_state = *state (:863)
         __syncthreads();
         if (tid == 0) state_boxplus(sm.x, sm.sol);                                         // :879
-        __syncthreads();
     } else {
         if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(reinterpret_cast<const double*>(s.old_state) + tid);
-        __syncthreads();                                                                   // *state = old_state (:890)
+    }                                                                                      // *state = old_state (:890)
+    __syncthreads();
+}
+
+template <int NT>
+__device__ __forceinline__ void vio_leader_finish(const VioSolveArgs& s, LeaderSmem& sm, const VioCtrl& c, bool first,
+                                                  bool store_always) {
+    const int tid = threadIdx.x;
+    const int accept = sm.flags[0], docov = sm.flags[1], newlevel = sm.flags[2];
+    if (accept) {
+        if (tid < 24) reinterpret_cast<double*>(s.old_state)[tid] = sm.xold[tid];
+        for (int e = tid; e < kDim * 6; e += NT) s.G_last[e] = sm.Gc[e];
     }
     if (docov) {
         if (!accept) {
@@ -1266,8 +1287,11 @@ __device__ __forceinline__ void vio_leader(const VioSolveArgs& s, LeaderSmem& sm
         if (!first) { load_cov_l2<NT>(&sm.x, s.state, tid); __syncthreads(); }
         leader_cov_update(sm, sm.Gc, tid, NT);                                             // :980
     }
-    store_state(s.state, &sm.x, tid, NT, docov != 0);
-    if (newlevel) store_state(s.old_state, &sm.x, tid, NT, false);                         // :747 of the next level
+    if (c.stop || store_always) {
+        store_state(s.state, &sm.x, tid, NT, docov != 0);
+        if (tid == 0) *s.ctrl = c;
+    }
+    if (newlevel && tid < 24) reinterpret_cast<double*>(s.old_state)[tid] = reinterpret_cast<const double*>(&sm.x)[tid];   // :747 of the next level
 }
 
 __global__ void __launch_bounds__(32) k_vio_begin(VioCtrl* ctrl, int Pn_total) {
@@ -1290,12 +1314,16 @@ __global__ void __launch_bounds__(32) k_vio_begin(VioCtrl* ctrl, int Pn_total) {
 
 __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
     __shared__ LeaderSmem sm;
+    __shared__ VioCtrl c;
     __shared__ float s_err[kErrChunk];
     if (s.ctrl->stop) return;
-    const int level = s.ctrl->level;
-    const bool first = (s.ctrl->passes[0] + s.ctrl->passes[1] + s.ctrl->passes[2]) == 0;
+    const int tid = threadIdx.x;
+    if (tid == 0) c = *s.ctrl;
+    load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     __syncthreads();
-    vio_leader<kLeaderBlock>(s, sm, s_err, first, level);
+    const bool first = (c.passes[0] + c.passes[1] + c.passes[2]) == 0;
+    vio_leader_solve<kLeaderBlock>(s, sm, c, s_err, first);
+    vio_leader_finish<kLeaderBlock>(s, sm, c, first, true);
 }
 
 // =======================================================================================
@@ -1364,28 +1392,140 @@ __device__ __forceinline__ bool grid_wait(GridBarrier* b, const unsigned* s_scra
 }
 
 // ---------------------------------------------------------------------------------------
+// Pose packet: barrier release and state broadcast in one L2 round trip
+// ---------------------------------------------------------------------------------------
+// The leader does not "open" a barrier and let every block re-read state and control from global
+// memory (three dependent L2 round trips per pass).  It publishes the new 24 pose/bias doubles and
+// the control block as 8-byte units {payload word, flag} with flag = epoch + pass number; a waiting
+// block polls the units themselves, so the first successful poll already carries the data (the
+// 8-byte unit is written and read by single instructions, so payload and flag travel together).
+// Whatever else later leaders need (prior block, VIO old_state / G_last, exchange counter) is
+// stored AFTER the packet and reaches them through the release of this block's next arrive and
+// the acquire of the next last arriver.  The arrive counter runs up monotonically during a
+// launch (ticket nblocks * (pass + 1) - 1 elects the leader) and is zeroed by the last leader.
+constexpr int kPktUnits = 96;
+constexpr int kStateWords = 48;                          // rot, pos, vel, bg, ba, grav as 32-bit words
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Arrive with release/acquire semantics; true (to every thread of the block) for the last arriver.
+__device__ __forceinline__ bool grid_arrive_ticket(GridBarrier* b, unsigned last_ticket, unsigned* s_scratch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&b->count) : "memory");
+        s_scratch[0] = (t == last_ticket) ? 1u : 0u;
+    }
+    __syncthreads();
+    return s_scratch[0] != 0;
+}
+// Leader: publish the pose/bias words of `x` and the NC control words of `c` (whole block).
+template <int NC>
+__device__ __forceinline__ void pkt_publish(unsigned long long* pkt, const State18& x, const void* c, unsigned flag) {
+    static_assert(kStateWords + NC <= kPktUnits, "packet too small");
+    const unsigned* xs = reinterpret_cast<const unsigned*>(&x);
+    const unsigned* cs = reinterpret_cast<const unsigned*>(c);
+    for (int e = threadIdx.x; e < kStateWords + NC; e += blockDim.x) {
+        const unsigned w = (e < kStateWords) ? xs[e] : cs[e - kStateWords];
+        st_relaxed_u64(pkt + e, ((unsigned long long)flag << 32) | w);
+    }
+}
+// Waiting block: warp 0 polls, then the words go to x / c in shared memory.  Returns false (to the
+// whole block) when the watchdog (~seconds) tripped: a would-be hang becomes FLB_ERR_TIMEOUT.
+template <int NC>
+__device__ __forceinline__ bool pkt_wait(const unsigned long long* pkt, State18& x, void* c, unsigned flag, GridBarrier* b,
+                                         unsigned* s_scratch) {
+    constexpr int N = kStateWords + NC;
+    constexpr int PER = (N + 31) / 32;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long v[PER];
+        unsigned long long spins = 0;
+        bool good = true;
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int e = lane + 32 * u;
+                if (e < N) {
+                    v[u] = ld_relaxed_u64(pkt + e);
+                    ok = ok && ((unsigned)(v[u] >> 32) == flag);
+                }
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(20);
+            ++spins;
+            bool bail = false;
+            if (spins > 3000000ull) { b->timeout = 1; bail = true; }
+            else if ((spins & 0xffff) == 0 && *((volatile int*)&b->timeout)) bail = true;
+            if (__any_sync(0xffffffffu, bail)) { good = false; break; }
+        }
+        if (good) {
+            unsigned* xs = reinterpret_cast<unsigned*>(&x);
+            unsigned* cs = reinterpret_cast<unsigned*>(c);
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int e = lane + 32 * u;
+                if (e < N) {
+                    if (e < kStateWords) xs[e] = (unsigned)v[u];
+                    else cs[e - kStateWords] = (unsigned)v[u];
+                }
+            }
+        }
+        if (lane == 0) s_scratch[1] = good ? 1u : 0u;
+    }
+    __syncthreads();
+    return s_scratch[1] != 0;
+}
+
+__device__ __forceinline__ void lio_pose_from(const LioParamsDev& prm, const State18& x, LioPose& pose) {
+    for (int i = 0; i < 9; ++i) { pose.R[i] = x.rot[i]; pose.R_LI[i] = prm.R_LI[i]; }
+    for (int i = 0; i < 3; ++i) { pose.p[i] = x.pos[i]; pose.t_LI[i] = prm.t_LI[i]; }
+    m3_T(pose.R, pose.Rt);
+    m3_T(pose.R_LI, pose.RLIt);
+}
+
+// ---------------------------------------------------------------------------------------
 // LIO: whole iterated update in one launch
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar,
+                                                                 unsigned long long* pkt, unsigned epoch,
                                                                  unsigned long long* trace, unsigned long long* dbg) {
     constexpr int K = lio_packed(6);
+    constexpr int NC = (int)(sizeof(LioCtrl) / sizeof(unsigned));
     __shared__ LioPose s_pose;
     __shared__ double s_acc[BLOCK / 32][K];
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
+    __shared__ LioCtrl s_ctrl;       // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
     __shared__ int s_rows[18][BLOCK];
     const int tid = threadIdx.x;
-    // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
-    int iterCount = -1, rematch_num = 0, nearest = 1;
     bool first = true;
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
+    // every block keeps the pose/bias part of state and state_propagat resident in shared memory
+    if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(s.state)[tid];
+    else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(s.state_prop)[tid - 24];
+    if (tid == 64) {
+        LioCtrl c;
+        c.iterCount = -1; c.rematch_num = 0; c.nearest_search_en = 1; c.stop = 0;
+        c.passes = c.knn_passes = c.n_eff_last = c.converged_last = 0; c.status = 0;
+        c.res_mean_last = 0.0; c.rows_total = 0;
+        s_ctrl = c;
+    }
+    __syncthreads();
     for (;;) {
         if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = global_ns();
-        if (tid == 0) lio_make_pose(a, s_pose, true);
+        if (tid == 0) lio_pose_from(a.prm, sm.x, s_pose);
         __syncthreads();
         if (dbg && tid == 0) dbg[blockIdx.x * 8 + 1] = global_ns();
+        const int nearest = s_ctrl.nearest_search_en;
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
@@ -1404,25 +1544,23 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         if (dbg && (tid & 31) == 0) dbg[blockIdx.x * 8 + 4 + (tid >> 5)] = global_ns();   // per warp: compute done
         block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
         if (dbg && tid == 0) dbg[blockIdx.x * 8 + 2] = global_ns();
-        const bool leader = grid_arrive(bar, gridDim.x, s_bar);
+        const bool leader = grid_arrive_ticket(bar, gridDim.x * (unsigned)(pass_no + 1) - 1u, s_bar);
         if (dbg && tid == 0) dbg[blockIdx.x * 8 + 3] = global_ns();
+        const unsigned flag = epoch + (unsigned)pass_no + 1u;
         if (leader) {
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
-            lio_leader<BLOCK>(s, sm, first, iterCount, rematch_num, nearest,
-                              (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr);
+            unsigned long long* fine = (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr;
+            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, fine);
+            pkt_publish<NC>(pkt, sm.x, &s_ctrl, flag);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
-            grid_release(bar, s_bar);
+            lio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, fine);
+            if (s_ctrl.stop && tid == 0) bar->count = 0;
         } else {
-            if (!grid_wait(bar, s_bar)) return;
+            if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar)) return;
         }
-        // every block: pick up the published control through L2
-        const int stop = __ldcg(&s.ctrl->stop);
-        nearest = __ldcg(&s.ctrl->nearest_search_en);
-        rematch_num = __ldcg(&s.ctrl->rematch_num);
-        iterCount = __ldcg(&s.ctrl->iterCount);
         first = false;
         ++pass_no;
-        if (stop) break;
+        if (s_ctrl.stop) break;
     }
 }
 
@@ -1431,24 +1569,38 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
+                                                                    unsigned long long* pkt, unsigned epoch,
                                                                     unsigned long long* trace) {
     constexpr int NW = BLOCK / 32;
+    constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     __shared__ VioPose s_pose;
     __shared__ float s_lat[NW][128];
     __shared__ double s_res[NW][64];
     __shared__ double s_acc[NW][kVioPacked];
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
+    __shared__ VioCtrl s_ctrl;
     __shared__ float s_err[kErrChunk];
     const int tid = threadIdx.x, warp = tid >> 5;
     if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
-    int level = 2;
     bool first = true;
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
+    if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(s.state)[tid];
+    else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(s.state_prop)[tid - 24];
+    if (tid == 64) {
+        VioCtrl c;
+        c.level = 2; c.iteration = 0; c.stop = 0;
+        c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;
+        for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
+        c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
+        s_ctrl = c;
+    }
+    __syncthreads();
     for (;;) {
-        if (tid == 0) vio_make_pose_from(a, s_pose, true);
+        if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
         __syncthreads();
+        const int level = s_ctrl.level;
         double acc[27];
 #pragma unroll
         for (int k = 0; k < 27; ++k) acc[k] = 0.0;
@@ -1456,20 +1608,21 @@ __global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, V
         for (int i = blockIdx.x * NW + warp; i < a.Pn; i += gridDim.x * NW)
             vio_patch(a, s_pose, level, i, s_lat[warp], s_res[warp], acc, n_meas, skipped);
         vio_block_reduce_store<BLOCK>(acc, n_meas, skipped, s_acc, a.partials);
-        const bool leader = grid_arrive(bar, gridDim.x, s_bar);
+        const bool leader = grid_arrive_ticket(bar, gridDim.x * (unsigned)(pass_no + 1) - 1u, s_bar);
+        const unsigned flag = epoch + (unsigned)pass_no + 1u;
         if (leader) {
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
-            vio_leader<BLOCK>(s, sm, s_err, first, level);
+            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first);
+            pkt_publish<NC>(pkt, sm.x, &s_ctrl, flag);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
-            grid_release(bar, s_bar);
+            vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false);
+            if (s_ctrl.stop && tid == 0) bar->count = 0;
         } else {
-            if (!grid_wait(bar, s_bar)) return;
+            if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar)) return;
         }
-        const int stop = __ldcg(&s.ctrl->stop);
-        level = __ldcg(&s.ctrl->level);
         first = false;
         ++pass_no;
-        if (stop) break;
+        if (s_ctrl.stop) break;
     }
 }
 
