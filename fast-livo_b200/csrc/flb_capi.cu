@@ -199,6 +199,8 @@ struct flb_handle {
     unsigned pkt_epoch = 0;            // flag base of the next launch (flags are never reused, see next_epoch)
     DevBuf<unsigned long long> trace;  // [0..kTraceLen) LIO, [kTraceLen..2*kTraceLen) VIO
     DevBuf<unsigned long long> dbg;    // per-block stage stamps of the last LIO pass (tracing only)
+    DevBuf<unsigned long long> dbg_vio;
+    int dbg_vio_blocks = 0;
     bool tracing = false;
     int num_sms = 0;
     int occ_lio = 0, occ_vio = 0;
@@ -331,11 +333,11 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, cudaMemset(h->lio_ctrl.p, 0, sizeof(LioCtrl)));
     FLB_CUDA(h, cudaMemset(h->vio_ctrl.p, 0, sizeof(VioCtrl)));
     FLB_CUDA(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
-    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_lio, k_lio_update_persistent<kLioBlock>, kLioBlock, 0));
+    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_lio, k_lio_update_persistent<kLioPersBlock>, kLioPersBlock, 0));
     FLB_CUDA(h, h->ik_states.reserve(2));
     FLB_CUDA(h, h->ik_ctrl.reserve(1));
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_ik, k_lio_update_ikfom_persistent<kLioBlock>, kLioBlock, 0));
-    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioBlock>, kVioBlock, 0));
+    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioPersBlock>, kVioPersBlock, 0));
     FLB_CUDA(h, h->pin_out.reserve(1 << 16));
     return FLB_OK;
 }
@@ -464,8 +466,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
         // whole multiples of the SM count (<= co-resident capacity): chunks are dealt round-robin to blocks
         const int cap = std::max(1, h->occ_lio * h->num_sms);
-        const int want = std::min(cap, std::max(h->num_sms, std::min(2, h->occ_lio) * h->num_sms));
-        const int grid = std::max(1, std::min((h->N + 31) / 32, want));
+        const int grid = std::max(1, std::min((h->N + 31) / 32, std::min(cap, h->num_sms)));
         FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * lio_packed(12), h->partials.cap)));
         a.partials = h->partials.p;
         s.partials = h->partials.p;
@@ -483,7 +484,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         { int rce = next_epoch(h, &epoch); if (rce) return rce; }
         void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg};
         LaunchScope ls(h, FAM_LIO_KNN);
-        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioBlock>, dim3(grid), dim3(kLioBlock), args, 0,
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_lio_update_persistent<kLioPersBlock>, dim3(grid), dim3(kLioPersBlock), args, 0,
                                                 h->stream));
         h->last_pass_valid = false;
         return FLB_OK;
@@ -572,9 +573,16 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         unsigned long long* pkt = h->pkt.p;
         unsigned epoch = 0;
         { int rce = next_epoch(h, &epoch); if (rce) return rce; }
-        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace};
+        unsigned long long* dbg = nullptr;
+        if (h->tracing) {
+            FLB_CUDA(h, h->dbg_vio.reserve((size_t)grid * kVioDbg));
+            FLB_CUDA(h, cudaMemsetAsync(h->dbg_vio.p, 0, (size_t)grid * kVioDbg * sizeof(unsigned long long), h->stream));
+            dbg = h->dbg_vio.p;
+            h->dbg_vio_blocks = grid;
+        }
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg};
         LaunchScope ls(h, FAM_VIO);
-        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioBlock>, dim3(grid), dim3(kVioBlock), args, 0,
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args, 0,
                                                 h->stream));
         h->last_vio_valid = false;
         return vio_inputs_release(h);
@@ -692,7 +700,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->dbg_vio.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
@@ -1478,6 +1486,18 @@ int flb_trace_enable(flb_handle* h, int on) {
     FLB_CHECK_H(h);
     h->tracing = on != 0;
     FLB_CUDA(h, cudaMemsetAsync(h->trace.p, 0, 2 * kTraceLen * sizeof(unsigned long long), h->stream));
+    return FLB_OK;
+}
+
+// Tracing aid (not part of the public header): per-block / per-warp stamps of the last VIO pass,
+// kVioDbg words per block.
+int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks, int* words_per_block) {
+    FLB_CHECK_H(h);
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int n = std::min(h->dbg_vio_blocks, max_blocks);
+    if (n > 0) FLB_CUDA(h, cudaMemcpy(out, h->dbg_vio.p, (size_t)n * kVioDbg * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *nblocks = n;
+    *words_per_block = kVioDbg;
     return FLB_OK;
 }
 

@@ -68,8 +68,10 @@ struct VioParamsDev {
 __host__ __device__ constexpr int lio_packed(int W) { return W * (W + 1) / 2 + W + 2; }
 constexpr int kVioPacked = 21 + 6 + 2;  // + n_meas, skipped
 
-constexpr int kLioBlock = 128;
+constexpr int kLioBlock = 128;          // kernel-per-pass / IKFoM kernels
 constexpr int kVioBlock = 256;
+constexpr int kLioPersBlock = 256;      // persistent kernels: one block per SM (half the partials and
+constexpr int kVioPersBlock = 512;      // arrive tickets of two smaller blocks; same warps per SM)
 constexpr int kLeaderBlock = 256;       // block size of the kernel-per-pass finalize kernels
 
 // Optional device-side pass trace (profiling aid): %globaltimer (ns) at kernel entry [0], then for
@@ -565,11 +567,13 @@ struct LatView {
 
 // One patch by one warp.  acc: per-lane partial sums (21 + 6); lane 0 also counts n_meas / skipped.
 __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, float* s_lat, double* s_res,
-                                          double (&acc)[27], double& n_meas, double& skipped) {
+                                          double (&acc)[27], double& n_meas, double& skipped,
+                                          unsigned long long* wdbg = nullptr) {
     const int lane = threadIdx.x & 31;
     PatchGeom g;
     const double pos[3] = {a.pos[3 * (size_t)i], a.pos[3 * (size_t)i + 1], a.pos[3 * (size_t)i + 2]};
     vio_patch_geom(a.cam, pose, pos, level, a.search_level[i], g);
+    if (wdbg && lane == 0) wdbg[0] = global_ns();
     if (g.valid) {
         // stage the 11x11 tap lattice (stride = scale px) as float
         const int W = a.cam.width;
@@ -583,6 +587,7 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
             }
         }
         __syncwarp();
+        if (wdbg && lane == 0) wdbg[1] = global_ns();
         LatView L{s_lat};
         const int x = lane >> 2, y0 = (lane & 3) * 2;
         const float* P = a.patch + (size_t)i * 192 + 64 * level;   // P[patch_size_total*level + x*8 + y]
@@ -607,6 +612,7 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
             }
         }
         __syncwarp();
+        if (wdbg && lane == 0) wdbg[2] = global_ns();
         if (lane == 0) {
             // patch_error += res*res : float accumulator, double addend (:843) -- sequential, exact
             float pe = 0.0f;
@@ -614,6 +620,7 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
             for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[e] * s_res[e]);
             a.errors[i] = pe;                                       // :851
             n_meas += 64.0;
+            if (wdbg) wdbg[3] = global_ns();
         }
         __syncwarp();
     } else {
@@ -706,7 +713,7 @@ struct LeaderSmem {
     double xold[24];          // VIO: the pose/bias block before the accepted step (old_state, :863)
     double top[6 * kDim];
     double packed[32];
-    double part[8][32];
+    double part[16][32];
     int flags[4];
     float error;
     int p2p_par;
@@ -740,15 +747,18 @@ __device__ __forceinline__ void store_state(State18* dst, const State18* src, in
     for (int e = tid; e < n; e += nt) d[e] = s[e];
 }
 
-// Fixed-order reduction of the block partials: PARTS = NT/32 contiguous slices per entry (one warp
-// each), every slice summed in block order from batches of 16 independent L2 loads (guarded at the
-// tail: adding +0.0 is exact), then the slices combined left to right.
-template <int K, int NT>
-__device__ __forceinline__ void leader_reduce(const double* partials, int nblocks, LeaderSmem& sm, int tid) {
-    constexpr int PARTS = NT / 32;
-    static_assert(PARTS <= 8 && K <= 32, "LeaderSmem::part is [8][32]");
+// Fixed-order reduction of the block partials by a team of TN threads: its first TN/32-1 warps take one
+// contiguous slice of the blocks each (summed in block order from batches of 16 independent L2 loads,
+// guarded at the tail: adding +0.0 is exact), then the slices are combined left to right.  Meanwhile
+// lane 0 of the team's LAST warp forms vec = state_propagat (-) state, which only needs sm.x / sm.xp.
+template <int K, int TN, class TeamT>
+__device__ __forceinline__ void team_reduce_vec(const double* partials, int nblocks, LeaderSmem& sm, int tid) {
+    constexpr int PARTS = TN / 32 - 1;
+    static_assert(PARTS >= 1 && PARTS <= 16 && K <= 32, "LeaderSmem::part is [16][32]");
     const int q = tid & 31, part = tid >> 5;
-    if (q < K) {
+    if (part == PARTS) {
+        if (q == 0) state_boxminus(sm.xp, sm.x, sm.vec);
+    } else if (q < K) {
         const int per = (nblocks + PARTS - 1) / PARTS;
         const int b0 = part * per, b1 = min(nblocks, b0 + per);
         double s = 0.0;
@@ -761,42 +771,20 @@ __device__ __forceinline__ void leader_reduce(const double* partials, int nblock
         }
         sm.part[part][q] = s;
     }
-    __syncthreads();
+    TeamT::sync();
     if (tid < K) {
         double s = sm.part[0][tid];
 #pragma unroll
         for (int p = 1; p < PARTS; ++p) s += sm.part[p][tid];
         sm.packed[tid] = s;
     }
-    __syncthreads();
+    TeamT::sync();
 }
 
-template <int K, int NT, class TeamT>
-__device__ __forceinline__ void team_reduce(const double* partials, int nblocks, LeaderSmem& sm, int tid) {
-    constexpr int PARTS = NT / 32;
-    static_assert(PARTS <= 8 && K <= 32, "LeaderSmem::part is [8][32]");
-    const int q = tid & 31, part = tid >> 5;
-    if (q < K) {
-        const int per = (nblocks + PARTS - 1) / PARTS;
-        const int b0 = part * per, b1 = min(nblocks, b0 + per);
-        double s = 0.0;
-        for (int b = b0; b < b1; b += 16) {
-            double v[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = (b + u < b1) ? __ldcg(partials + (size_t)(b + u) * K + q) : 0.0;
-#pragma unroll
-            for (int u = 0; u < 16; ++u) s += v[u];
-        }
-        sm.part[part][q] = s;
-    }
-    TeamT::sync();
-    if (tid < K) {
-        double s = sm.part[0][tid];
-#pragma unroll
-        for (int p = 1; p < PARTS; ++p) s += sm.part[p][tid];
-        sm.packed[tid] = s;
-    }
-    TeamT::sync();
+// packed upper triangle (row-major, as accumulated by lio_accumulate / vio_patch) -> element (i, j)
+__device__ __forceinline__ int sym6_index(int i, int j) {
+    const int r = i < j ? i : j, c = i < j ? j : i;
+    return r * 6 - (r * (r - 1)) / 2 + (c - r);
 }
 
 __device__ __forceinline__ void unpack_sym6(const double* packed, double* HTH, double* HTz) {
@@ -874,17 +862,63 @@ __device__ __forceinline__ void prior_commit(LeaderSmem& sm, double v, int tid) 
     if (tid < kPriorDoubles) reinterpret_cast<double*>(&sm.prior)[tid] = v;
 }
 
-// The per-pass step, executed by the team (tid < TeamT::size).  Requires sm.x, sm.xp, sm.HTH,
-// sm.HTz and, when !first, sm.prior (prior_prefetch/prior_commit); computes sm.K, sm.Gc, sm.sol.  sm.flags[3] != 0 afterwards
-// means a singular system.
+// The per-pass solve, by ONE warp, registers and shuffles only.  With K = K1[:, :6] = [Kt; B Kt]:
+//     solution = sign K HTz + vec - (K HTH6) vec[:6] = vec + [y; B y],   y = Kt w,  w = sign HTz - HTH6 vec[:6]
+// so a pass needs one 6x6 solve with a single right-hand side, not the gain itself (the gain is only
+// formed for the covariance update, leader_gain below).  Lane j < 6 holds column j of
+// A = HTH6 + sigma P11^-1, lanes >= 6 all hold the right-hand side; Gauss-Jordan without pivoting
+// (SPD).  Requires sm.packed, sm.vec, sm.prior; writes sm.sol; a bad pivot raises sm.flags[3].
+__device__ __forceinline__ void leader_fast_solve(LeaderSmem& sm, double sigma, double sign, int lane) {
+    const unsigned full = 0xffffffffu;
+    double col[6];
+    if (lane < 6) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) col[i] = sm.packed[sym6_index(i, lane)] + sigma * sm.prior.P11inv[i * 6 + lane];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a += sm.packed[sym6_index(i, k)] * sm.vec[k];
+            col[i] = sign * sm.packed[21 + i] - a;
+        }
+    }
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double ck[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ck[i] = __shfl_sync(full, col[i], k);
+        const double piv = ck[k];
+        bad = bad || !(fabs(piv) > 1e-300) || !isfinite(piv);
+        const double r = col[k] * __drcp_rn(piv);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) col[i] = (i == k) ? r : col[i] - ck[i] * r;
+    }
+    // lanes >= 6 now hold y
+    if (lane >= 8 && lane < 8 + kDim) {
+        const int idx = lane - 8;
+        double v = sm.vec[idx];
+        if (idx < 6) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) if (i == idx) v += col[i];
+        } else {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a += sm.prior.B[(idx - 6) * 6 + k] * col[k];
+            v += a;
+        }
+        sm.sol[idx] = v;
+    }
+    if (lane == 0 && bad) sm.flags[3] = 1;
+    __syncwarp();
+}
+
+// The gain of a pass, needed only where the reference updates the covariance with it
+// (src/laserMapping.cpp:1715, src/lidar_selection.cpp:980): Kt = (HTH6 + sigma P11^-1)^-1,
+// K = [Kt; B Kt], Gc = K HTH6 (the non-zero columns of G).  Whole team; HTH6 = sm.HTH.
 template <class TeamT>
-__device__ __forceinline__ void leader_step(LeaderSmem& sm, PriorBlock* prior_g, bool first, double sigma, double sign,
-                                            int tid) {
-    if (tid == TeamT::size - 1) state_boxminus(sm.xp, sm.x, sm.vec);  // vec = state_propagat - state
-    if (tid == 0) sm.flags[3] = 0;
-    static_assert(TeamT::size >= kPriorDoubles, "team too small for the prior prefetch");
-    if (first) leader_prior<TeamT>(sm, prior_g, tid);
-    TeamT::sync();
+__device__ __forceinline__ void leader_gain(LeaderSmem& sm, double sigma, int tid) {
     if (tid < 72) {
         const int i = tid / 12, j = tid - i * 12;
         sm.S[i * 13 + j] = (j < 6) ? sm.HTH[i * 6 + j] + sigma * sm.prior.P11inv[i * 6 + j] : ((j - 6 == i) ? 1.0 : 0.0);
@@ -907,16 +941,6 @@ __device__ __forceinline__ void leader_step(LeaderSmem& sm, PriorBlock* prior_g,
 #pragma unroll
         for (int k = 0; k < 6; ++k) s += sm.K[i * 6 + k] * sm.HTH[k * 6 + j];
         sm.Gc[tid] = s;
-    }
-    TeamT::sync();
-    if (tid < kDim) {
-        double kz = 0.0, gv = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            kz += sm.K[tid * 6 + k] * sm.HTz[k];
-            gv += sm.Gc[tid * 6 + k] * sm.vec[k];
-        }
-        sm.sol[tid] = sign * kz + sm.vec[tid] - gv;
     }
     TeamT::sync();
 }
@@ -1025,61 +1049,85 @@ struct LioSolveArgs {
     int* timeout_flag;       // GridBarrier::timeout
 };
 
-// One LIO leader step (whole block, NT threads), in two halves so that the persistent kernel can
-// publish the new pose between them.  Requires the 24 pose/bias doubles of sm.x and sm.xp and the
-// control block `c` (shared memory) to be current; `first`: first pass of this update.
-//   lio_leader_solve : reduce -> [exchange] -> solve -> state (+)= solution -> loop control (c)
+// Warp-level publication of the pose packet (see "Pose packet" below): 8-byte units {word, flag}.
+constexpr int kPktUnits = 96;
+constexpr int kStateWords = 48;                          // rot, pos, vel, bg, ba, grav as 32-bit words
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void pkt_publish_warp(unsigned long long* pkt, const State18& x, const void* c, unsigned flag, int lane) {
+    static_assert(kStateWords + NC <= kPktUnits, "packet too small");
+    const unsigned* xs = reinterpret_cast<const unsigned*>(&x);
+    const unsigned* cs = reinterpret_cast<const unsigned*>(c);
+#pragma unroll
+    for (int e = lane; e < kStateWords + NC; e += 32) {
+        const unsigned w = (e < kStateWords) ? xs[e] : cs[e - kStateWords];
+        st_relaxed_u64(pkt + e, ((unsigned long long)flag << 32) | w);
+    }
+}
+
+// One LIO leader step (whole block, NT threads), in two halves.  Requires the 24 pose/bias doubles of
+// sm.x and sm.xp and the control block `c` (shared memory) to be current; `first`: first pass of this update.
+//   lio_leader_solve : reduce -> [exchange] -> warp 0: solve, state (+)= solution, loop control (c) and,
+//                      in the persistent kernel (pkt != nullptr), publication of the new pose
 //   lio_leader_finish: covariance update on the stopping pass; stores what later launches / the host need
 #define FLB_STAMP(k) do { if (fine && threadIdx.x == 0) fine[k] = global_ns(); } while (0)
 template <int NT>
 __device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSmem& sm, LioCtrl& c, bool first,
-                                                 unsigned long long* fine = nullptr) {
+                                                 unsigned long long* pkt, unsigned flag, unsigned long long* fine = nullptr) {
     constexpr int K = lio_packed(6);
+    constexpr int NC = (int)(sizeof(LioCtrl) / sizeof(unsigned));
+    using T = Team<NT, false>;
     const int tid = threadIdx.x;
-    const int T = s.prm.max_iteration;
+    const int T_it = s.prm.max_iteration;
     if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
     // later leaders fetch the prior block while the partials are being reduced
     const double pri = first ? 0.0 : prior_prefetch(s.prior, tid);
+    if (tid == 0) sm.flags[3] = 0;
     FLB_STAMP(0);
-    leader_reduce<K, NT>(s.partials, s.nblocks, sm, tid);
+    team_reduce_vec<K, NT, T>(s.partials, s.nblocks, sm, tid);
     if (!first) prior_commit(sm, pri, tid);
-    if (s.p2p.world > 1) p2p_exchange<K, Team<NT, false>>(s.p2p, sm, nullptr, 0, tid, s.timeout_flag);
+    if (s.p2p.world > 1) p2p_exchange<K, T>(s.p2p, sm, nullptr, 0, tid, s.timeout_flag);
+    if (first) leader_prior<T>(sm, s.prior, tid);
+    __syncthreads();
     FLB_STAMP(1);
-    if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
-    __syncthreads();
-    leader_step<Team<NT, false>>(sm, s.prior, first, s.prm.sigma, +1.0, tid);
-    const bool ok = sm.flags[3] == 0;
-    __syncthreads();
-    FLB_STAMP(2);
-    if (tid == 0) {
-        const int iterCount = c.iterCount, rematch_num = c.rematch_num, nearest = c.nearest_search_en;
-        if (first) {
-            c.passes = c.knn_passes = 0;
-            c.rows_total = 0;
-            c.status = 0;
+    if (tid < 32) {
+        leader_fast_solve(sm, s.prm.sigma, +1.0, tid);
+        FLB_STAMP(2);
+        if (tid == 0) {
+            const bool ok = sm.flags[3] == 0;
+            const int iterCount = c.iterCount, rematch_num = c.rematch_num, nearest = c.nearest_search_en;
+            if (first) {
+                c.passes = c.knn_passes = 0;
+                c.rows_total = 0;
+                c.status = 0;
+            }
+            const int n_eff = (int)sm.packed[K - 2];
+            c.passes += 1;
+            c.knn_passes += nearest ? 1 : 0;
+            c.n_eff_last = n_eff;
+            c.res_mean_last = sm.packed[K - 1] / (double)n_eff;                            // :1602
+            c.rows_total += n_eff;
+            state_boxplus(sm.x, sm.sol);                                                   // :1683
+            bool converged = false;
+            if ((norm3(sm.sol) * 57.3 < s.prm.conv_rot_deg) && (norm3(sm.sol + 3) * 100 < s.prm.conv_pos_cm))
+                converged = true;                                                          // :1688
+            int nn = 0, rn = rematch_num;
+            if (converged || ((rn == 0) && (iterCount == (T_it - 2)))) { nn = 1; rn++; }    // :1700-1705
+            int stop = 0;
+            if (rn >= 2 || (iterCount == T_it - 1)) stop = 1;                               // :1708
+            if (!ok) { stop = 1; c.status = -5; }
+            c.converged_last = converged ? 1 : 0;
+            c.iterCount = iterCount + 1;
+            c.rematch_num = rn;
+            c.nearest_search_en = nn;
+            c.stop = stop;
+            sm.flags[0] = stop;
+            sm.flags[1] = ok ? 1 : 0;
         }
-        const int n_eff = (int)sm.packed[K - 2];
-        c.passes += 1;
-        c.knn_passes += nearest ? 1 : 0;
-        c.n_eff_last = n_eff;
-        c.res_mean_last = sm.packed[K - 1] / (double)n_eff;                            // :1602
-        c.rows_total += n_eff;
-        state_boxplus(sm.x, sm.sol);                                                   // :1683
-        bool converged = false;
-        if ((norm3(sm.sol) * 57.3 < s.prm.conv_rot_deg) && (norm3(sm.sol + 3) * 100 < s.prm.conv_pos_cm))
-            converged = true;                                                          // :1688
-        int nn = 0, rn = rematch_num;
-        if (converged || ((rn == 0) && (iterCount == (T - 2)))) { nn = 1; rn++; }       // :1700-1705
-        int stop = 0;
-        if (rn >= 2 || (iterCount == T - 1)) stop = 1;                                  // :1708
-        if (!ok) { stop = 1; c.status = -5; }
-        c.converged_last = converged ? 1 : 0;
-        c.iterCount = iterCount + 1;
-        c.rematch_num = rn;
-        c.nearest_search_en = nn;
-        c.stop = stop;
-        sm.flags[0] = stop;
-        sm.flags[1] = ok ? 1 : 0;
+        __syncwarp();
+        if (pkt) pkt_publish_warp<NC>(pkt, sm.x, &c, flag, tid);
     }
     __syncthreads();
     FLB_STAMP(3);
@@ -1093,7 +1141,10 @@ __device__ __forceinline__ void lio_leader_finish(const LioSolveArgs& s, LeaderS
     const bool stop = sm.flags[0] != 0;
     const bool do_cov = stop && sm.flags[1];
     if (do_cov) {
-        if (!first) { load_cov_l2<NT>(&sm.x, s.state, tid); __syncthreads(); }
+        if (tid < 36) sm.HTH[tid] = sm.packed[sym6_index(tid / 6, tid % 6)];
+        if (!first) load_cov_l2<NT>(&sm.x, s.state, tid);
+        __syncthreads();
+        leader_gain<Team<NT, false>>(sm, s.prm.sigma, tid);
         leader_cov_update(sm, sm.Gc, tid, NT);                                          // :1715
     }
     if (stop || store_always) {
@@ -1127,7 +1178,7 @@ __global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize(LioSolveArgs s) {
     load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     __syncthreads();
     const bool first = c.passes == 0;
-    lio_leader_solve<kLeaderBlock>(s, sm, c, first);
+    lio_leader_solve<kLeaderBlock>(s, sm, c, first, nullptr, 0u);
     lio_leader_finish<kLeaderBlock>(s, sm, c, first, true);
 }
 
@@ -1148,12 +1199,15 @@ struct VioSolveArgs {
 };
 
 constexpr int kErrChunk = 2048;
+constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 
 // One VIO leader step (whole block, NT threads), in two halves like the LIO one.  Requires the 24
 // pose/bias doubles of sm.x / sm.xp and the control block `c` (shared memory); c.level is the pyramid
 // level of the pass just done.
 template <int NT>
-__device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first) {
+__device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first,
+                                                 unsigned long long* pkt, unsigned flag, unsigned long long* fine = nullptr) {
+    constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     const int tid = threadIdx.x;
     const bool multi = s.p2p.world > 1;
     const int level = c.level;
@@ -1195,6 +1249,8 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
             }
         }
         if (lane == 0) sm.error = e_run;
+        if (fine && lane == 0) fine[3] = global_ns();
+        asm volatile("bar.sync 3, 64;" ::: "memory");                       // hand the error to warp 0
     } else {
         // Solve team (first NT-32 threads, named barrier 1).  The covariance is constant during ComputeJ
         // (only :980 changes it, on the last pass), so old_state carries the 24 pose/bias doubles only.
@@ -1202,74 +1258,85 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         if (first) load_cov_l2<NT - 32>(&sm.x, s.state, tid);
         const double pri = first ? 0.0 : prior_prefetch(s.prior, tid);
         if (first) store_state(s.old_state, &sm.x, tid, NT - 32, false);                 // old_state = *state (:747)
-        team_reduce<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
+        if (tid == 0) sm.flags[3] = 0;
+        team_reduce_vec<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
+        FLB_STAMP(1);
         if (!first) prior_commit(sm, pri, tid);
         if (multi) {
             const int par = p2p_exchange<kVioPacked, T>(s.p2p, sm, s.errors, s.Pn_total, tid, s.timeout_flag);
             if (tid == 0) sm.p2p_par = par;
             asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");              // release the error-sum warp
         }
-        if (tid == 0) unpack_sym6(sm.packed, sm.HTH, sm.HTz);
+        if (first) leader_prior<T>(sm, s.prior, tid);
         T::sync();
-        leader_step<T>(sm, s.prior, first, s.prm.sigma, -1.0, tid);                       // :871-878 (sign: :878)
-    }
-    __syncthreads();
-    const bool ok = sm.flags[3] == 0;
-    if (tid == 0) {
-        if (first) {
-            c.level = 2; c.iteration = 0; c.stop = 0;
-            c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;                   // :971
-            for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
-            c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
-        }
-        const long long nm = (long long)sm.packed[27];
-        const float error = sm.error / (float)(unsigned long long)nm;                      // :857
-        c.passes[level] += 1;
-        c.rows_total += nm;
-        c.skipped_last = (int)sm.packed[28];
-        bool EKF_end = false;
-        int accept = 0;
-        if (s.prm.force_all_passes || error <= c.last_error) {                             // :861
-            accept = 1;
-            c.last_error = error;
-            if (!s.prm.force_all_passes && (norm3(sm.sol) * 57.3f < s.prm.conv_rot_deg) &&
-                (norm3(sm.sol + 3) * 100.0f < s.prm.conv_pos_cm))
-                EKF_end = true;                                                            // :883
-            c.any_solved = 1;
-        } else {
-            EKF_end = true;                                                                // :890
-        }
-        if (!ok) { EKF_end = true; c.status = -5; }
-        c.iteration += 1;
-        int docov = 0, newlevel = 0;
-        if (EKF_end || c.iteration >= s.prm.max_iteration) {
-            // level finished -> ComputeJ advances (:974-977)
-            c.level_error[level] = c.last_error;
-            c.now_error = c.last_error;
-            c.level = level - 1;
-            c.iteration = 0;
-            c.last_error = 1e10f;
-            newlevel = 1;
-            if (c.level < 0 || !ok) {
-                c.stop = 1;
-                if (c.now_error < 1e10f && ok) { docov = 1; c.cov_updated = 1; }           // :978-981
+        if (tid < 32) {
+            leader_fast_solve(sm, s.prm.sigma, -1.0, tid);                                // :871-878 (sign: :878)
+            FLB_STAMP(2);
+            asm volatile("bar.sync 3, 64;" ::: "memory");                   // sm.error is ready
+            FLB_STAMP(4);
+            if (tid == 0) {
+                const bool ok = sm.flags[3] == 0;
+                if (first) {
+                    c.level = 2; c.iteration = 0; c.stop = 0;
+                    c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;           // :971
+                    for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
+                    c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
+                }
+                const long long nm = (long long)sm.packed[27];
+                const float error = sm.error / (float)(unsigned long long)nm;              // :857
+                c.passes[level] += 1;
+                c.rows_total += nm;
+                c.skipped_last = (int)sm.packed[28];
+                bool EKF_end = false;
+                int accept = 0;
+                if (s.prm.force_all_passes || error <= c.last_error) {                     // :861
+                    accept = 1;
+                    c.last_error = error;
+                    if (!s.prm.force_all_passes && (norm3(sm.sol) * 57.3f < s.prm.conv_rot_deg) &&
+                        (norm3(sm.sol + 3) * 100.0f < s.prm.conv_pos_cm))
+                        EKF_end = true;                                                    // :883
+                    c.any_solved = 1;
+                } else {
+                    EKF_end = true;                                                        // :890
+                }
+                if (!ok) { EKF_end = true; c.status = -5; }
+                c.iteration += 1;
+                int docov = 0, newlevel = 0;
+                if (EKF_end || c.iteration >= s.prm.max_iteration) {
+                    // level finished -> ComputeJ advances (:974-977)
+                    c.level_error[level] = c.last_error;
+                    c.now_error = c.last_error;
+                    c.level = level - 1;
+                    c.iteration = 0;
+                    c.last_error = 1e10f;
+                    newlevel = 1;
+                    if (c.level < 0 || !ok) {
+                        c.stop = 1;
+                        if (c.now_error < 1e10f && ok) { docov = 1; c.cov_updated = 1; }   // :978-981
+                    }
+                }
+                sm.flags[0] = accept;
+                sm.flags[1] = docov;
+                sm.flags[2] = newlevel;
             }
+            __syncwarp();
+            FLB_STAMP(5);
+            if (sm.flags[0]) {
+                if (tid < 24) sm.xold[tid] = reinterpret_cast<const double*>(&sm.x)[tid];  // old_state = *state (:863)
+                __syncwarp();
+                if (tid == 0) state_boxplus(sm.x, sm.sol);                                 // :879
+            } else {
+                if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(reinterpret_cast<const double*>(s.old_state) + tid);
+            }                                                                              // *state = old_state (:890)
+            __syncwarp();
+            if (pkt) pkt_publish_warp<NC>(pkt, sm.x, &c, flag, tid);
+            FLB_STAMP(6);
         }
-        sm.flags[0] = accept;
-        sm.flags[1] = docov;
-        sm.flags[2] = newlevel;
     }
-    __syncthreads();
-    if (sm.flags[0]) {
-        if (tid < 24) sm.xold[tid] = reinterpret_cast<const double*>(&sm.x)[tid];          // old_state = *state (:863)
-        __syncthreads();
-        if (tid == 0) state_boxplus(sm.x, sm.sol);                                         // :879
-    } else {
-        if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(reinterpret_cast<const double*>(s.old_state) + tid);
-    }                                                                                      // *state = old_state (:890)
     __syncthreads();
 }
 
+// G_last holds HTH6 of the last ACCEPTED pass (the gain itself is only formed when :980 runs).
 template <int NT>
 __device__ __forceinline__ void vio_leader_finish(const VioSolveArgs& s, LeaderSmem& sm, const VioCtrl& c, bool first,
                                                   bool store_always) {
@@ -1277,14 +1344,13 @@ __device__ __forceinline__ void vio_leader_finish(const VioSolveArgs& s, LeaderS
     const int accept = sm.flags[0], docov = sm.flags[1], newlevel = sm.flags[2];
     if (accept) {
         if (tid < 24) reinterpret_cast<double*>(s.old_state)[tid] = sm.xold[tid];
-        for (int e = tid; e < kDim * 6; e += NT) s.G_last[e] = sm.Gc[e];
+        if (tid < 36) s.G_last[tid] = sm.packed[sym6_index(tid / 6, tid % 6)];
     }
     if (docov) {
-        if (!accept) {
-            for (int e = tid; e < kDim * 6; e += NT) sm.Gc[e] = __ldcg(s.G_last + e);
-            __syncthreads();
-        }
-        if (!first) { load_cov_l2<NT>(&sm.x, s.state, tid); __syncthreads(); }
+        if (tid < 36) sm.HTH[tid] = accept ? sm.packed[sym6_index(tid / 6, tid % 6)] : __ldcg(s.G_last + tid);
+        if (!first) load_cov_l2<NT>(&sm.x, s.state, tid);
+        __syncthreads();
+        leader_gain<Team<NT, false>>(sm, s.prm.sigma, tid);
         leader_cov_update(sm, sm.Gc, tid, NT);                                             // :980
     }
     if (c.stop || store_always) {
@@ -1322,7 +1388,7 @@ __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
     load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     __syncthreads();
     const bool first = (c.passes[0] + c.passes[1] + c.passes[2]) == 0;
-    vio_leader_solve<kLeaderBlock>(s, sm, c, s_err, first);
+    vio_leader_solve<kLeaderBlock>(s, sm, c, s_err, first, nullptr, 0u);
     vio_leader_finish<kLeaderBlock>(s, sm, c, first, true);
 }
 
@@ -1403,11 +1469,6 @@ __device__ __forceinline__ bool grid_wait(GridBarrier* b, const unsigned* s_scra
 // stored AFTER the packet and reaches them through the release of this block's next arrive and
 // the acquire of the next last arriver.  The arrive counter runs up monotonically during a
 // launch (ticket nblocks * (pass + 1) - 1 elects the leader) and is zeroed by the last leader.
-constexpr int kPktUnits = 96;
-constexpr int kStateWords = 48;                          // rot, pos, vel, bg, ba, grav as 32-bit words
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1423,17 +1484,6 @@ __device__ __forceinline__ bool grid_arrive_ticket(GridBarrier* b, unsigned last
     }
     __syncthreads();
     return s_scratch[0] != 0;
-}
-// Leader: publish the pose/bias words of `x` and the NC control words of `c` (whole block).
-template <int NC>
-__device__ __forceinline__ void pkt_publish(unsigned long long* pkt, const State18& x, const void* c, unsigned flag) {
-    static_assert(kStateWords + NC <= kPktUnits, "packet too small");
-    const unsigned* xs = reinterpret_cast<const unsigned*>(&x);
-    const unsigned* cs = reinterpret_cast<const unsigned*>(c);
-    for (int e = threadIdx.x; e < kStateWords + NC; e += blockDim.x) {
-        const unsigned w = (e < kStateWords) ? xs[e] : cs[e - kStateWords];
-        st_relaxed_u64(pkt + e, ((unsigned long long)flag << 32) | w);
-    }
 }
 // Waiting block: warp 0 polls, then the words go to x / c in shared memory.  Returns false (to the
 // whole block) when the watchdog (~seconds) tripped: a would-be hang becomes FLB_ERR_TIMEOUT.
@@ -1494,7 +1544,7 @@ __device__ __forceinline__ void lio_pose_from(const LioParamsDev& prm, const Sta
 // LIO: whole iterated update in one launch
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar,
+__global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar,
                                                                  unsigned long long* pkt, unsigned epoch,
                                                                  unsigned long long* trace, unsigned long long* dbg) {
     constexpr int K = lio_packed(6);
@@ -1550,8 +1600,7 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
         if (leader) {
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr;
-            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, fine);
-            pkt_publish<NC>(pkt, sm.x, &s_ctrl, flag);
+            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, pkt, flag, fine);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             lio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, fine);
             if (s_ctrl.stop && tid == 0) bar->count = 0;
@@ -1568,9 +1617,9 @@ __global__ void __launch_bounds__(BLOCK) k_lio_update_persistent(LioArgs a, LioS
 // VIO: ComputeJ (3 levels x up to T passes) in one launch
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
+__global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
                                                                     unsigned long long* pkt, unsigned epoch,
-                                                                    unsigned long long* trace) {
+                                                                    unsigned long long* trace, unsigned long long* dbg) {
     constexpr int NW = BLOCK / 32;
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     __shared__ VioPose s_pose;
@@ -1598,22 +1647,27 @@ __global__ void __launch_bounds__(BLOCK, 2) k_vio_update_persistent(VioArgs a, V
     }
     __syncthreads();
     for (;;) {
+        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
         if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
         __syncthreads();
+        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();
         const int level = s_ctrl.level;
         double acc[27];
 #pragma unroll
         for (int k = 0; k < 27; ++k) acc[k] = 0.0;
         double n_meas = 0.0, skipped = 0.0;
         for (int i = blockIdx.x * NW + warp; i < a.Pn; i += gridDim.x * NW)
-            vio_patch(a, s_pose, level, i, s_lat[warp], s_res[warp], acc, n_meas, skipped);
+            vio_patch(a, s_pose, level, i, s_lat[warp], s_res[warp], acc, n_meas, skipped,
+                      dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr);
         vio_block_reduce_store<BLOCK>(acc, n_meas, skipped, s_acc, a.partials);
+        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();
         const bool leader = grid_arrive_ticket(bar, gridDim.x * (unsigned)(pass_no + 1) - 1u, s_bar);
+        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 3] = global_ns();
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
         if (leader) {
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
-            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first);
-            pkt_publish<NC>(pkt, sm.x, &s_ctrl, flag);
+            unsigned long long* fine = (trace && 32 + 8 * pass_no + 8 <= kTraceLen) ? trace + 32 + 8 * pass_no : nullptr;
+            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, fine);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false);
             if (s_ctrl.stop && tid == 0) bar->count = 0;
