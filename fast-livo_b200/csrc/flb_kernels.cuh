@@ -486,10 +486,10 @@ __device__ __forceinline__ void lio_accumulate(double (&acc)[lio_packed(W)], con
 #pragma unroll
     for (int r = 0; r < W; ++r) {
 #pragma unroll
-        for (int c = r; c < W; ++c) { acc[k] += row[r] * row[c]; ++k; }
+        for (int c = r; c < W; ++c) { acc[k] = fma(row[r], row[c], acc[k]); ++k; }
     }
 #pragma unroll
-    for (int r = 0; r < W; ++r) { acc[k] += row[r] * z; ++k; }
+    for (int r = 0; r < W; ++r) { acc[k] = fma(row[r], z, acc[k]); ++k; }
     acc[k] += 1.0;
     acc[k + 1] += absres;
 }
@@ -565,14 +565,47 @@ struct LatView {
     __device__ __forceinline__ float operator()(int r, int c) const { return p[r * 11 + c]; }
 };
 
-// One patch by one warp.  acc: per-lane partial sums (21 + 6); lane 0 also counts n_meas / skipped.
-__device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, float* s_lat, double* s_res,
-                                          double (&acc)[27], double& n_meas, double& skipped,
+// Per-warp inputs of one patch that do not depend on the pose: fetched once per launch when every
+// warp owns a single patch (the persistent kernel), otherwise once per pass.
+struct PatchIn {
+    double pos[3];
+    int search_level;
+    float ref[3][2];          // reference patch values of this lane's two pixels, per pyramid level
+};
+__device__ __forceinline__ void vio_patch_load(const VioArgs& a, int i, int lane, PatchIn& in) {
+    in.pos[0] = a.pos[3 * (size_t)i]; in.pos[1] = a.pos[3 * (size_t)i + 1]; in.pos[2] = a.pos[3 * (size_t)i + 2];
+    in.search_level = a.search_level[i];
+    const int x = lane >> 2, y0 = (lane & 3) * 2;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        // P[patch_size_total*level + x*8 + y]
+        const float2 v = __ldg(reinterpret_cast<const float2*>(a.patch + (size_t)i * 192 + 64 * l + x * 8 + y0));
+        in.ref[l][0] = v.x; in.ref[l][1] = v.y;
+    }
+}
+
+// (float)((double)pe + sq) for pe >= 0 held as a double, without the two conversions: round the
+// double sum to 24 significant bits, ties to even, on its bit pattern.  Exact whenever the result
+// is a normal float or zero (the caller checks the operands).
+__device__ __forceinline__ double round_to_f32_precision(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
+    u &= ~0x1FFFFFFFull;
+    return __longlong_as_double((long long)u);
+}
+
+// One patch by one warp.  The 21 + 6 sums of the patch are reduced across the warp right away: lane l < 27
+// adds the patch total of sum l to `accv` (so only one double per lane is carried from patch to patch);
+// lane 0 also counts n_meas / skipped.
+__device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
+                                          float* s_lat, double* s_res, double& accv, double& n_meas, double& skipped,
                                           unsigned long long* wdbg = nullptr) {
     const int lane = threadIdx.x & 31;
+    double acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.0;
     PatchGeom g;
-    const double pos[3] = {a.pos[3 * (size_t)i], a.pos[3 * (size_t)i + 1], a.pos[3 * (size_t)i + 2]};
-    vio_patch_geom(a.cam, pose, pos, level, a.search_level[i], g);
+    vio_patch_geom(a.cam, pose, in.pos, level, in.search_level, g);
     if (wdbg && lane == 0) wdbg[0] = global_ns();
     if (g.valid) {
         // stage the 11x11 tap lattice (stride = scale px) as float
@@ -590,39 +623,51 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
         if (wdbg && lane == 0) wdbg[1] = global_ns();
         LatView L{s_lat};
         const int x = lane >> 2, y0 = (lane & 3) * 2;
-        const float* P = a.patch + (size_t)i * 192 + 64 * level;   // P[patch_size_total*level + x*8 + y]
+        bool tiny = false;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int y = y0 + q;
             double row[6], res;
-            vio_pixel(L, g, pose, x, y, __ldg(P + x * 8 + y), row, &res);
-            s_res[x * 8 + y] = res;
+            const float refv = (level == 0) ? in.ref[0][q] : ((level == 1) ? in.ref[1][q] : in.ref[2][q]);
+            vio_pixel(L, g, pose, x, y, refv, row, &res);
+            const double sq = res * res;
+            s_res[x * 8 + y] = sq;
+            tiny = tiny || (sq != 0.0 && !(sq >= 1.1754943508222875e-38));
+            // H^T H / H^T z partial sums: fused multiply-adds (the summation order over pixels, warps and
+            // blocks already differs from the reference's dense product; parity is to tolerance here)
             int k = 0;
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
 #pragma unroll
-                for (int c = r; c < 6; ++c) { acc[k] += row[r] * row[c]; ++k; }
+                for (int c = r; c < 6; ++c) { acc[k] = fma(row[r], row[c], acc[k]); ++k; }
             }
 #pragma unroll
-            for (int r = 0; r < 6; ++r) acc[21 + r] += row[r] * res;
+            for (int r = 0; r < 6; ++r) acc[21 + r] = fma(row[r], res, acc[21 + r]);
             if (a.x_z) {
                 a.x_z[(size_t)i * 64 + x * 8 + y] = res;
 #pragma unroll
                 for (int r = 0; r < 6; ++r) a.x_H[((size_t)i * 64 + x * 8 + y) * 6 + r] = row[r];
             }
         }
+        tiny = __any_sync(0xffffffffu, tiny);
         __syncwarp();
         if (wdbg && lane == 0) wdbg[2] = global_ns();
         if (lane == 0) {
             // patch_error += res*res : float accumulator, double addend (:843) -- sequential, exact
-            float pe = 0.0f;
+            double ped = 0.0;
 #pragma unroll 8
-            for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[e] * s_res[e]);
+            for (int e = 0; e < 64; ++e) ped = round_to_f32_precision(ped + s_res[e]);
+            float pe = (float)ped;
+            if (tiny || !(ped < 3.0e38)) {                          // outside the shortcut's domain: literal form
+                pe = 0.0f;
+                for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[e]);
+            }
             a.errors[i] = pe;                                       // :851
             n_meas += 64.0;
             if (wdbg) wdbg[3] = global_ns();
         }
         __syncwarp();
+        accv += warp_transpose_reduce<27>(acc);
     } else {
         if (lane == 0) { a.errors[i] = 0.0f; skipped += 1.0; }
         if (a.x_z) {
@@ -644,12 +689,11 @@ __device__ __forceinline__ void vio_make_pose_from(const VioArgs& a, VioPose& po
 }
 
 template <int BLOCK>
-__device__ __forceinline__ void vio_block_reduce_store(const double (&acc)[27], double n_meas, double skipped,
+__device__ __forceinline__ void vio_block_reduce_store(double accv, double n_meas, double skipped,
                                                        double (*s_acc)[kVioPacked], double* partials) {
     constexpr int NW = BLOCK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double v = warp_transpose_reduce<27>(acc);
-    if (lane < 27) s_acc[warp][lane] = v;
+    if (lane < 27) s_acc[warp][lane] = accv;
     if (lane == 0) { s_acc[warp][27] = n_meas; s_acc[warp][28] = skipped; }   // only lane 0 counts patches
     __syncthreads();
     for (int q = threadIdx.x; q < kVioPacked; q += BLOCK) {
@@ -678,12 +722,13 @@ __global__ void __launch_bounds__(BLOCK) k_vio_pass(VioArgs a) {
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int i = blockIdx.x * NW + warp;
-    double acc[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = 0.0;
-    double n_meas = 0.0, skipped = 0.0;
-    if (i < a.Pn) vio_patch(a, s_pose, level, i, s_lat[warp], s_res[warp], acc, n_meas, skipped);
-    vio_block_reduce_store<BLOCK>(acc, n_meas, skipped, s_acc, a.partials);
+    double accv = 0.0, n_meas = 0.0, skipped = 0.0;
+    if (i < a.Pn) {
+        PatchIn in;
+        vio_patch_load(a, i, threadIdx.x & 31, in);
+        vio_patch(a, s_pose, level, i, in, s_lat[warp], s_res[warp], accv, n_meas, skipped);
+    }
+    vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
 }
 
 // =======================================================================================
@@ -711,6 +756,7 @@ struct LeaderSmem {
     double K[kDim * 6];       // K1[:, :6]
     double vec[kDim], sol[kDim], Gc[kDim * 6];
     double xold[24];          // VIO: the pose/bias block before the accepted step (old_state, :863)
+    double xspec[24];         // VIO: state (+) solution, formed before the accept test is known
     double top[6 * kDim];
     double packed[32];
     double part[16][32];
@@ -1236,11 +1282,23 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                 }
                 __syncwarp();
                 if (lane == 0) {
+                    // 16 addends per step, the next 16 fetched from shared memory while these are added:
+                    // the chain then runs at one FADD latency per patch
                     float e = e_run;
+                    const float4* s4 = reinterpret_cast<const float4*>(s_err);
                     int i = 0;
-                    for (; i + 8 <= nchunk; i += 8) {
-                        e = e + s_err[i]; e = e + s_err[i + 1]; e = e + s_err[i + 2]; e = e + s_err[i + 3];
-                        e = e + s_err[i + 4]; e = e + s_err[i + 5]; e = e + s_err[i + 6]; e = e + s_err[i + 7];
+                    float4 n0, n1, n2, n3;
+                    if (nchunk >= 16) { n0 = s4[0]; n1 = s4[1]; n2 = s4[2]; n3 = s4[3]; }
+                    for (; i + 16 <= nchunk; i += 16) {
+                        const float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+                        {   // unconditional, index clamped into the array (unused past the end of the chunk)
+                            const int q = min((i >> 2) + 4, kErrChunk / 4 - 4);
+                            n0 = s4[q]; n1 = s4[q + 1]; n2 = s4[q + 2]; n3 = s4[q + 3];
+                        }
+                        e = e + c0.x; e = e + c0.y; e = e + c0.z; e = e + c0.w;
+                        e = e + c1.x; e = e + c1.y; e = e + c1.z; e = e + c1.w;
+                        e = e + c2.x; e = e + c2.y; e = e + c2.z; e = e + c2.w;
+                        e = e + c3.x; e = e + c3.y; e = e + c3.z; e = e + c3.w;
                     }
                     for (; i < nchunk; ++i) e = e + s_err[i];
                     e_run = e;
@@ -1271,6 +1329,10 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         T::sync();
         if (tid < 32) {
             leader_fast_solve(sm, s.prm.sigma, -1.0, tid);                                // :871-878 (sign: :878)
+            // the accepted outcome (*state += solution, :879) is formed while the error sum is still running
+            if (tid < 24) sm.xspec[tid] = reinterpret_cast<const double*>(&sm.x)[tid];
+            __syncwarp();
+            if (tid == 0) state_boxplus(*reinterpret_cast<State18*>(sm.xspec), sm.sol);    // touches the 24 pose/bias doubles only
             FLB_STAMP(2);
             asm volatile("bar.sync 3, 64;" ::: "memory");                   // sm.error is ready
             FLB_STAMP(4);
@@ -1322,9 +1384,10 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
             __syncwarp();
             FLB_STAMP(5);
             if (sm.flags[0]) {
-                if (tid < 24) sm.xold[tid] = reinterpret_cast<const double*>(&sm.x)[tid];  // old_state = *state (:863)
-                __syncwarp();
-                if (tid == 0) state_boxplus(sm.x, sm.sol);                                 // :879
+                if (tid < 24) {
+                    sm.xold[tid] = reinterpret_cast<const double*>(&sm.x)[tid];            // old_state = *state (:863)
+                    reinterpret_cast<double*>(&sm.x)[tid] = sm.xspec[tid];                 // :879
+                }
             } else {
                 if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(reinterpret_cast<const double*>(s.old_state) + tid);
             }                                                                              // *state = old_state (:890)
@@ -1381,7 +1444,7 @@ __global__ void __launch_bounds__(32) k_vio_begin(VioCtrl* ctrl, int Pn_total) {
 __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl c;
-    __shared__ float s_err[kErrChunk];
+    __shared__ __align__(16) float s_err[kErrChunk];
     if (s.ctrl->stop) return;
     const int tid = threadIdx.x;
     if (tid == 0) c = *s.ctrl;
@@ -1629,7 +1692,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl s_ctrl;
-    __shared__ float s_err[kErrChunk];
+    __shared__ __align__(16) float s_err[kErrChunk];
     const int tid = threadIdx.x, warp = tid >> 5;
     if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
     bool first = true;
@@ -1645,6 +1708,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
         c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
         s_ctrl = c;
     }
+    // every warp owns at most one patch: its pose-independent inputs stay in registers for all passes
+    const bool single = gridDim.x * NW >= a.Pn;
+    PatchIn pin;
+    if (single && blockIdx.x * NW + warp < a.Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
     __syncthreads();
     for (;;) {
         if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
@@ -1652,14 +1719,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
         __syncthreads();
         if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();
         const int level = s_ctrl.level;
-        double acc[27];
-#pragma unroll
-        for (int k = 0; k < 27; ++k) acc[k] = 0.0;
-        double n_meas = 0.0, skipped = 0.0;
-        for (int i = blockIdx.x * NW + warp; i < a.Pn; i += gridDim.x * NW)
-            vio_patch(a, s_pose, level, i, s_lat[warp], s_res[warp], acc, n_meas, skipped,
+        double accv = 0.0, n_meas = 0.0, skipped = 0.0;
+        for (int i = blockIdx.x * NW + warp; i < a.Pn; i += gridDim.x * NW) {
+            if (!single) vio_patch_load(a, i, tid & 31, pin);
+            vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
                       dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr);
-        vio_block_reduce_store<BLOCK>(acc, n_meas, skipped, s_acc, a.partials);
+        }
+        vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
         if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();
         const bool leader = grid_arrive_ticket(bar, gridDim.x * (unsigned)(pass_no + 1) - 1u, s_bar);
         if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 3] = global_ns();
