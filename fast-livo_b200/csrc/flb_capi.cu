@@ -201,6 +201,7 @@ struct flb_handle {
     DevBuf<unsigned long long> dbg;    // per-block stage stamps of the last LIO pass (tracing only)
     DevBuf<unsigned long long> dbg_vio;
     int dbg_vio_blocks = 0;
+    int dbg_blocks = 0;
     bool tracing = false;
     int num_sms = 0;
     int occ_lio = 0, occ_vio = 0;
@@ -465,18 +466,24 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     if (h->cfg.persistent && (!h->comm || h->p2p.world > 1)) {
         // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
         // whole multiples of the SM count (<= co-resident capacity): chunks are dealt round-robin to blocks
-        const int cap = std::max(1, h->occ_lio * h->num_sms);
-        const int grid = std::max(1, std::min((h->N + 31) / 32, std::min(cap, h->num_sms)));
+        // worker blocks (one per SM, chunks dealt round-robin) + one leader block
+        const int cap = std::min(h->occ_lio * h->num_sms, h->num_sms);
+        if (cap < 2) return fail(h, FLB_ERR_STATE, "persistent mode needs two co-resident blocks");
+        const int workers = std::max(1, std::min((h->N + 31) / 32, cap - 1));
+        const int grid = workers + 1;
         FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * lio_packed(12), h->partials.cap)));
         a.partials = h->partials.p;
         s.partials = h->partials.p;
-        s.nblocks = grid;
+        s.nblocks = workers;
         GridBarrier* bar = h->barrier.p;
         unsigned long long* trace = h->tracing ? h->trace.p : nullptr;
         a.probe = h->tracing ? h->trace.p + 112 : nullptr;
+        a.chunk = std::max(1, std::min(32, (h->N + workers * (kLioPersBlock / 32) - 1) / (workers * (kLioPersBlock / 32))));
         unsigned long long* dbg = nullptr;
         if (h->tracing) {
-            FLB_CUDA(h, h->dbg.reserve((size_t)grid * 8));
+            FLB_CUDA(h, h->dbg.reserve((size_t)grid * 16));
+            FLB_CUDA(h, cudaMemsetAsync(h->dbg.p, 0, (size_t)grid * 16 * sizeof(unsigned long long), h->stream));
+            h->dbg_blocks = grid;
             dbg = h->dbg.p;
         }
         unsigned long long* pkt = h->pkt.p;
@@ -561,13 +568,15 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     a.partials = h->partials.p;
     const int nb = vio_nblocks(h);
     if (persistent) {
-        const int cap = std::max(1, h->occ_vio * h->num_sms);
-        // patches are dealt warp-round-robin: use every co-resident block so all SMs carry equal load
-        const int grid = std::max(1, std::min(std::max(h->Pn, 1), cap));
+        // patches are dealt warp-round-robin over the worker blocks; one more block is the leader
+        const int cap = h->occ_vio * h->num_sms;
+        if (cap < 2) return fail(h, FLB_ERR_STATE, "persistent mode needs two co-resident blocks");
+        const int workers = std::max(1, std::min(std::max(h->Pn, 1), cap - 1));
+        const int grid = workers + 1;
         FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * kVioPacked, h->partials.cap)));
         a.partials = h->partials.p;
         s.partials = h->partials.p;
-        s.nblocks = grid;
+        s.nblocks = workers;
         GridBarrier* bar = h->barrier.p;
         unsigned long long* trace = h->tracing ? h->trace.p + kTraceLen : nullptr;
         unsigned long long* pkt = h->pkt.p;
@@ -1504,8 +1513,8 @@ int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks,
 int flb_debug_block_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks) {
     FLB_CHECK_H(h);
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
-    const int n = (int)std::min<size_t>(h->dbg.cap / 8, (size_t)max_blocks);
-    if (n > 0) FLB_CUDA(h, cudaMemcpy(out, h->dbg.p, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const int n = std::min(h->dbg_blocks, max_blocks);     // 16 words per block: 4 block stamps, 8 warp stamps
+    if (n > 0) FLB_CUDA(h, cudaMemcpy(out, h->dbg.p, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     *nblocks = n;
     return FLB_OK;
 }

@@ -359,6 +359,7 @@ struct LioArgs {
     double* x_rows;              // N*W
     double* x_meas;              // N
     unsigned long long* probe;   // profiling aid: stage timestamps of one thread (or null)
+    int chunk;                   // persistent kernel: points per warp-chunk (1..32)
 };
 
 template <int W>
@@ -1537,17 +1538,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Arrive with release/acquire semantics; true (to every thread of the block) for the last arriver.
-__device__ __forceinline__ bool grid_arrive_ticket(GridBarrier* b, unsigned last_ticket, unsigned* s_scratch) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(&b->count) : "memory");
-        s_scratch[0] = (t == last_ticket) ? 1u : 0u;
-    }
-    __syncthreads();
-    return s_scratch[0] != 0;
-}
 // Waiting block: warp 0 polls, then the words go to x / c in shared memory.  Returns false (to the
 // whole block) when the watchdog (~seconds) tripped: a would-be hang becomes FLB_ERR_TIMEOUT.
 template <int NC>
@@ -1603,9 +1593,33 @@ __device__ __forceinline__ void lio_pose_from(const LioParamsDev& prm, const Sta
     m3_T(pose.R_LI, pose.RLIt);
 }
 
+// Workers: arrive (release) without waiting for the ticket.
+__device__ __forceinline__ void grid_arrive_release(GridBarrier* b) {
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&b->count) : "memory");
+}
+// Leader block: wait until `target` arrivals have been counted (acquire).  False when the watchdog tripped.
+__device__ __forceinline__ bool leader_wait_arrivals(GridBarrier* b, unsigned target, unsigned* s_scratch) {
+    if (threadIdx.x == 0) {
+        unsigned ok = 1u;
+        unsigned long long spins = 0;
+        while (ld_acquire_u32(&b->count) != target) {
+            if (++spins > 40000000ull) { ok = 0u; b->timeout = 1; break; }
+            if ((spins & 0xffff) == 0 && *((volatile int*)&b->timeout)) { ok = 0u; break; }
+        }
+        s_scratch[1] = ok;
+    }
+    __syncthreads();
+    return s_scratch[1] != 0u;
+}
+
 // ---------------------------------------------------------------------------------------
 // LIO: whole iterated update in one launch
 // ---------------------------------------------------------------------------------------
+// Grid = worker blocks + ONE leader block (the last one).  The leader owns no points: it waits for the
+// arrivals of each pass, reduces, solves and publishes the pose packet.  Keeping the leader on one SM
+// keeps its code and its constants (prior block, state_propagat, covariance) warm from pass to pass;
+// a last-arriver leader would run the solve on a different, cold SM every pass.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, LioSolveArgs s, GridBarrier* bar,
                                                                  unsigned long long* pkt, unsigned epoch,
@@ -1619,6 +1633,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     __shared__ LioCtrl s_ctrl;       // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
     __shared__ int s_rows[18][BLOCK];
     const int tid = threadIdx.x;
+    const int nworkers = (int)gridDim.x - 1;
+    const bool is_leader = (int)blockIdx.x == nworkers;
     bool first = true;
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
@@ -1634,33 +1650,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     }
     __syncthreads();
     for (;;) {
-        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = global_ns();
-        if (tid == 0) lio_pose_from(a.prm, sm.x, s_pose);
-        __syncthreads();
-        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 1] = global_ns();
-        const int nearest = s_ctrl.nearest_search_en;
-        double acc[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.0;
-        // 32-point (Morton-contiguous) chunks dealt round-robin to the blocks, so that every SM gets the
-        // same number of warps' worth of work whatever N is; the chunk -> thread map is the same in
-        // every pass, so each thread re-reads only its own per-point cache entries.
-        for (int c = (tid >> 5) * gridDim.x + blockIdx.x; c * 32 < a.N; c += (BLOCK / 32) * gridDim.x) {
-            const int i = c * 32 + (tid & 31);
-            if (i < a.N) {
-                bool active;
-                double row[6], z, absres;
-                lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres, &s_rows[0][tid], BLOCK);
-                if (active) lio_accumulate<6>(acc, row, z, absres);
-            }
-        }
-        if (dbg && (tid & 31) == 0) dbg[blockIdx.x * 8 + 4 + (tid >> 5)] = global_ns();   // per warp: compute done
-        block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
-        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 2] = global_ns();
-        const bool leader = grid_arrive_ticket(bar, gridDim.x * (unsigned)(pass_no + 1) - 1u, s_bar);
-        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 3] = global_ns();
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
-        if (leader) {
+        if (is_leader) {
+            if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr;
             lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, pkt, flag, fine);
@@ -1668,6 +1660,32 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
             lio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, fine);
             if (s_ctrl.stop && tid == 0) bar->count = 0;
         } else {
+            if (dbg && tid == 0) dbg[blockIdx.x * 16 + 0] = global_ns();
+            if (tid == 0) lio_pose_from(a.prm, sm.x, s_pose);
+            __syncthreads();
+            if (dbg && tid == 0) dbg[blockIdx.x * 16 + 1] = global_ns();
+            const int nearest = s_ctrl.nearest_search_en;
+            double acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = 0.0;
+            // Morton-contiguous chunks of a.chunk <= 32 points (sized by the host so that every warp of every
+            // worker gets one chunk when N allows: the pass is latency-bound, so spreading the points over all
+            // warps beats filling lanes) dealt round-robin to the worker blocks; the chunk -> thread map is the
+            // same in every pass, so each thread re-reads only its own per-point cache entries.
+            for (int c = (tid >> 5) * nworkers + blockIdx.x; c * a.chunk < a.N; c += (BLOCK / 32) * nworkers) {
+                const int i = c * a.chunk + (tid & 31);
+                if ((tid & 31) < a.chunk && i < a.N) {
+                    bool active;
+                    double row[6], z, absres;
+                    lio_point<6>(a, s_pose, nearest != 0, i, active, row, z, absres, &s_rows[0][tid], BLOCK);
+                    if (active) lio_accumulate<6>(acc, row, z, absres);
+                }
+            }
+            if (dbg && (tid & 31) == 0) dbg[blockIdx.x * 16 + 4 + (tid >> 5)] = global_ns();   // per warp: compute done
+            block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
+            if (dbg && tid == 0) dbg[blockIdx.x * 16 + 2] = global_ns();
+            grid_arrive_release(bar);
+            if (dbg && tid == 0) dbg[blockIdx.x * 16 + 3] = global_ns();
             if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar)) return;
         }
         first = false;
@@ -1677,7 +1695,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
 }
 
 // ---------------------------------------------------------------------------------------
-// VIO: ComputeJ (3 levels x up to T passes) in one launch
+// VIO: ComputeJ (3 levels x up to T passes) in one launch  (same worker / leader split)
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
@@ -1695,6 +1713,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __shared__ __align__(16) float s_err[kErrChunk];
     const int tid = threadIdx.x, warp = tid >> 5;
     if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
+    const int nworkers = (int)gridDim.x - 1;
+    const bool is_leader = (int)blockIdx.x == nworkers;
     bool first = true;
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
@@ -1709,28 +1729,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
         s_ctrl = c;
     }
     // every warp owns at most one patch: its pose-independent inputs stay in registers for all passes
-    const bool single = gridDim.x * NW >= a.Pn;
+    const bool single = nworkers * NW >= a.Pn;
     PatchIn pin;
-    if (single && blockIdx.x * NW + warp < a.Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
+    if (single && !is_leader && blockIdx.x * NW + warp < a.Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
     __syncthreads();
     for (;;) {
-        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
-        if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
-        __syncthreads();
-        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();
-        const int level = s_ctrl.level;
-        double accv = 0.0, n_meas = 0.0, skipped = 0.0;
-        for (int i = blockIdx.x * NW + warp; i < a.Pn; i += gridDim.x * NW) {
-            if (!single) vio_patch_load(a, i, tid & 31, pin);
-            vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
-                      dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr);
-        }
-        vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
-        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();
-        const bool leader = grid_arrive_ticket(bar, gridDim.x * (unsigned)(pass_no + 1) - 1u, s_bar);
-        if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 3] = global_ns();
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
-        if (leader) {
+        if (is_leader) {
+            if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 32 + 8 * pass_no + 8 <= kTraceLen) ? trace + 32 + 8 * pass_no : nullptr;
             vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, fine);
@@ -1738,6 +1744,21 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false);
             if (s_ctrl.stop && tid == 0) bar->count = 0;
         } else {
+            if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
+            if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
+            __syncthreads();
+            if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();
+            const int level = s_ctrl.level;
+            double accv = 0.0, n_meas = 0.0, skipped = 0.0;
+            for (int i = blockIdx.x * NW + warp; i < a.Pn; i += nworkers * NW) {
+                if (!single) vio_patch_load(a, i, tid & 31, pin);
+                vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
+                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr);
+            }
+            vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
+            if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();
+            grid_arrive_release(bar);
+            if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 3] = global_ns();
             if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar)) return;
         }
         first = false;

@@ -25,24 +25,25 @@ print("probe thread (last rematch pass): start", round(pr[0], 2), "knn", round(p
       "residual+row", round(pr[3] - pr[2], 2), "; pass began at", round(t[4], 2), "all arrived at", round(t[5], 2))
 # per-block stamps of the last pass
 h.L.flb_debug_block_stamps.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
-buf = np.zeros((512, 8), np.uint64); nb = C.c_int()
+buf = np.zeros((512, 16), np.uint64); nb = C.c_int()
 h.L.flb_debug_block_stamps(h.h, buf.ctypes.data_as(C.c_void_p), 512, C.byref(nb))
-b = buf[:nb.value].astype(np.float64)
+b = buf[:nb.value - 1].astype(np.float64)   # worker blocks
 t0 = b[:, 0].min()
 rel = (b - t0) * 1e-3
 def st(x): return "min %.2f p50 %.2f p90 %.2f max %.2f" % (x.min(), np.percentile(x, 50), np.percentile(x, 90), x.max())
 print("blocks", nb.value)
 print("wake (loop start)   ", st(rel[:, 0]))
 print("pose ready          ", st(rel[:, 1]))
-w = rel[:, 4:8]; w = w[w > 0]
+w = rel[:, 4:12]; w = w[w > 0]
 print("warp compute done   ", st(w))
 print("block reduce stored ", st(rel[:, 2]))
 print("arrived             ", st(rel[:, 3]))
-ww = rel[:, 4:8]
-for wi in range(4):
+ww = rel[:, 4:12]
+for wi in range(8):
     col = ww[:, wi]; col = col[col > 0]
     if len(col): print("warp slot", wi, "n", len(col), st(col))
-flat = [(ww[bi, wi], bi, wi, wi * nb.value + bi) for bi in range(nb.value) for wi in range(4) if ww[bi, wi] > 0]
+nwork = nb.value - 1
+flat = [(ww[bi, wi], bi, wi, wi * nwork + bi) for bi in range(nwork) for wi in range(8) if ww[bi, wi] > 0]
 flat.sort(reverse=True)
 print("slowest warps (done_us, block, warp, chunk):", [(round(a, 1), b_, w_, c_) for a, b_, w_, c_ in flat[:16]])
 chunks = np.array([c_ for _, _, _, c_ in flat]); times = np.array([a for a, _, _, _ in flat])
