@@ -531,8 +531,8 @@ FLB_HD void world2cam(const CamModel& cam, const double* pf, double* px) {
 
 // Patch-level quantities of src/lidar_selection.cpp:792-816.
 struct PatchGeom {
-    double Jdpi[6];      // dpi(pf), :92-103
-    double p_hat[9];     // skew(pf), :805
+    double Ja, Jb, Jc, Jd;   // the non-zero entries of dpi(pf) (:92-103): [Ja 0 Jb; 0 Jc Jd]
+    double pf[3];            // p_hat = skew(pf) (:805) is expanded where it is used
     float w_tl, w_tr, w_bl, w_br;
     int u_i, v_i;        // integer anchor
     int scale;
@@ -554,10 +554,10 @@ FLB_HD void vio_patch_geom(const CamModel& cam, const VioPose& vp, const double*
     if (!(fabs(pc[0]) < 1e6) || !(fabs(pc[1]) < 1e6)) return;
     {
         const double x = pf[0], y = pf[1], z_inv = 1. / pf[2], z_inv_2 = z_inv * z_inv;
-        g.Jdpi[0] = cam.jfx * z_inv; g.Jdpi[1] = 0.0; g.Jdpi[2] = -cam.jfx * x * z_inv_2;
-        g.Jdpi[3] = 0.0; g.Jdpi[4] = cam.jfy * z_inv; g.Jdpi[5] = -cam.jfy * y * z_inv_2;
+        g.Ja = cam.jfx * z_inv; g.Jb = -cam.jfx * x * z_inv_2;
+        g.Jc = cam.jfy * z_inv; g.Jd = -cam.jfy * y * z_inv_2;
     }
-    skew3(pf, g.p_hat);
+    g.pf[0] = pf[0]; g.pf[1] = pf[1]; g.pf[2] = pf[2];
     const float u_ref = (float)pc[0];
     const float v_ref = (float)pc[1];
     const int u_i = (int)(floorf((float)(pc[0] / scale)) * (float)scale);   // :809
@@ -591,13 +591,18 @@ FLB_HD void vio_pixel(const Lat& L, const PatchGeom& g, const VioPose& vp, int x
                              (wtl * L(r - 1, c) + wtr * L(r - 1, c + 1) + wbl * L(r, c) + wbr * L(r, c + 1)));
     const double inv_scale = (1.0 / g.scale);
     const double J0 = (double)du * inv_scale, J1 = (double)dv * inv_scale;
+    // Jimg * Jdpi, Jimg * Jdpi * p_hat and -Jimg * Jdpi (:829-833) with the structural zeros of Jdpi and of
+    // p_hat = [0 -z y; z 0 -x; -y x 0] dropped: x*0 + v == v, so only the sign of an exact zero can differ.
     double JJ[3], Jdphi[3], Jdp[3];
-    FLB_UNROLL
-    for (int k = 0; k < 3; ++k) JJ[k] = J0 * g.Jdpi[k] + J1 * g.Jdpi[3 + k];
-    FLB_UNROLL
-    for (int k = 0; k < 3; ++k) Jdphi[k] = JJ[0] * g.p_hat[k] + JJ[1] * g.p_hat[3 + k] + JJ[2] * g.p_hat[6 + k];
-    FLB_UNROLL
-    for (int k = 0; k < 3; ++k) Jdp[k] = (-J0) * g.Jdpi[k] + (-J1) * g.Jdpi[3 + k];
+    JJ[0] = J0 * g.Ja;
+    JJ[1] = J1 * g.Jc;
+    JJ[2] = J0 * g.Jb + J1 * g.Jd;
+    Jdphi[0] = JJ[1] * g.pf[2] + JJ[2] * (-g.pf[1]);
+    Jdphi[1] = JJ[0] * (-g.pf[2]) + JJ[2] * g.pf[0];
+    Jdphi[2] = JJ[0] * g.pf[1] + JJ[1] * (-g.pf[0]);
+    Jdp[0] = (-J0) * g.Ja;
+    Jdp[1] = (-J1) * g.Jc;
+    Jdp[2] = (-J0) * g.Jb + (-J1) * g.Jd;
     FLB_UNROLL
     for (int k = 0; k < 3; ++k)
         row[k] = (Jdphi[0] * vp.Jdphi_dR[k] + Jdphi[1] * vp.Jdphi_dR[3 + k] + Jdphi[2] * vp.Jdphi_dR[6 + k]) +

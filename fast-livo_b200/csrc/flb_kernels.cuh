@@ -624,30 +624,33 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
         if (wdbg && lane == 0) wdbg[1] = global_ns();
         LatView L{s_lat};
         const int x = lane >> 2, y0 = (lane & 3) * 2;
-        bool tiny = false;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int y = y0 + q;
-            double row[6], res;
-            const float refv = (level == 0) ? in.ref[0][q] : ((level == 1) ? in.ref[1][q] : in.ref[2][q]);
-            vio_pixel(L, g, pose, x, y, refv, row, &res);
-            const double sq = res * res;
-            s_res[x * 8 + y] = sq;
-            tiny = tiny || (sq != 0.0 && !(sq >= 1.1754943508222875e-38));
-            // H^T H / H^T z partial sums: fused multiply-adds (the summation order over pixels, warps and
-            // blocks already differs from the reference's dense product; parity is to tolerance here)
+        // both pixels of this lane first (the patch geometry is dead afterwards), then the 21 + 6 products
+        double row0[6], row1[6], res0, res1;
+        vio_pixel(L, g, pose, x, y0, (level == 0) ? in.ref[0][0] : ((level == 1) ? in.ref[1][0] : in.ref[2][0]), row0, &res0);
+        vio_pixel(L, g, pose, x, y0 + 1, (level == 0) ? in.ref[0][1] : ((level == 1) ? in.ref[1][1] : in.ref[2][1]), row1, &res1);
+        const double sq0 = res0 * res0, sq1 = res1 * res1;
+        s_res[x * 8 + y0] = sq0;
+        s_res[x * 8 + y0 + 1] = sq1;
+        bool tiny = (sq0 != 0.0 && !(sq0 >= 1.1754943508222875e-38)) || (sq1 != 0.0 && !(sq1 >= 1.1754943508222875e-38));
+        // H^T H / H^T z partial sums: fused multiply-adds (the summation order over pixels, warps and
+        // blocks already differs from the reference's dense product; parity is to tolerance here)
+        {
             int k = 0;
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
 #pragma unroll
-                for (int c = r; c < 6; ++c) { acc[k] = fma(row[r], row[c], acc[k]); ++k; }
+                for (int c = r; c < 6; ++c) { acc[k] = fma(row1[r], row1[c], row0[r] * row0[c]); ++k; }
             }
 #pragma unroll
-            for (int r = 0; r < 6; ++r) acc[21 + r] = fma(row[r], res, acc[21 + r]);
-            if (a.x_z) {
-                a.x_z[(size_t)i * 64 + x * 8 + y] = res;
+            for (int r = 0; r < 6; ++r) acc[21 + r] = fma(row1[r], res1, row0[r] * res0);
+        }
+        if (a.x_z) {
+            a.x_z[(size_t)i * 64 + x * 8 + y0] = res0;
+            a.x_z[(size_t)i * 64 + x * 8 + y0 + 1] = res1;
 #pragma unroll
-                for (int r = 0; r < 6; ++r) a.x_H[((size_t)i * 64 + x * 8 + y) * 6 + r] = row[r];
+            for (int r = 0; r < 6; ++r) {
+                a.x_H[((size_t)i * 64 + x * 8 + y0) * 6 + r] = row0[r];
+                a.x_H[((size_t)i * 64 + x * 8 + y0 + 1) * 6 + r] = row1[r];
             }
         }
         tiny = __any_sync(0xffffffffu, tiny);
