@@ -1125,21 +1125,24 @@ __device__ __forceinline__ void pkt_publish_warp(unsigned long long* pkt, const 
 #define FLB_STAMP(k) do { if (fine && threadIdx.x == 0) fine[k] = global_ns(); } while (0)
 template <int NT>
 __device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSmem& sm, LioCtrl& c, bool first,
-                                                 unsigned long long* pkt, unsigned flag, unsigned long long* fine = nullptr) {
+                                                 unsigned long long* pkt, unsigned flag, int resident,
+                                                 unsigned long long* fine = nullptr) {
     constexpr int K = lio_packed(6);
     constexpr int NC = (int)(sizeof(LioCtrl) / sizeof(unsigned));
     using T = Team<NT, false>;
     const int tid = threadIdx.x;
     const int T_it = s.prm.max_iteration;
-    if (first) load_cov_l2<NT>(&sm.x, s.state, tid);
-    // later leaders fetch the prior block while the partials are being reduced
-    const double pri = first ? 0.0 : prior_prefetch(s.prior, tid);
-    if (tid == 0) sm.flags[3] = 0;
+    // resident != 0 (persistent kernel): covariance and prior block already sit in this block's shared
+    // memory (leader_prepare); resident == 2 flags a singular prior.  Otherwise the first leader forms the
+    // prior block and later leaders fetch it while the partials are being reduced.
+    if (first && !resident) load_cov_l2<NT>(&sm.x, s.state, tid);
+    const double pri = (first || resident) ? 0.0 : prior_prefetch(s.prior, tid);
+    if (tid == 0) sm.flags[3] = (resident == 2) ? 1 : 0;
     FLB_STAMP(0);
     team_reduce_vec<K, NT, T>(s.partials, s.nblocks, sm, tid);
-    if (!first) prior_commit(sm, pri, tid);
+    if (!first && !resident) prior_commit(sm, pri, tid);
     if (s.p2p.world > 1) p2p_exchange<K, T>(s.p2p, sm, nullptr, 0, tid, s.timeout_flag);
-    if (first) leader_prior<T>(sm, s.prior, tid);
+    if (first && !resident) leader_prior<T>(sm, s.prior, tid);
     __syncthreads();
     FLB_STAMP(1);
     if (tid < 32) {
@@ -1186,13 +1189,13 @@ __device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSm
 // `store_always`: kernel-per-pass path (state and control live in global memory between launches).
 template <int NT>
 __device__ __forceinline__ void lio_leader_finish(const LioSolveArgs& s, LeaderSmem& sm, const LioCtrl& c, bool first,
-                                                  bool store_always, unsigned long long* fine = nullptr) {
+                                                  bool store_always, int resident, unsigned long long* fine = nullptr) {
     const int tid = threadIdx.x;
     const bool stop = sm.flags[0] != 0;
     const bool do_cov = stop && sm.flags[1];
     if (do_cov) {
         if (tid < 36) sm.HTH[tid] = sm.packed[sym6_index(tid / 6, tid % 6)];
-        if (!first) load_cov_l2<NT>(&sm.x, s.state, tid);
+        if (!first && !resident) load_cov_l2<NT>(&sm.x, s.state, tid);
         __syncthreads();
         leader_gain<Team<NT, false>>(sm, s.prm.sigma, tid);
         leader_cov_update(sm, sm.Gc, tid, NT);                                          // :1715
@@ -1228,8 +1231,8 @@ __global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize(LioSolveArgs s) {
     load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     __syncthreads();
     const bool first = c.passes == 0;
-    lio_leader_solve<kLeaderBlock>(s, sm, c, first, nullptr, 0u);
-    lio_leader_finish<kLeaderBlock>(s, sm, c, first, true);
+    lio_leader_solve<kLeaderBlock>(s, sm, c, first, nullptr, 0u, 0);
+    lio_leader_finish<kLeaderBlock>(s, sm, c, first, true, 0);
 }
 
 struct VioSolveArgs {
@@ -1256,7 +1259,8 @@ constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 // level of the pass just done.
 template <int NT>
 __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first,
-                                                 unsigned long long* pkt, unsigned flag, unsigned long long* fine = nullptr) {
+                                                 unsigned long long* pkt, unsigned flag, int resident,
+                                                 unsigned long long* fine = nullptr) {
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     const int tid = threadIdx.x;
     const bool multi = s.p2p.world > 1;
@@ -1317,19 +1321,19 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         // Solve team (first NT-32 threads, named barrier 1).  The covariance is constant during ComputeJ
         // (only :980 changes it, on the last pass), so old_state carries the 24 pose/bias doubles only.
         using T = Team<NT - 32, true>;
-        if (first) load_cov_l2<NT - 32>(&sm.x, s.state, tid);
-        const double pri = first ? 0.0 : prior_prefetch(s.prior, tid);
+        if (first && !resident) load_cov_l2<NT - 32>(&sm.x, s.state, tid);
+        const double pri = (first || resident) ? 0.0 : prior_prefetch(s.prior, tid);
         if (first) store_state(s.old_state, &sm.x, tid, NT - 32, false);                 // old_state = *state (:747)
-        if (tid == 0) sm.flags[3] = 0;
+        if (tid == 0) sm.flags[3] = (resident == 2) ? 1 : 0;
         team_reduce_vec<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
         FLB_STAMP(1);
-        if (!first) prior_commit(sm, pri, tid);
+        if (!first && !resident) prior_commit(sm, pri, tid);
         if (multi) {
             const int par = p2p_exchange<kVioPacked, T>(s.p2p, sm, s.errors, s.Pn_total, tid, s.timeout_flag);
             if (tid == 0) sm.p2p_par = par;
             asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");              // release the error-sum warp
         }
-        if (first) leader_prior<T>(sm, s.prior, tid);
+        if (first && !resident) leader_prior<T>(sm, s.prior, tid);
         T::sync();
         if (tid < 32) {
             leader_fast_solve(sm, s.prm.sigma, -1.0, tid);                                // :871-878 (sign: :878)
@@ -1406,7 +1410,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
 // G_last holds HTH6 of the last ACCEPTED pass (the gain itself is only formed when :980 runs).
 template <int NT>
 __device__ __forceinline__ void vio_leader_finish(const VioSolveArgs& s, LeaderSmem& sm, const VioCtrl& c, bool first,
-                                                  bool store_always) {
+                                                  bool store_always, int resident) {
     const int tid = threadIdx.x;
     const int accept = sm.flags[0], docov = sm.flags[1], newlevel = sm.flags[2];
     if (accept) {
@@ -1415,7 +1419,7 @@ __device__ __forceinline__ void vio_leader_finish(const VioSolveArgs& s, LeaderS
     }
     if (docov) {
         if (tid < 36) sm.HTH[tid] = accept ? sm.packed[sym6_index(tid / 6, tid % 6)] : __ldcg(s.G_last + tid);
-        if (!first) load_cov_l2<NT>(&sm.x, s.state, tid);
+        if (!first && !resident) load_cov_l2<NT>(&sm.x, s.state, tid);
         __syncthreads();
         leader_gain<Team<NT, false>>(sm, s.prm.sigma, tid);
         leader_cov_update(sm, sm.Gc, tid, NT);                                             // :980
@@ -1455,8 +1459,8 @@ __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
     load_poses_l2(&sm.x, s.state, &sm.xp, s.state_prop, tid);
     __syncthreads();
     const bool first = (c.passes[0] + c.passes[1] + c.passes[2]) == 0;
-    vio_leader_solve<kLeaderBlock>(s, sm, c, s_err, first, nullptr, 0u);
-    vio_leader_finish<kLeaderBlock>(s, sm, c, first, true);
+    vio_leader_solve<kLeaderBlock>(s, sm, c, s_err, first, nullptr, 0u, 0);
+    vio_leader_finish<kLeaderBlock>(s, sm, c, first, true, 0);
 }
 
 // =======================================================================================
@@ -1596,6 +1600,20 @@ __device__ __forceinline__ void lio_pose_from(const LioParamsDev& prm, const Sta
     m3_T(pose.R_LI, pose.RLIt);
 }
 
+// Leader block of a persistent kernel, before the first pass has even arrived: fetch the covariance and form
+// the prior block (P11^-1, P21 P11^-1) in shared memory, where both stay for the whole update.
+// Returns 1, or 2 when the prior is singular.
+template <int NT>
+__device__ __forceinline__ int leader_prepare(LeaderSmem& sm, const State18* state, PriorBlock* prior_g) {
+    const int tid = threadIdx.x;
+    load_cov_l2<NT>(&sm.x, state, tid);
+    if (tid == 0) sm.flags[3] = 0;
+    __syncthreads();
+    leader_prior<Team<NT, false>>(sm, prior_g, tid);
+    __syncthreads();
+    return sm.flags[3] ? 2 : 1;
+}
+
 // Workers: arrive (release) without waiting for the ticket.
 __device__ __forceinline__ void grid_arrive_release(GridBarrier* b) {
     __syncthreads();
@@ -1652,15 +1670,17 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
         s_ctrl = c;
     }
     __syncthreads();
+    int resident = 0;
+    if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
     for (;;) {
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
         if (is_leader) {
             if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr;
-            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, pkt, flag, fine);
+            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, pkt, flag, resident, fine);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
-            lio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, fine);
+            lio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, resident, fine);
             if (s_ctrl.stop && tid == 0) bar->count = 0;
         } else {
             if (dbg && tid == 0) dbg[blockIdx.x * 16 + 0] = global_ns();
@@ -1736,15 +1756,17 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     PatchIn pin;
     if (single && !is_leader && blockIdx.x * NW + warp < a.Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
     __syncthreads();
+    int resident = 0;
+    if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
     for (;;) {
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
         if (is_leader) {
             if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 32 + 8 * pass_no + 8 <= kTraceLen) ? trace + 32 + 8 * pass_no : nullptr;
-            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, fine);
+            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
-            vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false);
+            vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, resident);
             if (s_ctrl.stop && tid == 0) bar->count = 0;
         } else {
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
