@@ -12,6 +12,8 @@
 //        src/laserMapping.cpp:960-1094           (IKFoM-typed callback; rows from the GPU)
 //   flb::compute_j(h, prm, img, sub_sparse_map, state, state_propagat)   replaces
 //        LidarSelector::ComputeJ(cv::Mat)  src/lidar_selection.cpp:967-983
+//   flb::undistort_pcl(h, prm, carry, v_imu, pcl_beg_time, pcl_end_time, state_inout, pcl_out)   replaces
+//        ImuProcess::UndistortPcl from src/IMU_Processing.cpp:655 on (propagation + undistortion)
 //
 // Type requirements (all met by the reference's types):
 //   Mat3  : operator()(i,j) read/write (Eigen::Matrix3d)          Vec3 : operator()(i) / [i]
@@ -198,6 +200,58 @@ inline flb_vio_report compute_j(flb_handle* h, const flb_vio_params& prm, const 
     check(h, flb_vio_update(h, &prm, &x, &xp, &rep));
     from_abi(x, state);
     return rep;
+}
+
+// ---- IMU forward propagation + backward undistortion (src/IMU_Processing.cpp:655-808) ----------------
+// ImuDeque  : the reference's `v_imu` (std::deque<sensor_msgs::Imu::ConstPtr>, last_imu_ pushed to the front,
+//             :617-618): elements dereference to .header.stamp.toSec(), .angular_velocity.{x,y,z},
+//             .linear_acceleration.{x,y,z}
+// PointCloud: pcl_out (:623-639), already cut to this update's points, in time order; compensated in place.
+// `carry` holds ImuProcess::last_lidar_end_time_, acc_s_last, angvel_last (the caller keeps `last_imu_ =
+// v_imu.back()` itself, :760).  On return state_inout is the propagated state (rot/pos/vel_end, cov).
+template <class Mat3, class Vec3>
+inline flb_imu_params make_imu_params(const Vec3& cov_gyr, const Vec3& cov_acc, const Vec3& cov_bias_gyr, const Vec3& cov_bias_acc,
+                                      double G_m_s2, double mean_acc_norm, const Mat3& Lid_rot_to_IMU, const Vec3& Lid_offset_to_IMU) {
+    flb_imu_params p{};
+    for (int i = 0; i < 3; ++i) {
+        p.cov_gyr[i] = cov_gyr(i); p.cov_acc[i] = cov_acc(i); p.cov_bias_gyr[i] = cov_bias_gyr(i); p.cov_bias_acc[i] = cov_bias_acc(i);
+        p.t_LI[i] = Lid_offset_to_IMU(i);
+        for (int j = 0; j < 3; ++j) p.R_LI[3 * i + j] = Lid_rot_to_IMU(i, j);
+    }
+    p.G_m_s2 = G_m_s2;
+    p.mean_acc_norm = mean_acc_norm;
+    return p;
+}
+
+template <class ImuDeque, class StatesGroup, class PointCloud>
+inline void undistort_pcl(flb_handle* h, const flb_imu_params& prm, flb_imu_carry& carry, const ImuDeque& v_imu,
+                          double pcl_beg_time, double pcl_end_time, StatesGroup& state_inout, PointCloud& pcl_out) {
+    std::vector<flb_imu_sample> s;
+    s.reserve(v_imu.size());
+    for (const auto& m : v_imu) {
+        flb_imu_sample e;
+        e.t = m->header.stamp.toSec();
+        e.gyr[0] = m->angular_velocity.x; e.gyr[1] = m->angular_velocity.y; e.gyr[2] = m->angular_velocity.z;
+        e.acc[0] = m->linear_acceleration.x; e.acc[1] = m->linear_acceleration.y; e.acc[2] = m->linear_acceleration.z;
+        s.push_back(e);
+    }
+    flb_state18 x{};
+    to_abi(state_inout, x);
+    check(h, flb_state_upload(h, &x, &x));
+    static_assert(sizeof(pcl_out.points[0]) % sizeof(float) == 0, "point type must be float-packed");
+    const int stride = (int)(sizeof(pcl_out.points[0]) / sizeof(float));
+    const int n = (int)pcl_out.points.size();
+    const int off = n ? (int)(&pcl_out.points[0].curvature - &pcl_out.points[0].x) : 3;
+    std::vector<float> out((size_t)n * 3 + 1);
+    check(h, flb_imu_undistort(h, &prm, &carry, s.data(), (int)s.size(), pcl_beg_time, pcl_end_time,
+                               n ? &pcl_out.points[0].x : nullptr, n ? stride : 4, off, n, out.data(), nullptr, nullptr));
+    for (int i = 0; i < n; ++i) {
+        pcl_out.points[i].x = out[3 * (size_t)i];
+        pcl_out.points[i].y = out[3 * (size_t)i + 1];
+        pcl_out.points[i].z = out[3 * (size_t)i + 2];
+    }
+    check(h, flb_state_download(h, &x, nullptr, nullptr));
+    from_abi(x, state_inout);
 }
 
 }  // namespace flb

@@ -31,6 +31,18 @@ class Config(C.Structure):
                 ("plane_threshold", C.c_double), ("persistent", C.c_int), ("reserved", C.c_int * 7)]
 
 
+class ImuParams(C.Structure):
+    """flb_imu_params (include/fastlivo_b200.h)."""
+    _fields_ = [("cov_gyr", C.c_double * 3), ("cov_acc", C.c_double * 3), ("cov_bias_gyr", C.c_double * 3),
+                ("cov_bias_acc", C.c_double * 3), ("G_m_s2", C.c_double), ("mean_acc_norm", C.c_double),
+                ("R_LI", C.c_double * 9), ("t_LI", C.c_double * 3)]
+
+
+class ImuCarry(C.Structure):
+    """flb_imu_carry: last_lidar_end_time_, acc_s_last, angvel_last of ImuProcess."""
+    _fields_ = [("last_lidar_end_time", C.c_double), ("acc_s_last", C.c_double * 3), ("angvel_last", C.c_double * 3)]
+
+
 class State18(C.Structure):
     _fields_ = [("rot", C.c_double * 9), ("pos", C.c_double * 3), ("vel", C.c_double * 3),
                 ("bg", C.c_double * 3), ("ba", C.c_double * 3), ("grav", C.c_double * 3),
@@ -190,6 +202,8 @@ def lib():
         L.flb_lio_export.argtypes = [vp] + [vp] * 9 + [C.POINTER(C.c_int)]
         L.flb_lio_update.argtypes = [vp, C.POINTER(LioParams), C.POINTER(State18), C.POINTER(State18), C.POINTER(LioReport)]
         L.flb_lio_update_ikfom.argtypes = [vp, C.POINTER(IkfomParams), C.POINTER(StateIkfom), C.POINTER(IkfomReport)]
+        L.flb_imu_undistort.argtypes = [vp, C.POINTER(ImuParams), C.POINTER(ImuCarry), vp, C.c_int, C.c_double, C.c_double,
+                                        vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
         L.flb_image_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.flb_patches_upload.argtypes = [vp, vp, vp, vp, C.c_int]
         L.flb_camera_set.argtypes = [vp, C.POINTER(Camera)]
@@ -399,6 +413,23 @@ class Handle:
         rep = VioReport()
         self._ck(self.L.flb_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep)))
         return rep
+
+    # ---- IMU propagation + undistortion (row f3)
+    def imu_undistort(self, prm: ImuParams, carry: ImuCarry, v_imu, pcl_beg_time, pcl_end_time, pts, offset_index=3):
+        """flb_imu_undistort on the device state.  v_imu (K,7) [t, gyr, acc]; pts (n, stride) float32 with x,y,z
+        first and the time offset (ms) at column offset_index.  Returns (xyz (n,3) float32, IMUpose (n_poses,22));
+        carry is updated in place, the device state is propagated in place."""
+        v = np.ascontiguousarray(v_imu, np.float64)
+        pts = np.ascontiguousarray(pts, np.float32)
+        n = pts.shape[0]
+        out = np.zeros((n, 3), np.float32)
+        poses = np.zeros((len(v), 22), np.float64)
+        npo = C.c_int()
+        self._ck(self.L.flb_imu_undistort(self.h, C.byref(prm), C.byref(carry), v.ctypes.data_as(C.c_void_p), len(v),
+                                          float(pcl_beg_time), float(pcl_end_time), pts.ctypes.data_as(C.c_void_p),
+                                          pts.shape[1] if n else 4, offset_index, n, out.ctypes.data_as(C.c_void_p),
+                                          poses.ctypes.data_as(C.c_void_p), C.byref(npo)))
+        return out, poses[:npo.value]
 
     # ---- device-resident loop
     def state_upload(self, x: State18, x_prop: State18):

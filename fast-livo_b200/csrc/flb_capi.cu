@@ -200,6 +200,9 @@ struct flb_handle {
     DevBuf<unsigned long long> trace;  // [0..kTraceLen) LIO, [kTraceLen..2*kTraceLen) VIO
     DevBuf<unsigned long long> dbg;    // per-block stage stamps of the last LIO pass (tracing only)
     DevBuf<unsigned long long> dbg_vio;
+    DevBuf<double> imu_buf;            // flb_imu_undistort: samples | carry | aux | poses
+    DevBuf<float4> imu_pts;            // in | out
+    DevBuf<int> imu_heads;
     int dbg_vio_blocks = 0;
     int dbg_blocks = 0;
     bool tracing = false;
@@ -709,7 +712,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->dbg_vio.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->dbg_vio.release(); h->imu_buf.release(); h->imu_pts.release(); h->imu_heads.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
@@ -938,6 +941,94 @@ int flb_map_download(flb_handle* h, float* xyz, int capacity, int* M_out) {
     const int n = std::min(capacity, h->M);
     FLB_CUDA(h, cudaMemcpyAsync(xyz, h->map_raw.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+int flb_imu_undistort(flb_handle* h, const flb_imu_params* prm, flb_imu_carry* carry, const flb_imu_sample* v_imu, int n_imu,
+                      double pcl_beg_time, double pcl_end_time, const float* pts, int stride, int offset_index, int n_points,
+                      float* out_xyz, double* poses_out, int* n_poses_out) {
+    FLB_CHECK_H(h);
+    if (!prm || !carry || !v_imu || n_imu < 1 || n_points < 0 || (n_points > 0 && (!pts || !out_xyz)) || stride < 4 ||
+        offset_index < 3 || offset_index >= stride)
+        return fail(h, FLB_ERR_INVALID, "flb_imu_undistort: bad arguments");
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_imu_undistort: no device state (flb_state_upload)");
+    for (int i = 0; i + 1 < n_imu; ++i)
+        if (!(v_imu[i + 1].t >= v_imu[i].t)) return fail(h, FLB_ERR_INVALID, "flb_imu_undistort: IMU times must be non-decreasing");
+    static_assert(sizeof(ImuSampleDev) == sizeof(flb_imu_sample) && sizeof(ImuCarryDev) == sizeof(flb_imu_carry), "ABI layout");
+    static_assert(sizeof(ImuPose) == 22 * sizeof(double), "IMUpose layout");
+    ImuParamsDev d;
+    std::memcpy(d.cov_gyr, prm->cov_gyr, sizeof(d.cov_gyr));
+    std::memcpy(d.cov_acc, prm->cov_acc, sizeof(d.cov_acc));
+    std::memcpy(d.cov_bias_gyr, prm->cov_bias_gyr, sizeof(d.cov_bias_gyr));
+    std::memcpy(d.cov_bias_acc, prm->cov_bias_acc, sizeof(d.cov_bias_acc));
+    d.G_m_s2 = prm->G_m_s2;
+    d.mean_acc_norm = prm->mean_acc_norm;
+    std::memcpy(d.R_LI, prm->R_LI, sizeof(d.R_LI));
+    std::memcpy(d.t_LI, prm->t_LI, sizeof(d.t_LI));
+    const size_t n1 = (size_t)std::max(n_points, 1);
+    // device buffers: samples + carry + aux + poses packed in one double array, points as float4 in/out
+    const size_t off_carry = (size_t)n_imu * 7, off_aux = off_carry + 7, off_poses = off_aux + 16, total = off_poses + (size_t)n_imu * 22;
+    FLB_CUDA(h, h->imu_buf.reserve(total));
+    FLB_CUDA(h, h->imu_pts.reserve(n1 * 2));
+    FLB_CUDA(h, h->imu_heads.reserve(n1));
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_scan.acquire(n1 * 4 * sizeof(float) + (off_aux) * sizeof(double), &stv));
+    double* st_d = static_cast<double*>(stv);
+    std::memcpy(st_d, v_imu, (size_t)n_imu * sizeof(flb_imu_sample));
+    std::memcpy(st_d + off_carry, carry, sizeof(flb_imu_carry));
+    float* st_p = reinterpret_cast<float*>(st_d + off_aux);
+    for (int i = 0; i < n_points; ++i) {
+        st_p[4 * (size_t)i] = pts[(size_t)i * stride];
+        st_p[4 * (size_t)i + 1] = pts[(size_t)i * stride + 1];
+        st_p[4 * (size_t)i + 2] = pts[(size_t)i * stride + 2];
+        st_p[4 * (size_t)i + 3] = pts[(size_t)i * stride + offset_index];
+    }
+    FLB_CUDA(h, cudaMemcpyAsync(h->imu_buf.p, st_d, off_aux * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    float4* d_in = h->imu_pts.p;
+    float4* d_out = h->imu_pts.p + n1;
+    if (n_points > 0)
+        FLB_CUDA(h, cudaMemcpyAsync(d_in, st_p, (size_t)n_points * 4 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_scan.mark(h->stream));
+    const ImuSampleDev* d_imu = reinterpret_cast<const ImuSampleDev*>(h->imu_buf.p);
+    ImuCarryDev* d_carry = reinterpret_cast<ImuCarryDev*>(h->imu_buf.p + off_carry);
+    ImuAux* d_aux = reinterpret_cast<ImuAux*>(h->imu_buf.p + off_aux);
+    ImuPose* d_poses = reinterpret_cast<ImuPose*>(h->imu_buf.p + off_poses);
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_imu_propagate<<<1, 352, 0, h->stream>>>(&h->states.p[0], d_imu, n_imu, d, pcl_beg_time, pcl_end_time, d_carry, d_poses, d_aux);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    if (n_points > 0) {                                                           // :776
+        const int g = (n_points + 255) / 256;
+        const float* in_f = reinterpret_cast<const float*>(d_in);
+        LaunchScope ls(h, FAM_OTHER);
+        k_imu_heads<<<g, 256, 0, h->stream>>>(in_f + 3, 4, n_points, d_poses, d_aux, h->imu_heads.p);
+        k_suffix_min<<<1, 1024, 0, h->stream>>>(h->imu_heads.p, n_points);
+        k_imu_undistort<<<g, 256, 0, h->stream>>>(in_f, 4, in_f + 3, 4, n_points, d_poses, d_aux, h->imu_heads.p, d, d_out);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 2;
+    }
+    // results: carry, aux (n_poses), poses, points
+    const size_t out_bytes = (7 + 16 + (size_t)n_imu * 22) * sizeof(double) + n1 * 4 * sizeof(float);
+    FLB_CUDA(h, h->pin_out.reserve(out_bytes));
+    char* po = static_cast<char*>(h->pin_out.p);
+    FLB_CUDA(h, cudaMemcpyAsync(po, h->imu_buf.p + off_carry, (7 + 16 + (size_t)n_imu * 22) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    float* po_pts = reinterpret_cast<float*>(po + (7 + 16 + (size_t)n_imu * 22) * sizeof(double));
+    if (n_points > 0)
+        FLB_CUDA(h, cudaMemcpyAsync(po_pts, d_out, (size_t)n_points * 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(carry, po, sizeof(flb_imu_carry));
+    ImuAux aux;
+    std::memcpy(&aux, po + 7 * sizeof(double), sizeof(aux));
+    if (n_poses_out) *n_poses_out = aux.n_poses;
+    if (poses_out) std::memcpy(poses_out, po + (7 + 16) * sizeof(double), (size_t)aux.n_poses * 22 * sizeof(double));
+    for (int i = 0; i < n_points; ++i) {
+        out_xyz[3 * (size_t)i] = po_pts[4 * (size_t)i];
+        out_xyz[3 * (size_t)i + 1] = po_pts[4 * (size_t)i + 1];
+        out_xyz[3 * (size_t)i + 2] = po_pts[4 * (size_t)i + 2];
+    }
+    h->last_pass_valid = false;
+    h->last_vio_valid = false;
     return FLB_OK;
 }
 

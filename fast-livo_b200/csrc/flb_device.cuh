@@ -654,6 +654,58 @@ FLB_HD void state_boxminus(const State18& a, const State18& b, double* out) {
 }
 
 
+
+// ------------------------------------------------------------------ IMU propagation / undistortion (row f3)
+// Exp(ang_vel, dt), include/so3_math.h:30-51
+FLB_HD void so3_exp_dt(const double* w, double dt, double* R) {
+    const double nrm = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    FLB_UNROLL
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (nrm > 0.0000001) {
+        const double r[3] = {w[0] / nrm, w[1] / nrm, w[2] / nrm};
+        double K[9], KK[9];
+        skew3(r, K);
+        m3_mul(K, K, KK);
+        const double ang = nrm * dt, s = sin(ang), c1 = 1.0 - cos(ang);
+        FLB_UNROLL
+        for (int i = 0; i < 9; ++i) R[i] = R[i] + s * K[i] + c1 * KK[i];
+    }
+}
+
+// Pose6D (include/common_lib.h set_pose6d): one entry of IMUpose, src/IMU_Processing.cpp:658, :737
+struct ImuPose {
+    double t;            // offset_time relative to pcl_beg_time
+    double acc[3], gyr[3], vel[3], pos[3], rot[9];
+};
+
+struct ImuParamsDev {
+    double cov_gyr[3], cov_acc[3], cov_bias_gyr[3], cov_bias_acc[3];
+    double G_m_s2, mean_acc_norm;
+    double R_LI[9], t_LI[3];
+};
+
+// One point of the backward pass, src/IMU_Processing.cpp:792-805: compensate p (lidar frame, float) taken at
+// time t (seconds after pcl_beg_time) to the frame end, given the IMU pose `head` that precedes it.
+FLB_HD void imu_compensate_point(const ImuPose& head, const double* R_LI, const double* t_LI, const double* extR_Ri,
+                                 const double* exrR_extT, const double* pos_end, double t, float* p) {
+    const double dt = t - head.t;
+    double E[9], R_i[9], T_ei[3], a[3], b[3], c[3];
+    so3_exp_dt(head.gyr, dt, E);
+    m3_mul(head.rot, E, R_i);                                                    // :796
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) T_ei[k] = head.pos[k] + head.vel[k] * dt + 0.5 * head.acc[k] * dt * dt - pos_end[k];   // :797
+    const double P_i[3] = {(double)p[0], (double)p[1], (double)p[2]};
+    m3_vec(R_LI, P_i, a);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) a[k] += t_LI[k];
+    m3_vec(R_i, a, b);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) b[k] += T_ei[k];
+    m3_vec(extR_Ri, b, c);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) p[k] = (float)(c[k] - exrR_extT[k]);              // :800-805
+}
+
 // ------------------------------------------------------------------ IKFoM manifold algebra (row a8)
 // state_ikfom = pos, rot(SO3), offset_R_L_I(SO3), offset_T_L_I, vel, bg, ba, grav(S2, |g| = 9.8090)
 // (include/use-ikfom.hpp:12-21; DOF 23).  Quaternions are (x, y, z, w) like Eigen's coeffs().

@@ -1792,6 +1792,208 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     }
 }
 
+// =======================================================================================
+// IMU forward propagation + backward undistortion:
+// ImuProcess::UndistortPcl from src/IMU_Processing.cpp:655 on.
+// =======================================================================================
+struct ImuSampleDev { double t, gyr[3], acc[3]; };            // == flb_imu_sample
+struct ImuCarryDev { double last_lidar_end_time, acc_s_last[3], angvel_last[3]; };   // == flb_imu_carry
+struct ImuAux { double extR_Ri[9], exrR_extT[3], pos_end[3]; int n_poses; int pad; };
+
+// One block.  The loop over IMU samples is sequential by nature (K ~ 10-50 per frame); thread 0 carries the
+// 3-vectors and builds F_x / cov_w, all threads do the two 18x18x18 products of
+// cov = F cov F^T + cov_w (:720), summed in the reference's (Eigen's) index order.
+__global__ void __launch_bounds__(352) k_imu_propagate(State18* x, const ImuSampleDev* v_imu, int n_imu, ImuParamsDev prm,
+                                                       double pcl_beg_time, double pcl_end_time, ImuCarryDev* carry,
+                                                       ImuPose* poses, ImuAux* aux) {
+    __shared__ double P[324], T[324], F[324], W[324];
+    __shared__ double R_imu[9], vel_imu[3], pos_imu[3], acc_imu[3], angvel_avr[3];
+    __shared__ int s_skip, s_np;
+    const int tid = threadIdx.x;
+    if (tid < 324) P[tid] = x->cov[tid];
+    if (tid == 0) {
+        for (int k = 0; k < 9; ++k) R_imu[k] = x->rot[k];
+        for (int k = 0; k < 3; ++k) {
+            vel_imu[k] = x->vel[k]; pos_imu[k] = x->pos[k];
+            acc_imu[k] = carry->acc_s_last[k]; angvel_avr[k] = carry->angvel_last[k];
+        }
+        ImuPose p0;                                                               // :658
+        p0.t = 0.0;
+        for (int k = 0; k < 3; ++k) { p0.acc[k] = acc_imu[k]; p0.gyr[k] = angvel_avr[k]; p0.vel[k] = vel_imu[k]; p0.pos[k] = pos_imu[k]; }
+        for (int k = 0; k < 9; ++k) p0.rot[k] = R_imu[k];
+        poses[0] = p0;
+        s_np = 1;
+    }
+    __syncthreads();
+    const double last_end = carry->last_lidar_end_time;
+    for (int it = 0; it + 1 < n_imu; ++it) {                                      // :666
+        if (tid < 324) { F[tid] = ((tid / 18) == (tid % 18)) ? 1.0 : 0.0; W[tid] = 0.0; }
+        __syncthreads();
+        if (tid == 0) {
+            const ImuSampleDev head = v_imu[it], tail = v_imu[it + 1];
+            s_skip = (tail.t < last_end) ? 1 : 0;                                 // :671
+            if (!s_skip) {
+                double acc_avr[3];
+                for (int k = 0; k < 3; ++k) {
+                    angvel_avr[k] = 0.5 * (head.gyr[k] + tail.gyr[k]);            // :673-681
+                    acc_avr[k] = 0.5 * (head.acc[k] + tail.acc[k]);
+                }
+                for (int k = 0; k < 3; ++k) {
+                    angvel_avr[k] -= x->bg[k];                                    // :687
+                    acc_avr[k] = acc_avr[k] * prm.G_m_s2 / prm.mean_acc_norm - x->ba[k];   // :688
+                }
+                const double dt = (head.t < last_end) ? (tail.t - last_end) : (tail.t - head.t);   // :690-697
+                double Exp_f[9], Exp_m[9], askew[9], Ra[9];
+                so3_exp_dt(angvel_avr, dt, Exp_f);                                // :701
+                so3_exp_dt(angvel_avr, -dt, Exp_m);                               // :707
+                skew3(acc_avr, askew);
+                m3_mul(R_imu, askew, Ra);
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) {
+                        F[i * 18 + j] = Exp_m[i * 3 + j];                         // (0,0)
+                        F[i * 18 + 9 + j] = (i == j) ? -dt : 0.0;                 // (0,9)  = -I dt
+                        F[(3 + i) * 18 + 6 + j] = (i == j) ? dt : 0.0;            // (3,6)  =  I dt
+                        F[(6 + i) * 18 + j] = -Ra[i * 3 + j] * dt;                // (6,0)  = -R [a]x dt
+                        F[(6 + i) * 18 + 12 + j] = -R_imu[i * 3 + j] * dt;        // (6,12) = -R dt
+                        F[(6 + i) * 18 + 15 + j] = (i == j) ? dt : 0.0;           // (6,15) =  I dt
+                    }
+                for (int i = 0; i < 3; ++i) {
+                    W[i * 18 + i] = prm.cov_gyr[i] * dt * dt;                     // :715
+                    W[(9 + i) * 18 + 9 + i] = prm.cov_bias_gyr[i] * dt * dt;      // :717
+                    W[(12 + i) * 18 + 12 + i] = prm.cov_bias_acc[i] * dt * dt;    // :718
+                }
+                {
+                    double RD[9], Rt[9], RDRt[9];                                 // :716, left to right
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) RD[i * 3 + j] = R_imu[i * 3 + j] * prm.cov_acc[j];
+                    m3_T(R_imu, Rt);
+                    m3_mul(RD, Rt, RDRt);
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) W[(6 + i) * 18 + 6 + j] = RDRt[i * 3 + j] * dt * dt;
+                }
+                double Rn[9], Ra_v[3];
+                m3_mul(R_imu, Exp_f, Rn);                                         // :723
+                for (int k = 0; k < 9; ++k) R_imu[k] = Rn[k];
+                m3_vec(R_imu, acc_avr, Ra_v);
+                for (int k = 0; k < 3; ++k) acc_imu[k] = Ra_v[k] + x->grav[k];    // :726
+                for (int k = 0; k < 3; ++k) pos_imu[k] = pos_imu[k] + vel_imu[k] * dt + 0.5 * acc_imu[k] * dt * dt;   // :729
+                for (int k = 0; k < 3; ++k) vel_imu[k] = vel_imu[k] + acc_imu[k] * dt;   // :732
+                ImuPose p;
+                p.t = tail.t - pcl_beg_time;                                      // :737
+                for (int k = 0; k < 3; ++k) { p.acc[k] = acc_imu[k]; p.gyr[k] = angvel_avr[k]; p.vel[k] = vel_imu[k]; p.pos[k] = pos_imu[k]; }
+                for (int k = 0; k < 9; ++k) p.rot[k] = R_imu[k];
+                poses[s_np] = p;
+                s_np = s_np + 1;
+            }
+        }
+        __syncthreads();
+        if (s_skip) continue;
+        if (tid < 324) {                                                          // cov = F cov F^T + cov_w, :720
+            const int i = tid / 18, j = tid % 18;
+            double acc = 0.0;
+            for (int k = 0; k < 18; ++k) acc += F[i * 18 + k] * P[k * 18 + j];
+            T[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < 324) {
+            const int i = tid / 18, j = tid % 18;
+            double acc = 0.0;
+            for (int k = 0; k < 18; ++k) acc += T[i * 18 + k] * F[j * 18 + k];
+            P[tid] = acc + W[tid];
+        }
+        __syncthreads();
+    }
+    if (tid < 324) x->cov[tid] = P[tid];
+    if (tid == 0) {
+        // frame-end prediction, :743-758
+        const double imu_end_time = v_imu[n_imu - 1].t;
+        double note, dt;
+        if (imu_end_time > pcl_beg_time) {
+            note = pcl_end_time > imu_end_time ? 1.0 : -1.0;
+            dt = note * (pcl_end_time - imu_end_time);
+        } else {
+            note = pcl_end_time > pcl_beg_time ? 1.0 : -1.0;
+            dt = note * (pcl_end_time - pcl_beg_time);
+        }
+        const double w[3] = {note * angvel_avr[0], note * angvel_avr[1], note * angvel_avr[2]};
+        double E[9], Rn[9];
+        so3_exp_dt(w, dt, E);
+        m3_mul(R_imu, E, Rn);
+        for (int k = 0; k < 3; ++k) {
+            x->vel[k] = vel_imu[k] + note * acc_imu[k] * dt;
+            x->pos[k] = pos_imu[k] + note * vel_imu[k] * dt + note * 0.5 * acc_imu[k] * dt * dt;
+        }
+        for (int k = 0; k < 9; ++k) x->rot[k] = Rn[k];
+        for (int k = 0; k < 3; ++k) { carry->acc_s_last[k] = acc_imu[k]; carry->angvel_last[k] = angvel_avr[k]; }   // :735-736
+        carry->last_lidar_end_time = pcl_end_time;                                // :761
+        double RLIt[9], rot_end_T[9];
+        m3_T(prm.R_LI, RLIt);
+        m3_T(Rn, rot_end_T);
+        m3_mul(RLIt, rot_end_T, aux->extR_Ri);                                    // :763
+        m3_vec(RLIt, prm.t_LI, aux->exrR_extT);                                   // :764
+        for (int k = 0; k < 3; ++k) aux->pos_end[k] = x->pos[k];
+        aux->n_poses = s_np;
+    }
+}
+
+// Backward pass, :778-808.  The reference walks the time-ordered points from the last one down with a pose
+// cursor that only moves to earlier IMU poses: point i is compensated with head H_i = min over j >= i of
+// v_j, v_j = the last pose whose offset_time is < t_j (-1: none, the walk has ended and the remaining points
+// stay as they are).  v is per point, the suffix minimum is one scan, the compensation is per point again.
+__global__ void k_imu_heads(const float* __restrict__ offset_ms, int os, int n, const ImuPose* __restrict__ poses,
+                            const ImuAux* __restrict__ aux, int* __restrict__ heads) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t = (double)offset_ms[(size_t)i * os] / double(1000);
+    int v = -1;
+    for (int H = aux->n_poses - 2; H >= 0; --H)
+        if (t > poses[H].t) { v = H; break; }
+    heads[i] = v;
+}
+
+// In-place suffix minimum of heads[0..n) by one block.
+__global__ void __launch_bounds__(1024) k_suffix_min(int* __restrict__ heads, int n) {
+    __shared__ int smin[1024];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int a = min(n, tid * per), b = min(n, a + per);
+    int m = 0x7fffffff;
+    for (int i = a; i < b; ++i) m = min(m, heads[i]);
+    smin[tid] = m;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {            // inclusive suffix scan of the segment minima
+        const int o = (tid + off < 1024) ? smin[tid + off] : 0x7fffffff;
+        __syncthreads();
+        smin[tid] = min(smin[tid], o);
+        __syncthreads();
+    }
+    int run = (tid + 1 < 1024) ? smin[tid + 1] : 0x7fffffff;
+    for (int i = b - 1; i >= a; --i) {
+        run = min(run, heads[i]);
+        heads[i] = run;
+    }
+}
+
+__global__ void k_imu_undistort(const float* __restrict__ in_xyz, int stride, const float* __restrict__ offset_ms, int os, int n,
+                                const ImuPose* __restrict__ poses, const ImuAux* __restrict__ aux, const int* __restrict__ heads,
+                                ImuParamsDev prm, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float p[3] = {in_xyz[(size_t)i * stride], in_xyz[(size_t)i * stride + 1], in_xyz[(size_t)i * stride + 2]};
+    const float off = offset_ms[(size_t)i * os];
+    const double t = (double)off / double(1000);
+    const int H = heads[i];
+    if (H >= 0) {
+        imu_compensate_point(poses[H], prm.R_LI, prm.t_LI, aux->extR_Ri, aux->exrR_extT, aux->pos_end, t, p);
+        // The first point is the reference's loop exit (:807): the outer loop still visits the earlier poses and
+        // compensates that point again for every one of them that precedes it in time.
+        if (i == 0)
+            for (int h = H - 1; h >= 0; --h)
+                if (t > poses[h].t) imu_compensate_point(poses[h], prm.R_LI, prm.t_LI, aux->extR_Ri, aux->exrR_extT, aux->pos_end, t, p);
+    }
+    out[i] = make_float4(p[0], p[1], p[2], off);
+}
+
 }  // namespace flb
 
 // =======================================================================================

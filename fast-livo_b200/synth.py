@@ -325,3 +325,60 @@ def make_frame(cfg: FrameConfig | str, seed: int | None = None) -> dict:
     frame.update(image=image, ref_image=ref_img, patch_pos=patch_pos.astype(np.float64),
                  patch_ref=patch_ref, patch_level=level, patch_px=np.stack([pu, pv], axis=1))
     return frame
+
+
+# ---------------------------------------------------------------------------------------------------------
+# IMU propagation / undistortion inputs
+# ---------------------------------------------------------------------------------------------------------
+def make_imu_frame(seed=1, n_points=24000, imu_hz=200.0, scan_s=0.1, variant="nominal"):
+    """One LidarMeasureGroup worth of inputs for ImuProcess::UndistortPcl (reference src/IMU_Processing.cpp:611):
+    v_imu (last_imu_ + meas.imu) as (K,7) [t, gyr xyz, acc xyz], time-ordered lidar points with their offset in ms,
+    the incoming state and the ImuProcess members that carry over.  `variant` moves the time stamps into the
+    corner cases of the reference's branches."""
+    rng = np.random.default_rng(seed)
+    t0 = 1000.0 + 0.1 * seed
+    pcl_beg = t0
+    pcl_end = t0 + scan_s
+    dt_imu = 1.0 / imu_hz
+    k = int(round(scan_s * imu_hz)) + 2
+    times = t0 - 0.6 * dt_imu + dt_imu * np.arange(k)            # last_imu_ lies before the scan start
+    last_end = t0                                                # last_lidar_end_time_
+    if variant == "late_imu":            # IMU stops before the scan ends   -> note = +1 (:745)
+        times = times[times < pcl_end - 2.5 * dt_imu]
+    elif variant == "imu_past_end":      # IMU runs past the scan end        -> note = -1 (:745)
+        times = np.concatenate([times, [times[-1] + dt_imu, times[-1] + 2 * dt_imu]])
+    elif variant == "stale_imu":         # leading samples older than last_lidar_end_time_ -> `continue` (:671), dt rule (:690)
+        times = np.concatenate([t0 - dt_imu * np.arange(4, 1, -1) - 0.6 * dt_imu, times])
+    elif variant == "imu_before_scan":   # every sample before pcl_beg_time -> the else branch of :743
+        times = t0 - dt_imu * np.arange(6, 0, -1) - 1e-4
+        last_end = times[2] + 1e-5
+    w = 0.4 * np.sin(2 * np.pi * 1.3 * (times - t0))[:, None] * np.array([0.3, -0.5, 1.0]) + rng.normal(0, 0.01, (len(times), 3))
+    a = np.array([0.2, -0.1, 9.81]) + 0.8 * np.cos(2 * np.pi * 0.9 * (times - t0))[:, None] * np.array([1.0, 0.4, -0.2]) \
+        + rng.normal(0, 0.05, (len(times), 3))
+    v_imu = np.concatenate([times[:, None], w, a], 1)
+    off = np.sort(rng.uniform(0.0, scan_s * 1000.0, n_points)).astype(np.float32)
+    if variant == "unsorted_points" and n_points > 64:   # local disorder + a late first point (the :807 quirk)
+        idx = rng.integers(1, n_points - 1, n_points // 50)
+        off[idx] = off[np.clip(idx + rng.integers(-40, 40, len(idx)), 0, n_points - 1)]
+        off[0] = np.float32(3.7 * dt_imu * 1000.0)
+    if variant == "early_points" and n_points > 64:      # offsets <= 0: the walk ends, those points stay (:790)
+        off[:37] = np.float32(0.0)
+        off[:5] = np.float32(-1.5)
+    rng2 = np.random.default_rng(seed + 77)
+    d = rng2.uniform(1.0, 60.0, n_points)
+    az = rng2.uniform(-0.6, 0.6, n_points)
+    el = rng2.uniform(-0.6, 0.6, n_points)
+    pts = np.stack([d * np.cos(el) * np.cos(az), d * np.cos(el) * np.sin(az), d * np.sin(el)], 1).astype(np.float32)
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    R0 = exp_so3(ax * 0.3)
+    cov = np.diag(np.concatenate([np.full(3, 1e-4), np.full(3, 1e-3), np.full(3, 1e-2), np.full(3, 1e-5), np.full(3, 1e-4), np.full(3, 1e-6)]))
+    m = rng.normal(0, 1e-4, (18, 18))
+    cov = cov + m @ m.T
+    return dict(v_imu=v_imu, pcl_beg_time=pcl_beg, pcl_end_time=pcl_end, last_lidar_end_time=last_end,
+                pts=pts, offset_ms=off, R=R0, p=np.array([1.5, -0.7, 0.3]), vel=np.array([0.8, -0.3, 0.05]),
+                bg=np.array([0.002, -0.001, 0.0015]), ba=np.array([0.03, -0.02, 0.01]), grav=np.array([0.0, 0.0, -9.81]),
+                cov=cov, acc_s_last=np.array([0.1, 0.05, -0.02]), angvel_last=np.array([0.01, -0.02, 0.03]),
+                cov_gyr=np.array([0.1, 0.1, 0.1]), cov_acc=np.array([0.1, 0.1, 0.1]),
+                cov_bias_gyr=np.array([1e-4, 1e-4, 1e-4]), cov_bias_acc=np.array([1e-4, 1e-4, 1e-4]),
+                G_m_s2=9.81, mean_acc_norm=9.79,
+                R_LI=exp_so3(np.array([0.01, -0.02, 0.015])), t_LI=np.array([0.04165, 0.02326, -0.0284]))

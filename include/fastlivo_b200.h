@@ -101,6 +101,33 @@ int flb_map_delete_boxes(flb_handle* h, const float* boxes, int nb);
 int flb_map_size(const flb_handle* h);
 int flb_map_download(flb_handle* h, float* xyz, int capacity_points, int* M_out);
 
+/* ---- IMU forward propagation + backward undistortion ----------------------
+ * Replaces ImuProcess::UndistortPcl from src/IMU_Processing.cpp:655 on (called by Process2, :811-849, at
+ * src/laserMapping.cpp:1353): per IMU interval the mid-point propagation of attitude / velocity / position
+ * and of the 18x18 covariance (cov = F_x cov F_x^T + cov_w, :699-720), the frame-end prediction (:743-758),
+ * and the per-point backward motion compensation to the frame end (:778-808).  The LidarMeasureGroup
+ * bookkeeping of :613-652 (which points belong to this update, pcl_beg_time, pcl_end_time) stays with the
+ * caller.
+ *   The device state (flb_state_upload) is state_inout: it is propagated in place (rot_end, pos_end, vel_end,
+ *   cov; biases and gravity unchanged), so x_prop and P are on the device for the update that follows
+ *   (flb_state_set_prior_enqueue makes it state_propagat, src/laserMapping.cpp:1354).
+ *   v_imu: last_imu_ followed by meas.imu (:617-618), times non-decreasing.  carry: the ImuProcess members
+ *   that survive from frame to frame (last_lidar_end_time_, acc_s_last, angvel_last), in/out.
+ *   pts: n_points lidar-frame points in time order, stride_floats floats apart, x,y,z at [0..2] and the time
+ *   offset in ms (PointType::curvature) at [offset_index] (pcl::PointXYZINormal: stride 12, offset_index 9).
+ *   out_xyz: n_points x 3 compensated coordinates.  poses_out (optional, capacity n_imu entries of 22 doubles:
+ *   offset_time, acc, gyr, vel, pos, rot) receives IMUpose; n_poses_out its length. */
+typedef struct flb_imu_sample { double t; double gyr[3]; double acc[3]; } flb_imu_sample;   /* sensor_msgs::Imu */
+typedef struct flb_imu_params {
+    double cov_gyr[3], cov_acc[3], cov_bias_gyr[3], cov_bias_acc[3];   /* src/IMU_Processing.cpp:15-20, :58-83 */
+    double G_m_s2, mean_acc_norm;                                      /* acc * G_m_s2 / mean_acc.norm(), :688 */
+    double R_LI[9], t_LI[3];                                           /* Lid_rot_to_IMU, Lid_offset_to_IMU */
+} flb_imu_params;
+typedef struct flb_imu_carry { double last_lidar_end_time; double acc_s_last[3]; double angvel_last[3]; } flb_imu_carry;
+int flb_imu_undistort(flb_handle* h, const flb_imu_params* prm, flb_imu_carry* carry, const flb_imu_sample* v_imu, int n_imu,
+                      double pcl_beg_time, double pcl_end_time, const float* pts, int stride_floats, int offset_index,
+                      int n_points, float* out_xyz, double* poses_out, int* n_poses_out);
+
 /* ---- scan ------------------------------------------------------------------------
  * feats_down_body (src/laserMapping.cpp:1398-1399): N already-downsampled points in
  * the LiDAR body frame. */

@@ -141,6 +141,22 @@ void flo_quat_to_R(const double* q_xyzw, double* R9);
 /* esekfom.hpp:1619-1928 driven by h_share_model (laserMapping.cpp:960-1094) */
 int  flo_ikfom_update(flo_lio*, const flo_ikfom_params*, flo_state_ikfom* x, flo_ikfom_report* rep);
 
+/* ---- IMU forward propagation + backward undistortion (oracle/flo_imu.cpp) ----
+ * ImuProcess::UndistortPcl from :655 on (src/IMU_Processing.cpp:655-808). */
+typedef struct flo_imu_sample { double t; double gyr[3]; double acc[3]; } flo_imu_sample;   /* sensor_msgs::Imu */
+typedef struct flo_imu_params {
+    double cov_gyr[3], cov_acc[3], cov_bias_gyr[3], cov_bias_acc[3];   /* ImuProcess members, :15-20 */
+    double G_m_s2, mean_acc_norm;                                      /* :688 */
+    double R_LI[9], t_LI[3];                                           /* Lid_rot_to_IMU, Lid_offset_to_IMU */
+} flo_imu_params;
+typedef struct flo_imu_carry { double last_lidar_end_time; double acc_s_last[3]; double angvel_last[3]; } flo_imu_carry;
+/* v_imu = last_imu_ followed by meas.imu (:617-618).  x: state_inout (in/out).  pts_xyz (n_points x 3 float,
+ * in/out) with offset_ms = PointType::curvature.  poses_out (optional): IMUpose as 22 doubles per entry
+ * [offset_time, acc, gyr, vel, pos, rot]. */
+int flo_imu_undistort(const flo_imu_params* prm, flo_imu_carry* carry, const flo_imu_sample* v_imu, int n_imu,
+                      double pcl_beg_time, double pcl_end_time, flo_state18* x, float* pts_xyz,
+                      const float* offset_ms, int n_points, int* n_poses_out, double* poses_out);
+
 /* ---- VIO ---------------------------------------------------------------------- */
 typedef struct flo_vio flo_vio;
 

@@ -113,6 +113,32 @@ class IkfomReport(C.Structure):
                 ("res_mean_last", C.c_double), ("rows_total", C.c_int64)]
 
 
+class ImuParams(C.Structure):
+    """flo_imu_params (oracle/flo_oracle.h): ImuProcess members, reference src/IMU_Processing.cpp:15-20."""
+    _fields_ = [("cov_gyr", C.c_double * 3), ("cov_acc", C.c_double * 3), ("cov_bias_gyr", C.c_double * 3),
+                ("cov_bias_acc", C.c_double * 3), ("G_m_s2", C.c_double), ("mean_acc_norm", C.c_double),
+                ("R_LI", C.c_double * 9), ("t_LI", C.c_double * 3)]
+
+
+class ImuCarry(C.Structure):
+    _fields_ = [("last_lidar_end_time", C.c_double), ("acc_s_last", C.c_double * 3), ("angvel_last", C.c_double * 3)]
+
+
+def imu_undistort(prm: ImuParams, carry: ImuCarry, v_imu, pcl_beg_time, pcl_end_time, x: State18, pts_xyz, offset_ms):
+    """flo_imu_undistort: v_imu (K,7) [t, gyr, acc]; x and carry are updated in place.
+    Returns (compensated xyz float32 (n,3), IMUpose (n_poses,22))."""
+    v = np.ascontiguousarray(v_imu, np.float64)
+    pts = np.ascontiguousarray(pts_xyz, np.float32).copy()
+    off = np.ascontiguousarray(offset_ms, np.float32)
+    poses = np.zeros((len(v), 22), np.float64)
+    n = C.c_int()
+    rc = lib().flo_imu_undistort(C.byref(prm), C.byref(carry), _p(v), len(v), float(pcl_beg_time), float(pcl_end_time),
+                                 C.byref(x), _p(pts), _p(off), len(pts), C.byref(n), _p(poses))
+    if rc:
+        raise RuntimeError(f"flo_imu_undistort failed ({rc})")
+    return pts, poses[:n.value]
+
+
 def quat_from_R(R):
     """Rotation matrix -> quaternion (x, y, z, w), w >= 0."""
     R = np.asarray(R, np.float64)
@@ -164,7 +190,7 @@ KNN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void
 def build(force: bool = False) -> None:
     """Compile the checker (and, when /root/reference is present, the reference ikd-Tree)."""
     need = force or not os.path.exists(_LIB) or \
-        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_ikfom.cpp", "flo_oracle.h"))
+        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_ikfom.cpp", "flo_imu.cpp", "flo_oracle.h"))
     if need:
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     if os.path.isdir("/root/reference/include/ikd-Tree") and (force or not os.path.exists(_REF)):
@@ -211,6 +237,8 @@ def lib():
         L.flo_ikfom_boxminus.argtypes = [C.POINTER(StateIkfom), C.POINTER(StateIkfom), C.c_void_p]
         L.flo_quat_to_R.argtypes = [C.c_void_p, C.c_void_p]
         L.flo_ikfom_update.argtypes = [C.c_void_p, C.POINTER(IkfomParams), C.POINTER(StateIkfom), C.POINTER(IkfomReport)]
+        L.flo_imu_undistort.argtypes = [C.POINTER(ImuParams), C.POINTER(ImuCarry), C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                        C.POINTER(State18), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         _lib = L
     return _lib
 

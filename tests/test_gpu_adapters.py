@@ -82,3 +82,54 @@ def test_adapters_match_oracle(flb, po, frames, tmp_path):
     ref = np.concatenate([x.R.ravel(), x.p, x.P.ravel()])
     assert np.abs(st[:12] - ref[:12]).max() / np.abs(ref[:12]).max() < 1e-9
     np.testing.assert_allclose(st[12:], ref[12:], rtol=1e-6, atol=1e-14)
+
+
+SRC_IMU = os.path.join(ROOT, "tests", "adapters", "test_adapter_imu.cpp")
+EXE_IMU = os.path.join(ROOT, "tests", "adapters", "test_adapter_imu")
+
+
+def build_exe_imu():
+    hdr = os.path.join(ROOT, "fast-livo_b200", "adapters", "fastlivo_b200_adapters.hpp")
+    if not os.path.exists(EXE_IMU) or os.path.getmtime(EXE_IMU) < max(os.path.getmtime(SRC_IMU), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-o", EXE_IMU, SRC_IMU,
+                               "-L" + os.path.join(ROOT, "fast-livo_b200"), "-lfastlivo_b200",
+                               "-Wl,-rpath," + os.path.join(ROOT, "fast-livo_b200")])
+
+
+def test_imu_adapter_compiles(flb):
+    flb.build()
+    build_exe_imu()
+    assert os.path.exists(EXE_IMU)
+
+
+@pytest.mark.gpu
+def test_imu_adapter_matches_oracle(flb, po, tmp_path):
+    """flb::undistort_pcl with mock sensor_msgs::Imu / PCL / StatesGroup types == the oracle's UndistortPcl."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from imu_util import oracle_inputs
+    flb.build()
+    build_exe_imu()
+    f = flb.synth.make_imu_frame(seed=31, n_points=5000)
+    inp, out = tmp_path / "imu_in.bin", tmp_path / "imu_out.bin"
+    n = len(f["pts"])
+    with open(inp, "wb") as fh:
+        fh.write(np.array([len(f["v_imu"]), n], np.int32).tobytes())
+        fh.write(np.ascontiguousarray(f["v_imu"], np.float64).tobytes())
+        fh.write(np.array([f["pcl_beg_time"], f["pcl_end_time"], f["last_lidar_end_time"]], np.float64).tobytes())
+        fh.write(np.concatenate([f["R"].ravel(), f["p"], f["vel"], f["bg"], f["ba"], f["grav"], f["cov"].ravel()]).astype(np.float64).tobytes())
+        fh.write(np.concatenate([f["acc_s_last"], f["angvel_last"]]).astype(np.float64).tobytes())
+        fh.write(np.concatenate([f["cov_gyr"], f["cov_acc"], f["cov_bias_gyr"], f["cov_bias_acc"], [f["G_m_s2"], f["mean_acc_norm"]],
+                                 np.asarray(f["R_LI"]).ravel(), f["t_LI"]]).astype(np.float64).tobytes())
+        fh.write(np.concatenate([f["pts"], f["offset_ms"][:, None]], 1).astype(np.float32).tobytes())
+    r = subprocess.run([EXE_IMU, str(inp), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    st = np.frombuffer(raw, np.float64, 346, 0)
+    pts = np.frombuffer(raw, np.float32, n * 3, 346 * 8).reshape(n, 3)
+    P, C, x = oracle_inputs(po, f)
+    ref_pts, _ = po.imu_undistort(P, C, f["v_imu"], f["pcl_beg_time"], f["pcl_end_time"], x, f["pts"], f["offset_ms"])
+    ref = np.concatenate([x.rot[:], x.pos[:], x.vel[:], x.cov[:], [C.last_lidar_end_time], C.acc_s_last[:], C.angvel_last[:]])
+    scale = np.maximum(np.abs(ref), 1e-12)
+    assert (np.abs(st - ref) / np.maximum(scale, np.abs(ref[15:339]).max() * (np.arange(346) >= 15) * (np.arange(346) < 339))).max() < 1e-11
+    assert np.abs(pts - ref_pts).max() <= 1e-5 and (pts == ref_pts).mean() > 0.999
