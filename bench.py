@@ -328,21 +328,38 @@ def main():
     # the library then skips its staging copy
     pin_img, pin_pos, pin_ref, pin_lev = (h.pinned_like(a) for a in (img, ppos, pref.reshape(len(ppos), 192), plev)) if has_vio else (None,) * 4
 
-    def e2e_frame(pinned=False):
-        # All of this frame's host inputs go in first (uploads are enqueue-only: the library packs them into
-        # pinned staging and returns), then the two blocking updates.  The map stays resident.
+    def e2e_frame(pinned=False, blocking=False):
+        # One frame through the C ABI with HOST buffers; the map stays resident.
+        #   default : the device-resident loop of the public header -- uploads and both updates are enqueued
+        #             (the library packs host inputs into pinned staging and returns), the image / patch list
+        #             are staged while the LIO update runs, ONE blocking call (flb_state_download) ends the frame.
+        #   blocking: the reference's call shape -- flb_lio_update / flb_vio_update each upload the state, run,
+        #             download and synchronise.
         h.scan_upload(scan)
+        if blocking:
+            if has_vio:
+                h.image_upload(pin_img if pinned else img)
+                if pinned:
+                    h.patches_upload(pin_pos, pin_ref, pin_lev)
+                else:
+                    h.patches_upload(ppos, pref, plev)
+            x = x0.copy()
+            h.lio_update(lprm, x, x0)
+            if has_vio:
+                xp = x.copy()
+                h.vio_update(vprm, x, xp)
+            return x
+        h.state_upload(x0, x0)
+        h.lio_update_enqueue(lprm)
         if has_vio:
             h.image_upload(pin_img if pinned else img)
             if pinned:
                 h.patches_upload(pin_pos, pin_ref, pin_lev)
             else:
                 h.patches_upload(ppos, pref, plev)
-        x = x0.copy()
-        h.lio_update(lprm, x, x0)
-        if has_vio:
-            xp = x.copy()
-            h.vio_update(vprm, x, xp)
+            h.state_set_prior_enqueue()          # state_propagat of the VIO step = the LIO result, on the device
+            h.vio_update_enqueue(vprm)
+        x, _, _ = h.state_download()
         return x
     for _ in range(3):
         xe = e2e_frame()
@@ -366,6 +383,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_fps = e2e_steps / e2e_dt
+    e2e_blocking_fps = None
+    if world == 1:
+        for _ in range(3):
+            xb = e2e_frame(blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            xb = e2e_frame(blocking=True)
+        barrier()
+        e2e_blocking_fps = e2e_steps / (time.perf_counter() - t0)
+        assert np.array_equal(np.array(xb.rot[:]), np.array(xe.rot[:])) and np.array_equal(np.array(xb.cov[:]), np.array(xe.cov[:])), \
+            "enqueue and blocking call shapes must give the same state"
     e2e_pinned_fps = None
     if has_vio and world == 1:
         for _ in range(3):
@@ -377,8 +406,9 @@ def main():
         barrier()
         e2e_pinned_fps = e2e_steps / (time.perf_counter() - t0)
     state_b = 2736
-    h2d = len(scan) * 12 + 2 * state_b + ((img.size + len(ppos) * (24 + 768 + 4) + 2 * state_b) if has_vio else 0)
-    d2h = (state_b + 64) * (2 if has_vio else 1)
+    # device-resident loop: scan + x, x_prop (+ image + patch list); one state + two reports come back
+    h2d = len(scan) * 12 + 2 * state_b + ((img.size + len(ppos) * (24 + 768 + 4)) if has_vio else 0)
+    d2h = state_b + 2 * 64
 
     # ---- per-kernel-family device time (separate profiled run: one event pair per launch)
     prof_steps = max(min(args.steps, 20), 3)
@@ -473,6 +503,35 @@ def main():
         map_maint = {"add_points_ms": 1e3 * t_add, "points_added": int(len(world_pts)), "map_size_after": int(m_after),
                      "full_map_upload_ms": 1e3 * t_up, "note": "ikdtree.Add_Points(scan, downsample) on the device vs re-uploading the whole map"}
 
+    # row f3: ImuProcess::UndistortPcl through the C ABI (host buffers in, host buffers out) next to the CPU port
+    imu_f3 = None
+    if rank == 0 and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from imu_util import oracle_inputs, product_inputs
+        fi = flb.synth.make_imu_frame(seed=41, n_points=cfg.n_scan if hasattr(cfg, "n_scan") else 24000)
+        Pg, Cg, xg = product_inputs(flb, fi)
+        packed = np.concatenate([fi["pts"], fi["offset_ms"][:, None]], 1).astype(np.float32)
+        reps = 20
+        t_gpu = []
+        for it in range(reps + 3):
+            Pg, Cg, xg = product_inputs(flb, fi)         # the call updates the carry in place: fresh inputs every time
+            h.state_upload(xg, xg.copy())
+            barrier()
+            t0 = time.perf_counter()
+            got, _ = h.imu_undistort(Pg, Cg, fi["v_imu"], fi["pcl_beg_time"], fi["pcl_end_time"], packed, offset_index=3)
+            t_gpu.append(time.perf_counter() - t0)
+        po = fastlivo_loader.oracle()
+        t_cpu = []
+        for it in range(5):
+            Po, Co, xo = oracle_inputs(po, fi)
+            t0 = time.perf_counter()
+            ref, _ = po.imu_undistort(Po, Co, fi["v_imu"], fi["pcl_beg_time"], fi["pcl_end_time"], xo, fi["pts"], fi["offset_ms"])
+            t_cpu.append(time.perf_counter() - t0)
+        imu_f3 = {"abi_call_ms": 1e3 * float(np.median(t_gpu[3:])), "cpu_port_ms": 1e3 * float(np.median(t_cpu)),
+                  "points": int(len(packed)), "imu_samples": int(len(fi["v_imu"])),
+                  "points_identical_frac": float((got == ref).mean()), "points_max_abs_diff": float(np.abs(got - ref).max()),
+                  "note": "flb_imu_undistort (H2D + propagate + undistort + D2H, blocking) vs the single-thread oracle port of UndistortPcl"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -486,10 +545,13 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "residuals_per_sec": rows_per_frame * e2e_fps,
-                    "pinned_caller_buffers_value": e2e_pinned_fps,
-                    "note": "value: pageable caller buffers (staged by the library), L2 flushed between frames; "
-                            "pinned_caller_buffers_value: image/patch buffers from flb_host_alloc, no L2 flush"},
-            "roofline": roofline, "kernels": fams, "pass_trace": trace, "map_maintenance": map_maint, "cpu_baseline": cpu, "parity": parity,
+                    "pinned_caller_buffers_value": e2e_pinned_fps, "blocking_calls_value": e2e_blocking_fps,
+                    "note": "value: device-resident loop of the C ABI (uploads + both updates enqueued, one blocking "
+                            "flb_state_download per frame), pageable caller buffers staged by the library, L2 flushed between "
+                            "frames; pinned_caller_buffers_value: image/patch buffers from flb_host_alloc, no L2 flush; "
+                            "blocking_calls_value: flb_lio_update + flb_vio_update (two synchronisations and state round "
+                            "trips per frame, the reference's call shape), no L2 flush"},
+            "roofline": roofline, "kernels": fams, "pass_trace": trace, "map_maintenance": map_maint, "imu_undistort": imu_f3, "cpu_baseline": cpu, "parity": parity,
         }
         print(json.dumps(line), flush=True)
     h.close()

@@ -1039,14 +1039,24 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     void* stv = nullptr;
     FLB_CUDA(h, h->st_scan.acquire(n1 * 3 * sizeof(float), &stv));
     float* st = static_cast<float*>(stv);
-    float lo[3] = {INFINITY, INFINITY, INFINITY};
-    for (int i = 0; i < N; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const float v = body_xyz[(size_t)i * stride + k];
-            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: non-finite coordinate at point %d", i);
-            st[3 * (size_t)i + k] = v;
-            lo[k] = std::min(lo[k], v);
+    // pack + bounds + finiteness in branch-free passes the compiler vectorises (x - x is 0 only for finite x)
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (stride == 3) std::memcpy(st, body_xyz, (size_t)N * 3 * sizeof(float));
+    else
+        for (int i = 0; i < N; ++i) {
+            st[3 * (size_t)i] = body_xyz[(size_t)i * stride];
+            st[3 * (size_t)i + 1] = body_xyz[(size_t)i * stride + 1];
+            st[3 * (size_t)i + 2] = body_xyz[(size_t)i * stride + 2];
         }
+    float bad = 0.0f;
+    for (int i = 0; i < N; ++i) {
+        const float x = st[3 * (size_t)i], y = st[3 * (size_t)i + 1], z = st[3 * (size_t)i + 2];
+        lo[0] = std::min(lo[0], x); lo[1] = std::min(lo[1], y); lo[2] = std::min(lo[2], z);
+        hi[0] = std::max(hi[0], x); hi[1] = std::max(hi[1], y); hi[2] = std::max(hi[2], z);
+        bad += (x - x) + (y - y) + (z - z);          // NaN for any non-finite coordinate
+    }
+    if (!(bad == 0.0f) || (N > 0 && !(std::isfinite(lo[0] + lo[1] + lo[2] + hi[0] + hi[1] + hi[2]))))
+        return fail(h, FLB_ERR_INVALID, "flb_scan_upload: non-finite coordinate");
     FLB_CUDA(h, h->scan_raw.reserve(n1 * 3));
     FLB_CUDA(h, h->skeys.reserve(n1));
     FLB_CUDA(h, h->skeys_sorted.reserve(n1));
@@ -1061,8 +1071,8 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     if (N > 0) {
         FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         FLB_CUDA(h, h->st_scan.mark(h->stream));
-        // Morton order in the body frame (cell = the map grid's cell): spatially coherent warps at any pose
-        const float inv_cell = 1.0f / (float)h->cfg.cell_size;
+        // Morton order in the body frame (cell = twice the map grid's cell): spatially coherent warps at any pose
+        const float inv_cell = 0.5f / (float)h->cfg.cell_size;
         const int g = (N + 255) / 256;
         {
             LaunchScope ls(h, FAM_OTHER);
@@ -1071,10 +1081,10 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
         }
         size_t tmp_bytes = 0;
         FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
-                                                    h->svals_sorted.p, N, 0, 30, h->stream));
+                                                    h->svals_sorted.p, N, 0, 24, h->stream));
         FLB_CUDA(h, h->cub_tmp.reserve(tmp_bytes));
         FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
-                                                    h->svals_sorted.p, N, 0, 30, h->stream));
+                                                    h->svals_sorted.p, N, 0, 24, h->stream));
         h->launches += 3;
         {
             LaunchScope ls(h, FAM_OTHER);
