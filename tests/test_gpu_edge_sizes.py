@@ -1,0 +1,58 @@
+"""GPU tier: degenerate sizes of the persistent update kernels (worker blocks + one leader block, chunked
+points, warp-per-patch): one point, one patch, fewer points than a warp, counts around the chunk / block
+boundaries, zero iterations -- both execution modes against the oracle."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import STATE_RTOL, _gstate, _ostate, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=[1, 0], ids=["persistent", "kernel-per-pass"])
+def handle(flb, request):
+    h = flb.Handle(device=0, persistent=request.param)
+    yield h
+    h.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 33, 64, 147, 148, 149, 1175, 1176, 1177, 1185])
+def test_lio_update_small_scans(flb, po, frames, handle, n):
+    f = dict(frames("T1"))
+    rng = np.random.default_rng(n)
+    keep = np.sort(rng.choice(len(f["scan_body"]), n, replace=False))
+    f["scan_body"] = np.ascontiguousarray(f["scan_body"][keep])
+    handle.map_upload(f["map_xyz"])
+    for T in (0, 1, 4):
+        handle.scan_upload(f["scan_body"])
+        lio = po.Lio(f["map_xyz"], f["scan_body"])
+        xo, xpo = _ostate(po, f), _ostate(po, f)
+        orep = lio.update(po.lio_params(f, T), xo, xpo)
+        xg, xpg = _gstate(flb, f), _gstate(flb, f)
+        grep = handle.lio_update(flb.capi.lio_params(f, T), xg, xpg)
+        assert (grep.passes, grep.knn_passes, grep.n_eff_last, grep.rows_total) == (orep.passes, orep.knn_passes, orep.n_eff_last, orep.rows_total)
+        if orep.n_eff_last > 0:
+            assert rel(xg.vector(), xo.vector()) < STATE_RTOL
+            assert rel(xg.P, xo.P) < 1e-7
+
+
+@pytest.mark.parametrize("pn", [1, 2, 3, 15, 16, 17, 33, 150])
+def test_vio_update_few_patches(flb, po, frames, handle, pn):
+    f = frames("T1")
+    rng = np.random.default_rng(100 + pn)
+    keep = np.sort(rng.choice(len(f["patch_pos"]), pn, replace=False))
+    ppos, pref, plev = f["patch_pos"][keep], f["patch_ref"][keep], f["patch_level"][keep]
+    handle.camera_set(f["cam"])
+    handle.image_upload(f["image"])
+    handle.patches_upload(ppos, pref, plev)
+    vio = po.Vio(f["image"], ppos, pref, plev, f["cam"])
+    for T, force in ((1, False), (3, True), (4, False)):
+        xo, xpo = _ostate(po, f), _ostate(po, f)
+        orep = vio.update(po.vio_params(f, T, force_all_passes=force), xo, xpo)
+        xg, xpg = _gstate(flb, f), _gstate(flb, f)
+        grep = handle.vio_update(flb.capi.vio_params(f, T, force_all_passes=force), xg, xpg)
+        assert list(grep.passes) == list(orep.passes)
+        assert grep.rows_total == orep.rows_total and grep.cov_updated == orep.cov_updated
+        np.testing.assert_allclose(list(grep.last_error), list(orep.last_error), rtol=1e-6)
+        assert rel(xg.vector(), xo.vector()) < STATE_RTOL
+        assert rel(xg.P, xo.P) < 1e-7
