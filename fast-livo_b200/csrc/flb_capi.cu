@@ -1039,8 +1039,7 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     void* stv = nullptr;
     FLB_CUDA(h, h->st_scan.acquire(n1 * 3 * sizeof(float), &stv));
     float* st = static_cast<float*>(stv);
-    // pack + bounds + finiteness in branch-free passes the compiler vectorises (x - x is 0 only for finite x)
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float lo[3] = {INFINITY, INFINITY, INFINITY};
     if (stride == 3) std::memcpy(st, body_xyz, (size_t)N * 3 * sizeof(float));
     else
         for (int i = 0; i < N; ++i) {
@@ -1048,15 +1047,31 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
             st[3 * (size_t)i + 1] = body_xyz[(size_t)i * stride + 1];
             st[3 * (size_t)i + 2] = body_xyz[(size_t)i * stride + 2];
         }
-    float bad = 0.0f;
-    for (int i = 0; i < N; ++i) {
-        const float x = st[3 * (size_t)i], y = st[3 * (size_t)i + 1], z = st[3 * (size_t)i + 2];
-        lo[0] = std::min(lo[0], x); lo[1] = std::min(lo[1], y); lo[2] = std::min(lo[2], z);
-        hi[0] = std::max(hi[0], x); hi[1] = std::max(hi[1], y); hi[2] = std::max(hi[2], z);
-        bad += (x - x) + (y - y) + (z - z);          // NaN for any non-finite coordinate
+    {
+        // bounds + finiteness over the packed floats, 24 (= 8 points) at a time into 24 independent accumulators:
+        // no cross-iteration dependency, so the host compiler vectorises the inner loop as it stands
+        float mn[24];
+        for (int j = 0; j < 24; ++j) mn[j] = INFINITY;
+        unsigned bad = 0;
+        const size_t n3 = (size_t)N * 3;
+        size_t i = 0;
+        for (; i + 24 <= n3; i += 24)
+            for (int j = 0; j < 24; ++j) {
+                const float v = st[i + j];
+                unsigned bits;
+                std::memcpy(&bits, &v, sizeof(bits));
+                bad |= ((bits & 0x7F800000u) == 0x7F800000u) ? 1u : 0u;
+                mn[j] = v < mn[j] ? v : mn[j];
+            }
+        for (; i < n3; ++i) {
+            const float v = st[i];
+            const int j = (int)(i % 24);
+            bad |= std::isfinite(v) ? 0u : 1u;
+            mn[j] = v < mn[j] ? v : mn[j];
+        }
+        for (int j = 0; j < 24; ++j) lo[j % 3] = std::min(lo[j % 3], mn[j]);
+        if (bad) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: non-finite coordinate");
     }
-    if (!(bad == 0.0f) || (N > 0 && !(std::isfinite(lo[0] + lo[1] + lo[2] + hi[0] + hi[1] + hi[2]))))
-        return fail(h, FLB_ERR_INVALID, "flb_scan_upload: non-finite coordinate");
     FLB_CUDA(h, h->scan_raw.reserve(n1 * 3));
     FLB_CUDA(h, h->skeys.reserve(n1));
     FLB_CUDA(h, h->skeys_sorted.reserve(n1));
@@ -1405,25 +1420,34 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     FLB_CUDA(h, h->errors.reserve(n));
     const int nb = (Pn + 7) / 8;
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)std::max(nb, 1) * kVioPacked, h->partials.cap)));
-    const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int));
+    const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int)) + 16;
     if (Pn > 0) {
-        const void *st = pos, *st2 = patch, *st3 = search_level;
         const bool direct = is_pinned(pos) && is_pinned(patch) && is_pinned(search_level);
-        if (!direct) {
+        { int rcq = vio_copy_begin(h); if (rcq) return rcq; }
+        if (direct) {
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, pos, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, patch, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, search_level, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+        } else {
+            // pageable caller buffers: pack into pinned staging and hand each piece to the copy engine as soon
+            // as it is packed, the reference patches (96 % of the bytes) in four slices, so that the transfer
+            // runs behind the host memcpy instead of after it
             void* stv = nullptr;
             FLB_CUDA(h, h->st_patch.acquire(bytes, &stv));
             char* b = static_cast<char*>(stv);
             std::memcpy(b, pos, (size_t)Pn * 3 * sizeof(double));
-            char* b2 = b + (size_t)Pn * 3 * sizeof(double);
-            std::memcpy(b2, patch, (size_t)Pn * 192 * sizeof(float));
-            char* b3 = b2 + (size_t)Pn * 192 * sizeof(float);
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, b, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+            char* b3 = b + (size_t)Pn * 3 * sizeof(double);
             std::memcpy(b3, search_level, (size_t)Pn * sizeof(int));
-            st = b; st2 = b2; st3 = b3;
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, b3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+            char* b2 = b3 + (((size_t)Pn * sizeof(int) + 15) & ~(size_t)15);
+            const size_t total = (size_t)Pn * 192, slice = (total + 3) / 4;
+            for (size_t o = 0; o < total; o += slice) {
+                const size_t cnt = std::min(slice, total - o);
+                std::memcpy(b2 + o * sizeof(float), patch + o, cnt * sizeof(float));
+                FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p + o, b2 + o * sizeof(float), cnt * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+            }
         }
-        { int rcq = vio_copy_begin(h); if (rcq) return rcq; }
-        FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, st, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
-        FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, st2, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
-        FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, st3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
         if (!direct) FLB_CUDA(h, h->st_patch.mark(h->copy_stream));
         { int rcq = vio_copy_end(h); if (rcq) return rcq; }
     }

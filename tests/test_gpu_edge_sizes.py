@@ -56,3 +56,18 @@ def test_vio_update_few_patches(flb, po, frames, handle, pn):
         np.testing.assert_allclose(list(grep.last_error), list(orep.last_error), rtol=1e-6)
         assert rel(xg.vector(), xo.vector()) < STATE_RTOL
         assert rel(xg.P, xo.P) < 1e-7
+
+
+@pytest.mark.parametrize("n,pos", [(1, 0), (7, 6), (8, 3), (9, 8), (1000, 0), (1000, 999), (1000, 503)])
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf])
+def test_scan_upload_rejects_non_finite(flb, n, pos, bad):
+    """The vectorised bounds / finiteness pass of flb_scan_upload (24 floats at a time + scalar tail)."""
+    h = flb.Handle(device=0)
+    pts = np.random.default_rng(n).uniform(-5, 5, (n, 3)).astype(np.float32)
+    h.scan_upload(pts)                                   # clean input is accepted
+    for axis in range(3):
+        q = pts.copy()
+        q[pos, axis] = bad
+        with pytest.raises(flb.capi.FlbError):
+            h.scan_upload(q)
+    h.close()
