@@ -204,6 +204,7 @@ def lib():
         L.flb_lio_update_ikfom.argtypes = [vp, C.POINTER(IkfomParams), C.POINTER(StateIkfom), C.POINTER(IkfomReport)]
         L.flb_imu_undistort.argtypes = [vp, C.POINTER(ImuParams), C.POINTER(ImuCarry), vp, C.c_int, C.c_double, C.c_double,
                                         vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
+        L.flb_visual_candidates.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.flb_image_upload.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.flb_patches_upload.argtypes = [vp, vp, vp, vp, C.c_int]
         L.flb_camera_set.argtypes = [vp, C.POINTER(Camera)]
@@ -413,6 +414,20 @@ class Handle:
         rep = VioReport()
         self._ck(self.L.flb_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep)))
         return rep
+
+    # ---- visual-map growth: candidate scoring (row f4)
+    def visual_candidates(self, Rcw, Pcw, world_xyz, grid_size, border, map_value):
+        """flb_visual_candidates on the uploaded image / camera.  Returns (map_value_out, winner) per grid cell."""
+        R = np.ascontiguousarray(Rcw, np.float64)
+        P = np.ascontiguousarray(Pcw, np.float64)
+        pts = np.ascontiguousarray(world_xyz, np.float32)
+        mv = np.ascontiguousarray(map_value, np.float32).copy()
+        win = np.zeros(len(mv), np.int32)
+        self._ck(self.L.flb_visual_candidates(self.h, R.ctypes.data_as(C.c_void_p), P.ctypes.data_as(C.c_void_p),
+                                              pts.ctypes.data_as(C.c_void_p), len(pts), pts.shape[1] if len(pts) else 3,
+                                              int(grid_size), int(border), mv.ctypes.data_as(C.c_void_p),
+                                              win.ctypes.data_as(C.c_void_p)))
+        return mv, win
 
     # ---- IMU propagation + undistortion (row f3)
     def imu_undistort(self, prm: ImuParams, carry: ImuCarry, v_imu, pcl_beg_time, pcl_end_time, pts, offset_index=3):

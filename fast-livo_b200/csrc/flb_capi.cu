@@ -203,6 +203,10 @@ struct flb_handle {
     DevBuf<double> imu_buf;            // flb_imu_undistort: samples | carry | aux | poses
     DevBuf<float4> imu_pts;            // in | out
     DevBuf<int> imu_heads;
+    DevBuf<unsigned long long> vm_key;   // flb_visual_candidates: per-cell {score, ~index}
+    DevBuf<float> vm_val, vm_pts;
+    DevBuf<int> vm_win;
+    DevBuf<double> vm_pose;
     int dbg_vio_blocks = 0;
     int dbg_blocks = 0;
     bool tracing = false;
@@ -712,7 +716,7 @@ int flb_destroy(flb_handle* h) {
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
-    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->dbg_vio.release(); h->imu_buf.release(); h->imu_pts.release(); h->imu_heads.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
+    h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->dbg_vio.release(); h->imu_buf.release(); h->imu_pts.release(); h->imu_heads.release(); h->vm_key.release(); h->vm_val.release(); h->vm_pts.release(); h->vm_win.release(); h->vm_pose.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
@@ -1030,6 +1034,59 @@ int flb_imu_undistort(flb_handle* h, const flb_imu_params* prm, flb_imu_carry* c
     h->last_pass_valid = false;
     h->last_vio_valid = false;
     return FLB_OK;
+}
+
+int flb_visual_candidates(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* world_xyz, int n, int stride,
+                          int grid_size, int border, float* map_value, int* winner) {
+    FLB_CHECK_H(h);
+    if (!Rcw || !Pcw || n < 0 || (n > 0 && !world_xyz) || stride < 3 || grid_size < 1 || border < 0 || !map_value || !winner)
+        return fail(h, FLB_ERR_INVALID, "flb_visual_candidates: bad arguments");
+    if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_visual_candidates: camera and image must be set first");
+    const int gw = h->img_w / grid_size, gh = h->img_h / grid_size, ncell = gw * gh;      // :55-57
+    if (ncell < 1) return fail(h, FLB_ERR_INVALID, "flb_visual_candidates: grid_size larger than the image");
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }                           // the image upload has landed
+    const size_t n1 = (size_t)std::max(n, 1);
+    FLB_CUDA(h, h->vm_key.reserve((size_t)ncell));
+    FLB_CUDA(h, h->vm_val.reserve((size_t)ncell));
+    FLB_CUDA(h, h->vm_win.reserve((size_t)ncell));
+    FLB_CUDA(h, h->vm_pts.reserve(n1 * 3));
+    FLB_CUDA(h, h->vm_pose.reserve(12));
+    void* stv = nullptr;
+    const size_t st_bytes = n1 * 3 * sizeof(float) + (size_t)ncell * sizeof(float) + 12 * sizeof(double);
+    FLB_CUDA(h, h->st_scan.acquire(st_bytes, &stv));
+    double* st_pose = static_cast<double*>(stv);
+    std::memcpy(st_pose, Rcw, 9 * sizeof(double));
+    std::memcpy(st_pose + 9, Pcw, 3 * sizeof(double));
+    float* st_val = reinterpret_cast<float*>(st_pose + 12);
+    std::memcpy(st_val, map_value, (size_t)ncell * sizeof(float));
+    float* st_pts = st_val + ncell;
+    for (int i = 0; i < n; ++i) {
+        st_pts[3 * (size_t)i] = world_xyz[(size_t)i * stride];
+        st_pts[3 * (size_t)i + 1] = world_xyz[(size_t)i * stride + 1];
+        st_pts[3 * (size_t)i + 2] = world_xyz[(size_t)i * stride + 2];
+    }
+    FLB_CUDA(h, cudaMemcpyAsync(h->vm_pose.p, st_pose, 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(h->vm_val.p, st_val, (size_t)ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) FLB_CUDA(h, cudaMemcpyAsync(h->vm_pts.p, st_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_scan.mark(h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vmap_seed<<<(ncell + 255) / 256, 256, 0, h->stream>>>(h->vm_val.p, ncell, h->vm_key.p);
+        if (n > 0)
+            k_vmap_candidates<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cam, h->vm_pose.p, h->img.p, h->vm_pts.p, n, grid_size, gh, border,
+                                                                      h->vm_key.p);
+        k_vmap_resolve<<<(ncell + 255) / 256, 256, 0, h->stream>>>(h->vm_key.p, ncell, h->vm_val.p, h->vm_win.p);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 2;
+    }
+    FLB_CUDA(h, h->pin_out.reserve((size_t)ncell * (sizeof(float) + sizeof(int))));
+    char* po = static_cast<char*>(h->pin_out.p);
+    FLB_CUDA(h, cudaMemcpyAsync(po, h->vm_val.p, (size_t)ncell * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + (size_t)ncell * sizeof(float), h->vm_win.p, (size_t)ncell * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(map_value, po, (size_t)ncell * sizeof(float));
+    std::memcpy(winner, po + (size_t)ncell * sizeof(float), (size_t)ncell * sizeof(int));
+    return vio_inputs_release(h);
 }
 
 int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {

@@ -706,6 +706,48 @@ FLB_HD void imu_compensate_point(const ImuPose& head, const double* R_LI, const 
     for (int k = 0; k < 3; ++k) p[k] = (float)(c[k] - exrR_extT[k]);              // :800-805
 }
 
+// ------------------------------------------------------------------ visual-map growth: candidate scoring (row f4)
+// vk::shiTomasiScore (rpg_vikit vikit_common/src/vision.cpp): 8x8 box of central differences around (u, v), smaller
+// eigenvalue of the normalised structure tensor.  Every partial sum is an integer < 2^24, exact in float.
+FLB_HD float shi_tomasi_score(const unsigned char* img, int width, int height, int stride, int u, int v) {
+    const int x_min = u - 4, x_max = u + 4, y_min = v - 4, y_max = v + 4;
+    if (x_min < 1 || x_max >= width - 1 || y_min < 1 || y_max >= height - 1) return 0.0f;
+    float dXX = 0.0f, dYY = 0.0f, dXY = 0.0f;
+    for (int y = y_min; y < y_max; ++y) {
+        const unsigned char* row = img + (size_t)stride * y + x_min;
+        FLB_UNROLL
+        for (int x = 0; x < 8; ++x) {
+            const float dx = (float)((int)row[x + 1] - (int)row[x - 1]);
+            const float dy = (float)((int)row[x + stride] - (int)row[x - stride]);
+            dXX += dx * dx;
+            dYY += dy * dy;
+            dXY += dx * dy;
+        }
+    }
+    dXX = (float)((double)dXX / (2.0 * 64));
+    dYY = (float)((double)dYY / (2.0 * 64));
+    dXY = (float)((double)dXY / (2.0 * 64));
+    const float tr = dXX + dYY;
+    return (float)(0.5 * (double)(tr - sqrtf(tr * tr - 4 * (dXX * dYY - dXY * dXY))));
+}
+
+// One scan point of LidarSelector::addSparseMap's first loop (src/lidar_selection.cpp:152-158): grid cell it
+// falls into (-1: not in the frame with the `border` margin) and its corner score.
+FLB_HD int visual_candidate(const CamModel& cam, const double* Rcw, const double* Pcw, const unsigned char* img, int stride,
+                            const float* p, int grid_size, int grid_n_height, int border, float* score) {
+    const double pt[3] = {(double)p[0], (double)p[1], (double)p[2]};
+    double pf[3], pc[2];
+    m3_vec(Rcw, pt, pf);
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) pf[k] += Pcw[k];
+    world2cam(cam, pf, pc);                                                         // Frame::w2c, include/frame.h:89
+    if (!(fabs(pc[0]) < 1e9) || !(fabs(pc[1]) < 1e9)) return -1;
+    const int ox = (int)pc[0], oy = (int)pc[1];                                     // pc.cast<int>()
+    if (!(ox >= border && ox < cam.width - border && oy >= border && oy < cam.height - border)) return -1;   // isInFrame
+    *score = shi_tomasi_score(img, cam.width, cam.height, stride, ox, oy);          // :158
+    return (int)(pc[0] / grid_size) * grid_n_height + (int)(pc[1] / grid_size);     // :156
+}
+
 // ------------------------------------------------------------------ IKFoM manifold algebra (row a8)
 // state_ikfom = pos, rot(SO3), offset_R_L_I(SO3), offset_T_L_I, vel, bg, ba, grav(S2, |g| = 9.8090)
 // (include/use-ikfom.hpp:12-21; DOF 23).  Quaternions are (x, y, z, w) like Eigen's coeffs().

@@ -1996,6 +1996,51 @@ __global__ void k_imu_undistort(const float* __restrict__ in_xyz, int stride, co
     out[i] = make_float4(p[0], p[1], p[2], off);
 }
 
+// =======================================================================================
+// Visual-map growth, candidate scoring: first loop of
+// LidarSelector::addSparseMap, src/lidar_selection.cpp:150-168.
+// =======================================================================================
+// The reference walks the points in order and lets a point take its grid cell when its score is strictly above
+// the cell's current value.  The outcome per cell is "the first point that reaches the cell's maximum, if that
+// maximum exceeds the incoming value": one 64-bit atomicMax per point on {order-preserving score bits,
+// ~index}; the seed carries index bits 0xFFFFFFFF so that an equal score never displaces it.
+__device__ __forceinline__ unsigned ordered_f32(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_f32(unsigned o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+__global__ void k_vmap_seed(const float* __restrict__ map_value, int ncell, unsigned long long* __restrict__ key) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncell) key[c] = ((unsigned long long)ordered_f32(map_value[c]) << 32) | 0xFFFFFFFFull;
+}
+__global__ void k_vmap_candidates(CamModel cam, const double* __restrict__ Rcw_Pcw, const unsigned char* __restrict__ img,
+                                  const float* __restrict__ xyz, int n, int grid_size, int grid_n_height, int border,
+                                  unsigned long long* __restrict__ key) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double Rcw[9], Pcw[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rcw[k] = Rcw_Pcw[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Pcw[k] = Rcw_Pcw[9 + k];
+    float score = 0.0f;
+    const float p[3] = {xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]};
+    const int cell = visual_candidate(cam, Rcw, Pcw, img, cam.width, p, grid_size, grid_n_height, border, &score);
+    if (cell < 0) return;
+    atomicMax(key + cell, ((unsigned long long)ordered_f32(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+}
+__global__ void k_vmap_resolve(const unsigned long long* __restrict__ key, int ncell, float* __restrict__ map_value,
+                               int* __restrict__ winner) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const unsigned long long k = key[c];
+    const unsigned low = (unsigned)k;
+    winner[c] = (low == 0xFFFFFFFFu) ? -1 : (int)(0xFFFFFFFFu - low);
+    if (low != 0xFFFFFFFFu) map_value[c] = unordered_f32((unsigned)(k >> 32));
+}
+
 }  // namespace flb
 
 // =======================================================================================

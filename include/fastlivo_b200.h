@@ -273,6 +273,19 @@ int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, 
 int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, const int* search_level, int Pn);
 int flb_camera_set(flb_handle* h, const flb_camera* cam);
 
+/* ---- visual-map growth: candidate scoring -----------------------------------
+ * Replaces the first loop of LidarSelector::addSparseMap (src/lidar_selection.cpp:150-168): every point of pg
+ * (world frame) is projected into the new frame (T_f_w = [Rcw | Pcw], include/frame.h:89), kept when it lies
+ * inside the image with the `border` margin ((patch_size_half+1)*8, :154), scored with vk::shiTomasiScore
+ * on the uploaded image (flb_image_upload + flb_camera_set) and takes its grid cell
+ * (int(u/grid_size)*grid_n_height + int(v/grid_size), :156) when the score is STRICTLY above the cell's value.
+ *   map_value (grid_n_width*grid_n_height floats, grid_n_* = image size / grid_size, :55-56): in = the values
+ *   addFromSparseMap left there (:447-455), out = updated.  winner: per cell the index into world_xyz of the
+ *   point that took the cell in this call (the reference's add_voxel_points_[cell] / TYPE_POINTCLOUD), -1
+ *   otherwise.  Creating the Point / Feature objects for the winners (:174-195) stays with the caller. */
+int flb_visual_candidates(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* world_xyz, int n,
+                          int stride_floats, int grid_size, int border, float* map_value, int* winner);
+
 /* One measurement pass of LidarSelector::UpdateState (src/lidar_selection.cpp:772-857)
  * at pose (R,p) and pyramid level `level`. */
 int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], const double p[3], int level,

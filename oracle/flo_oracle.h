@@ -203,6 +203,12 @@ int flo_vio_update(flo_vio*, const flo_vio_params*, flo_state18* x, const flo_st
 /* vikit PinholeCamera::world2cam(Vector3d). */
 void flo_world2cam(const flo_cam* cam, const double pf[3], double px[2]);
 
+/* ---- visual-map growth: candidate scoring (oracle/flo_vmap.cpp) ------------ */
+float flo_shi_tomasi(const uint8_t* img, int width, int height, int stride, int u, int v);   /* vk::shiTomasiScore */
+/* first loop of LidarSelector::addSparseMap, src/lidar_selection.cpp:150-168 */
+void flo_visual_candidates(const flo_cam* cam, const double* Rcw, const double* Pcw, const uint8_t* img, int stride,
+                           const float* world_xyz, int n, int grid_size, int border, float* map_value, int* winner);
+
 #ifdef __cplusplus
 }
 #endif

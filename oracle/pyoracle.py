@@ -139,6 +139,23 @@ def imu_undistort(prm: ImuParams, carry: ImuCarry, v_imu, pcl_beg_time, pcl_end_
     return pts, poses[:n.value]
 
 
+def visual_candidates(cam: dict, Rcw, Pcw, image, world_xyz, grid_size, border, map_value):
+    """flo_visual_candidates (first loop of addSparseMap).  Returns (map_value_out, winner) per grid cell."""
+    c = make_cam(cam)
+    img = np.ascontiguousarray(image, np.uint8)
+    pts = np.ascontiguousarray(world_xyz, np.float32)
+    mv = np.ascontiguousarray(map_value, np.float32).copy()
+    win = np.zeros(len(mv), np.int32)
+    lib().flo_visual_candidates(C.byref(c), _p(f64(Rcw)), _p(f64(Pcw)), _p(img), img.shape[1], _p(pts), len(pts),
+                                int(grid_size), int(border), _p(mv), _p(win))
+    return mv, win
+
+
+def shi_tomasi(image, u, v):
+    img = np.ascontiguousarray(image, np.uint8)
+    return np.float32(lib().flo_shi_tomasi(_p(img), img.shape[1], img.shape[0], img.shape[1], int(u), int(v)))
+
+
 def quat_from_R(R):
     """Rotation matrix -> quaternion (x, y, z, w), w >= 0."""
     R = np.asarray(R, np.float64)
@@ -190,7 +207,7 @@ KNN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void
 def build(force: bool = False) -> None:
     """Compile the checker (and, when /root/reference is present, the reference ikd-Tree)."""
     need = force or not os.path.exists(_LIB) or \
-        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_ikfom.cpp", "flo_imu.cpp", "flo_oracle.h"))
+        os.path.getmtime(_LIB) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("flo_oracle.cpp", "flo_ikfom.cpp", "flo_imu.cpp", "flo_vmap.cpp", "flo_oracle.h"))
     if need:
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     if os.path.isdir("/root/reference/include/ikd-Tree") and (force or not os.path.exists(_REF)):
@@ -237,6 +254,10 @@ def lib():
         L.flo_ikfom_boxminus.argtypes = [C.POINTER(StateIkfom), C.POINTER(StateIkfom), C.c_void_p]
         L.flo_quat_to_R.argtypes = [C.c_void_p, C.c_void_p]
         L.flo_ikfom_update.argtypes = [C.c_void_p, C.POINTER(IkfomParams), C.POINTER(StateIkfom), C.POINTER(IkfomReport)]
+        L.flo_shi_tomasi.restype = C.c_float
+        L.flo_shi_tomasi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.flo_visual_candidates.argtypes = [C.POINTER(Cam), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.flo_imu_undistort.argtypes = [C.POINTER(ImuParams), C.POINTER(ImuCarry), C.c_void_p, C.c_int, C.c_double, C.c_double,
                                         C.POINTER(State18), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         _lib = L

@@ -105,6 +105,22 @@ void emu_vio(const double* camv, const double* Rci, const double* Pci, const dou
     }
 }
 
+// row f4: per-point candidate of addSparseMap's first loop; cell[i] = -1 when the point is not in the frame
+void emu_visual_candidates(const double* camv, const double* Rcw, const double* Pcw, const unsigned char* img, const float* xyz,
+                           int n, int grid_size, int border, int* cell, float* score) {
+    CamModel cam;
+    cam.width = (int)camv[0]; cam.height = (int)camv[1];
+    cam.fx = camv[2]; cam.fy = camv[3]; cam.cx = camv[4]; cam.cy = camv[5];
+    for (int i = 0; i < 5; ++i) cam.d[i] = camv[6 + i];
+    cam.jfx = cam.jfy = 0.0;
+    const int gh = cam.height / grid_size;
+    for (int i = 0; i < n; ++i) {
+        score[i] = 0.0f;
+        cell[i] = visual_candidate(cam, Rcw, Pcw, img, cam.width, xyz + 3 * i, grid_size, gh, border, &score[i]);
+    }
+}
+float emu_shi_tomasi(const unsigned char* img, int w, int h, int u, int v) { return shi_tomasi_score(img, w, h, w, u, v); }
+
 void emu_exp3(const double* v, double* R) { so3_exp(v, R); }
 void emu_log3(const double* R, double* o) { so3_log(R, o); }
 
