@@ -8,8 +8,9 @@
 //                 convergence / rematch / stop control -- all on the device
 //   * map / scan preparation (cell sort, Morton sort)
 // Two execution modes share all of the above:
-//   persistent      one cooperative launch per update; passes separated by a grid barrier whose last
-//                   arriver becomes the leader block (k_lio_update_persistent / k_vio_update_persistent)
+//   persistent      one cooperative launch per update: worker blocks run the passes, ONE leader block (no
+//                   points / patches of its own) reduces, solves and publishes the next pose as a flagged
+//                   packet the workers poll (k_lio_update_persistent / k_vio_update_persistent)
 //   kernel-per-pass k_*_pass + k_*_finalize (one block running the same leader code)
 // No tensor cores: nothing here is a dense contraction.  No floating-point atomics: every reduction
 // has a fixed order, so results are bit-reproducible run to run and identical across ranks.
@@ -1468,10 +1469,12 @@ __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
 // =======================================================================================
 // Persistent (one launch per update) kernels
 // =======================================================================================
-// All blocks are co-resident (cooperative launch, grid <= SMs x occupancy).  Every pass ends in a
-// grid barrier whose LAST ARRIVER becomes the leader: it runs the leader step above with its whole
-// block, publishes state + control through L2, and releases the other blocks.  No host round trip,
-// no empty launch; bit-identical to the kernel-per-pass path.
+// All blocks are co-resident (cooperative launch, grid <= SMs x occupancy).  LIO / VIO: worker blocks + one
+// dedicated leader block; a pass ends when every worker has arrived (red.release on a counter the leader
+// acquire-polls), the leader runs the leader step above with its whole block and publishes the pose packet
+// (below).  No host round trip, no empty launch; bit-identical to the kernel-per-pass path.
+// The IKFoM kernel still uses the classic form below (grid_arrive / grid_release / grid_wait: the last
+// arriver becomes the leader and re-opens a generation barrier).
 struct GridBarrier {
     unsigned int count;
     unsigned int gen;
@@ -1538,10 +1541,10 @@ __device__ __forceinline__ bool grid_wait(GridBarrier* b, const unsigned* s_scra
 // the control block as 8-byte units {payload word, flag} with flag = epoch + pass number; a waiting
 // block polls the units themselves, so the first successful poll already carries the data (the
 // 8-byte unit is written and read by single instructions, so payload and flag travel together).
-// Whatever else later leaders need (prior block, VIO old_state / G_last, exchange counter) is
-// stored AFTER the packet and reaches them through the release of this block's next arrive and
-// the acquire of the next last arriver.  The arrive counter runs up monotonically during a
-// launch (ticket nblocks * (pass + 1) - 1 elects the leader) and is zeroed by the last leader.
+// The leader is always the same block, so whatever it needs from pass to pass (prior block, covariance, VIO
+// old_state / G_last, exchange counter) stays in its shared memory or is re-read by the block that wrote it.
+// The arrive counter runs up monotonically during a launch (the leader waits for nworkers * (pass + 1)) and
+// is zeroed by the leader on the stopping pass.
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
