@@ -1680,6 +1680,14 @@ int flb_trace_enable(flb_handle* h, int on) {
     return FLB_OK;
 }
 
+// Test aid (not part of the public header): move the pose-packet flag base, e.g. next to its wrap-around point
+// (the base advances by 4096 per persistent launch and is re-based, with the packet cleared, before it overflows).
+int flb_debug_set_packet_epoch(flb_handle* h, unsigned epoch) {
+    FLB_CHECK_H(h);
+    h->pkt_epoch = epoch;
+    return FLB_OK;
+}
+
 // Tracing aid (not part of the public header): per-block / per-warp stamps of the last VIO pass,
 // kVioDbg words per block.
 int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks, int* words_per_block) {

@@ -71,3 +71,29 @@ def test_scan_upload_rejects_non_finite(flb, n, pos, bad):
         with pytest.raises(flb.capi.FlbError):
             h.scan_upload(q)
     h.close()
+
+
+def test_packet_flag_wraparound(flb, po, frames):
+    """The pose-packet flag base advances by 4096 per persistent launch; before it overflows 32 bits the library
+    re-bases it and clears the packet.  Run updates across that point: every one must still match the oracle."""
+    import ctypes as C
+    f = frames("T1")
+    h = flb.Handle(device=0, persistent=1)
+    h.load_frame(f)
+    lio = po.Lio(f["map_xyz"], f["scan_body"])
+    xo, xpo = _ostate(po, f), _ostate(po, f)
+    lio.update(po.lio_params(f, 4), xo, xpo)
+    vio = po.Vio(f["image"], f["patch_pos"], f["patch_ref"], f["patch_level"], f["cam"])
+    xv, xpv = _ostate(po, f), _ostate(po, f)
+    vio.update(po.vio_params(f, 3), xv, xpv)
+    fn = h.L.flb_debug_set_packet_epoch
+    fn.argtypes = [C.c_void_p, C.c_uint]
+    h._ck(fn(h.h, 0xFFFF0000 - 3 * 4096))
+    for it in range(8):                                   # launches 4 and 5 straddle the re-base
+        xg, xpg = _gstate(flb, f), _gstate(flb, f)
+        h.lio_update(flb.capi.lio_params(f, 4), xg, xpg)
+        assert rel(xg.vector(), xo.vector()) < STATE_RTOL, it
+        xg, xpg = _gstate(flb, f), _gstate(flb, f)
+        h.vio_update(flb.capi.vio_params(f, 3), xg, xpg)
+        assert rel(xg.vector(), xv.vector()) < STATE_RTOL, it
+    h.close()
