@@ -121,6 +121,24 @@ void emu_visual_candidates(const double* camv, const double* Rcw, const double* 
 }
 float emu_shi_tomasi(const unsigned char* img, int w, int h, int u, int v) { return shi_tomasi_score(img, w, h, w, u, v); }
 
+// row f3: the per-point backward compensation with pose `head` (22 doubles: t, acc, gyr, vel, pos, rot)
+void emu_imu_compensate(const double* head22, const double* R_LI, const double* t_LI, const double* rot_end, const double* pos_end,
+                        const float* xyz, const float* offset_ms, int n, float* out) {
+    ImuPose hp;
+    std::memcpy(&hp, head22, sizeof(hp));
+    double RLIt[9], RendT[9], extR_Ri[9], exrR_extT[3];
+    m3_T(R_LI, RLIt);
+    m3_T(rot_end, RendT);
+    m3_mul(RLIt, RendT, extR_Ri);
+    m3_vec(RLIt, t_LI, exrR_extT);
+    for (int i = 0; i < n; ++i) {
+        float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        imu_compensate_point(hp, R_LI, t_LI, extR_Ri, exrR_extT, pos_end, (double)offset_ms[i] / double(1000), p);
+        out[3 * i] = p[0]; out[3 * i + 1] = p[1]; out[3 * i + 2] = p[2];
+    }
+}
+void emu_exp_w_dt(const double* w, double dt, double* R) { so3_exp_dt(w, dt, R); }
+
 void emu_exp3(const double* v, double* R) { so3_exp(v, R); }
 void emu_log3(const double* R, double* o) { so3_log(R, o); }
 
