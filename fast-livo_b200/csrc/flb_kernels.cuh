@@ -1472,7 +1472,8 @@ __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
 // All blocks are co-resident (cooperative launch, grid <= SMs x occupancy).  LIO / VIO: worker blocks + one
 // dedicated leader block; a pass ends when every worker has arrived (red.release on a counter the leader
 // acquire-polls), the leader runs the leader step above with its whole block and publishes the pose packet
-// (below).  No host round trip, no empty launch; bit-identical to the kernel-per-pass path.
+// (below).  No host round trip, no empty launch.  Same pass and leader code as the kernel-per-pass path; the two
+// group a pass's partial sums by different block sizes, so their states agree to rounding, not bit for bit.
 // The IKFoM kernel still uses the classic form below (grid_arrive / grid_release / grid_wait: the last
 // arriver becomes the leader and re-opens a generation barrier).
 struct GridBarrier {
