@@ -13,10 +13,13 @@ disabled) so that the GPU and CPU arms do identical work.
   e2e   : frames/s through the C ABI with HOST buffers: per step the scan, image, patch list
           and both states go host->device and the updated state + reports come back
   roofline / cpu_baseline : see DESIGN.md §5.
+  other_workloads : BASELINE.json configs[2], configs[3] (C3, C4) measured in the same run (N = 1)
+  batched : B independent frames per launch: the roofline where it is physically meaningful
 
 N > 1 (torchrun, one rank per GPU): the scan points and patches are block-sharded, map / image /
-state replicated, packed normal equations all-reduced with NCCL every pass (BASELINE.json
-config 5) -- total work is fixed, so scaling is "strong".
+state replicated, the packed normal equations exchanged every pass (BASELINE.json config 5) --
+total work is fixed, so scaling is "strong".  Every N > 1 line carries `parity` (state vs the
+unsharded CPU path, rank-to-rank bit equality) and the NCCL-collective number as a secondary key.
 """
 from __future__ import annotations
 
@@ -25,7 +28,7 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
+import threading
 import time
 
 import numpy as np
@@ -50,43 +53,95 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the run, sampled by a thread through NVML (nvidia_ml_py); falls back to
+    an `nvidia-smi -lms` child whose stdout is read line by line (a block-buffered child killed by SIGTERM loses
+    its output: that is why round 1 reported 0 samples)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.sm, self.smax, self.reasons, self.power = [], [], set(), []
+        self.stop_flag = False
+        self.mode = None
+        self.t_mark = None
+        self.marks = []
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                       "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+            self.mode = "nvml"
+            self.th = threading.Thread(target=self._run_nvml, daemon=True)
+            self.th.start()
+        except Exception:
+            try:
+                q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                           "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+                self.mode = "nvidia-smi"
+                self.th = threading.Thread(target=self._run_smi, daemon=True)
+                self.th.start()
+            except OSError:
+                self.mode = None
 
-    def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().strip().splitlines():
+    def _run_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        for line in self.p.stdout:
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 7:
                 continue
             try:
-                sm.append(float(c[1]))
-                smax.append(float(c[2]))
+                self.sm.append(float(c[0]))
+                self.smax.append(float(c[1]))
+                self.power.append(float(c[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                    self.reasons.add(name)
+            if self.stop_flag:
+                break
+
+    def mark(self):
+        """Start of the timed region: the median is taken over the samples from here on (if any)."""
+        self.t_mark = len(self.sm)
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable"]}
+        self.stop_flag = True
+        if self.mode == "nvidia-smi":
+            try:
+                self.p.terminate()
+                self.p.wait(timeout=5)
+            except Exception:
+                pass
+        self.th.join(timeout=5)
+        sm = self.sm[self.t_mark:] if (self.t_mark is not None and len(self.sm) > self.t_mark + 2) else self.sm
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(self.smax) if self.smax else None,
+                "samples": len(sm), "samples_total": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                "reasons": sorted(self.reasons), "source": self.mode}
 
 
 def pass_counts(cfg):
@@ -119,6 +174,16 @@ def cpu_frame_runner(po, frame, nthreads):
     return run, kind
 
 
+def workload_config(cfg, gpus):
+    """Identical in both arms (GPU and --impl reference): names the workload only."""
+    pc = pass_counts(cfg)
+    return {"workload": f"{cfg.name}: {cfg.n_scan} scan pts vs {cfg.n_map}-pt map, {cfg.img_w}x{cfg.img_h} image, "
+                        f"{cfg.n_patch} 8x8 patches; {cfg.lio_passes} LIO passes ({pc['lio_knn']} with kNN) + "
+                        f"3x{cfg.vio_passes} VIO passes per frame, early stop disabled",
+            "parallelism": "single GPU" if gpus == 1 else f"scan/patch block-sharded over {gpus} GPUs, normal equations exchanged every pass",
+            "seed": cfg.seed}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -130,17 +195,22 @@ def run_reference(args):
     frame = flb.synth.make_frame(cfg)
     cores = os.cpu_count() or 1
     # the reference compiles its OpenMP team size in (MP_PROC_NUM = 4, CMakeLists.txt:19-37); more threads
-    # can be SLOWER (per-query heap allocation inside ikd-Tree), so pick the fastest team size <= cores.
-    best = None
+    # can be SLOWER (per-query heap allocation inside ikd-Tree), so pick the fastest team size <= cores from the
+    # median of 3 timed frames per setting (after one untimed frame each).
+    trials = {}
+    runners = {}
     for nt in sorted({t for t in (4, 8, 16, 32, cores) if t <= cores}):
         r, kind = cpu_frame_runner(po, frame, nt)
         r()
-        t0 = time.perf_counter()
-        r()
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[0]:
-            best = (dt, nt, r)
-    _, nthreads, run = best
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r()
+            ts.append(time.perf_counter() - t0)
+        trials[nt] = float(np.median(ts))
+        runners[nt] = r
+    nthreads = min(trials, key=trials.get)
+    run = runners[nthreads]
     for _ in range(args.warmup):
         run()
     t0 = time.perf_counter()
@@ -154,29 +224,200 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": workload_config(cfg, args.gpus, "n/a"),
+        "config": workload_config(cfg, args.gpus),
         "residuals_per_sec": rows / dt,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "port", "host_cores": cores,
+                         "fps_4_threads": (1.0 / trials[4]) if 4 in trials else None,
+                         "team_size_trials_fps": {str(k): 1.0 / v for k, v in trials.items()},
                          "sample": f"{args.steps} frames of {cfg.name}; {kind}; OpenMP over scan points "
-                                   f"({nthreads} threads = fastest of 4/8/16/32/all on this host), VIO serial as in the reference"},
+                                   f"({nthreads} threads = fastest of 4/8/16/32/all on this host by the median of 3 frames each; "
+                                   f"the reference compiles 4 in), VIO serial as in the reference"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(cfg, gpus, l2, coll="fused NVLink peer-memory exchange (in-kernel)"):
-    pc = pass_counts(cfg)
-    return {"workload": f"{cfg.name}: {cfg.n_scan} scan pts vs {cfg.n_map}-pt map, {cfg.img_w}x{cfg.img_h} image, "
-                        f"{cfg.n_patch} 8x8 patches; {cfg.lio_passes} LIO passes ({pc['lio_knn']} with kNN) + "
-                        f"3x{cfg.vio_passes} VIO passes per frame, early stop disabled",
-            "parallelism": "single GPU" if gpus == 1 else f"scan/patch block-sharded over {gpus} GPUs, {coll} of the normal equations per pass",
-            "l2": l2, "seed": cfg.seed}
 
 
 def shard(n, rank, world):
     per = (n + world - 1) // world
     lo = min(rank * per, n)
     return lo, min(lo + per, n)
+
+
+class Rig:
+    """One workload set up on one handle: uploads, the per-frame enqueue, timing helpers."""
+
+    def __init__(self, flb, torch, cfg, frame, h, dev, stream, rank=0, world=1, dist=None, flush=None):
+        self.flb, self.torch, self.cfg, self.frame, self.h = flb, torch, cfg, frame, h
+        self.dev, self.stream, self.rank, self.world, self.dist, self.flush = dev, stream, rank, world, dist, flush
+        self.pc = pass_counts(cfg)
+        s0, s1 = shard(cfg.n_scan, rank, world)
+        p0, p1 = shard(cfg.n_patch, rank, world)
+        self.scan = frame["scan_body"][s0:s1]
+        self.ppos, self.pref, self.plev = frame["patch_pos"][p0:p1], frame["patch_ref"][p0:p1], frame["patch_level"][p0:p1]
+        self.has_vio = cfg.n_patch > 0
+        self.lprm = flb.capi.lio_params(frame, self.pc["lio_T"], early_stop=False)
+        self.vprm = flb.capi.vio_params(frame, self.pc["vio_T"], early_stop=False, force_all_passes=True)
+        self.x0 = flb.capi.State18.from_frame(frame)
+
+    def upload(self, with_map=True):
+        h = self.h
+        if with_map:
+            h.map_upload(self.frame["map_xyz"])
+        h.scan_upload(self.scan)
+        if self.has_vio:
+            h.camera_set(self.frame["cam"])
+            h.image_upload(self.frame["image"])
+            h.patches_upload(self.ppos, self.pref, self.plev)
+        h.state_upload(self.x0, self.x0.copy())
+
+    def enqueue_frame(self):
+        # x := x_prop := prior ; LIO update ; x_prop := x (zero-motion propagation) ; VIO update
+        h = self.h
+        h.state_reset_enqueue()
+        h.lio_update_enqueue(self.lprm)
+        if self.has_vio:
+            h.state_set_prior_enqueue()
+            h.vio_update_enqueue(self.vprm)
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def time_resident(self, steps):
+        """`steps` frames with inputs resident, one CUDA-event pair per frame on the launching stream, L2 flushed
+        between frames; returns (total_ms as max over ranks, launches, wall_s)."""
+        torch = self.torch
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        l0 = self.h.launch_count()
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            if self.flush is not None:
+                self.flush.zero_()
+            starts[i].record(self.stream)
+            self.enqueue_frame()
+            ends[i].record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        total_ms = float(sum(s.elapsed_time(e) for s, e in zip(starts, ends)))
+        if self.dist is not None:
+            t = torch.tensor([total_ms], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, self.h.launch_count() - l0, wall
+
+    def pass_trace(self):
+        """Device-side per-pass trace of the persistent kernels (one extra frame, outside any timed region)."""
+        h = self.h
+        h.trace_enable(True)
+        if self.flush is not None:
+            self.flush.zero_()
+        self.enqueue_frame()
+        self.barrier()
+        tl, tv = h.trace_download(0), h.trace_download(1)
+        h.trace_enable(False)
+
+        def split(t):
+            t = t[:63]
+            t = t[:int(np.argmax(t == 0))] if (t == 0).any() else t     # entries 64.. are the fine leader stamps
+            t = np.concatenate([[0.0], t])
+            return {"pass_us": [round(float(t[i + 1] - t[i]), 2) for i in range(0, len(t) - 1, 2)],
+                    "solve_us": [round(float(t[i + 2] - t[i + 1]), 2) for i in range(0, len(t) - 2, 2)]}
+        return {"lio": split(tl), "vio": split(tv),
+                "note": "per pass: time until every block reached the barrier / leader reduce+solve+publish (globaltimer)"}
+
+    def families(self, prof_steps, persistent, hbm):
+        """Per-kernel-family device time (separate profiled run: one event pair per launch) + algorithmic GB/s."""
+        h, pc = self.h, self.pc
+        h.profile_start()
+        for _ in range(prof_steps):
+            if self.flush is not None:
+                self.flush.zero_()
+            self.enqueue_frame()
+        fam_ms, fam_n = h.profile_stop()
+        self.barrier()
+        n_loc, pn_loc = len(self.scan), len(self.ppos)
+        if persistent:
+            # one cooperative kernel per update: its algorithmic bytes are the sum over its passes
+            fam_bytes = [(B_LIO_KNN * pc["lio_knn"] + B_LIO_PLAIN * pc["lio_plain"]) * n_loc, 0, B_VIO * pc["vio_passes"] * pn_loc, 0]
+            fam_names = [f"k_lio_update_persistent ({pc['lio_knn']} kNN + {pc['lio_plain']} plain passes + solves)", "-",
+                         f"k_vio_update_persistent ({pc['vio_passes']} passes + solves)", "-"]
+        else:
+            fam_bytes = [B_LIO_KNN * n_loc, B_LIO_PLAIN * n_loc, B_VIO * pn_loc, 0]
+            fam_names = ["k_lio_pass(kNN+plane+residual)", "k_lio_pass(cached plane)", "k_vio_pass", "k_*_finalize/begin(solve)"]
+        fams = []
+        for i in range(4):
+            if fam_n[i] == 0:
+                continue
+            avg_us = 1e3 * fam_ms[i] / fam_n[i]
+            gbs = fam_bytes[i] / (avg_us * 1e-6) / 1e9 if fam_bytes[i] else 0.0
+            fams.append({"kernel": fam_names[i], "launches_per_frame": float(fam_n[i]) / prof_steps, "avg_us": avg_us,
+                         "share_of_frame": float(fam_ms[i] / max(fam_ms.sum(), 1e-12)), "algorithmic_bytes": int(fam_bytes[i]),
+                         "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm})
+        return fams
+
+
+def traffic_table():
+    """dram__bytes_read+write per launch of the persistent kernels from this round's ncu --set full captures
+    (profiles/r02_traffic.json, regenerated by profiles/make_traffic.py whenever a kernel changes)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                return json.load(f), name
+    return {}, None
+
+
+def roofline_of(fams, hbm, peak_src, workload, note):
+    dom = max((f for f in fams if f["algorithmic_bytes"] > 0), key=lambda f: f["share_of_frame"], default=None)
+    if dom is None:
+        return None
+    tj, tname = traffic_table()
+    key = dom["kernel"].split(" ")[0]
+    traffic = (tj.get(workload) or {}).get(key) if isinstance(tj.get(workload), dict) else (tj.get(key) if workload == "C2" else None)
+    return {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+            "frac": dom["achieved_gbs"] / hbm, "traffic": traffic,
+            "traffic_source": f"ncu --set full capture of this code, profiles/{tname}" if traffic else None,
+            "peak_source": peak_src, "avg_launch_us": dom["avg_us"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+            "note": note}
+
+
+def measure_other_workload(flb, torch, name, local, dev, stream, flush, hbm, peak_src, po, steps=10):
+    """BASELINE.json configs[2] / configs[3] on one GPU: value, per-kernel roofline, pass trace, parity vs the CPU path."""
+    cfg = flb.synth.CONFIGS[name]
+    frame = flb.synth.make_frame(cfg)
+    h = flb.Handle(device=local, cell_size=cfg.cell_size)
+    h.set_stream(stream.cuda_stream)
+    rig = Rig(flb, torch, cfg, frame, h, dev, stream, flush=flush)
+    rig.upload()
+    for _ in range(3):
+        rig.enqueue_frame()
+    rig.barrier()
+    xw, lrep, vrep = h.state_download()
+    rows = lrep.rows_total + (vrep.rows_total if rig.has_vio else 0)
+    total_ms, launches, _ = rig.time_resident(steps)
+    fps = steps / (total_ms * 1e-3)
+    trace = rig.pass_trace()
+    fams = rig.families(min(steps, 5), True, hbm)
+    out = {"config": workload_config(cfg, 1), "value": fps, "unit": UNIT, "steps": steps, "warmup": 3, "ms_per_step": total_ms / steps,
+           "rows_per_frame": int(rows), "residuals_per_sec": rows * fps, "gpu_launches": int(launches), "kernels": fams,
+           "roofline": roofline_of(fams, hbm, peak_src, name, "see DESIGN.md section 4: which pipe bounds each kernel at this size"),
+           "pass_trace": trace}
+    if po is not None:
+        cores = os.cpu_count() or 1
+        run4, kind = cpu_frame_runner(po, frame, min(4, cores))
+        t0 = time.perf_counter()
+        xo, _ = run4()
+        dt = time.perf_counter() - t0
+        vo = xo.vector()
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": min(4, cores), "kind": "port",
+                               "sample": f"1 frame of {cfg.name} (first call, includes the ikd-Tree build); {kind}"}
+        out["parity"] = {"state_rel_err_vs_cpu": float(np.abs(xw.vector() - vo).max() / np.abs(vo).max())}
+    h.close()
+    return out
 
 
 def main():
@@ -191,6 +432,7 @@ def main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: fused NVLink exchange inside the persistent kernels (default) or NCCL between per-pass kernels")
     ap.add_argument("--quick", action="store_true", help="profiling aid: skip the e2e / profile / cpu_baseline legs")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads (C3, C4) and batched legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -230,98 +472,56 @@ def main():
         handles = [None] * world
         dist.all_gather_object(handles, h.p2p_export())
         h.p2p_attach(rank, world, handles)
-    s0, s1 = shard(cfg.n_scan, rank, world)
-    p0, p1 = shard(cfg.n_patch, rank, world)
-    scan = frame["scan_body"][s0:s1]
-    ppos, pref, plev = frame["patch_pos"][p0:p1], frame["patch_ref"][p0:p1], frame["patch_level"][p0:p1]
-    h.map_upload(frame["map_xyz"])
-    h.scan_upload(scan)
-    has_vio = cfg.n_patch > 0
-    if has_vio:
-        h.camera_set(frame["cam"])
-        h.image_upload(frame["image"])
-        h.patches_upload(ppos, pref, plev)
-    lprm = flb.capi.lio_params(frame, pc["lio_T"], early_stop=False)
-    vprm = flb.capi.vio_params(frame, pc["vio_T"], early_stop=False, force_all_passes=True)
-    x0 = flb.capi.State18.from_frame(frame)
-    h.state_upload(x0, x0.copy())
-
-    def enqueue_frame():
-        # x := x_prop := prior ; LIO update ; x_prop := x (zero-motion propagation) ; VIO update
-        h.state_reset_enqueue()
-        h.lio_update_enqueue(lprm)
-        if has_vio:
-            h.state_set_prior_enqueue()
-            h.vio_update_enqueue(vprm)
-
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rig = Rig(flb, torch, cfg, frame, h, dev, stream, rank, world, dist, flush)
+    rig.upload()
+    scan, ppos, pref, plev, has_vio, x0, lprm, vprm = rig.scan, rig.ppos, rig.pref, rig.plev, rig.has_vio, rig.x0, rig.lprm, rig.vprm
+    barrier = rig.barrier
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- warm-up (the clock sampler starts here: the timed region may be shorter than one nvidia-smi period)
+    # ---- warm-up (the clock sampler starts here: the timed region may be shorter than one sampling period)
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
-        enqueue_frame()
+        rig.enqueue_frame()
     barrier()
     xw, lrep, vrep = h.state_download()
-    rows_per_frame = lrep.rows_total + (vrep.rows_total if has_vio else 0)
-    if world > 1:
-        pass  # rows are already global: the reduced n_eff / n_meas come out of the all-reduce
+    rows_per_frame = lrep.rows_total + (vrep.rows_total if has_vio else 0)   # N > 1: already global (reduced n_eff / n_meas)
 
     # ---- timed region: value (inputs resident)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    l0 = h.launch_count()
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.zero_()
-        starts[i].record(stream)
-        enqueue_frame()
-        ends[i].record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = h.launch_count() - l0
-    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
-    total_ms = float(step_ms.sum())
-    if dist is not None:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    if sampler:
+        sampler.mark()
+    total_ms, launches, t_wall = rig.time_resident(args.steps)
     clocks = sampler.stop() if sampler else None
     fps = args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: host buffers through the blocking C ABI, H2D + D2H inside the timed region
-    trace = None
-    if world == 1:
-        # device-side per-pass trace of the persistent kernels (one extra frame, outside the timed region)
-        h.trace_enable(True)
-        if flush is not None:
-            flush.zero_()
-        enqueue_frame()
-        barrier()
-        tl, tv = h.trace_download(0), h.trace_download(1)
-        h.trace_enable(False)
-
-        def split(t):
-            t = t[:63]
-            t = t[:int(np.argmax(t == 0))] if (t == 0).any() else t     # entries 64.. are the fine leader stamps
-            t = np.concatenate([[0.0], t])
-            return {"pass_us": [round(float(t[i + 1] - t[i]), 2) for i in range(0, len(t) - 1, 2)],
-                    "solve_us": [round(float(t[i + 2] - t[i + 1]), 2) for i in range(0, len(t) - 2, 2)]}
-        trace = {"lio": split(tl), "vio": split(tv),
-                 "note": "per pass: time until every block reached the barrier / leader reduce+solve+publish (globaltimer)"}
+    trace = rig.pass_trace() if world == 1 else None
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": fps, "unit": UNIT, "ms_per_step": total_ms / args.steps,
                               "gpu_launches": int(launches), "quick": True, "trace": trace}), flush=True)
         h.close()
+        if dist is not None:
+            dist.destroy_process_group()
         return
+
+    # ---- N > 1: parity of the sharded result (driver-visible): every rank's state bit-identical, and equal to the
+    # unsharded CPU path within the bar
+    parity = None
+    if world > 1:
+        vecs = [None] * world
+        dist.all_gather_object(vecs, (xw.vector().tolist(), list(xw.cov[:])))
+        if rank == 0:
+            po = fastlivo_loader.oracle()
+            run4, kind = cpu_frame_runner(po, frame, min(4, os.cpu_count() or 1))
+            xo, _ = run4()
+            vo = xo.vector()
+            v0 = np.array(vecs[0][0])
+            identical = all(vecs[r][0] == vecs[0][0] and vecs[r][1] == vecs[0][1] for r in range(world))
+            parity = {"state_rel_err_vs_cpu": float(np.abs(v0 - vo).max() / np.abs(vo).max()),
+                      "cov_rel_err_vs_cpu": float(np.abs(np.array(vecs[0][1]) - np.array(xo.cov[:])).max() / np.abs(np.array(xo.cov[:])).max()),
+                      "ranks_bit_identical": bool(identical), "ranks": world,
+                      "cpu_path": f"unsharded; {kind}", "bar": 1e-5}
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
     e2e_steps = max(min(args.steps, 50), 3)
     img = frame["image"]
     # e2e_pinned: the same calls with the caller's image / patch buffers page-locked (flb_host_alloc):
@@ -410,55 +610,40 @@ def main():
     h2d = len(scan) * 12 + 2 * state_b + ((img.size + len(ppos) * (24 + 768 + 4)) if has_vio else 0)
     d2h = state_b + 2 * 64
 
-    # ---- per-kernel-family device time (separate profiled run: one event pair per launch)
-    prof_steps = max(min(args.steps, 20), 3)
-    h.profile_start()
-    for _ in range(prof_steps):
-        if flush is not None:
-            flush.zero_()
-        enqueue_frame()
-    fam_ms, fam_n = h.profile_stop()
-    barrier()
+    # ---- per-kernel-family device time + roofline of the dominant kernel
     hbm, peak_src = peaks()
-    n_loc, pn_loc = len(scan), len(ppos)
     persistent = world == 1 or args.collective == "p2p"   # the NCCL path runs kernel-per-pass
-    if persistent:
-        # one cooperative kernel per update: its algorithmic bytes are the sum over its passes
-        fam_bytes = [(B_LIO_KNN * pc["lio_knn"] + B_LIO_PLAIN * pc["lio_plain"]) * n_loc, 0, B_VIO * pc["vio_passes"] * pn_loc, 0]
-        fam_names = [f"k_lio_update_persistent ({pc['lio_knn']} kNN + {pc['lio_plain']} plain passes + solves)", "-",
-                     f"k_vio_update_persistent ({pc['vio_passes']} passes + solves)", "-"]
-    else:
-        fam_bytes = [B_LIO_KNN * n_loc, B_LIO_PLAIN * n_loc, B_VIO * pn_loc, 0]
-        fam_names = ["k_lio_pass(kNN+plane+residual)", "k_lio_pass(cached plane)", "k_vio_pass", "k_*_finalize/begin(solve)"]
-    fams = []
-    for i in range(4):
-        if fam_n[i] == 0:
-            continue
-        avg_us = 1e3 * fam_ms[i] / fam_n[i]
-        gbs = fam_bytes[i] / (avg_us * 1e-6) / 1e9 if fam_bytes[i] else 0.0
-        fams.append({"kernel": fam_names[i], "launches_per_frame": float(fam_n[i]) / prof_steps, "avg_us": avg_us,
-                     "share_of_frame": float(fam_ms[i] / max(fam_ms.sum(), 1e-12)), "algorithmic_bytes": int(fam_bytes[i]),
-                     "achieved_gbs": gbs})
-    dom = max((f for f in fams if f["algorithmic_bytes"] > 0), key=lambda f: f["share_of_frame"], default=None)
-    roofline = None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if dom and persistent and args.workload == "C2" and os.path.exists(tpath):
-        with open(tpath) as tf:
-            tj = json.load(tf)
-        traffic = tj.get(dom["kernel"].split(" ")[0])
-    if dom:
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                    "frac": dom["achieved_gbs"] / hbm, "traffic": traffic,
-                    "traffic_source": "ncu --set full capture, profiles/r01_traffic.json" if traffic else None,
-                    "peak_source": peak_src,
-                    "avg_launch_us": dom["avg_us"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
-                    "note": "the whole working set (~8 MB) is L2-resident and every pass is a dependent step: the kernel is "
-                            "latency-bound, not bandwidth-bound, at this size (SURVEY.md section 7 H2; DESIGN.md section 4)"}
+    fams = rig.families(max(min(args.steps, 20), 3), persistent, hbm)
+    roofline = roofline_of(fams, hbm, peak_src, args.workload,
+                           "the whole working set (~8 MB) is L2-resident and every pass is a dependent step: the kernel is "
+                           "latency-bound, not bandwidth-bound, at this size (SURVEY.md section 7 H2; DESIGN.md section 4); "
+                           "see `batched` and `other_workloads` for the sizes where the bandwidth roofline is meaningful")
+
+    # ---- N > 1, fused exchange: the NCCL-collective number beside it (kernel-per-pass + ncclAllReduce / AllGather)
+    nccl_alt = None
+    if world > 1 and args.collective == "p2p":
+        barrier()
+        h.p2p_detach()
+        uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+        if has_vio:
+            h.patches_upload(ppos, pref, plev)       # agrees on the all-gather shard size
+        h.state_upload(x0, x0.copy())
+        for _ in range(3):
+            rig.enqueue_frame()
+        barrier()
+        xn, _, _ = h.state_download()
+        n_steps = max(min(args.steps, 50), 3)
+        ms_n, _, _ = rig.time_resident(n_steps)
+        nccl_alt = {"value": n_steps / (ms_n * 1e-3), "unit": UNIT, "ms_per_step": ms_n / n_steps, "steps": n_steps,
+                    "state_rel_diff_vs_fused": float(np.abs(xn.vector() - xw.vector()).max() / np.abs(xw.vector()).max()),
+                    "note": "kernel-per-pass path with ncclAllReduce(29 doubles) + ncclAllGather(per-patch errors) between the "
+                            "pass and finalize kernels: the baseline collective BASELINE.json names"}
 
     # ---- cpu_baseline (rank 0, N == 1 only): bounded sample on the host cores
     cpu = None
-    parity = None
+    po = None
     if rank == 0 and world == 1:
         po = fastlivo_loader.oracle()
         cores = os.cpu_count() or 1
@@ -480,7 +665,7 @@ def main():
                "fps_4_threads": 1.0 / dt4, "fps_all_cores": 1.0 / dtall, "host_cores": cores}
         ve, vo = xe.vector(), xo.vector()
         parity = {"state_rel_err_vs_cpu": float(np.abs(ve - vo).max() / np.abs(vo).max()),
-                  "state_rel_err_resident_vs_cpu": float(np.abs(xw.vector() - vo).max() / np.abs(vo).max())}
+                  "state_rel_err_resident_vs_cpu": float(np.abs(xw.vector() - vo).max() / np.abs(vo).max()), "bar": 1e-5}
 
     # ---- map maintenance, informational: one Add_Points(downsample) of the scan, host buffer
     # in, device map + kNN grid refreshed, vs a full re-upload of the map
@@ -491,16 +676,21 @@ def main():
         h.map_add_points(world_pts, cfg.pitch)       # first call allocates the scratch buffers
         h.map_upload(frame["map_xyz"])
         barrier()
-        t0 = time.perf_counter()
-        h.map_add_points(world_pts, cfg.pitch)
-        barrier()
-        t_add = time.perf_counter() - t0
-        m_after = h.M
+        t_adds = []
+        m_after = 0
+        for _ in range(5):
+            t0 = time.perf_counter()
+            h.map_add_points(world_pts, cfg.pitch)
+            barrier()
+            t_adds.append(time.perf_counter() - t0)
+            m_after = h.M
+            h.map_upload(frame["map_xyz"])
+            barrier()
         t0 = time.perf_counter()
         h.map_upload(frame["map_xyz"])
         barrier()
         t_up = time.perf_counter() - t0
-        map_maint = {"add_points_ms": 1e3 * t_add, "points_added": int(len(world_pts)), "map_size_after": int(m_after),
+        map_maint = {"add_points_ms": 1e3 * float(np.median(t_adds)), "points_added": int(len(world_pts)), "map_size_after": int(m_after),
                      "full_map_upload_ms": 1e3 * t_up, "note": "ikdtree.Add_Points(scan, downsample) on the device vs re-uploading the whole map"}
 
     # row f3: ImuProcess::UndistortPcl through the C ABI (host buffers in, host buffers out) next to the CPU port
@@ -520,26 +710,38 @@ def main():
             t0 = time.perf_counter()
             got, _ = h.imu_undistort(Pg, Cg, fi["v_imu"], fi["pcl_beg_time"], fi["pcl_end_time"], packed, offset_index=3)
             t_gpu.append(time.perf_counter() - t0)
-        po = fastlivo_loader.oracle()
         t_cpu = []
         for it in range(5):
-            Po, Co, xo = oracle_inputs(po, fi)
+            Po, Co, xo_i = oracle_inputs(po, fi)
             t0 = time.perf_counter()
-            ref, _ = po.imu_undistort(Po, Co, fi["v_imu"], fi["pcl_beg_time"], fi["pcl_end_time"], xo, fi["pts"], fi["offset_ms"])
+            ref, _ = po.imu_undistort(Po, Co, fi["v_imu"], fi["pcl_beg_time"], fi["pcl_end_time"], xo_i, fi["pts"], fi["offset_ms"])
             t_cpu.append(time.perf_counter() - t0)
         imu_f3 = {"abi_call_ms": 1e3 * float(np.median(t_gpu[3:])), "cpu_port_ms": 1e3 * float(np.median(t_cpu)),
                   "points": int(len(packed)), "imu_samples": int(len(fi["v_imu"])),
                   "points_identical_frac": float((got == ref).mean()), "points_max_abs_diff": float(np.abs(got - ref).max()),
                   "note": "flb_imu_undistort (H2D + propagate + undistort + D2H, blocking) vs the single-thread oracle port of UndistortPcl"}
+    h.close()
+
+    # ---- BASELINE.json configs[2], configs[3] in the same run (N = 1): the sizes where a bandwidth roofline can be met
+    others = None
+    if rank == 0 and world == 1 and not args.no_others and args.workload == "C2":
+        others = {}
+        for name in ("C3", "C4"):
+            try:
+                others[name] = measure_other_workload(flb, torch, name, local, dev, stream, flush, hbm, peak_src, po)
+            except Exception as e:      # never lose the headline line to a secondary leg
+                others[name] = {"error": repr(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
-            "config": workload_config(cfg, world, "inputs resident; L2 flushed (256 MiB write) between timed steps"
-                                      if flush is not None else "inputs resident; L2 NOT flushed (working set < L2)",
-                                      "NCCL all-reduce" if args.collective == "nccl" else "fused NVLink peer-memory exchange (in-kernel)"),
+            "config": workload_config(cfg, world),
+            "l2": "inputs resident; L2 flushed (256 MiB write) between timed steps" if flush is not None
+                  else "inputs resident; L2 NOT flushed (working set < L2)",
+            "collective": None if world == 1 else ("NCCL all-reduce between per-pass kernels" if args.collective == "nccl"
+                                                   else "fused NVLink peer-memory exchange inside the persistent kernels (LL units)"),
             "residuals_per_sec": rows_per_frame * fps, "rows_per_frame": int(rows_per_frame),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "gpu_launches": int(launches), "clocks": clocks,
@@ -551,10 +753,10 @@ def main():
                             "frames; pinned_caller_buffers_value: image/patch buffers from flb_host_alloc, no L2 flush; "
                             "blocking_calls_value: flb_lio_update + flb_vio_update (two synchronisations and state round "
                             "trips per frame, the reference's call shape), no L2 flush"},
-            "roofline": roofline, "kernels": fams, "pass_trace": trace, "map_maintenance": map_maint, "imu_undistort": imu_f3, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "kernels": fams, "pass_trace": trace, "map_maintenance": map_maint, "imu_undistort": imu_f3,
+            "cpu_baseline": cpu, "parity": parity, "nccl_collective": nccl_alt, "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
-    h.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -154,7 +154,9 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_image_upload", "flb_patches_upload", "flb_camera_set", "flb_vio_pass", "flb_vio_export",
            "flb_vio_update", "flb_state_upload", "flb_state_download", "flb_lio_update_enqueue",
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
-           "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach"]
+           "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach",
+           "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
+           "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps"]
 
 
 def lib_path() -> str:
@@ -210,6 +212,7 @@ def lib():
         L.flb_camera_set.argtypes = [vp, C.POINTER(Camera)]
         L.flb_vio_pass.argtypes = [vp, C.POINTER(VioParams), vp, vp, C.c_int, C.POINTER(VioEq)]
         L.flb_vio_export.argtypes = [vp, vp, vp, vp]
+        L.flb_vio_errors.argtypes = [vp, vp, C.c_int]
         L.flb_vio_update.argtypes = [vp, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18), C.POINTER(VioReport)]
         L.flb_state_upload.argtypes = [vp, C.POINTER(State18), C.POINTER(State18)]
         L.flb_state_download.argtypes = [vp, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
@@ -410,6 +413,12 @@ class Handle:
             out.update(z=z, H_sub=H, errors=err)
         return out
 
+    def vio_errors(self):
+        """sub_sparse_map->errors as the last update's last pass left them (flb_vio_errors)."""
+        err = np.zeros(self.Pn, np.float32)
+        self._ck(self.L.flb_vio_errors(self.h, _p(err), self.Pn))
+        return err
+
     def vio_update(self, prm: VioParams, x: State18, x_prop: State18) -> VioReport:
         rep = VioReport()
         self._ck(self.L.flb_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep)))
@@ -525,6 +534,9 @@ class Handle:
         assert len(blob) == 64 * world
         buf = C.create_string_buffer(blob, len(blob))
         self._ck(self.L.flb_p2p_attach(self.h, rank, world, buf))
+
+    def p2p_detach(self):
+        self._ck(self.L.flb_p2p_detach(self.h))
 
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, 128)

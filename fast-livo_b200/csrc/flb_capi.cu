@@ -223,7 +223,8 @@ struct flb_handle {
     DevBuf<double> patch_pos;
     DevBuf<float> patch_ref;
     DevBuf<int> patch_level;
-    DevBuf<float> errors;        // Pn (local shard)
+    DevBuf<float> errors;        // 2 x err_stride (local shard; the persistent kernel's passes alternate between the halves)
+    int err_stride = 0;
     DevBuf<float> errors_all;    // padded shard * world (multi-GPU)
     DevBuf<double> x_z, x_H;
     bool cam_set = false;
@@ -452,7 +453,9 @@ int next_epoch(flb_handle* h, unsigned* epoch) {
 }
 
 int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
-    if (h->M <= 0 || h->N <= 0) return fail(h, FLB_ERR_STATE, "flb_lio_update: map and scan must be uploaded first");
+    // fused multi-GPU mode: a rank whose shard is empty still launches (its leader takes part in every exchange)
+    if (h->M <= 0 || (h->N <= 0 && !(h->p2p.world > 1 && h->scan.p)))
+        return fail(h, FLB_ERR_STATE, "flb_lio_update: map and scan must be uploaded first");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_lio_update: no device state (flb_state_upload)");
     if (prm->max_iteration < 0 || prm->max_iteration > 1000) return fail(h, FLB_ERR_INVALID, "max_iteration outside [0, 1000]");
     if (h->p2p.world > 1 && !h->cfg.persistent)
@@ -530,6 +533,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
 
 int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update: camera and image must be set first");
+    if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_vio_update: no device state (flb_state_upload)");
     if (prm->max_iteration > 1000) return fail(h, FLB_ERR_INVALID, "max_iteration outside [0, 1000]");
     VioParamsDev d;
@@ -544,6 +548,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     s.partials = h->partials.p;
     s.nblocks = vio_nblocks(h);
     s.errors = h->errors.p;
+    s.err_stride = h->err_stride;
     s.Pn_total = h->Pn;
     s.prm = d;
     s.p2p = h->p2p;
@@ -572,7 +577,9 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     a.ctrl = h->vio_ctrl.p;
     a.force_level = -1;
     a.errors = h->errors.p;
+    a.err_stride = h->err_stride;
     a.partials = h->partials.p;
+    a.p2p = h->p2p;
     const int nb = vio_nblocks(h);
     if (persistent) {
         // patches are dealt warp-round-robin over the worker blocks; one more block is the leader
@@ -1091,7 +1098,7 @@ int flb_visual_candidates(flb_handle* h, const double Rcw[9], const double Pcw[3
 
 int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CHECK_H(h);
-    if (!body_xyz || N < 0 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: bad arguments");
+    if ((!body_xyz && N != 0) || N < 0 || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: bad arguments");
     const size_t n1 = (size_t)std::max(N, 1);
     void* stv = nullptr;
     FLB_CUDA(h, h->st_scan.acquire(n1 * 3 * sizeof(float), &stv));
@@ -1474,7 +1481,8 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     FLB_CUDA(h, h->patch_pos.reserve(n * 3));
     FLB_CUDA(h, h->patch_ref.reserve(n * 192));
     FLB_CUDA(h, h->patch_level.reserve(n));
-    FLB_CUDA(h, h->errors.reserve(n));
+    FLB_CUDA(h, h->errors.reserve(2 * n));
+    h->err_stride = (int)n;
     const int nb = (Pn + 7) / 8;
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)std::max(nb, 1) * kVioPacked, h->partials.cap)));
     const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int)) + 16;
@@ -1519,7 +1527,8 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
         FLB_CUDA(h, cudaMemcpyAsync(&shard, dmax, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         FLB_CUDA(h, cudaStreamSynchronize(h->stream));
         h->err_shard = std::max(shard, 1);
-        FLB_CUDA(h, h->errors.reserve((size_t)h->err_shard));
+        h->err_stride = std::max(h->err_stride, h->err_shard);
+        FLB_CUDA(h, h->errors.reserve(2 * (size_t)h->err_stride));
         FLB_CUDA(h, h->errors_all.reserve((size_t)h->err_shard * (size_t)h->world));
     }
     FLB_CUDA(h, cudaMemsetAsync(h->errors.p, 0, h->errors.cap * sizeof(float), h->stream));
@@ -1578,6 +1587,7 @@ int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], co
     a.ctrl = h->vio_ctrl.p;
     a.force_level = level;
     a.errors = h->errors.p;
+    a.err_stride = h->err_stride;
     a.partials = h->partials.p;
     a.x_z = h->x_z.p;
     a.x_H = h->x_H.p;
@@ -1624,6 +1634,21 @@ int flb_vio_export(flb_handle* h, double* z, double* H_sub, float* errors) {
     if (z) FLB_CUDA(h, cudaMemcpyAsync(z, h->x_z.p, Pn * 64 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (H_sub) FLB_CUDA(h, cudaMemcpyAsync(H_sub, h->x_H.p, Pn * 64 * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (errors) FLB_CUDA(h, cudaMemcpyAsync(errors, h->errors.p, Pn * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+int flb_vio_errors(flb_handle* h, float* errors, int capacity) {
+    FLB_CHECK_H(h);
+    if (!errors || capacity < 0) return fail(h, FLB_ERR_INVALID, "flb_vio_errors: bad arguments");
+    const int n = std::min(capacity, h->Pn);
+    if (n == 0) return FLB_OK;
+    // which half the last executed pass of the last update wrote is part of the device control block
+    VioCtrl c;
+    FLB_CUDA(h, cudaMemcpyAsync(&c, h->vio_ctrl.p, sizeof(VioCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int buf = (c.err_buf == 1) ? 1 : 0;
+    FLB_CUDA(h, cudaMemcpyAsync(errors, h->errors.p + (size_t)buf * h->err_stride, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     return FLB_OK;
 }

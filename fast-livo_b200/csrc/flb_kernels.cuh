@@ -47,6 +47,7 @@ struct VioCtrl {
     float level_error[3];
     long long rows_total;
     int skipped_last, cov_updated, status;
+    int err_buf;        // which half of the double-buffered per-patch errors the last executed pass wrote
 };
 
 struct LioParamsDev {
@@ -544,6 +545,51 @@ __global__ void __launch_bounds__(32) k_reduce_only(const double* partials, int 
 }
 
 // ---------------------------------------------------------------------------------------
+// Multi-GPU mailbox types and LL-style unit stores / loads (protocol: see "Fused NVLink exchange" below)
+// ---------------------------------------------------------------------------------------
+constexpr int kP2PMaxWorld = 8;
+constexpr int kP2PErrCap = 16384;        // per-rank patch shard capacity of the error gather
+struct __align__(16) P2PLine { unsigned d0, f0, d1, f1; };
+struct P2PMailbox {
+    P2PLine sums[2][kP2PMaxWorld][32];                       // [parity][source rank][k]; k = 31: that rank's patch count
+    unsigned long long errs[2][kP2PMaxWorld][kP2PErrCap];    // [parity][source rank][local patch] = {tag : float bits}
+};
+struct P2PArgs {
+    int world, rank;
+    P2PMailbox* mail[kP2PMaxWorld];      // mail[rank] is the local one; others are peer mappings
+    unsigned long long* seq;             // device-resident exchange counter (same value on every rank)
+};
+
+__device__ __forceinline__ void ll_store_line(P2PLine* p, double v, unsigned tag) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)u), "r"(tag),
+                 "r"((unsigned)(u >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_load_line(const P2PLine* p, unsigned tag, double& v) {
+    unsigned a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
+    return b == tag && d == tag;
+}
+__device__ __forceinline__ void ll_store_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr unsigned long long kP2PSpinLimit = 6000000ull;    // ~ seconds of polling: ranks may start far apart
+
+// Worker side: publish one patch error to every rank (own mailbox included).
+__device__ __forceinline__ void p2p_push_error(const P2PArgs& pp, unsigned tag, int local_patch, float err) {
+    const unsigned long long unit = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(err);
+    const int par = (int)(tag & 1u);
+    for (int r = 0; r < pp.world; ++r) ll_store_u64(&pp.mail[r]->errs[par][pp.rank][local_patch], unit);
+}
+
+// ---------------------------------------------------------------------------------------
 // VIO pass body: warp per patch, 2 pixels per lane
 // ---------------------------------------------------------------------------------------
 struct VioArgs {
@@ -558,10 +604,12 @@ struct VioArgs {
     VioParamsDev prm;
     VioCtrl* ctrl;
     int force_level;             // >= 0 : use this level and ignore ctrl
-    float* errors;               // Pn  (sub_sparse_map->errors)
+    float* errors;               // 2 x err_stride (sub_sparse_map->errors; successive passes of the persistent
+    int err_stride;              // kernel alternate between the halves, the kernel-per-pass path uses the first)
     double* partials;            // gridDim.x * kVioPacked
     double* x_z;                 // Pn*64 or null
     double* x_H;                 // Pn*64*6 or null
+    P2PArgs p2p;                 // world > 1 (persistent kernel only): per-patch errors are pushed to every rank
 };
 
 struct LatView {
@@ -603,8 +651,9 @@ __device__ __forceinline__ double round_to_f32_precision(double d) {
 // lane 0 also counts n_meas / skipped.
 __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
                                           float* s_lat, double* s_res, double& accv, double& n_meas, double& skipped,
-                                          unsigned long long* wdbg = nullptr) {
+                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0) {
     const int lane = threadIdx.x & 31;
+    float* const err_out = a.errors + (size_t)err_buf * a.err_stride;
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0.0;
@@ -669,14 +718,19 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
                 pe = 0.0f;
                 for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[e]);
             }
-            a.errors[i] = pe;                                       // :851
+            err_out[i] = pe;                                        // :851
+            if (p2p_tag) p2p_push_error(a.p2p, p2p_tag, i, pe);
             n_meas += 64.0;
             if (wdbg) wdbg[3] = global_ns();
         }
         __syncwarp();
         accv += warp_transpose_reduce<27>(acc);
     } else {
-        if (lane == 0) { a.errors[i] = 0.0f; skipped += 1.0; }
+        if (lane == 0) {
+            err_out[i] = 0.0f;
+            skipped += 1.0;
+            if (p2p_tag) p2p_push_error(a.p2p, p2p_tag, i, 0.0f);
+        }
         if (a.x_z) {
             for (int e = lane; e < 64; e += 32) {
                 a.x_z[(size_t)i * 64 + e] = 0.0;
@@ -767,9 +821,9 @@ struct LeaderSmem {
     double top[6 * kDim];
     double packed[32];
     double part[16][32];
-    int flags[4];
+    int flags[8];             // [0] accept [1] docov [2] newlevel [3] singular [4] speculated [5] mispredicted
     float error;
-    int p2p_par;
+    VioCtrl cspec;            // VIO: the control block of the speculated next pass
 };
 
 // The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
@@ -1015,79 +1069,51 @@ __device__ __forceinline__ void leader_cov_update(LeaderSmem& sm, const double* 
 // =======================================================================================
 // Fused NVLink exchange (multi-GPU): no NCCL in the data path
 // =======================================================================================
-// Every rank owns a mailbox in its device memory; peers map it (CUDA IPC) and the LEADER BLOCK of
-// each rank writes its packed normal-equation sums (and, for VIO, its shard of per-patch errors)
-// straight into every rank's mailbox over NVLink, publishes a sequence number with a
-// system-scope release store, and waits for the other ranks' sequence numbers in its OWN memory.
-// All ranks then add the contributions in rank order: bit-identical sums everywhere, so the
-// replicated solve yields bit-identical states with no broadcast.  Slots are double-buffered by
-// sequence parity: a rank can only be one exchange ahead of the slowest rank.
-constexpr int kP2PMaxWorld = 8;
-constexpr int kP2PErrCap = 16384;        // per-rank patch shard capacity of the error gather
-struct P2PSlot {
-    unsigned long long seq;
-    double data[32];                     // packed sums; data[31] = number of error entries sent
-};
-struct P2PMailbox {
-    P2PSlot slot[2][kP2PMaxWorld];
-    float errs[2][kP2PMaxWorld][kP2PErrCap];
-};
-struct P2PArgs {
-    int world, rank;
-    P2PMailbox* mail[kP2PMaxWorld];      // mail[rank] is the local one; others are peer mappings
-    unsigned long long* seq;             // device-resident exchange counter (same value on every rank)
-};
-
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// All-reduce sm.packed[0..K) across ranks in rank order, executed by a team of threads (TeamT).
-// If errs_local != nullptr the team also pushes n_err floats to every rank's gather area.
-// Returns the sequence parity used (the gather area of this exchange is mail[rank]->errs[par]).
+// Every rank owns a mailbox in its device memory; peers map it (CUDA IPC).  All traffic is "LL" style
+// (NCCL's low-latency protocol): every unit a peer writes carries its own validity tag next to the payload,
+// inside one store instruction whose 8-byte halves are atomic, so the reader polls the DATA -- there is no
+// separate flag, no __threadfence_system, and one NVLink traversal per exchange:
+//   * packed normal-equation sums: one 16-byte line {lo32, tag, hi32, tag} per double, written by the leader
+//     block of each rank straight into every rank's mailbox (own included) and summed in rank order by
+//     everyone: bit-identical sums everywhere, so the replicated solve yields bit-identical states;
+//   * VIO per-patch float errors: one 8-byte unit {float bits, tag} per patch, pushed to every rank by the
+//     WORKER warp that computed it, as soon as the patch is done (long before the pass ends); the leader's
+//     error-sum warp stages them into shared memory in global patch order while it checks the tags.
+// The tag is the exchange number (a device-resident counter that advances identically on every rank: one
+// per pass).  Slots are double-buffered by tag parity: a rank can be at most one exchange ahead of the
+// slowest one (it cannot finish exchange k+1 without that rank's k+1 contribution, which that rank only
+// sends after it has consumed exchange k).
+// All-reduce sm.packed[0..K) across ranks in rank order, executed by a team of threads (TeamT); `n_err` rides in
+// line 31 (this rank's number of per-patch errors of this exchange).  Uses sm.part as the receive staging.
 template <int K, class TeamT>
-__device__ __forceinline__ int p2p_exchange(const P2PArgs& pp, LeaderSmem& sm, const float* errs_local, int n_err, int tid,
-                                            int* timeout_flag) {
-    __shared__ unsigned long long s_seq;
-    if (tid == 0) {
-        const unsigned long long q = __ldcg(pp.seq) + 1ull;
-        *pp.seq = q;
-        s_seq = q;
+__device__ __forceinline__ void p2p_exchange(const P2PArgs& pp, LeaderSmem& sm, unsigned tag, double n_err, int tid,
+                                             int* timeout_flag) {
+    static_assert(K <= 31, "line 31 is the error count");
+    const int par = (int)(tag & 1u);
+    const int nline = pp.world * 32;
+    for (int e = tid; e < nline; e += TeamT::size) {
+        const int r = e >> 5, k = e & 31;
+        if (k < K || k == 31) ll_store_line(&pp.mail[r]->sums[par][pp.rank][k], k == 31 ? n_err : sm.packed[k], tag);
     }
-    TeamT::sync();
-    const unsigned long long seq = s_seq;
-    const int par = (int)(seq & 1ull);
-    for (int r = 0; r < pp.world; ++r) {
-        P2PMailbox* m = pp.mail[r];
-        if (tid < K) m->slot[par][pp.rank].data[tid] = sm.packed[tid];
-        if (tid == K) m->slot[par][pp.rank].data[31] = (double)n_err;
-        if (errs_local)
-            for (int e = tid; e < n_err; e += TeamT::size) m->errs[par][pp.rank][e] = __ldcg(errs_local + e);
-    }
-    __threadfence_system();
-    TeamT::sync();
-    if (tid < pp.world) st_release_sys_u64(&pp.mail[tid]->slot[par][pp.rank].seq, seq);
-    if (tid < pp.world) {
-        const unsigned long long* f = &pp.mail[pp.rank]->slot[par][tid].seq;
-        unsigned long long spins = 0;
-        while (ld_acquire_sys_u64(f) != seq) {
-            __nanosleep(50);
-            if (++spins > 60000000ull) { *timeout_flag = 1; break; }   // ~5 s: ranks may start far apart
+    for (int e = tid; e < nline; e += TeamT::size) {
+        const int r = e >> 5, k = e & 31;
+        if (k < K) {
+            const P2PLine* src = &pp.mail[pp.rank]->sums[par][r][k];
+            double v;
+            unsigned long long spins = 0;
+            while (!ll_load_line(src, tag, v)) {
+                if (++spins > kP2PSpinLimit) { *timeout_flag = 1; break; }
+            }
+            sm.part[r][k] = v;
         }
     }
     TeamT::sync();
     if (tid < K) {
         double s = 0.0;
-        for (int r = 0; r < pp.world; ++r) s += __ldcv(&pp.mail[pp.rank]->slot[par][r].data[tid]);
+        for (int r = 0; r < pp.world; ++r) s += sm.part[r][tid];
         sm.packed[tid] = s;
     }
     TeamT::sync();
-    return par;
 }
 
 struct LioSolveArgs {
@@ -1129,7 +1155,7 @@ __device__ __forceinline__ void pkt_publish_warp(unsigned long long* pkt, const 
 template <int NT>
 __device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSmem& sm, LioCtrl& c, bool first,
                                                  unsigned long long* pkt, unsigned flag, int resident,
-                                                 unsigned long long* fine = nullptr) {
+                                                 unsigned long long* fine = nullptr, unsigned p2p_tag = 0u) {
     constexpr int K = lio_packed(6);
     constexpr int NC = (int)(sizeof(LioCtrl) / sizeof(unsigned));
     using T = Team<NT, false>;
@@ -1144,7 +1170,7 @@ __device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSm
     FLB_STAMP(0);
     team_reduce_vec<K, NT, T>(s.partials, s.nblocks, sm, tid);
     if (!first && !resident) prior_commit(sm, pri, tid);
-    if (s.p2p.world > 1) p2p_exchange<K, T>(s.p2p, sm, nullptr, 0, tid, s.timeout_flag);
+    if (p2p_tag) p2p_exchange<K, T>(s.p2p, sm, p2p_tag, 0.0, tid, s.timeout_flag);
     if (first && !resident) leader_prior<T>(sm, s.prior, tid);
     __syncthreads();
     FLB_STAMP(1);
@@ -1247,7 +1273,8 @@ struct VioSolveArgs {
     double* G_last;          // 18x6, the G of the last accepted solve (:874, used at :980)
     const double* partials;
     int nblocks;
-    const float* errors;     // all patches, patch order (local shard in the fused multi-GPU mode)
+    const float* errors;     // all patches, patch order (local shard in the fused multi-GPU mode); two halves of
+    int err_stride;          // err_stride floats, written alternately by successive passes of the persistent kernel
     int Pn_total;
     VioParamsDev prm;
     P2PArgs p2p;             // world <= 1: single GPU
@@ -1263,15 +1290,16 @@ constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 template <int NT>
 __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first,
                                                  unsigned long long* pkt, unsigned flag, int resident,
-                                                 unsigned long long* fine = nullptr) {
+                                                 unsigned long long* fine = nullptr, unsigned p2p_tag = 0u, int err_buf = 0) {
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     const int tid = threadIdx.x;
-    const bool multi = s.p2p.world > 1;
+    const bool multi = p2p_tag != 0u;
     const int level = c.level;
+    const float* errs_pass = s.errors + (size_t)err_buf * s.err_stride;     // this pass's half of the error buffer
     // Stage the (first chunk of) per-patch errors with the whole block -- one coalesced L2 round trip.
-    // (Fused multi-GPU mode: the errors of ALL ranks arrive with the exchange instead.)
+    // (Fused multi-GPU mode: the errors of ALL ranks arrive in the mailbox, pushed by the worker warps.)
     if (!multi)
-        for (int e = tid; e < min(kErrChunk, s.Pn_total); e += NT) s_err[e] = __ldcg(s.errors + e);
+        for (int e = tid; e < min(kErrChunk, s.Pn_total); e += NT) s_err[e] = __ldcg(errs_pass + e);
     __syncthreads();
     static_assert(NT - 32 >= kDim * 6, "solve team too small");
     if (tid >= NT - 32) {
@@ -1279,17 +1307,39 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         // chain of one FADD latency per patch, hidden behind the other warps' reduce + solve.
         const int lane = tid - (NT - 32);
         float e_run = 0.0f;
-        if (multi) asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");   // wait for the exchange
         const int nsrc = multi ? s.p2p.world : 1;
+        const int par = (int)(p2p_tag & 1u);
+        bool dead = false;
         for (int r = 0; r < nsrc; ++r) {
-            // patch order = rank 0's shard, then rank 1's, ... (contiguous block partition)
-            const float* src = multi ? s.p2p.mail[s.p2p.rank]->errs[sm.p2p_par][r] : s.errors;
-            const int n_r = multi ? (int)__ldcv(&s.p2p.mail[s.p2p.rank]->slot[sm.p2p_par][r].data[31]) : s.Pn_total;
+            // patch order = rank 0's shard, then rank 1's, ... (contiguous block partition).  Fused multi-GPU
+            // mode: rank r's patch count rides in line 31 of its sums (it arrives when r's pass is complete);
+            // its errors were pushed by r's worker warps during the pass and are validated unit by unit.
+            const unsigned long long* units = multi ? s.p2p.mail[s.p2p.rank]->errs[par][r] : nullptr;
+            int n_r = s.Pn_total;
+            if (multi) {
+                double cnt = 0.0;
+                unsigned long long spins = 0;
+                while (!dead && !ll_load_line(&s.p2p.mail[s.p2p.rank]->sums[par][r][31], p2p_tag, cnt))
+                    if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; dead = true; }
+                dead = __any_sync(0xffffffffu, dead);
+                n_r = dead ? 0 : (int)cnt;
+            }
             for (int base = 0; base < n_r; base += kErrChunk) {
                 const int nchunk = min(kErrChunk, n_r - base);
-                if (multi || base > 0) {   // staged by this warp alone (single GPU: only for Pn > kErrChunk)
+                if (multi) {
+                    for (int e = lane; e < nchunk; e += 32) {
+                        unsigned long long u = ll_load_u64(units + base + e);
+                        unsigned long long spins = 0;
+                        while ((unsigned)(u >> 32) != p2p_tag && !dead) {
+                            if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; dead = true; }
+                            u = ll_load_u64(units + base + e);
+                        }
+                        s_err[e] = __uint_as_float((unsigned)u);
+                    }
+                    dead = __any_sync(0xffffffffu, dead);
+                } else if (base > 0) {     // staged by this warp alone (single GPU: only for Pn > kErrChunk)
 #pragma unroll 8
-                    for (int e = lane; e < nchunk; e += 32) s_err[e] = __ldcv(src + base + e);
+                    for (int e = lane; e < nchunk; e += 32) s_err[e] = __ldcv(errs_pass + base + e);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -1331,19 +1381,40 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         team_reduce_vec<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
         FLB_STAMP(1);
         if (!first && !resident) prior_commit(sm, pri, tid);
-        if (multi) {
-            const int par = p2p_exchange<kVioPacked, T>(s.p2p, sm, s.errors, s.Pn_total, tid, s.timeout_flag);
-            if (tid == 0) sm.p2p_par = par;
-            asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");              // release the error-sum warp
-        }
+        if (multi) p2p_exchange<kVioPacked, T>(s.p2p, sm, p2p_tag, (double)s.Pn_total, tid, s.timeout_flag);
         if (first && !resident) leader_prior<T>(sm, s.prior, tid);
         T::sync();
         if (tid < 32) {
             leader_fast_solve(sm, s.prm.sigma, -1.0, tid);                                // :871-878 (sign: :878)
-            // the accepted outcome (*state += solution, :879) is formed while the error sum is still running
+            // The accepted outcome (*state += solution, :879) is formed while the error sum is still running, and -- in
+            // the persistent kernel -- PUBLISHED right away: the accept test (:861) is the only thing the error sum
+            // decides, everything else about the next pass (state, level, iteration) follows from the solve.  The
+            // workers start the next pass on the accept branch; if the sum then says "reject" (at most once per
+            // level: a rejection ends it) that pass is discarded and the corrected packet follows (see the kernel).
+            // No speculation when the accept branch ends the update (nothing to overlap) or the solve failed.
             if (tid < 24) sm.xspec[tid] = reinterpret_cast<const double*>(&sm.x)[tid];
             __syncwarp();
-            if (tid == 0) state_boxplus(*reinterpret_cast<State18*>(sm.xspec), sm.sol);    // touches the 24 pose/bias doubles only
+            if (tid == 0) {
+                state_boxplus(*reinterpret_cast<State18*>(sm.xspec), sm.sol);               // touches the 24 pose/bias doubles only
+                const bool ok_p = sm.flags[3] == 0;
+                const bool conv_p = !s.prm.force_all_passes && (norm3(sm.sol) * 57.3f < s.prm.conv_rot_deg) &&
+                                    (norm3(sm.sol + 3) * 100.0f < s.prm.conv_pos_cm);
+                const int it1 = c.iteration + 1;
+                const bool done_p = conv_p || it1 >= s.prm.max_iteration;
+                const bool stop_p = !ok_p || (done_p && level - 1 < 0);
+                const int spec = (pkt != nullptr && !stop_p) ? 1 : 0;
+                sm.flags[4] = spec;
+                sm.flags[5] = 0;
+                if (spec) {
+                    sm.cspec = c;
+                    sm.cspec.level = done_p ? level - 1 : level;
+                    sm.cspec.iteration = done_p ? 0 : it1;
+                    sm.cspec.stop = 0;
+                }
+            }
+            __syncwarp();
+            const bool spec = sm.flags[4] != 0;
+            if (spec) pkt_publish_warp<NC>(pkt, *reinterpret_cast<const State18*>(sm.xspec), &sm.cspec, flag, tid);
             FLB_STAMP(2);
             asm volatile("bar.sync 3, 64;" ::: "memory");                   // sm.error is ready
             FLB_STAMP(4);
@@ -1353,7 +1424,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                     c.level = 2; c.iteration = 0; c.stop = 0;
                     c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;           // :971
                     for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
-                    c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
+                    c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0; c.err_buf = 0;
                 }
                 const long long nm = (long long)sm.packed[27];
                 const float error = sm.error / (float)(unsigned long long)nm;              // :857
@@ -1388,9 +1459,11 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                         if (c.now_error < 1e10f && ok) { docov = 1; c.cov_updated = 1; }   // :978-981
                     }
                 }
+                c.err_buf = err_buf;
                 sm.flags[0] = accept;
                 sm.flags[1] = docov;
                 sm.flags[2] = newlevel;
+                if (spec && !accept) sm.flags[5] = 1;       // mispredicted: the pass now running is discarded
             }
             __syncwarp();
             FLB_STAMP(5);
@@ -1403,7 +1476,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                 if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = __ldcg(reinterpret_cast<const double*>(s.old_state) + tid);
             }                                                                              // *state = old_state (:890)
             __syncwarp();
-            if (pkt) pkt_publish_warp<NC>(pkt, sm.x, &c, flag, tid);
+            if (pkt && !spec) pkt_publish_warp<NC>(pkt, sm.x, &c, flag, tid);
             FLB_STAMP(6);
         }
     }
@@ -1448,6 +1521,7 @@ __global__ void __launch_bounds__(32) k_vio_begin(VioCtrl* ctrl, int Pn_total) {
         c.skipped_last = 0;
         c.cov_updated = 0;
         c.status = 0;
+        c.err_buf = 0;
         *ctrl = c;
     }
 }
@@ -1555,7 +1629,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 // whole block) when the watchdog (~seconds) tripped: a would-be hang becomes FLB_ERR_TIMEOUT.
 template <int NC>
 __device__ __forceinline__ bool pkt_wait(const unsigned long long* pkt, State18& x, void* c, unsigned flag, GridBarrier* b,
-                                         unsigned* s_scratch) {
+                                         unsigned* s_scratch, unsigned long long spin_limit = 3000000ull) {
     constexpr int N = kStateWords + NC;
     constexpr int PER = (N + 31) / 32;
     if (threadIdx.x < 32) {
@@ -1577,7 +1651,7 @@ __device__ __forceinline__ bool pkt_wait(const unsigned long long* pkt, State18&
             __nanosleep(20);
             ++spins;
             bool bail = false;
-            if (spins > 3000000ull) { b->timeout = 1; bail = true; }
+            if (spins > spin_limit) { b->timeout = 1; bail = true; }
             else if ((spins & 0xffff) == 0 && *((volatile int*)&b->timeout)) bail = true;
             if (__any_sync(0xffffffffu, bail)) { good = false; break; }
         }
@@ -1659,12 +1733,15 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     __shared__ LeaderSmem sm;
     __shared__ LioCtrl s_ctrl;       // block-local mirror of the loop state (src/laserMapping.cpp:1472-1473, :1506)
     __shared__ int s_rows[18][BLOCK];
+    __shared__ unsigned long long s_seq_base;
     const int tid = threadIdx.x;
     const int nworkers = (int)gridDim.x - 1;
     const bool is_leader = (int)blockIdx.x == nworkers;
+    const bool multi = s.p2p.world > 1;
     bool first = true;
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
+    if (tid == 96) s_seq_base = multi ? *s.p2p.seq : 0ull;     // exchange counter: identical on every rank
     // every block keeps the pose/bias part of state and state_propagat resident in shared memory
     if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(s.state)[tid];
     else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(s.state_prop)[tid - 24];
@@ -1684,10 +1761,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
             if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 64 + 8 * pass_no + 8 <= kTraceLen) ? trace + 64 + 8 * pass_no : nullptr;
-            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, pkt, flag, resident, fine);
+            const unsigned p2p_tag = multi ? ((unsigned)(s_seq_base + (unsigned long long)pass_no + 1ull) | 0x80000000u) : 0u;
+            lio_leader_solve<BLOCK>(s, sm, s_ctrl, first, pkt, flag, resident, fine, p2p_tag);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             lio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, resident, fine);
-            if (s_ctrl.stop && tid == 0) bar->count = 0;
+            if (s_ctrl.stop && tid == 0) {
+                bar->count = 0;
+                if (multi) *s.p2p.seq = s_seq_base + (unsigned long long)pass_no + 1ull;
+            }
         } else {
             if (dbg && tid == 0) dbg[blockIdx.x * 16 + 0] = global_ns();
             if (tid == 0) lio_pose_from(a.prm, sm.x, s_pose);
@@ -1715,7 +1796,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
             if (dbg && tid == 0) dbg[blockIdx.x * 16 + 2] = global_ns();
             grid_arrive_release(bar);
             if (dbg && tid == 0) dbg[blockIdx.x * 16 + 3] = global_ns();
-            if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar)) return;
+            if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar, multi ? 40000000ull : 3000000ull)) return;
         }
         first = false;
         ++pass_no;
@@ -1740,13 +1821,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl s_ctrl;
     __shared__ __align__(16) float s_err[kErrChunk];
+    __shared__ unsigned long long s_seq_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
     const int nworkers = (int)gridDim.x - 1;
     const bool is_leader = (int)blockIdx.x == nworkers;
+    const bool multi = s.p2p.world > 1;
     bool first = true;
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
+    if (tid == 96) s_seq_base = multi ? *s.p2p.seq : 0ull;     // exchange counter: identical on every rank
     if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(s.state)[tid];
     else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(s.state_prop)[tid - 24];
     if (tid == 64) {
@@ -1754,7 +1838,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
         c.level = 2; c.iteration = 0; c.stop = 0;
         c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;
         for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
-        c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0;
+        c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0; c.err_buf = 0;
         s_ctrl = c;
     }
     // every warp owns at most one patch: its pose-independent inputs stay in registers for all passes
@@ -1766,14 +1850,34 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
     for (;;) {
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
+        const unsigned p2p_tag = multi ? ((unsigned)(s_seq_base + (unsigned long long)pass_no + 1ull) | 0x80000000u) : 0u;
         if (is_leader) {
             if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 32 + 8 * pass_no + 8 <= kTraceLen) ? trace + 32 + 8 * pass_no : nullptr;
-            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine);
+            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine, p2p_tag, pass_no & 1);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, resident);
-            if (s_ctrl.stop && tid == 0) bar->count = 0;
+            if (sm.flags[5]) {
+                // The error sum rejected the step whose accept branch was published ahead of it (:861 / :890): the
+                // pass now running started from the wrong state.  Wait for it, drop it, publish the real
+                // continuation (the rejected step's old_state at the next level, or stop).  Fused multi-GPU mode:
+                // every rank mispredicts identically; one (payload-free) exchange keeps the mailbox parity rule.
+                ++pass_no;
+                if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
+                if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
+                if (multi) {
+                    const unsigned tag2 = (unsigned)(s_seq_base + (unsigned long long)pass_no + 1ull) | 0x80000000u;
+                    p2p_exchange<kVioPacked, Team<BLOCK, false>>(s.p2p, sm, tag2, 0.0, tid, s.timeout_flag);
+                }
+                if (tid < 32) pkt_publish_warp<NC>(pkt, sm.x, &s_ctrl, epoch + (unsigned)pass_no + 1u, tid);
+                if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
+                __syncthreads();
+            }
+            if (s_ctrl.stop && tid == 0) {
+                bar->count = 0;
+                if (multi) *s.p2p.seq = s_seq_base + (unsigned long long)pass_no + 1ull;
+            }
         } else {
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
             if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
@@ -1784,13 +1888,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             for (int i = blockIdx.x * NW + warp; i < a.Pn; i += nworkers * NW) {
                 if (!single) vio_patch_load(a, i, tid & 31, pin);
                 vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
-                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr);
+                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1);
             }
             vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();
             grid_arrive_release(bar);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 3] = global_ns();
-            if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar)) return;
+            if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar, multi ? 40000000ull : 3000000ull)) return;
         }
         first = false;
         ++pass_no;

@@ -298,6 +298,10 @@ int flb_vio_export(flb_handle* h, double* z, double* H_sub, float* errors);
  * for level = 2,1,0, then cov -= G*cov, all on the device. */
 int flb_vio_update(flb_handle* h, const flb_vio_params* prm, flb_state18* x, const flb_state18* x_prop,
                    flb_vio_report* rep);
+/* sub_sparse_map->errors[i] as ComputeJ leaves them (src/lidar_selection.cpp:851: the per-patch errors of the
+ * LAST pass executed by the last flb_vio_update / flb_vio_update_enqueue; read by display_keypatch, :995).
+ * errors: up to `capacity` floats, patch order. */
+int flb_vio_errors(flb_handle* h, float* errors, int capacity);
 
 /* ---- device-resident frame loop (benchmark / pipeline use) ---------------------------
  * Enqueue-only variants: state stays on the device between calls, nothing is copied
@@ -338,15 +342,25 @@ int flb_comm_unique_id(void* unique_id_128b);
 int flb_comm_init(flb_handle* h, const void* unique_id_128b, int rank, int world_size);
 int flb_comm_destroy(flb_handle* h);
 
-/* Fused NVLink exchange: the B200-idiomatic alternative to the NCCL path.  The persistent update
- * kernel's leader block writes its packed sums (and VIO per-patch errors) straight into every rank's
- * mailbox over NVLink peer memory and waits on sequence flags -- one kernel per update, no NCCL call,
- * bit-identical results on every rank and to the single-GPU run up to the summation order.
+/* Fused NVLink exchange: the B200-idiomatic alternative to the NCCL path.  Inside the persistent update
+ * kernel every rank writes its packed sums (leader block) and its VIO per-patch errors (the worker warp that
+ * computed each one) straight into every rank's mailbox over NVLink peer memory as self-validating units
+ * {payload, exchange tag} -- one store instruction per unit, no separate flag, no system fence, one NVLink
+ * traversal per exchange; one kernel per update, no NCCL call, bit-identical results on every rank and to the
+ * single-GPU run up to the summation order.  After FLB_ERR_TIMEOUT in this mode the exchange counters of the
+ * ranks may differ: repeat flb_p2p_export / flb_p2p_attach on every rank.
  * Each rank: flb_p2p_export() -> 64-byte CUDA IPC handle; gather all handles (rank order) with any host
  * transport; flb_p2p_attach().  One process per GPU, all GPUs NVLink peers; <= 8 ranks. */
 int flb_p2p_export(flb_handle* h, void* handle_64b);
 int flb_p2p_attach(flb_handle* h, int rank, int world_size, const void* handles_world_x_64b);
 int flb_p2p_detach(flb_handle* h);
+
+/* ---- test / tracing aids (not needed by a caller of the path) -------------------------------------------
+ * flb_debug_set_packet_epoch: move the pose-packet flag base (wrap-around test).  flb_debug_block_stamps /
+ * flb_debug_vio_stamps: per-block %globaltimer stamps of the last traced LIO / VIO update. */
+int flb_debug_set_packet_epoch(flb_handle* h, unsigned epoch);
+int flb_debug_block_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks);
+int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks, int* words_per_block);
 
 #ifdef __cplusplus
 }

@@ -811,6 +811,8 @@ float flo_vio_pass(flo_vio* V, const flo_vio_params* prm, const double R[9], con
     return e;
 }
 
+void flo_vio_errors(const flo_vio* V, float* errors) { std::memcpy(errors, V->errors.data(), sizeof(float) * V->Pn); }
+
 // ComputeJ (lidar_selection.cpp:967-983) driving UpdateState (:743-902) for level = 2,1,0.
 int flo_vio_update(flo_vio* V, const flo_vio_params* prm, flo_state18* x, const flo_state18* x_prop,
                    flo_vio_report* rep) {
@@ -847,6 +849,7 @@ int flo_vio_update(flo_vio* V, const flo_vio_params* prm, flo_state18* x, const 
             } else {
                 *x = old_state;                                                  // :890
                 EKF_end = true;
+                r.rejects++;
             }
             if (EKF_end) break;                                                  // :897
         }

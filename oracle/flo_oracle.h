@@ -182,6 +182,7 @@ typedef struct flo_vio_report {
     int64_t rows_total;      /* n_meas summed over passes */
     int   skipped_last;      /* patches skipped by the bounds/depth guard in the last pass */
     int   cov_updated;
+    int   rejects;           /* passes whose error exceeded last_error (:888-892): test scenarios assert on it */
 } flo_vio_report;
 
 flo_vio* flo_vio_create(const uint8_t* gray, int width, int height, int stride,
@@ -199,6 +200,9 @@ float flo_vio_pass(flo_vio*, const flo_vio_params*, const double R[9], const dou
 /* ComputeJ (lidar_selection.cpp:967-983): levels 2,1,0 of UpdateState (:743-902). */
 int flo_vio_update(flo_vio*, const flo_vio_params*, flo_state18* x, const flo_state18* x_prop,
                    flo_vio_report* rep);
+
+/* sub_sparse_map->errors as the last pass executed left them (lidar_selection.cpp:851). */
+void flo_vio_errors(const flo_vio*, float* errors);
 
 /* vikit PinholeCamera::world2cam(Vector3d). */
 void flo_world2cam(const flo_cam* cam, const double pf[3], double px[2]);

@@ -80,7 +80,7 @@ class VioParams(C.Structure):
 
 class VioReport(C.Structure):
     _fields_ = [("passes", C.c_int * 3), ("last_error", C.c_float * 3), ("rows_total", C.c_int64),
-                ("skipped_last", C.c_int), ("cov_updated", C.c_int)]
+                ("skipped_last", C.c_int), ("cov_updated", C.c_int), ("rejects", C.c_int)]
 
 
 class StateIkfom(C.Structure):
@@ -243,6 +243,7 @@ def lib():
         L.flo_vio_pass.argtypes = [C.c_void_p, C.POINTER(VioParams), C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.flo_vio_update.argtypes = [C.c_void_p, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18),
                                      C.POINTER(VioReport)]
+        L.flo_vio_errors.argtypes = [C.c_void_p, C.c_void_p]
         L.flo_world2cam.argtypes = [C.POINTER(Cam), C.c_void_p, C.c_void_p]
         L.flo_exp3.argtypes = [C.c_void_p, C.c_void_p]
         L.flo_log3.argtypes = [C.c_void_p, C.c_void_p]
@@ -491,6 +492,12 @@ class Vio:
         rep = VioReport()
         self.L.flo_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep))
         return rep
+
+    def errors(self):
+        """sub_sparse_map->errors as the last executed pass left them (lidar_selection.cpp:851)."""
+        err = np.zeros(self.Pn, np.float32)
+        self.L.flo_vio_errors(self.h, _p(err))
+        return err
 
 
 def world2cam(cam: dict, pf):

@@ -87,6 +87,17 @@ def test_shard_partition_properties():
             assert max(b - a for a, b in cuts) <= (n + w - 1) // w
 
 
+def _trim(f, mode):
+    """'p2p-ragged': a frame so small that rank 1's shards are EMPTY (1 scan point, 1 patch over 2 ranks)."""
+    if mode != "p2p-ragged":
+        return f
+    g = dict(f)
+    g["scan_body"] = f["scan_body"][:1]
+    for k in ("patch_pos", "patch_ref", "patch_level"):
+        g[k] = f[k][:1]
+    return g
+
+
 def _gpu_worker(rank, world, port, out, mode="nccl"):
     import torch
     import torch.distributed as dist
@@ -94,7 +105,7 @@ def _gpu_worker(rank, world, port, out, mode="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)      # only to hand the NCCL id around
     flb = fastlivo_loader.load()
-    f = flb.synth.make_frame("T1")
+    f = _trim(flb.synth.make_frame("T1"), mode)
     h = flb.Handle(device=rank)
     if mode == "nccl":
         uid = [flb.Handle.comm_unique_id() if rank == 0 else None]
@@ -124,10 +135,12 @@ def _gpu_worker(rank, world, port, out, mode="nccl"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p-ragged"])
 def test_sharded_update_matches_oracle(flb, po, frames, tmp_path, mode):
     """Both collectives: NCCL all-reduce between per-pass kernels, and the fused NVLink exchange inside
-    the persistent kernel's leader block."""
+    the persistent kernels (T1 with early stop has a rejected VIO step: the speculated pass is discarded on
+    every rank alike).  'p2p-ragged': rank 1 owns no scan point and no patch and still takes part in every
+    exchange."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
@@ -136,7 +149,7 @@ def test_sharded_update_matches_oracle(flb, po, frames, tmp_path, mode):
     world = 2
     mp.spawn(_gpu_worker, args=(world, _free_port(), out, mode), nprocs=world, join=True)
     r = np.load(out)
-    f = frames("T1")
+    f = _trim(frames("T1"), mode)
     lio = po.Lio(f["map_xyz"], f["scan_body"])
     vio = po.Vio(f["image"], f["patch_pos"], f["patch_ref"], f["patch_level"], f["cam"])
     x = po.state_from_frame(f)
