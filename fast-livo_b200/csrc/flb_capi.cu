@@ -295,6 +295,7 @@ struct LaunchScope {
     }
 };
 enum { FAM_LIO_KNN = 0, FAM_LIO_PLAIN = 1, FAM_VIO = 2, FAM_SOLVE = 3, FAM_OTHER = 4 };
+constexpr int kVioErrCapMax = 40960;     // floats of dynamic shared memory (160 KB) for the VIO leader's error staging
 
 void to_dev_params(const flb_lio_params* p, LioParamsDev& d) {
     std::memcpy(d.R_LI, p->R_LI, sizeof(d.R_LI));
@@ -346,7 +347,11 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, h->ik_states.reserve(2));
     FLB_CUDA(h, h->ik_ctrl.reserve(1));
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_ik, k_lio_update_ikfom_persistent<kLioBlock>, kLioBlock, 0));
-    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioPersBlock>, kVioPersBlock, 0));
+    // the VIO leader stages the per-patch errors of a pass in dynamic shared memory (up to kVioErrCapMax floats)
+    FLB_CUDA(h, cudaFuncSetAttribute(k_vio_update_persistent<kVioPersBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kVioErrCapMax * (int)sizeof(float)));
+    FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_vio, k_vio_update_persistent<kVioPersBlock>, kVioPersBlock,
+                                                             kVioErrCapMax * sizeof(float)));
     FLB_CUDA(h, h->pin_out.reserve(1 << 16));
     return FLB_OK;
 }
@@ -368,6 +373,8 @@ LioArgs make_lio_args(flb_handle* h, const LioParamsDev& prm, bool exports, int 
     a.plane = h->plane.p;
     a.plane_ok = h->plane_ok.p;
     a.partials = h->partials.p;
+    a.M = h->M;
+    a.prefetch = 0;
     if (exports) {
         a.x_world = h->x_world.p;
         a.x_nn_idx = h->x_nn_idx.p;
@@ -489,6 +496,12 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         unsigned long long* trace = h->tracing ? h->trace.p : nullptr;
         a.probe = h->tracing ? h->trace.p + 112 : nullptr;
         a.chunk = std::max(1, std::min(32, (h->N + workers * (kLioPersBlock / 32) - 1) / (workers * (kLioPersBlock / 32))));
+        {
+            // L2 prefetch of the map: on by default for maps above 8 MB (points + cell table); FLB_PREFETCH=0/1 overrides
+            const size_t bytes = (size_t)h->M * 16 + ((size_t)h->ncell + 1) * 4;
+            static const int env = [] { const char* e = getenv("FLB_PREFETCH"); return e ? atoi(e) : -1; }();
+            a.prefetch = env >= 0 ? env : (bytes > (8u << 20) ? 1 : 0);
+        }
         unsigned long long* dbg = nullptr;
         if (h->tracing) {
             FLB_CUDA(h, h->dbg.reserve((size_t)grid * 16));
@@ -603,10 +616,12 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
             dbg = h->dbg_vio.p;
             h->dbg_vio_blocks = grid;
         }
-        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg};
+        // staging capacity for the errors of ALL ranks (the peers' shard sizes are not known here: assume like ours + slack)
+        int err_cap = (int)std::min<long long>(kVioErrCapMax, std::max<long long>(2048, ((long long)h->Pn * std::max(h->p2p.world, 1) * 5 / 4 + 319) / 256 * 256));
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap};
         LaunchScope ls(h, FAM_VIO);
-        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args, 0,
-                                                h->stream));
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args,
+                                                (size_t)err_cap * sizeof(float), h->stream));
         h->last_vio_valid = false;
         return vio_inputs_release(h);
     }

@@ -12,6 +12,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define FLB_HD __host__ __device__ __forceinline__
@@ -22,6 +23,25 @@
 #endif
 
 namespace flb {
+
+FLB_HD float u32_as_float(unsigned u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, sizeof(f));
+    return f;
+#endif
+}
+FLB_HD unsigned float_as_u32(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    unsigned u;
+    memcpy(&u, &f, sizeof(u));
+    return u;
+#endif
+}
 
 constexpr int kMatch = 5;    // NUM_MATCH_POINTS, include/common_lib.h:39
 constexpr int kDim = 18;     // DIM_STATE,        include/common_lib.h:34
@@ -746,6 +766,344 @@ FLB_HD int visual_candidate(const CamModel& cam, const double* Rcw, const double
     if (!(ox >= border && ox < cam.width - border && oy >= border && oy < cam.height - border)) return -1;   // isInFrame
     *score = shi_tomasi_score(img, cam.width, cam.height, stride, ox, oy);          // :158
     return (int)(pc[0] / grid_size) * grid_n_height + (int)(pc[1] / grid_size);     // :156
+}
+
+// ------------------------------------------------------------------ visual map: selection + warp (row f2), growth (row f4)
+// Per-element math of LidarSelector::addFromSparseMap (src/lidar_selection.cpp:346-587) and its helpers.  vikit /
+// Sophus / OpenCV pieces are restated from their published sources exactly as in oracle/flo_vmap.cpp.
+FLB_HD void se3_apply(const double* R, const double* t, const double* p, double* o) {      // T * p
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) o[k] = R[3 * k] * p[0] + R[3 * k + 1] * p[1] + R[3 * k + 2] * p[2] + t[k];
+}
+FLB_HD void se3_pos(const double* R, const double* t, double* o) {                          // T.inverse().translation()
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) o[k] = -(R[k] * t[0] + R[3 + k] * t[1] + R[6 + k] * t[2]);
+}
+
+// vikit PinholeCamera::cam2world(px): unit bearing.  Distorted: cv::undistortPoints on one CV_32FC2 point
+// (float in, five fixed-point iterations in double, float out).
+FLB_HD void cam2world(const CamModel& cam, double u, double v, double* f) {
+    double x, y;
+    if (!(fabs(cam.d[0]) > 0.0000001)) {
+        x = (u - cam.cx) / cam.fx;
+        y = (v - cam.cy) / cam.fy;
+    } else {
+        const float uf = (float)u, vf = (float)v;
+        const double x0 = ((double)uf - cam.cx) / cam.fx, y0 = ((double)vf - cam.cy) / cam.fy;
+        double xx = x0, yy = y0;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = xx * xx + yy * yy;
+            const double icdist = 1. / (1 + ((cam.d[4] * r2 + cam.d[1]) * r2 + cam.d[0]) * r2);
+            const double deltaX = 2 * cam.d[2] * xx * yy + cam.d[3] * (r2 + 2 * xx * xx);
+            const double deltaY = cam.d[2] * (r2 + 2 * yy * yy) + 2 * cam.d[3] * xx * yy;
+            xx = (x0 - deltaX) * icdist;
+            yy = (y0 - deltaY) * icdist;
+        }
+        x = (double)(float)xx;
+        y = (double)(float)yy;
+    }
+    const double n = sqrt(x * x + y * y + 1.0);
+    f[0] = x / n; f[1] = y / n; f[2] = 1.0 / n;
+}
+
+// vk::interpolateMat_8u
+FLB_HD float interpolate_8u(const unsigned char* img, int stride, float u, float v) {
+    const int x = (int)floorf(u), y = (int)floorf(v);
+    const float subpix_x = u - x, subpix_y = v - y;
+    const float w00 = (1.0f - subpix_x) * (1.0f - subpix_y);
+    const float w01 = (1.0f - subpix_x) * subpix_y;
+    const float w10 = subpix_x * (1.0f - subpix_y);
+    const float w11 = 1.0f - w00 - w01 - w10;
+    const unsigned char* ptr = img + (size_t)y * stride + x;
+    return w00 * ptr[0] + w01 * ptr[stride] + w10 * ptr[1] + w11 * ptr[stride + 1];
+}
+
+// AbstractCamera::isInFrame(px.cast<int>(), boundary)
+FLB_HD bool vm_in_frame(const CamModel& cam, double px0, double px1, int boundary) {
+    if (!(fabs(px0) < 1e9) || !(fabs(px1) < 1e9)) return false;
+    const int ox = (int)px0, oy = (int)px1;
+    return ox >= boundary && ox < cam.width - boundary && oy >= boundary && oy < cam.height - boundary;
+}
+
+// Voxel keys.  sub_feat_map (:384-388): floor(pt / 0.5f) per axis; feat_map (AddPoint, :204-216): float quotient,
+// "-= 1.0" for negatives, truncation.  Packed into 21 bits per axis (+-2^20 voxels of 0.5 m).
+FLB_HD unsigned long long vm_pack_key(long long x, long long y, long long z) {
+    const unsigned long long b = 1ull << 20;
+    return (((unsigned long long)(z + (long long)b) & 0x1fffffull) << 42) | (((unsigned long long)(y + (long long)b) & 0x1fffffull) << 21) |
+           ((unsigned long long)(x + (long long)b) & 0x1fffffull);
+}
+FLB_HD unsigned long long vm_scan_key(const float* p) {
+    const float voxel_size = 0.5;
+    long long k[3];
+    FLB_UNROLL
+    for (int j = 0; j < 3; ++j) k[j] = (long long)(int)floor((double)p[j] / voxel_size);
+    return vm_pack_key(k[0], k[1], k[2]);
+}
+FLB_HD void vm_feat_key(const double* pt_w, long long* key) {
+    const double voxel_size = 0.5;
+    FLB_UNROLL
+    for (int j = 0; j < 3; ++j) {
+        float loc = (float)(pt_w[j] / voxel_size);
+        if (loc < 0) loc -= 1.0;
+        key[j] = (long long)loc;
+    }
+}
+
+// getWarpMatrixAffine (:232-256) with level_ref = 0, pyramid_level = 0 (the only call site, :528-530).
+// Rcr, tcr = T_cur_ref = T_cur * T_ref^-1.  A row-major 2x2.
+FLB_HD void vm_warp_matrix(const CamModel& cam, const double* px_ref, const double* f_ref, double depth_ref, const double* Rcr,
+                           const double* tcr, int halfpatch_size, double* A) {
+    const double xyz_ref[3] = {f_ref[0] * depth_ref, f_ref[1] * depth_ref, f_ref[2] * depth_ref};
+    const double step = (double)(halfpatch_size * (1 << 0) * (1 << 0));
+    double xyz_du[3], xyz_dv[3];
+    cam2world(cam, px_ref[0] + step, px_ref[1], xyz_du);
+    cam2world(cam, px_ref[0], px_ref[1] + step, xyz_dv);
+    const double su = xyz_ref[2] / xyz_du[2], sv = xyz_ref[2] / xyz_dv[2];
+    FLB_UNROLL
+    for (int k = 0; k < 3; ++k) { xyz_du[k] *= su; xyz_dv[k] *= sv; }
+    double pc[3], pdu[3], pdv[3], px_cur[2], px_du[2], px_dv[2];
+    se3_apply(Rcr, tcr, xyz_ref, pc);
+    se3_apply(Rcr, tcr, xyz_du, pdu);
+    se3_apply(Rcr, tcr, xyz_dv, pdv);
+    world2cam(cam, pc, px_cur);
+    world2cam(cam, pdu, px_du);
+    world2cam(cam, pdv, px_dv);
+    A[0] = (px_du[0] - px_cur[0]) / halfpatch_size;
+    A[2] = (px_du[1] - px_cur[1]) / halfpatch_size;
+    A[1] = (px_dv[0] - px_cur[0]) / halfpatch_size;
+    A[3] = (px_dv[1] - px_cur[1]) / halfpatch_size;
+}
+
+FLB_HD int vm_best_search_level(const double* A, int max_level) {      // :317-331
+    int search_level = 0;
+    double D = A[0] * A[3] - A[1] * A[2];
+    while (D > 3.0 && search_level < max_level) {
+        search_level += 1;
+        D *= 0.25;
+    }
+    return search_level;
+}
+
+// A_ref_cur = A_cur_ref.inverse().cast<float>() (:268): adjugate / determinant.  Returns false when NaN (:269).
+FLB_HD bool vm_warp_inverse(const double* A_cur_ref, float* a) {
+    const double det = A_cur_ref[0] * A_cur_ref[3] - A_cur_ref[1] * A_cur_ref[2];
+    const double inv = 1.0 / det;
+    a[0] = (float)(A_cur_ref[3] * inv); a[1] = (float)(-A_cur_ref[1] * inv);
+    a[2] = (float)(-A_cur_ref[2] * inv); a[3] = (float)(A_cur_ref[0] * inv);
+    return !(a[0] != a[0]);
+}
+
+// One element of warpAffine (:279-295): patch[64 * pyramid_level + 8 * y + x]
+FLB_HD float vm_warp_pixel(const float* a, const unsigned char* img_ref, int width, int height, const double* px_ref,
+                           int search_level, int pyramid_level, int halfpatch_size, int x, int y) {
+    float px_patch0 = (float)(x - halfpatch_size), px_patch1 = (float)(y - halfpatch_size);
+    px_patch0 *= (float)(1 << search_level); px_patch1 *= (float)(1 << search_level);
+    px_patch0 *= (float)(1 << pyramid_level); px_patch1 *= (float)(1 << pyramid_level);
+    const float pxr0 = (float)px_ref[0], pxr1 = (float)px_ref[1];
+    const float px0 = a[0] * px_patch0 + a[1] * px_patch1 + pxr0, px1 = a[2] * px_patch0 + a[3] * px_patch1 + pxr1;
+    if (px0 < 0 || px1 < 0 || px0 >= width - 1 || px1 >= height - 1) return 0.0f;
+    return interpolate_8u(img_ref, width, px0, px1);
+}
+
+// One element of getpatch at level 0 (:121-141): patch_tmp[x * 8 + y], x = row, y = column.
+struct VmPatchGeom { int u_i, v_i; float w_tl, w_tr, w_bl, w_br; };
+FLB_HD void vm_getpatch_geom(const double* pc, VmPatchGeom& g) {
+    const float u_ref = pc[0];
+    const float v_ref = pc[1];
+    const int scale = 1;
+    g.u_i = floorf(pc[0] / scale) * scale;
+    g.v_i = floorf(pc[1] / scale) * scale;
+    const float subpix_u_ref = (u_ref - g.u_i) / scale;
+    const float subpix_v_ref = (v_ref - g.v_i) / scale;
+    g.w_tl = (1.0 - subpix_u_ref) * (1.0 - subpix_v_ref);
+    g.w_tr = subpix_u_ref * (1.0 - subpix_v_ref);
+    g.w_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
+    g.w_br = subpix_u_ref * subpix_v_ref;
+}
+FLB_HD float vm_getpatch_pixel(const unsigned char* img, int width, const VmPatchGeom& g, int halfpatch_size, int x, int y) {
+    const unsigned char* p = img + (size_t)(g.v_i - halfpatch_size + x) * width + (g.u_i - halfpatch_size) + y;
+    return g.w_tl * p[0] + g.w_tr * p[1] + g.w_bl * p[width] + g.w_br * p[width + 1];
+}
+
+// The device-resident visual map: Point (include/point.h) and Feature (include/feature.h) flattened.
+constexpr int kVmMaxObs = 20;            // addObservation keeps obs_.size() < 20 before adding one (:946-952)
+struct VmFeature {
+    double px[2], f[3];                  // pixel on level 0, unit bearing
+    double R[9], t[3];                   // T_f_w
+    float score;
+    int level, id, img;                  // img: slot of the keyframe image in the pool
+};
+struct VmPoint {
+    double pos[3];
+    float value;
+    int n_obs;
+    long long key[3];                    // feat_map voxel (AddPoint)
+    int obs[kVmMaxObs + 1];              // obs[0] = newest (addFrameRef: push_front)
+    int pad;
+};
+struct VmParams {
+    int grid_size, grid_n_width, grid_n_height, length;
+    int halfpatch;                       // patch_size_half = 4
+    int ncc_en;
+    double outlier_threshold, ncc_thre;
+};
+
+// Point::getCloseViewObs (src/point.cpp:141-178): the observation whose viewing direction is closest to the current
+// one; -1 when there is none within 60 degrees.
+FLB_HD int vm_close_view_obs(const VmPoint& pt, const VmFeature* feats, const double* frame_pos) {
+    if (pt.n_obs <= 0) return -1;
+    double obs_dir[3] = {frame_pos[0] - pt.pos[0], frame_pos[1] - pt.pos[1], frame_pos[2] - pt.pos[2]};
+    {
+        const double nn = norm3(obs_dir);
+        FLB_UNROLL
+        for (int k = 0; k < 3; ++k) obs_dir[k] /= nn;
+    }
+    int min_it = pt.obs[0];
+    double min_cos_angle = 0;
+    for (int q = 0; q < pt.n_obs; ++q) {
+        const VmFeature& ft = feats[pt.obs[q]];
+        double fpos[3], dir[3];
+        se3_pos(ft.R, ft.t, fpos);
+        FLB_UNROLL
+        for (int k = 0; k < 3; ++k) dir[k] = fpos[k] - pt.pos[k];
+        const double nn = norm3(dir);
+        FLB_UNROLL
+        for (int k = 0; k < 3; ++k) dir[k] /= nn;
+        const double cos_angle = obs_dir[0] * dir[0] + obs_dir[1] * dir[1] + obs_dir[2] * dir[2];
+        if (cos_angle > min_cos_angle) { min_cos_angle = cos_angle; min_it = pt.obs[q]; }
+    }
+    if (min_cos_angle < 0.5) return -1;
+    return min_it;
+}
+
+// One grid cell of the third loop of addFromSparseMap (:479-580), executed by a team of cx.n lanes (a warp on the
+// device, a single "lane" in the host emulation): depth-continuity test, closest-view observation, affine warp of the
+// reference patch at three pyramid levels, current patch, NCC / SSD gates.  depth_img holds {scan index + 1 : depth
+// bits} per pixel (the last scan point projecting into a pixel wins, :408-414).  Writes patch_wrap[192] and returns
+// true (to every lane) when the cell is selected.
+template <class Ctx>
+FLB_HD bool vm_build_cell(const Ctx& cx, const CamModel& cam, const VmParams& prm, const double* Rcw, const double* Pcw,
+                          const double* frame_pos, const VmPoint& pt, const VmFeature* feats, const unsigned char* img_pool,
+                          const unsigned char* img_cur, const unsigned long long* depth_img, float* patch_wrap, float* patch_cur,
+                          double* shared8, int* search_level_out, float* error_out) {
+    const int width = cam.width, height = cam.height, hp = prm.halfpatch;
+    double pt_cam[3], pc[2];
+    se3_apply(Rcw, Pcw, pt.pos, pt_cam);
+    world2cam(cam, pt_cam, pc);
+    // depth continuity (:492-514): any scan depth in the (2hp+1)^2 window (centre excluded) more than 1.5 m off
+    bool bad = false;
+    const int side = 2 * hp + 1;
+    for (int e = cx.lane; e < side * side; e += cx.n) {
+        const int u = e / side - hp, v = e % side - hp;
+        if (u == 0 && v == 0) continue;
+        const unsigned long long cell = depth_img[(size_t)width * (v + (int)pc[1]) + u + (int)pc[0]];
+        const float depth = u32_as_float((unsigned)cell);
+        if (depth == 0.) continue;
+        const double delta_dist = fabs(pt_cam[2] - depth);
+        if (delta_dist > 1.5) bad = true;
+    }
+    if (cx.any(bad)) return false;
+    // closest-view observation + warp matrix: lane 0, then shared with the team
+    if (cx.lane == 0) {
+        const int fi = vm_close_view_obs(pt, feats, frame_pos);
+        shared8[7] = (double)fi;
+        if (fi >= 0) {
+            const VmFeature& ref = feats[fi];
+            double Rcr[9], tcr[3], rpos[3];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    Rcr[3 * a + b] = Rcw[3 * a] * ref.R[3 * b] + Rcw[3 * a + 1] * ref.R[3 * b + 1] + Rcw[3 * a + 2] * ref.R[3 * b + 2];
+            se3_pos(ref.R, ref.t, rpos);
+            se3_apply(Rcw, Pcw, rpos, tcr);
+            const double dvec[3] = {rpos[0] - pt.pos[0], rpos[1] - pt.pos[1], rpos[2] - pt.pos[2]};
+            vm_warp_matrix(cam, ref.px, ref.f, norm3(dvec), Rcr, tcr, hp, shared8);             // :528-530
+            shared8[4] = (double)vm_best_search_level(shared8, 2);                               // :532
+        }
+    }
+    cx.sync();
+    const int fi = (int)shared8[7];
+    const int search_level = (int)shared8[4];
+    float a[4];
+    const bool inv_ok = vm_warp_inverse(shared8, a);
+    cx.sync();                                    // every lane has read lane 0's results: shared8 may be reused
+    if (fi < 0) return false;
+    const VmFeature& ref = feats[fi];
+    const unsigned char* img_ref = img_pool + (size_t)ref.img * (size_t)width * (size_t)height;
+    const int ps = 2 * hp, total = ps * ps;
+    for (int e = cx.lane; e < 3 * total; e += cx.n) {                                           // :542-545
+        const int lvl = e / total, r = e % total, y = r / ps, x = r % ps;
+        patch_wrap[e] = inv_ok ? vm_warp_pixel(a, img_ref, width, height, ref.px, search_level, lvl, hp, x, y) : 0.0f;
+    }
+    VmPatchGeom g;
+    vm_getpatch_geom(pc, g);
+    for (int e = cx.lane; e < total; e += cx.n) patch_cur[e] = vm_getpatch_pixel(img_cur, width, g, hp, e / ps, e % ps);   // :547
+    cx.sync();
+    if (cx.lane == 0) {
+        bool keep = true;
+        if (prm.ncc_en) {                                                                        // NCC, :298-315
+            double sum_ref = 0.0, sum_cur = 0.0;
+            for (int i = 0; i < total; ++i) sum_ref += patch_wrap[i];
+            const double mean_ref = sum_ref / total;
+            for (int i = 0; i < total; ++i) sum_cur += patch_cur[i];
+            const double mean_curr = sum_cur / total;
+            double numerator = 0, demoniator1 = 0, demoniator2 = 0;
+            for (int i = 0; i < total; i++) {
+                const double n = (patch_wrap[i] - mean_ref) * (patch_cur[i] - mean_curr);
+                numerator += n;
+                demoniator1 += (patch_wrap[i] - mean_ref) * (patch_wrap[i] - mean_ref);
+                demoniator2 += (patch_cur[i] - mean_curr) * (patch_cur[i] - mean_curr);
+            }
+            const double ncc = numerator / sqrt(demoniator1 * demoniator2 + 1e-10);
+            if (ncc < prm.ncc_thre) keep = false;
+        }
+        float error = 0.0;
+        for (int ind = 0; ind < total; ind++) error += (patch_wrap[ind] - patch_cur[ind]) * (patch_wrap[ind] - patch_cur[ind]);
+        if (error > prm.outlier_threshold * total) keep = false;                                 // :560
+        shared8[5] = keep ? 1.0 : 0.0;
+        shared8[6] = (double)error;
+    }
+    cx.sync();
+    const bool keep = shared8[5] != 0.0;
+    *search_level_out = search_level;
+    *error_out = (float)shared8[6];
+    cx.sync();
+    return keep;
+}
+
+// One selected patch of addObservation (:913-965): should a new observation be added (pose / pixel-distance tests),
+// which observation goes when the list is full (Point::getFurthestViewObs, src/point.cpp:219-247).
+FLB_HD bool vm_observation_test(const CamModel& cam, const double* Rcw, const double* Pcw, const double* cur_pos, const VmPoint& pt,
+                                const VmFeature* feats, double* pc, int* erase_slot) {
+    double pf[3];
+    se3_apply(Rcw, Pcw, pt.pos, pf);
+    world2cam(cam, pf, pc);
+    bool add_flag = false;
+    const VmFeature& last = feats[pt.obs[pt.n_obs - 1]];                                         // obs_.back()
+    double Rd[9], td[3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) Rd[3 * a + b] = last.R[3 * a] * Rcw[3 * b] + last.R[3 * a + 1] * Rcw[3 * b + 1] + last.R[3 * a + 2] * Rcw[3 * b + 2];
+    se3_apply(last.R, last.t, cur_pos, td);
+    const double delta_p = norm3(td);
+    const double tr = Rd[0] + Rd[4] + Rd[8];
+    const double delta_theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
+    if (delta_p > 0.5 || delta_theta > 10) add_flag = true;
+    const double dpx[2] = {pc[0] - last.px[0], pc[1] - last.px[1]};
+    const double pixel_dist = sqrt(dpx[0] * dpx[0] + dpx[1] * dpx[1]);
+    if (pixel_dist > 40) add_flag = true;
+    *erase_slot = -1;
+    if (pt.n_obs >= kVmMaxObs) {
+        int max_it = 0;
+        double maxdist = 0.0;
+        for (int q = 0; q < pt.n_obs; ++q) {
+            double fpos[3];
+            se3_pos(feats[pt.obs[q]].R, feats[pt.obs[q]].t, fpos);
+            const double d[3] = {fpos[0] - cur_pos[0], fpos[1] - cur_pos[1], fpos[2] - cur_pos[2]};
+            const double dist = norm3(d);
+            if (dist > maxdist) { maxdist = dist; max_it = q; }
+        }
+        *erase_slot = max_it;
+    }
+    return add_flag;
 }
 
 // ------------------------------------------------------------------ IKFoM manifold algebra (row a8)

@@ -364,6 +364,8 @@ struct LioArgs {
     double* x_meas;              // N
     unsigned long long* probe;   // profiling aid: stage timestamps of one thread (or null)
     int chunk;                   // persistent kernel: points per warp-chunk (1..32)
+    int M;                       // map points (for the L2 prefetch)
+    int prefetch;                // persistent kernel: stream the map + cell table into L2 before the first pass
 };
 
 template <int W>
@@ -824,6 +826,7 @@ struct LeaderSmem {
     int flags[8];             // [0] accept [1] docov [2] newlevel [3] singular [4] speculated [5] mispredicted
     float error;
     VioCtrl cspec;            // VIO: the control block of the speculated next pass
+    int p2p_cnt[8];           // VIO: per-rank patch counts of this pass (kP2PMaxWorld)
 };
 
 // The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
@@ -1083,17 +1086,16 @@ __device__ __forceinline__ void leader_cov_update(LeaderSmem& sm, const double* 
 // per pass).  Slots are double-buffered by tag parity: a rank can be at most one exchange ahead of the
 // slowest one (it cannot finish exchange k+1 without that rank's k+1 contribution, which that rank only
 // sends after it has consumed exchange k).
-// All-reduce sm.packed[0..K) across ranks in rank order, executed by a team of threads (TeamT); `n_err` rides in
-// line 31 (this rank's number of per-patch errors of this exchange).  Uses sm.part as the receive staging.
+// All-reduce sm.packed[0..K) across ranks in rank order, executed by a team of threads (TeamT).  Uses sm.part as
+// the receive staging.  (Line 31 of every rank's slot is the VIO patch count, pushed at the start of the pass.)
 template <int K, class TeamT>
-__device__ __forceinline__ void p2p_exchange(const P2PArgs& pp, LeaderSmem& sm, unsigned tag, double n_err, int tid,
-                                             int* timeout_flag) {
-    static_assert(K <= 31, "line 31 is the error count");
+__device__ __forceinline__ void p2p_exchange(const P2PArgs& pp, LeaderSmem& sm, unsigned tag, int tid, int* timeout_flag) {
+    static_assert(K <= 31, "line 31 is the patch count");
     const int par = (int)(tag & 1u);
     const int nline = pp.world * 32;
     for (int e = tid; e < nline; e += TeamT::size) {
         const int r = e >> 5, k = e & 31;
-        if (k < K || k == 31) ll_store_line(&pp.mail[r]->sums[par][pp.rank][k], k == 31 ? n_err : sm.packed[k], tag);
+        if (k < K) ll_store_line(&pp.mail[r]->sums[par][pp.rank][k], sm.packed[k], tag);
     }
     for (int e = tid; e < nline; e += TeamT::size) {
         const int r = e >> 5, k = e & 31;
@@ -1170,7 +1172,7 @@ __device__ __forceinline__ void lio_leader_solve(const LioSolveArgs& s, LeaderSm
     FLB_STAMP(0);
     team_reduce_vec<K, NT, T>(s.partials, s.nblocks, sm, tid);
     if (!first && !resident) prior_commit(sm, pri, tid);
-    if (p2p_tag) p2p_exchange<K, T>(s.p2p, sm, p2p_tag, 0.0, tid, s.timeout_flag);
+    if (p2p_tag) p2p_exchange<K, T>(s.p2p, sm, p2p_tag, tid, s.timeout_flag);
     if (first && !resident) leader_prior<T>(sm, s.prior, tid);
     __syncthreads();
     FLB_STAMP(1);
@@ -1281,7 +1283,8 @@ struct VioSolveArgs {
     int* timeout_flag;
 };
 
-constexpr int kErrChunk = 2048;
+constexpr int kErrChunk = 2048;          // staging capacity of the kernel-per-pass finalize kernel (static shared memory)
+constexpr int kErrTeam = 128;            // threads of the leader block that gather the per-patch errors
 constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 
 // One VIO leader step (whole block, NT threads), in two halves like the LIO one.  Requires the 24
@@ -1290,56 +1293,72 @@ constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 template <int NT>
 __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first,
                                                  unsigned long long* pkt, unsigned flag, int resident,
-                                                 unsigned long long* fine = nullptr, unsigned p2p_tag = 0u, int err_buf = 0) {
+                                                 unsigned long long* fine = nullptr, unsigned p2p_tag = 0u, int err_buf = 0,
+                                                 int err_cap = kErrChunk) {
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     const int tid = threadIdx.x;
     const bool multi = p2p_tag != 0u;
     const int level = c.level;
     const float* errs_pass = s.errors + (size_t)err_buf * s.err_stride;     // this pass's half of the error buffer
-    // Stage the (first chunk of) per-patch errors with the whole block -- one coalesced L2 round trip.
-    // (Fused multi-GPU mode: the errors of ALL ranks arrive in the mailbox, pushed by the worker warps.)
-    if (!multi)
-        for (int e = tid; e < min(kErrChunk, s.Pn_total); e += NT) s_err[e] = __ldcg(errs_pass + e);
-    __syncthreads();
-    static_assert(NT - 32 >= kDim * 6, "solve team too small");
-    if (tid >= NT - 32) {
-        // The last warp forms the exact sequential float sum of the per-patch errors (:852): a serial
-        // chain of one FADD latency per patch, hidden behind the other warps' reduce + solve.
-        const int lane = tid - (NT - 32);
-        float e_run = 0.0f;
-        const int nsrc = multi ? s.p2p.world : 1;
-        const int par = (int)(p2p_tag & 1u);
-        bool dead = false;
-        for (int r = 0; r < nsrc; ++r) {
-            // patch order = rank 0's shard, then rank 1's, ... (contiguous block partition).  Fused multi-GPU
-            // mode: rank r's patch count rides in line 31 of its sums (it arrives when r's pass is complete);
-            // its errors were pushed by r's worker warps during the pass and are validated unit by unit.
-            const unsigned long long* units = multi ? s.p2p.mail[s.p2p.rank]->errs[par][r] : nullptr;
-            int n_r = s.Pn_total;
-            if (multi) {
+    const int nsrc = multi ? s.p2p.world : 1;
+    const int par = (int)(p2p_tag & 1u);
+    // Per-patch errors of this pass, in global patch order (rank 0's shard, then rank 1's, ...: contiguous block
+    // partition).  Single GPU: this rank's error buffer.  Fused multi-GPU mode: every rank's worker warps pushed
+    // {error, tag} units into this rank's mailbox while the pass was running, and each rank's patch count came
+    // with the first block of its pass (line 31); every unit is validated by its tag.
+    static_assert(NT - kErrTeam >= kDim * 6 && NT - kErrTeam >= 64, "solve team too small");
+    if (tid >= NT - kErrTeam) {
+        // ---- error team (the last kErrTeam threads): gather, then its last warp sums
+        const int et = tid - (NT - kErrTeam);
+        if (multi) {
+            if (et < nsrc) {
                 double cnt = 0.0;
                 unsigned long long spins = 0;
-                while (!dead && !ll_load_line(&s.p2p.mail[s.p2p.rank]->sums[par][r][31], p2p_tag, cnt))
-                    if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; dead = true; }
-                dead = __any_sync(0xffffffffu, dead);
-                n_r = dead ? 0 : (int)cnt;
+                while (!ll_load_line(&s.p2p.mail[s.p2p.rank]->sums[par][et][31], p2p_tag, cnt))
+                    if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; cnt = 0.0; break; }
+                sm.p2p_cnt[et] = (int)cnt;
             }
-            for (int base = 0; base < n_r; base += kErrChunk) {
-                const int nchunk = min(kErrChunk, n_r - base);
-                if (multi) {
-                    for (int e = lane; e < nchunk; e += 32) {
-                        unsigned long long u = ll_load_u64(units + base + e);
-                        unsigned long long spins = 0;
-                        while ((unsigned)(u >> 32) != p2p_tag && !dead) {
-                            if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; dead = true; }
-                            u = ll_load_u64(units + base + e);
-                        }
-                        s_err[e] = __uint_as_float((unsigned)u);
-                    }
-                    dead = __any_sync(0xffffffffu, dead);
-                } else if (base > 0) {     // staged by this warp alone (single GPU: only for Pn > kErrChunk)
-#pragma unroll 8
-                    for (int e = lane; e < nchunk; e += 32) s_err[e] = __ldcv(errs_pass + base + e);
+        } else if (et == 0) {
+            sm.p2p_cnt[0] = s.Pn_total;
+        }
+        asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
+        int total = 0;
+        for (int r = 0; r < nsrc; ++r) total += sm.p2p_cnt[r];
+        auto fetch = [&](int e) -> float {
+            if (!multi) return __ldcg(errs_pass + e);
+            int r = 0;
+            while (r + 1 < nsrc && e >= sm.p2p_cnt[r]) { e -= sm.p2p_cnt[r]; ++r; }
+            const unsigned long long* unit = &s.p2p.mail[s.p2p.rank]->errs[par][r][e];
+            unsigned long long u = ll_load_u64(unit);
+            unsigned long long spins = 0;
+            while ((unsigned)(u >> 32) != p2p_tag) {
+                if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; break; }
+                u = ll_load_u64(unit);
+            }
+            return __uint_as_float((unsigned)u);
+        };
+        // stage (the first err_cap of) them: independent loads, a few L2 round trips for the whole team
+        {
+            const int n0 = min(err_cap, total);
+            int e = et;
+            for (; e + 3 * kErrTeam < n0; e += 4 * kErrTeam) {
+                const float v0 = fetch(e), v1 = fetch(e + kErrTeam), v2 = fetch(e + 2 * kErrTeam), v3 = fetch(e + 3 * kErrTeam);
+                s_err[e] = v0; s_err[e + kErrTeam] = v1; s_err[e + 2 * kErrTeam] = v2; s_err[e + 3 * kErrTeam] = v3;
+            }
+            for (; e < n0; e += kErrTeam) s_err[e] = fetch(e);
+        }
+        asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
+        if (tid >= NT - 32) {
+        // The last warp forms the exact sequential float sum of the per-patch errors (:852): a serial
+        // chain of one FADD latency per patch, hidden behind the other warps' reduce + solve -- and, in the
+        // persistent kernel, behind the next pass, which has already been started on the accept branch.
+        const int lane = tid - (NT - 32);
+        float e_run = 0.0f;
+        {
+            for (int base = 0; base < total; base += err_cap) {
+                const int nchunk = min(err_cap, total - base);
+                if (base > 0) {            // beyond the staged capacity: this warp stages the next chunk itself
+                    for (int e = lane; e < nchunk; e += 32) s_err[e] = fetch(base + e);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -1353,7 +1372,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                     for (; i + 16 <= nchunk; i += 16) {
                         const float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
                         {   // unconditional, index clamped into the array (unused past the end of the chunk)
-                            const int q = min((i >> 2) + 4, kErrChunk / 4 - 4);
+                            const int q = min((i >> 2) + 4, err_cap / 4 - 4);
                             n0 = s4[q]; n1 = s4[q + 1]; n2 = s4[q + 2]; n3 = s4[q + 3];
                         }
                         e = e + c0.x; e = e + c0.y; e = e + c0.z; e = e + c0.w;
@@ -1370,18 +1389,19 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         if (lane == 0) sm.error = e_run;
         if (fine && lane == 0) fine[3] = global_ns();
         asm volatile("bar.sync 3, 64;" ::: "memory");                       // hand the error to warp 0
+        }
     } else {
         // Solve team (first NT-32 threads, named barrier 1).  The covariance is constant during ComputeJ
         // (only :980 changes it, on the last pass), so old_state carries the 24 pose/bias doubles only.
-        using T = Team<NT - 32, true>;
-        if (first && !resident) load_cov_l2<NT - 32>(&sm.x, s.state, tid);
+        using T = Team<NT - kErrTeam, true>;
+        if (first && !resident) load_cov_l2<NT - kErrTeam>(&sm.x, s.state, tid);
         const double pri = (first || resident) ? 0.0 : prior_prefetch(s.prior, tid);
-        if (first) store_state(s.old_state, &sm.x, tid, NT - 32, false);                 // old_state = *state (:747)
+        if (first) store_state(s.old_state, &sm.x, tid, NT - kErrTeam, false);           // old_state = *state (:747)
         if (tid == 0) sm.flags[3] = (resident == 2) ? 1 : 0;
-        team_reduce_vec<kVioPacked, NT - 32, T>(s.partials, s.nblocks, sm, tid);
+        team_reduce_vec<kVioPacked, NT - kErrTeam, T>(s.partials, s.nblocks, sm, tid);
         FLB_STAMP(1);
         if (!first && !resident) prior_commit(sm, pri, tid);
-        if (multi) p2p_exchange<kVioPacked, T>(s.p2p, sm, p2p_tag, (double)s.Pn_total, tid, s.timeout_flag);
+        if (multi) p2p_exchange<kVioPacked, T>(s.p2p, sm, p2p_tag, tid, s.timeout_flag);
         if (first && !resident) leader_prior<T>(sm, s.prior, tid);
         T::sync();
         if (tid < 32) {
@@ -1755,6 +1775,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     __syncthreads();
     int resident = 0;
     if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
+    else if (a.prefetch) {
+        // A map larger than a few MB is cold in L2 when the frame starts (other work ran in between): the kNN walk
+        // would then pay one DRAM latency per dependent step.  Stream the sorted points and the cell table into L2
+        // with bulk prefetches (asynchronous: nobody waits for them), 4 KB per instruction.
+        const size_t nb_pts = (size_t)a.M * sizeof(float4);
+        const size_t nb_cells = ((size_t)a.grid.nx * a.grid.ny * a.grid.nz + 1) * sizeof(int) / 16 * 16;
+        const size_t step = 4096, stride = (size_t)nworkers * BLOCK * step;
+        for (size_t off = ((size_t)blockIdx.x * BLOCK + tid) * step; off < nb_pts; off += stride)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.map_pts) + off),
+                         "r"((unsigned)min(step, nb_pts - off)) : "memory");
+        for (size_t off = ((size_t)blockIdx.x * BLOCK + tid) * step; off < nb_cells; off += stride)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(a.cell_start) + off),
+                         "r"((unsigned)min(step, nb_cells - off)) : "memory");
+    }
     for (;;) {
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
         if (is_leader) {
@@ -1810,7 +1844,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
                                                                     unsigned long long* pkt, unsigned epoch,
-                                                                    unsigned long long* trace, unsigned long long* dbg) {
+                                                                    unsigned long long* trace, unsigned long long* dbg, int err_cap) {
     constexpr int NW = BLOCK / 32;
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     __shared__ VioPose s_pose;
@@ -1820,7 +1854,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl s_ctrl;
-    __shared__ __align__(16) float s_err[kErrChunk];
+    extern __shared__ __align__(16) float s_err[];     // err_cap floats (dynamic): the leader's staging of the per-patch errors
     __shared__ unsigned long long s_seq_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
@@ -1855,7 +1889,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 32 + 8 * pass_no + 8 <= kTraceLen) ? trace + 32 + 8 * pass_no : nullptr;
-            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine, p2p_tag, pass_no & 1);
+            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine, p2p_tag, pass_no & 1, err_cap);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, resident);
             if (sm.flags[5]) {
@@ -1868,7 +1902,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
                 if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
                 if (multi) {
                     const unsigned tag2 = (unsigned)(s_seq_base + (unsigned long long)pass_no + 1ull) | 0x80000000u;
-                    p2p_exchange<kVioPacked, Team<BLOCK, false>>(s.p2p, sm, tag2, 0.0, tid, s.timeout_flag);
+                    p2p_exchange<kVioPacked, Team<BLOCK, false>>(s.p2p, sm, tag2, tid, s.timeout_flag);
                 }
                 if (tid < 32) pkt_publish_warp<NC>(pkt, sm.x, &s_ctrl, epoch + (unsigned)pass_no + 1u, tid);
                 if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
@@ -1880,6 +1914,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             }
         } else {
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
+            // fused multi-GPU mode: this rank's patch count of the pass goes out first (the leaders size their gather by it)
+            if (multi && blockIdx.x == 0 && tid >= 32 && tid < 32 + s.p2p.world)
+                ll_store_line(&s.p2p.mail[tid - 32]->sums[p2p_tag & 1u][s.p2p.rank][31], (double)a.Pn, p2p_tag);
             if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
             __syncthreads();
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();

@@ -382,3 +382,65 @@ def make_imu_frame(seed=1, n_points=24000, imu_hz=200.0, scan_s=0.1, variant="no
                 cov_bias_gyr=np.array([1e-4, 1e-4, 1e-4]), cov_bias_acc=np.array([1e-4, 1e-4, 1e-4]),
                 G_m_s2=9.81, mean_acc_norm=9.79,
                 R_LI=exp_so3(np.array([0.01, -0.02, 0.015])), t_LI=np.array([0.04165, 0.02326, -0.0284]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Visual-map sequences: several frames of ONE scene along a short trajectory
+# ---------------------------------------------------------------------------------------------------------
+def voxel_centroids(xyz: np.ndarray, leaf: float) -> np.ndarray:
+    """Stand-in for the caller's pcl::VoxelGrid (centroid per leaf-sized voxel), float32 in / out.  The selection
+    takes the filtered cloud as an INPUT, so any deterministic filter serves the tests."""
+    key = np.floor(xyz.astype(np.float64) / leaf).astype(np.int64)
+    _, inv = np.unique(key, axis=0, return_inverse=True)
+    inv = inv.ravel()
+    n = inv.max() + 1
+    out = np.zeros((n, 3))
+    cnt = np.bincount(inv, minlength=n).astype(np.float64)
+    for a in range(3):
+        out[:, a] = np.bincount(inv, weights=xyz[:, a].astype(np.float64), minlength=n) / cnt
+    return out.astype(np.float32)
+
+
+def make_visual_sequence(cfg: FrameConfig | str = "T0", n_frames: int = 3, seed: int | None = None, step=(0.18, 0.06, 0.02),
+                         yaw_step_deg: float = 2.5) -> dict:
+    """n_frames camera frames of one scene: image, camera pose T_f_w = (Rcw, Pcw) as LidarSelector::updateFrameState
+    forms it (src/lidar_selection.cpp:905-911), the scan in WORLD coordinates (`pg` of LidarSelector::detect) and its
+    0.2 m voxel-filtered version (`pg_down`, :7, :351-352)."""
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    seed = cfg.seed if seed is None else seed
+    rng = np.random.default_rng(np.random.PCG64(seed + 77))
+    room_l = _room_for(cfg.n_map, cfg.pitch, cfg.room_h)
+    scene = Scene(rng, room_l, cfg.room_h)
+    yaw0 = rng.uniform(-np.pi, np.pi)
+    p0 = np.array([rng.uniform(-0.04, 0.04) * room_l, rng.uniform(-0.04, 0.04) * room_l, rng.uniform(1.2, 1.8)])
+    R_LI, t_LI = AVIA_EXTRINSIC_R.copy(), AVIA_EXTRINSIC_T.copy()
+    sx, sy = cfg.img_w / PINHOLE["width"], cfg.img_h / PINHOLE["height"]
+    cam = dict(width=cfg.img_w, height=cfg.img_h, fx=PINHOLE["fx"] * sx, fy=PINHOLE["fy"] * sy, cx=PINHOLE["cx"] * sx,
+               cy=PINHOLE["cy"] * sy, d=tuple(PINHOLE["d"]) if cfg.distortion else (0.0, 0.0, 0.0, 0.0, 0.0))
+    Rli, Pli = R_LI.T, -R_LI.T @ t_LI
+    Rci = AVIA_RCL @ Rli
+    Pci = AVIA_RCL @ Pli + AVIA_PCL
+    vv, uu = np.meshgrid(np.arange(cfg.img_h, dtype=np.float64), np.arange(cfg.img_w, dtype=np.float64), indexing="ij")
+    rays_c = pixel_rays(cam, uu.ravel(), vv.ravel())
+    frames = []
+    for k in range(n_frames):
+        R = exp_so3(np.array([0, 0, yaw0 + np.deg2rad(yaw_step_deg) * k])) @ exp_so3(np.array([0.01 * k, -0.006 * k, 0]))
+        fwd = R[:, 0]
+        p = p0 + k * (step[0] * fwd + step[1] * R[:, 1] + np.array([0, 0, step[2]]))
+        Rcw = Rci @ R.T
+        Pcw = -Rci @ R.T @ p + Pci
+        R_wc = Rcw.T
+        c_w = -Rcw.T @ Pcw
+        t_px = scene.raycast(c_w, rays_c @ R_wc.T)
+        clean = scene.texture(c_w + (rays_c @ R_wc.T) * t_px[:, None]).reshape(cfg.img_h, cfg.img_w)
+        image = np.clip(np.rint(clean + rng.normal(0.0, 2.0, size=clean.shape)), 0, 255).astype(np.uint8)
+        az = rng.uniform(-np.deg2rad(35.2), np.deg2rad(35.2), size=cfg.n_scan)
+        el = rng.uniform(-np.deg2rad(38.6), np.deg2rad(38.6), size=cfg.n_scan)
+        d_l = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], axis=1)
+        o_w = R @ t_LI + p
+        d_w = d_l @ (R @ R_LI).T
+        rng_t = scene.raycast(o_w, d_w) + rng.normal(0.0, 0.01, size=cfg.n_scan)
+        pg = (o_w + d_w * rng_t[:, None]).astype(np.float32)
+        frames.append(dict(image=image, Rcw=Rcw, Pcw=Pcw, R=R, p=p, pg=pg, pg_down=voxel_centroids(pg, 0.2), frame_id=k))
+    return dict(cfg=cfg, cam=cam, frames=frames, Rci=Rci, Pci=Pci, R_LI=R_LI, t_LI=t_LI, Rcl=AVIA_RCL.copy(), Pcl=AVIA_PCL.copy())

@@ -213,6 +213,22 @@ float flo_shi_tomasi(const uint8_t* img, int width, int height, int stride, int 
 void flo_visual_candidates(const flo_cam* cam, const double* Rcw, const double* Pcw, const uint8_t* img, int stride,
                            const float* world_xyz, int n, int grid_size, int border, float* map_value, int* winner);
 
+/* ---- visual map: visible-patch selection + warp (row f2) and growth (row f4); oracle/flo_vmap.cpp -------- */
+typedef struct flo_vmap flo_vmap;
+flo_vmap* flo_vmap_create(const flo_cam* cam, int grid_size, double outlier_threshold, int ncc_en, double ncc_thre);
+void      flo_vmap_destroy(flo_vmap*);
+int       flo_vmap_counts(const flo_vmap*, int* n_points, int* n_features, int* n_images);   /* returns the grid length */
+void      flo_vmap_map_value(const flo_vmap*, float* out);
+/* LidarSelector::addFromSparseMap, src/lidar_selection.cpp:346-587 */
+int       flo_vmap_select(flo_vmap*, const uint8_t* img, const double* Rcw, const double* Pcw, const float* pg_down, int n);
+void      flo_vmap_selected(const flo_vmap*, int* index, int* point, int* search_level, float* error, double* pos, float* patch);
+/* LidarSelector::addSparseMap, :142-202 */
+int       flo_vmap_grow(flo_vmap*, const uint8_t* img, const double* Rcw, const double* Pcw, const float* pg, int n, int frame_id);
+/* LidarSelector::addObservation, :913-965 */
+int       flo_vmap_add_observations(flo_vmap*, const uint8_t* img, const double* Rcw, const double* Pcw, int frame_id);
+void      flo_vmap_dump_points(const flo_vmap*, double* pos, float* value, int* n_obs, int* obs20);
+void      flo_vmap_dump_features(const flo_vmap*, double* geo17, float* score, int* level_id_img);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,6 +244,18 @@ def lib():
         L.flo_vio_update.argtypes = [C.c_void_p, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18),
                                      C.POINTER(VioReport)]
         L.flo_vio_errors.argtypes = [C.c_void_p, C.c_void_p]
+        vp = C.c_void_p
+        L.flo_vmap_create.restype = vp
+        L.flo_vmap_create.argtypes = [C.POINTER(Cam), C.c_int, C.c_double, C.c_int, C.c_double]
+        L.flo_vmap_destroy.argtypes = [vp]
+        L.flo_vmap_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.flo_vmap_map_value.argtypes = [vp, vp]
+        L.flo_vmap_select.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        L.flo_vmap_selected.argtypes = [vp] * 7
+        L.flo_vmap_grow.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.flo_vmap_add_observations.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.flo_vmap_dump_points.argtypes = [vp] * 5
+        L.flo_vmap_dump_features.argtypes = [vp] * 4
         L.flo_world2cam.argtypes = [C.POINTER(Cam), C.c_void_p, C.c_void_p]
         L.flo_exp3.argtypes = [C.c_void_p, C.c_void_p]
         L.flo_log3.argtypes = [C.c_void_p, C.c_void_p]
@@ -498,6 +510,62 @@ class Vio:
         err = np.zeros(self.Pn, np.float32)
         self.L.flo_vio_errors(self.h, _p(err))
         return err
+
+
+class VMap:
+    """flo_vmap: the CPU restatement of the visual map (addFromSparseMap / addSparseMap / addObservation)."""
+
+    def __init__(self, cam: dict, grid_size=40, outlier_threshold=100.0, ncc_en=0, ncc_thre=0.0):
+        self.L = lib()
+        self.cam = make_cam(cam)
+        self.w, self.h_img = cam["width"], cam["height"]
+        self.h = self.L.flo_vmap_create(C.byref(self.cam), int(grid_size), float(outlier_threshold), int(ncc_en), float(ncc_thre))
+
+    def __del__(self):
+        try:
+            self.L.flo_vmap_destroy(self.h)
+        except Exception:
+            pass
+
+    def counts(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        length = self.L.flo_vmap_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(points=a.value, features=b.value, images=c.value, length=length)
+
+    def map_value(self):
+        out = np.zeros(self.counts()["length"], np.float32)
+        self.L.flo_vmap_map_value(self.h, _p(out))
+        return out
+
+    def select(self, img, Rcw, Pcw, pg_down):
+        img = np.ascontiguousarray(img, np.uint8)
+        pg = f32(pg_down).reshape(-1, 3)
+        Rcw, Pcw = f64(Rcw), f64(Pcw)
+        n = self.L.flo_vmap_select(self.h, _p(img), _p(Rcw), _p(Pcw), _p(pg), len(pg))
+        index, point, level = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        error, pos, patch = np.zeros(n, np.float32), np.zeros((n, 3)), np.zeros((n, 192), np.float32)
+        self.L.flo_vmap_selected(self.h, _p(index), _p(point), _p(level), _p(error), _p(pos), _p(patch))
+        return dict(index=index, point=point, search_level=level, error=error, pos=pos, patch=patch)
+
+    def grow(self, img, Rcw, Pcw, pg, frame_id):
+        img = np.ascontiguousarray(img, np.uint8)
+        pg = f32(pg).reshape(-1, 3)
+        Rcw, Pcw = f64(Rcw), f64(Pcw)
+        return self.L.flo_vmap_grow(self.h, _p(img), _p(Rcw), _p(Pcw), _p(pg), len(pg), int(frame_id))
+
+    def add_observations(self, img, Rcw, Pcw, frame_id):
+        img = np.ascontiguousarray(img, np.uint8)
+        Rcw, Pcw = f64(Rcw), f64(Pcw)
+        return self.L.flo_vmap_add_observations(self.h, _p(img), _p(Rcw), _p(Pcw), int(frame_id))
+
+    def dump(self):
+        c = self.counts()
+        n, m = c["points"], c["features"]
+        pos, value, n_obs, obs = np.zeros((n, 3)), np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros((n, 20), np.int32)
+        self.L.flo_vmap_dump_points(self.h, _p(pos), _p(value), _p(n_obs), _p(obs))
+        geo, score, lii = np.zeros((m, 17)), np.zeros(m, np.float32), np.zeros((m, 3), np.int32)
+        self.L.flo_vmap_dump_features(self.h, _p(geo), _p(score), _p(lii))
+        return dict(pos=pos, value=value, n_obs=n_obs, obs=obs, ft_geo=geo, ft_score=score, ft_level_id_img=lii)
 
 
 def world2cam(cam: dict, pf):

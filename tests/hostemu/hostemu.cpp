@@ -167,3 +167,244 @@ void emu_ikfom_proj(const double* grav_x, const double* grav_prop, const double*
     transpose_small(A, 3, 3, AT);
 }
 }
+
+// ---- visual map: selection + warp (row f2), growth + observations (row f4) ---------------------------------
+// A sequential stand-in for the device kernels of fast-livo_b200/csrc (same per-element functions, the atomics
+// replaced by their sequential meaning), so that the CPU tier can check the device math against the oracle.
+#include <unordered_set>
+#include <vector>
+
+namespace {
+struct HostCtx {
+    int lane = 0, n = 1;
+    void sync() const {}
+    bool any(bool b) const { return b; }
+};
+struct EmuVm {
+    CamModel cam;
+    VmParams prm;
+    std::vector<VmPoint> pts;
+    std::vector<VmFeature> fts;
+    std::vector<unsigned char> pool;
+    std::vector<float> map_value;
+    int img_frame = -1, img_slot = -1, n_img = 0;
+    std::vector<int> sel_index, sel_point, sel_level;
+    std::vector<float> sel_error, sel_patch;
+};
+int emu_store_image(EmuVm* vm, const unsigned char* img, int frame_id) {
+    if (vm->img_frame == frame_id && vm->img_slot >= 0) return vm->img_slot;
+    const size_t sz = (size_t)vm->cam.width * vm->cam.height;
+    vm->pool.insert(vm->pool.end(), img, img + sz);
+    vm->img_frame = frame_id;
+    vm->img_slot = vm->n_img++;
+    return vm->img_slot;
+}
+void emu_push_feature(EmuVm* vm, int point, const double* pc, const double* Rcw, const double* Pcw, float score, int level, int id, int img) {
+    VmFeature ft;
+    ft.px[0] = pc[0]; ft.px[1] = pc[1];
+    cam2world(vm->cam, pc[0], pc[1], ft.f);
+    std::memcpy(ft.R, Rcw, sizeof(ft.R));
+    std::memcpy(ft.t, Pcw, sizeof(ft.t));
+    ft.score = score; ft.level = level; ft.id = id; ft.img = img;
+    vm->fts.push_back(ft);
+    VmPoint& p = vm->pts[point];
+    for (int q = p.n_obs; q > 0; --q) p.obs[q] = p.obs[q - 1];      // push_front
+    p.obs[0] = (int)vm->fts.size() - 1;
+    p.n_obs++;
+}
+}  // namespace
+
+extern "C" {
+
+void* emu_vm_create(const double* camv, int grid_size, double outlier_threshold, int ncc_en, double ncc_thre) {
+    EmuVm* vm = new EmuVm;
+    CamModel& cam = vm->cam;
+    cam.width = (int)camv[0]; cam.height = (int)camv[1];
+    cam.fx = camv[2]; cam.fy = camv[3]; cam.cx = camv[4]; cam.cy = camv[5];
+    for (int i = 0; i < 5; ++i) cam.d[i] = camv[6 + i];
+    cam.jfx = fabs(cam.fx);
+    cam.jfy = fabs(4.0 * cam.fx * cam.fy) / (4. * cam.jfx);
+    vm->prm.grid_size = grid_size;
+    vm->prm.grid_n_width = cam.width / grid_size;
+    vm->prm.grid_n_height = cam.height / grid_size;
+    vm->prm.length = vm->prm.grid_n_width * vm->prm.grid_n_height;
+    vm->prm.halfpatch = 4;
+    vm->prm.ncc_en = ncc_en;
+    vm->prm.outlier_threshold = outlier_threshold;
+    vm->prm.ncc_thre = ncc_thre;
+    vm->map_value.assign(vm->prm.length, 0.0f);
+    return vm;
+}
+void emu_vm_destroy(void* h) { delete static_cast<EmuVm*>(h); }
+void emu_vm_counts(void* h, int* out3) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    out3[0] = (int)vm->pts.size(); out3[1] = (int)vm->fts.size(); out3[2] = vm->n_img;
+}
+void emu_vm_map_value(void* h, float* out) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    std::memcpy(out, vm->map_value.data(), sizeof(float) * vm->prm.length);
+}
+
+int emu_vm_select(void* h, const unsigned char* img, const double* Rcw, const double* Pcw, const float* pg_down, int n) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    vm->sel_index.clear(); vm->sel_point.clear(); vm->sel_level.clear(); vm->sel_error.clear(); vm->sel_patch.clear();
+    if (vm->pts.empty()) return 0;
+    const CamModel& cam = vm->cam;
+    const VmParams& prm = vm->prm;
+    const int width = cam.width, border = (prm.halfpatch + 1) * 8;
+    std::fill(vm->map_value.begin(), vm->map_value.end(), 0.0f);
+    std::vector<unsigned long long> depth((size_t)width * cam.height, 0ull);
+    std::unordered_set<unsigned long long> keys;
+    // kernel 1: per scan point -- voxel set + depth image (atomicMax on {index + 1 : depth bits})
+    for (int i = 0; i < n; ++i) {
+        keys.insert(vm_scan_key(pg_down + 3 * i));
+        const double pt_w[3] = {pg_down[3 * i], pg_down[3 * i + 1], pg_down[3 * i + 2]};
+        double pt_c[3];
+        se3_apply(Rcw, Pcw, pt_w, pt_c);
+        if (pt_c[2] > 0) {
+            const double px0 = cam.jfx * pt_c[0] / pt_c[2] + cam.cx, px1 = cam.jfy * pt_c[1] / pt_c[2] + cam.cy;
+            if (vm_in_frame(cam, px0, px1, border)) {
+                const float d = pt_c[2];
+                const unsigned long long v = ((unsigned long long)(i + 1) << 32) | float_as_u32(d);
+                unsigned long long& c = depth[(size_t)width * (int)px1 + (int)px0];
+                if (v > c) c = v;
+            }
+        }
+    }
+    // kernel 2: per visual-map point -- cell claims (atomicMin on {dist bits : ~index}, atomicMax on the value)
+    double frame_pos[3];
+    se3_pos(Rcw, Pcw, frame_pos);
+    std::vector<unsigned long long> best(prm.length, ~0ull);
+    std::vector<unsigned char> type(prm.length, 0);
+    for (size_t j = 0; j < vm->pts.size(); ++j) {
+        const VmPoint& pt = vm->pts[j];
+        if (!keys.count(vm_pack_key(pt.key[0], pt.key[1], pt.key[2]))) continue;
+        double pt_cam[3], pc[2];
+        se3_apply(Rcw, Pcw, pt.pos, pt_cam);
+        if (pt_cam[2] < 0) continue;
+        world2cam(cam, pt_cam, pc);
+        if (!vm_in_frame(cam, pc[0], pc[1], border)) continue;
+        const int index = (int)(pc[0] / prm.grid_size) * prm.grid_n_height + (int)(pc[1] / prm.grid_size);
+        type[index] = 1;
+        const double ov[3] = {frame_pos[0] - pt.pos[0], frame_pos[1] - pt.pos[1], frame_pos[2] - pt.pos[2]};
+        const float cur_dist = norm3(ov);
+        if (cur_dist <= 10000.0f) {
+            const unsigned long long v = ((unsigned long long)float_as_u32(cur_dist) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)j);
+            if (v < best[index]) best[index] = v;
+        }
+        if (pt.value >= vm->map_value[index]) vm->map_value[index] = pt.value;
+    }
+    // kernel 3 + compaction: per cell
+    HostCtx cx;
+    std::vector<float> patch_wrap(192), patch_cur(64);
+    double shared8[8];
+    for (int i = 0; i < prm.length; ++i) {
+        if (!type[i] || best[i] == ~0ull) continue;
+        const int pj = (int)(0xFFFFFFFFu - (unsigned)(best[i] & 0xFFFFFFFFull));
+        int level;
+        float error;
+        if (!vm_build_cell(cx, cam, prm, Rcw, Pcw, frame_pos, vm->pts[pj], vm->fts.data(), vm->pool.data(), img, depth.data(),
+                           patch_wrap.data(), patch_cur.data(), shared8, &level, &error))
+            continue;
+        vm->sel_index.push_back(i);
+        vm->sel_point.push_back(pj);
+        vm->sel_level.push_back(level);
+        vm->sel_error.push_back(error);
+        vm->sel_patch.insert(vm->sel_patch.end(), patch_wrap.begin(), patch_wrap.end());
+    }
+    return (int)vm->sel_index.size();
+}
+
+void emu_vm_selected(void* h, int* index, int* point, int* level, float* error, double* pos, float* patch) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    const size_t n = vm->sel_index.size();
+    std::memcpy(index, vm->sel_index.data(), n * sizeof(int));
+    std::memcpy(point, vm->sel_point.data(), n * sizeof(int));
+    std::memcpy(level, vm->sel_level.data(), n * sizeof(int));
+    std::memcpy(error, vm->sel_error.data(), n * sizeof(float));
+    std::memcpy(patch, vm->sel_patch.data(), n * 192 * sizeof(float));
+    for (size_t i = 0; i < n; ++i) std::memcpy(pos + 3 * i, vm->pts[vm->sel_point[i]].pos, 3 * sizeof(double));
+}
+
+int emu_vm_grow(void* h, const unsigned char* img, const double* Rcw, const double* Pcw, const float* pg, int n, int frame_id) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    const CamModel& cam = vm->cam;
+    const VmParams& prm = vm->prm;
+    const int border = (prm.halfpatch + 1) * 8;
+    // candidate scoring: {ordered score bits : ~index} atomicMax per cell, seeded with the incoming value
+    std::vector<int> winner(prm.length, -1);
+    for (int i = 0; i < n; ++i) {
+        float score = 0.0f;
+        const int cell = visual_candidate(cam, Rcw, Pcw, img, cam.width, pg + 3 * i, prm.grid_size, prm.grid_n_height, border, &score);
+        if (cell < 0) continue;
+        if (score > vm->map_value[cell]) { vm->map_value[cell] = score; winner[cell] = i; }
+    }
+    int add = 0;
+    for (int c = 0; c < prm.length; ++c) {
+        if (winner[c] < 0) continue;
+        const double pt[3] = {pg[3 * winner[c]], pg[3 * winner[c] + 1], pg[3 * winner[c] + 2]};
+        double pf[3], pc[2];
+        se3_apply(Rcw, Pcw, pt, pf);
+        world2cam(cam, pf, pc);
+        VmPoint p;
+        std::memset(&p, 0, sizeof(p));
+        std::memcpy(p.pos, pt, sizeof(pt));
+        p.value = vm->map_value[c];
+        p.n_obs = 0;
+        vm_feat_key(pt, p.key);
+        vm->pts.push_back(p);
+        const int slot = emu_store_image(vm, img, frame_id);
+        emu_push_feature(vm, (int)vm->pts.size() - 1, pc, Rcw, Pcw, vm->map_value[c], 0, frame_id, slot);
+        add++;
+    }
+    return add;
+}
+
+int emu_vm_add_observations(void* h, const unsigned char* img, const double* Rcw, const double* Pcw, int frame_id) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    double cur_pos[3];
+    se3_pos(Rcw, Pcw, cur_pos);
+    int added = 0;
+    for (size_t i = 0; i < vm->sel_index.size(); ++i) {
+        VmPoint& pt = vm->pts[vm->sel_point[i]];
+        double pc[2];
+        int erase_slot;
+        const bool add_flag = vm_observation_test(vm->cam, Rcw, Pcw, cur_pos, pt, vm->fts.data(), pc, &erase_slot);
+        if (erase_slot >= 0) {
+            for (int q = erase_slot; q + 1 < pt.n_obs; ++q) pt.obs[q] = pt.obs[q + 1];
+            pt.n_obs--;
+        }
+        if (add_flag) {
+            pt.value = shi_tomasi_score(img, vm->cam.width, vm->cam.height, vm->cam.width, (int)pc[0], (int)pc[1]);
+            const int slot = emu_store_image(vm, img, frame_id);
+            emu_push_feature(vm, vm->sel_point[i], pc, Rcw, Pcw, pt.value, vm->sel_level[i], frame_id, slot);
+            added++;
+        }
+    }
+    return added;
+}
+
+void emu_vm_dump_points(void* h, double* pos, float* value, int* n_obs, int* obs20) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    for (size_t j = 0; j < vm->pts.size(); ++j) {
+        std::memcpy(pos + 3 * j, vm->pts[j].pos, 3 * sizeof(double));
+        value[j] = vm->pts[j].value;
+        n_obs[j] = vm->pts[j].n_obs;
+        for (int q = 0; q < 20; ++q) obs20[20 * j + q] = q < vm->pts[j].n_obs ? vm->pts[j].obs[q] : -1;
+    }
+}
+void emu_vm_dump_features(void* h, double* geo17, float* score, int* level_id_img) {
+    EmuVm* vm = static_cast<EmuVm*>(h);
+    for (size_t j = 0; j < vm->fts.size(); ++j) {
+        const VmFeature& f = vm->fts[j];
+        double* g = geo17 + 17 * j;
+        g[0] = f.px[0]; g[1] = f.px[1];
+        std::memcpy(g + 2, f.f, 3 * sizeof(double));
+        std::memcpy(g + 5, f.R, 9 * sizeof(double));
+        std::memcpy(g + 14, f.t, 3 * sizeof(double));
+        score[j] = f.score;
+        level_id_img[3 * j] = f.level; level_id_img[3 * j + 1] = f.id; level_id_img[3 * j + 2] = f.img;
+    }
+}
+
+}  // extern "C"
