@@ -143,6 +143,12 @@ class VioReport(C.Structure):
                 ("skipped_last", C.c_int), ("cov_updated", C.c_int), ("status", C.c_int)]
 
 
+class VmapParams(C.Structure):
+    """flb_vmap_params (include/fastlivo_b200.h)."""
+    _fields_ = [("grid_size", C.c_int), ("ncc_en", C.c_int), ("outlier_threshold", C.c_double), ("ncc_thre", C.c_double),
+                ("Rcl", C.c_double * 9), ("Pcl", C.c_double * 3), ("R_LI", C.c_double * 9), ("t_LI", C.c_double * 3)]
+
+
 class VioEq(C.Structure):
     _fields_ = [("HTH", C.c_double * 36), ("HTz", C.c_double * 6), ("error", C.c_float),
                 ("n_meas", C.c_int64), ("skipped", C.c_int)]
@@ -156,6 +162,8 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
            "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach",
            "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
+           "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
+           "flb_vmap_map_value", "flb_vmap_dump",
            "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps"]
 
 
@@ -213,6 +221,14 @@ def lib():
         L.flb_vio_pass.argtypes = [vp, C.POINTER(VioParams), vp, vp, C.c_int, C.POINTER(VioEq)]
         L.flb_vio_export.argtypes = [vp, vp, vp, vp]
         L.flb_vio_errors.argtypes = [vp, vp, C.c_int]
+        L.flb_vmap_reset.argtypes = [vp, C.POINTER(VmapParams)]
+        L.flb_vmap_select.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        L.flb_vmap_selected.argtypes = [vp, C.c_int, C.POINTER(C.c_int)] + [vp] * 6
+        L.flb_vmap_grow.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
+        L.flb_vmap_add_observations.argtypes = [vp, vp, vp, C.c_int]
+        L.flb_vmap_counts.argtypes = [vp] + [C.POINTER(C.c_int)] * 5
+        L.flb_vmap_map_value.argtypes = [vp, vp, C.c_int]
+        L.flb_vmap_dump.argtypes = [vp, C.c_int, C.c_int] + [vp] * 7
         L.flb_vio_update.argtypes = [vp, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18), C.POINTER(VioReport)]
         L.flb_state_upload.argtypes = [vp, C.POINTER(State18), C.POINTER(State18)]
         L.flb_state_download.argtypes = [vp, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
@@ -437,6 +453,76 @@ class Handle:
                                               int(grid_size), int(border), mv.ctypes.data_as(C.c_void_p),
                                               win.ctypes.data_as(C.c_void_p)))
         return mv, win
+
+    # ---- device-resident visual map (rows f2 / f4)
+    def vmap_reset(self, seq_or_frame, grid_size=40, outlier_threshold=100.0, ncc_en=0, ncc_thre=0.0):
+        """flb_vmap_reset; the extrinsics come from a synthetic frame / sequence dict (Rcl, Pcl, R_LI, t_LI)."""
+        p = VmapParams()
+        p.grid_size, p.ncc_en, p.outlier_threshold, p.ncc_thre = int(grid_size), int(ncc_en), float(outlier_threshold), float(ncc_thre)
+        p.Rcl[:] = np.asarray(seq_or_frame["Rcl"], np.float64).ravel()
+        p.Pcl[:] = np.asarray(seq_or_frame["Pcl"], np.float64)
+        p.R_LI[:] = np.asarray(seq_or_frame["R_LI"], np.float64).ravel()
+        p.t_LI[:] = np.asarray(seq_or_frame["t_LI"], np.float64)
+        self._ck(self.L.flb_vmap_reset(self.h, C.byref(p)))
+
+    @staticmethod
+    def _pose(Rcw, Pcw):
+        if Rcw is None:
+            return None, None, None, None
+        R = np.ascontiguousarray(Rcw, np.float64)
+        P = np.ascontiguousarray(Pcw, np.float64)
+        return R, P, R.ctypes.data_as(C.c_void_p), P.ctypes.data_as(C.c_void_p)
+
+    def vmap_select(self, Rcw, Pcw, pg_down, blocking=True):
+        """flb_vmap_select.  blocking: returns the number of selected patches; else enqueue-only (returns None)."""
+        R, P, pr, pp = self._pose(Rcw, Pcw)
+        pg = np.ascontiguousarray(pg_down, np.float32).reshape(-1, 3)
+        n = C.c_int()
+        self._ck(self.L.flb_vmap_select(self.h, pr, pp, _p(pg), len(pg), 3, C.byref(n) if blocking else None))
+        if blocking:
+            self.Pn = n.value
+            return n.value
+        return None
+
+    def vmap_selected(self):
+        n = C.c_int()
+        self._ck(self.L.flb_vmap_selected(self.h, 0, C.byref(n), None, None, None, None, None, None))
+        m = n.value
+        o = dict(index=np.zeros(m, np.int32), point=np.zeros(m, np.int32), search_level=np.zeros(m, np.int32),
+                 error=np.zeros(m, np.float32), pos=np.zeros((m, 3)), patch=np.zeros((m, 192), np.float32))
+        if m:
+            self._ck(self.L.flb_vmap_selected(self.h, m, C.byref(n), _p(o["index"]), _p(o["point"]), _p(o["search_level"]), _p(o["error"]),
+                                              _p(o["pos"]), _p(o["patch"])))
+        self.Pn = m
+        return o
+
+    def vmap_grow(self, Rcw, Pcw, pg, frame_id):
+        R, P, pr, pp = self._pose(Rcw, Pcw)
+        pg = np.ascontiguousarray(pg, np.float32).reshape(-1, 3)
+        self._ck(self.L.flb_vmap_grow(self.h, pr, pp, _p(pg), len(pg), 3, int(frame_id)))
+
+    def vmap_add_observations(self, Rcw, Pcw, frame_id):
+        R, P, pr, pp = self._pose(Rcw, Pcw)
+        self._ck(self.L.flb_vmap_add_observations(self.h, pr, pp, int(frame_id)))
+
+    def vmap_counts(self):
+        v = [C.c_int() for _ in range(5)]
+        self._ck(self.L.flb_vmap_counts(self.h, *[C.byref(x) for x in v]))
+        return dict(points=v[0].value, features=v[1].value, images=v[2].value, selected=v[3].value, last_added=v[4].value)
+
+    def vmap_map_value(self, length):
+        out = np.zeros(length, np.float32)
+        self._ck(self.L.flb_vmap_map_value(self.h, _p(out), length))
+        return out
+
+    def vmap_dump(self):
+        c = self.vmap_counts()
+        n, m = c["points"], c["features"]
+        d = dict(pos=np.zeros((n, 3)), value=np.zeros(n, np.float32), n_obs=np.zeros(n, np.int32), obs=np.zeros((n, 20), np.int32),
+                 ft_geo=np.zeros((m, 17)), ft_score=np.zeros(m, np.float32), ft_level_id_img=np.zeros((m, 3), np.int32))
+        self._ck(self.L.flb_vmap_dump(self.h, n, m, _p(d["pos"]), _p(d["value"]), _p(d["n_obs"]), _p(d["obs"]), _p(d["ft_geo"]),
+                                      _p(d["ft_score"]), _p(d["ft_level_id_img"])))
+        return d
 
     # ---- IMU propagation + undistortion (row f3)
     def imu_undistort(self, prm: ImuParams, carry: ImuCarry, v_imu, pcl_beg_time, pcl_end_time, pts, offset_index=3):

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "flb_kernels.cuh"
+#include "flb_vmap.cuh"
 
 using namespace flb;
 
@@ -230,6 +231,28 @@ struct flb_handle {
     bool cam_set = false;
     CamModel cam{};
     bool last_vio_valid = false;
+
+    // device-resident visual map (rows f2 / f4)
+    struct Vm {
+        bool on = false;
+        VmParams prm{};
+        double Rci_Pci[12] = {0};            // camera <- IMU extrinsic (LidarSelector::init, :44-45)
+        DevBuf<VmPoint> pts;
+        DevBuf<VmFeature> fts;
+        DevBuf<unsigned char> pool;          // keyframe images, pool_slots x (w * h)
+        int pool_slots = 0;
+        int pts_ub = 0, fts_ub = 0, img_ub = 0;   // host-side upper bounds of the device counters
+        DevBuf<int> counters;
+        DevBuf<double> pose, rci;            // T_f_w of the current frame (12) ; Rci | Pci (12)
+        DevBuf<float> pg;                    // scan points of the current call
+        DevBuf<unsigned long long> depth, keyset, cell_best, cand_key;
+        unsigned key_mask = 0;
+        DevBuf<unsigned char> cell_type;
+        DevBuf<float> map_value, cell_err, cell_patch, sel_error;
+        DevBuf<int> cell_flag, cell_rank, cell_level, cell_point, sel_index, sel_point, winner, scan_tmp;
+        Staging st_pg;
+    } vm;
+    bool pn_on_device = false;   // the patch list was built on the device (flb_vmap_select without a count readback)
 
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -544,11 +567,26 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     return FLB_OK;
 }
 
+// The patch list of the last flb_vmap_select lives on the device; calls that need its length on the host fetch it here.
+int resolve_pn(flb_handle* h) {
+    if (!h->pn_on_device) return FLB_OK;
+    int n = 0;
+    FLB_CUDA(h, cudaMemcpyAsync(&n, h->vm.counters.p + VM_N_SEL, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->Pn = n;
+    h->pn_on_device = false;
+    return FLB_OK;
+}
+
 int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update: camera and image must be set first");
     if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_vio_update: no device state (flb_state_upload)");
     if (prm->max_iteration > 1000) return fail(h, FLB_ERR_INVALID, "max_iteration outside [0, 1000]");
+    if (h->pn_on_device && !(h->cfg.persistent && h->p2p.world <= 1 && !h->comm && prm->max_iteration > 0)) {
+        int rcp = resolve_pn(h);             // only the single-GPU persistent kernel reads the count on the device
+        if (rcp) return rcp;
+    }
     VioParamsDev d;
     to_dev_params(prm, d);
     VioSolveArgs s{};
@@ -571,7 +609,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (fused && !h->cfg.persistent)
         return fail(h, FLB_ERR_STATE, "the fused NVLink exchange lives in the persistent kernels (flb_config.persistent = 1)");
     if (fused && h->Pn > kP2PErrCap) return fail(h, FLB_ERR_INVALID, "fused multi-GPU mode: at most %d patches per rank", kP2PErrCap);
-    const bool persistent = h->cfg.persistent && (fused || (!h->comm && h->Pn > 0)) && prm->max_iteration > 0;
+    const bool persistent = h->cfg.persistent && (fused || (!h->comm && (h->Pn > 0 || h->pn_on_device))) && prm->max_iteration > 0;
     if (!persistent) {
         LaunchScope ls(h, FAM_SOLVE);
         k_vio_begin<<<1, 32, 0, h->stream>>>(h->vio_ctrl.p, h->Pn);
@@ -593,12 +631,18 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     a.err_stride = h->err_stride;
     a.partials = h->partials.p;
     a.p2p = h->p2p;
+    a.Pn_dev = nullptr;
+    if (h->pn_on_device) {                   // capacity = one patch per grid cell; the kernel reads the real count
+        a.Pn = h->vm.prm.length;
+        a.Pn_dev = h->vm.counters.p + VM_N_SEL;
+        s.Pn_total = a.Pn;
+    }
     const int nb = vio_nblocks(h);
     if (persistent) {
         // patches are dealt warp-round-robin over the worker blocks; one more block is the leader
         const int cap = h->occ_vio * h->num_sms;
         if (cap < 2) return fail(h, FLB_ERR_STATE, "persistent mode needs two co-resident blocks");
-        const int workers = std::max(1, std::min(std::max(h->Pn, 1), cap - 1));
+        const int workers = std::max(1, std::min(std::max(a.Pn, 1), cap - 1));
         const int grid = workers + 1;
         FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)grid * kVioPacked, h->partials.cap)));
         a.partials = h->partials.p;
@@ -617,7 +661,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
             h->dbg_vio_blocks = grid;
         }
         // staging capacity for the errors of ALL ranks (the peers' shard sizes are not known here: assume like ours + slack)
-        int err_cap = (int)std::min<long long>(kVioErrCapMax, std::max<long long>(2048, ((long long)h->Pn * std::max(h->p2p.world, 1) * 5 / 4 + 319) / 256 * 256));
+        int err_cap = (int)std::min<long long>(kVioErrCapMax, std::max<long long>(2048, ((long long)a.Pn * std::max(h->p2p.world, 1) * 5 / 4 + 319) / 256 * 256));
         void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap};
         LaunchScope ls(h, FAM_VIO);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args,
@@ -731,6 +775,14 @@ int flb_destroy(flb_handle* h) {
         if (h->p2p_peer_ptr[r]) cudaIpcCloseMemHandle(h->p2p_peer_ptr[r]);
     h->mailbox.release();
     h->p2p_seq.release();
+    {
+        auto& vm = h->vm;
+        vm.pts.release(); vm.fts.release(); vm.pool.release(); vm.counters.release(); vm.pose.release(); vm.rci.release(); vm.pg.release();
+        vm.depth.release(); vm.keyset.release(); vm.cell_best.release(); vm.cand_key.release(); vm.cell_type.release(); vm.map_value.release();
+        vm.cell_err.release(); vm.cell_patch.release(); vm.sel_error.release(); vm.cell_flag.release(); vm.cell_rank.release();
+        vm.cell_level.release(); vm.cell_point.release(); vm.sel_index.release(); vm.sel_point.release(); vm.winner.release();
+        vm.scan_tmp.release(); vm.st_pg.release();
+    }
     for (auto& ev : h->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     h->map_raw.release(); h->keys.release(); h->keys_sorted.release(); h->vals.release(); h->vals_sorted.release();
     h->map_comb.release(); h->boxes.release(); h->vkeys.release(); h->vkeys_sorted.release(); h->keep.release(); h->sel_idx.release();
@@ -1548,6 +1600,7 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     }
     FLB_CUDA(h, cudaMemsetAsync(h->errors.p, 0, h->errors.cap * sizeof(float), h->stream));
     h->Pn = Pn;
+    h->pn_on_device = false;
     h->last_vio_valid = false;
     return FLB_OK;
 }
@@ -1575,6 +1628,7 @@ int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], co
     if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_pass: camera and image must be set first");
     if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
     std::memset(out, 0, sizeof(*out));
+    { int rcp = resolve_pn(h); if (rcp) return rcp; }
     if (h->Pn == 0) return FLB_OK;
     { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
     const size_t Pn = h->Pn;
@@ -1656,6 +1710,7 @@ int flb_vio_export(flb_handle* h, double* z, double* H_sub, float* errors) {
 int flb_vio_errors(flb_handle* h, float* errors, int capacity) {
     FLB_CHECK_H(h);
     if (!errors || capacity < 0) return fail(h, FLB_ERR_INVALID, "flb_vio_errors: bad arguments");
+    { int rcp = resolve_pn(h); if (rcp) return rcp; }
     const int n = std::min(capacity, h->Pn);
     if (n == 0) return FLB_OK;
     // which half the last executed pass of the last update wrote is part of the device control block
@@ -1843,6 +1898,351 @@ int flb_comm_destroy(flb_handle* h) {
     if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     h->world = 1;
     h->rank = 0;
+    return FLB_OK;
+}
+
+}  // extern "C"
+
+// =======================================================================================
+// Device-resident visual map
+// =======================================================================================
+namespace {
+
+int vm_check(flb_handle* h, const char* who) {
+    if (!h->vm.on) return fail(h, FLB_ERR_STATE, "%s: flb_vmap_reset first", who);
+    if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "%s: camera and image must be set first", who);
+    if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
+    return FLB_OK;
+}
+
+// Upload (or derive from the device state) T_f_w of the current frame into vm.pose.
+int vm_set_pose(flb_handle* h, const double* Rcw, const double* Pcw) {
+    if (Rcw && Pcw) {
+        void* stv = nullptr;
+        FLB_CUDA(h, h->st_misc.acquire(12 * sizeof(double), &stv));
+        double* st = static_cast<double*>(stv);
+        std::memcpy(st, Rcw, 9 * sizeof(double));
+        std::memcpy(st + 9, Pcw, 3 * sizeof(double));
+        FLB_CUDA(h, cudaMemcpyAsync(h->vm.pose.p, st, 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        FLB_CUDA(h, h->st_misc.mark(h->stream));
+    } else {
+        if (!h->state_valid) return fail(h, FLB_ERR_STATE, "visual map: no pose given and no device state");
+        LaunchScope ls(h, FAM_OTHER);
+        k_vm_pose_from_state<<<1, 32, 0, h->stream>>>(&h->states.p[0], h->vm.rci.p, h->vm.pose.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    return FLB_OK;
+}
+
+// points of this call -> vm.pg (packed xyz)
+int vm_upload_points(flb_handle* h, const float* xyz, int n, int stride) {
+    const size_t n1 = (size_t)std::max(n, 1);
+    FLB_CUDA(h, h->vm.pg.reserve(n1 * 3));
+    if (n == 0) return FLB_OK;
+    void* stv = nullptr;
+    FLB_CUDA(h, h->vm.st_pg.acquire(n1 * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v) || std::fabs(v) > 5.0e5f) return fail(h, FLB_ERR_INVALID, "visual map: coordinate %d non-finite or beyond 2^20 voxels", i);
+            st[3 * (size_t)i + k] = v;
+        }
+    FLB_CUDA(h, cudaMemcpyAsync(h->vm.pg.p, st, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->vm.st_pg.mark(h->stream));
+    return FLB_OK;
+}
+
+template <typename T>
+int vm_grow_buf(flb_handle* h, DevBuf<T>& b, size_t used_ub, size_t need) {
+    if (need <= b.cap) return FLB_OK;
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    DevBuf<T> nb;
+    FLB_CUDA(h, nb.reserve(std::max(need, b.cap * 2)));
+    if (b.p && used_ub) FLB_CUDA(h, cudaMemcpy(nb.p, b.p, std::min(used_ub, b.cap) * sizeof(T), cudaMemcpyDeviceToDevice));
+    b.release();
+    b = nb;
+    return FLB_OK;
+}
+
+// Make room for `add_p` more points, `add_f` more features and one more keyframe image.  The host only keeps upper
+// bounds of the device counters; when a bound hits the capacity it is refreshed from the device before anything grows.
+int vm_ensure_capacity(flb_handle* h, int add_p, int add_f) {
+    auto& vm = h->vm;
+    const size_t img_bytes = (size_t)h->img_w * h->img_h;
+    if ((size_t)(vm.pts_ub + add_p) > vm.pts.cap || (size_t)(vm.fts_ub + add_f) > vm.fts.cap || vm.img_ub + 1 > vm.pool_slots) {
+        int c[VM_COUNTERS];
+        FLB_CUDA(h, cudaMemcpyAsync(c, vm.counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+        FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+        vm.pts_ub = c[VM_N_POINTS];
+        vm.fts_ub = c[VM_N_FEATS];
+        vm.img_ub = c[VM_N_IMAGES];
+    }
+    { int rc = vm_grow_buf(h, vm.pts, (size_t)vm.pts_ub, (size_t)(vm.pts_ub + add_p)); if (rc) return rc; }
+    { int rc = vm_grow_buf(h, vm.fts, (size_t)vm.fts_ub, (size_t)(vm.fts_ub + add_f)); if (rc) return rc; }
+    if (vm.img_ub + 1 > vm.pool_slots) {
+        const int slots = std::max(vm.pool_slots * 2, 16);
+        FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+        DevBuf<unsigned char> nb;
+        FLB_CUDA(h, nb.reserve((size_t)slots * img_bytes));
+        if (vm.pool.p && vm.img_ub) FLB_CUDA(h, cudaMemcpy(nb.p, vm.pool.p, (size_t)vm.img_ub * img_bytes, cudaMemcpyDeviceToDevice));
+        vm.pool.release();
+        vm.pool = nb;
+        vm.pool_slots = slots;
+    }
+    return FLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flb_vmap_reset(flb_handle* h, const flb_vmap_params* p) {
+    FLB_CHECK_H(h);
+    if (!p || p->grid_size < 1) return fail(h, FLB_ERR_INVALID, "flb_vmap_reset: bad parameters");
+    if (!h->cam_set) return fail(h, FLB_ERR_STATE, "flb_vmap_reset: flb_camera_set first");
+    auto& vm = h->vm;
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    VmParams q{};
+    q.grid_size = p->grid_size;
+    q.grid_n_width = h->cam.width / p->grid_size;                  // :55-57
+    q.grid_n_height = h->cam.height / p->grid_size;
+    q.length = q.grid_n_width * q.grid_n_height;
+    q.halfpatch = 4;
+    q.ncc_en = p->ncc_en;
+    q.outlier_threshold = p->outlier_threshold;
+    q.ncc_thre = p->ncc_thre;
+    if (q.length < 1) return fail(h, FLB_ERR_INVALID, "flb_vmap_reset: grid_size larger than the image");
+    vm.prm = q;
+    {   // Rci / Pci (LidarSelector::init :44-45, set_extrinsic :35-39)
+        double Rli[9], Pli[3], t[3];
+        m3_T(p->R_LI, Rli);
+        m3_vec(Rli, p->t_LI, t);
+        for (int i = 0; i < 3; ++i) Pli[i] = -t[i];
+        m3_mul(p->Rcl, Rli, vm.Rci_Pci);
+        m3_vec(p->Rcl, Pli, t);
+        for (int i = 0; i < 3; ++i) vm.Rci_Pci[9 + i] = t[i] + p->Pcl[i];
+    }
+    const size_t L = (size_t)q.length, npix = (size_t)h->cam.width * h->cam.height;
+    FLB_CUDA(h, vm.counters.reserve(VM_COUNTERS));
+    FLB_CUDA(h, vm.pose.reserve(12));
+    FLB_CUDA(h, vm.rci.reserve(12));
+    FLB_CUDA(h, vm.depth.reserve(npix));
+    FLB_CUDA(h, vm.cell_best.reserve(L));
+    FLB_CUDA(h, vm.cand_key.reserve(L));
+    FLB_CUDA(h, vm.cell_type.reserve(L));
+    FLB_CUDA(h, vm.map_value.reserve(L));
+    FLB_CUDA(h, vm.cell_err.reserve(L));
+    FLB_CUDA(h, vm.cell_patch.reserve(L * 192));
+    FLB_CUDA(h, vm.sel_error.reserve(L));
+    FLB_CUDA(h, vm.cell_flag.reserve(L));
+    FLB_CUDA(h, vm.cell_rank.reserve(L));
+    FLB_CUDA(h, vm.cell_level.reserve(L));
+    FLB_CUDA(h, vm.cell_point.reserve(L));
+    FLB_CUDA(h, vm.sel_index.reserve(L));
+    FLB_CUDA(h, vm.sel_point.reserve(L));
+    FLB_CUDA(h, vm.winner.reserve(L));
+    FLB_CUDA(h, vm.scan_tmp.reserve(2 * L));
+    FLB_CUDA(h, vm.pts.reserve(std::max<size_t>(4 * L, 1024)));
+    FLB_CUDA(h, vm.fts.reserve(std::max<size_t>(8 * L, 2048)));
+    // the VIO kernel's inputs are the selection's outputs: one patch per grid cell at most
+    FLB_CUDA(h, h->patch_pos.reserve(L * 3));
+    FLB_CUDA(h, h->patch_ref.reserve(L * 192));
+    FLB_CUDA(h, h->patch_level.reserve(L));
+    int c[VM_COUNTERS] = {0};
+    c[VM_IMG_FRAME] = -1;
+    c[VM_IMG_SLOT] = -1;
+    FLB_CUDA(h, cudaMemcpy(vm.counters.p, c, sizeof(c), cudaMemcpyHostToDevice));
+    FLB_CUDA(h, cudaMemcpy(vm.rci.p, vm.Rci_Pci, sizeof(vm.Rci_Pci), cudaMemcpyHostToDevice));
+    FLB_CUDA(h, cudaMemset(vm.map_value.p, 0, L * sizeof(float)));   // init(), :66
+    vm.pts_ub = vm.fts_ub = vm.img_ub = 0;
+    vm.on = true;
+    return FLB_OK;
+}
+
+int flb_vmap_select(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* pg_down, int n, int stride, int* n_selected) {
+    FLB_CHECK_H(h);
+    { int rc = vm_check(h, "flb_vmap_select"); if (rc) return rc; }
+    if (n < 0 || (n > 0 && !pg_down) || stride < 3) return fail(h, FLB_ERR_INVALID, "flb_vmap_select: bad arguments");
+    auto& vm = h->vm;
+    const int L = vm.prm.length, border = (vm.prm.halfpatch + 1) * 8;
+    { int rc = vm_set_pose(h, Rcw, Pcw); if (rc) return rc; }
+    { int rc = vm_upload_points(h, pg_down, n, stride); if (rc) return rc; }
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }                 // the current image has landed
+    size_t nkeys = 1024;
+    while (nkeys < 2 * (size_t)std::max(n, 1)) nkeys <<= 1;
+    FLB_CUDA(h, vm.keyset.reserve(nkeys));
+    vm.key_mask = (unsigned)(nkeys - 1);
+    const size_t npix = (size_t)h->cam.width * h->cam.height;
+    // per-patch error buffers of the VIO update that follows: capacity = one patch per grid cell
+    FLB_CUDA(h, h->errors.reserve(2 * (size_t)L));
+    h->err_stride = std::max(h->err_stride, L);
+    FLB_CUDA(h, h->errors.reserve(2 * (size_t)h->err_stride));
+    FLB_CUDA(h, h->partials.reserve(std::max<size_t>((size_t)(L / 8 + 2) * kVioPacked, h->partials.cap)));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vm_clear<<<h->num_sms * 2, 256, 0, h->stream>>>(vm.depth.p, npix, vm.keyset.p, nkeys, vm.cell_best.p, vm.cell_type.p, vm.map_value.p,
+                                                          vm.cell_flag.p, L, vm.counters.p);
+        if (n > 0)
+            k_vm_scan<<<(n + 255) / 256, 256, 0, h->stream>>>(h->cam, vm.pose.p, vm.pg.p, n, border, vm.keyset.p, vm.key_mask, vm.depth.p,
+                                                              vm.counters.p);
+        const int np = std::max(vm.pts_ub, 1);
+        k_vm_candidates<<<(np + 255) / 256, 256, 0, h->stream>>>(h->cam, vm.prm, vm.pose.p, vm.pts.p, vm.counters.p, vm.keyset.p, vm.key_mask,
+                                                                 border, vm.cell_best.p, vm.cell_type.p,
+                                                                 reinterpret_cast<int*>(vm.map_value.p));
+        k_vm_build<<<(L + kVmBuildWarps - 1) / kVmBuildWarps, kVmBuildWarps * 32, 0, h->stream>>>(
+            h->cam, vm.prm, vm.pose.p, vm.pts.p, vm.fts.p, vm.pool.p, h->img.p, vm.depth.p, vm.cell_best.p, vm.cell_type.p, vm.counters.p,
+            vm.cell_flag.p, vm.cell_level.p, vm.cell_point.p, vm.cell_err.p, vm.cell_patch.p);
+        k_vm_rank<<<1, 1024, 0, h->stream>>>(vm.cell_flag.p, L, vm.cell_rank.p, vm.counters.p);
+        k_vm_scatter<<<(L + 7) / 8, 256, 0, h->stream>>>(L, vm.cell_flag.p, vm.cell_rank.p, vm.cell_level.p, vm.cell_point.p, vm.cell_err.p,
+                                                         vm.cell_patch.p, vm.pts.p, h->patch_pos.p, h->patch_ref.p, h->patch_level.p,
+                                                         vm.sel_index.p, vm.sel_point.p, vm.sel_error.p);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 5;
+    }
+    { int rcq = vio_inputs_release(h); if (rcq) return rcq; }
+    h->pn_on_device = true;
+    h->Pn = L;
+    h->last_vio_valid = false;
+    if (n_selected) {
+        int rc = resolve_pn(h);
+        if (rc) return rc;
+        *n_selected = h->Pn;
+    }
+    return FLB_OK;
+}
+
+int flb_vmap_selected(flb_handle* h, int capacity, int* n_out, int* index, int* point, int* search_level, float* error, double* pos,
+                      float* patch) {
+    FLB_CHECK_H(h);
+    { int rc = vm_check(h, "flb_vmap_selected"); if (rc) return rc; }
+    auto& vm = h->vm;
+    int n = 0;
+    FLB_CUDA(h, cudaMemcpyAsync(&n, vm.counters.p + VM_N_SEL, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n_out) *n_out = n;
+    const size_t m = (size_t)std::min(std::max(capacity, 0), n);
+    if (m == 0) return FLB_OK;
+    cudaStream_t s = h->stream;
+    if (index) FLB_CUDA(h, cudaMemcpyAsync(index, vm.sel_index.p, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (point) FLB_CUDA(h, cudaMemcpyAsync(point, vm.sel_point.p, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (search_level) FLB_CUDA(h, cudaMemcpyAsync(search_level, h->patch_level.p, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (error) FLB_CUDA(h, cudaMemcpyAsync(error, vm.sel_error.p, m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (pos) FLB_CUDA(h, cudaMemcpyAsync(pos, h->patch_pos.p, m * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (patch) FLB_CUDA(h, cudaMemcpyAsync(patch, h->patch_ref.p, m * 192 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    FLB_CUDA(h, cudaStreamSynchronize(s));
+    return FLB_OK;
+}
+
+int flb_vmap_grow(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* pg, int n, int stride, int frame_id) {
+    FLB_CHECK_H(h);
+    { int rc = vm_check(h, "flb_vmap_grow"); if (rc) return rc; }
+    if (n < 0 || (n > 0 && !pg) || stride < 3 || frame_id < 0) return fail(h, FLB_ERR_INVALID, "flb_vmap_grow: bad arguments");
+    auto& vm = h->vm;
+    const int L = vm.prm.length, border = (vm.prm.halfpatch + 1) * 8;
+    { int rc = vm_ensure_capacity(h, L, L); if (rc) return rc; }
+    { int rc = vm_set_pose(h, Rcw, Pcw); if (rc) return rc; }
+    { int rc = vm_upload_points(h, pg, n, stride); if (rc) return rc; }
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
+    const size_t img_bytes = (size_t)h->img_w * h->img_h;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vm_store_image<<<h->num_sms, 256, 0, h->stream>>>(h->img.p, img_bytes, vm.pool.p, vm.counters.p, frame_id);
+        k_vmap_seed<<<(L + 255) / 256, 256, 0, h->stream>>>(vm.map_value.p, L, vm.cand_key.p);
+        if (n > 0)
+            k_vmap_candidates<<<(n + 127) / 128, 128, 0, h->stream>>>(h->cam, vm.pose.p, h->img.p, vm.pg.p, n, vm.prm.grid_size, vm.prm.grid_n_height,
+                                                                      border, vm.cand_key.p);
+        k_vmap_resolve<<<(L + 255) / 256, 256, 0, h->stream>>>(vm.cand_key.p, L, vm.map_value.p, vm.winner.p);
+        k_vm_materialise<<<1, 1024, 0, h->stream>>>(h->cam, L, vm.pose.p, vm.pg.p, vm.winner.p, vm.map_value.p, vm.scan_tmp.p, vm.pts.p, vm.fts.p,
+                                                    vm.counters.p, frame_id, (int)vm.pts.cap, (int)vm.fts.cap);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 4;
+    }
+    vm.pts_ub += L;
+    vm.fts_ub += L;
+    vm.img_ub += 1;
+    return vio_inputs_release(h);
+}
+
+int flb_vmap_add_observations(flb_handle* h, const double Rcw[9], const double Pcw[3], int frame_id) {
+    FLB_CHECK_H(h);
+    { int rc = vm_check(h, "flb_vmap_add_observations"); if (rc) return rc; }
+    if (frame_id < 0) return fail(h, FLB_ERR_INVALID, "flb_vmap_add_observations: bad arguments");
+    auto& vm = h->vm;
+    const int L = vm.prm.length;
+    { int rc = vm_ensure_capacity(h, 0, L); if (rc) return rc; }
+    { int rc = vm_set_pose(h, Rcw, Pcw); if (rc) return rc; }
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
+    const size_t img_bytes = (size_t)h->img_w * h->img_h;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vm_store_image<<<h->num_sms, 256, 0, h->stream>>>(h->img.p, img_bytes, vm.pool.p, vm.counters.p, frame_id);
+        k_vm_observe<<<1, 1024, 0, h->stream>>>(h->cam, vm.pose.p, h->img.p, vm.sel_point.p, h->patch_level.p, vm.scan_tmp.p, L, vm.pts.p,
+                                                vm.fts.p, vm.counters.p, frame_id, (int)vm.fts.cap);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    vm.fts_ub += L;
+    vm.img_ub += 1;
+    return vio_inputs_release(h);
+}
+
+int flb_vmap_counts(flb_handle* h, int* points, int* features, int* images, int* selected, int* last_added) {
+    FLB_CHECK_H(h);
+    if (!h->vm.on) return fail(h, FLB_ERR_STATE, "flb_vmap_counts: flb_vmap_reset first");
+    int c[VM_COUNTERS];
+    FLB_CUDA(h, cudaMemcpyAsync(c, h->vm.counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->vm.pts_ub = c[VM_N_POINTS];
+    h->vm.fts_ub = c[VM_N_FEATS];
+    h->vm.img_ub = c[VM_N_IMAGES];
+    if (points) *points = c[VM_N_POINTS];
+    if (features) *features = c[VM_N_FEATS];
+    if (images) *images = c[VM_N_IMAGES];
+    if (selected) *selected = c[VM_N_SEL];
+    if (last_added) *last_added = c[VM_LAST_ADDED];
+    if (c[VM_LAST_ADDED] < 0) return fail(h, FLB_ERR_STATE, "visual map: an append did not fit its buffers (internal capacity bound violated)");
+    return FLB_OK;
+}
+
+int flb_vmap_map_value(flb_handle* h, float* out, int capacity) {
+    FLB_CHECK_H(h);
+    if (!h->vm.on || !out) return fail(h, FLB_ERR_STATE, "flb_vmap_map_value: flb_vmap_reset first");
+    const size_t n = (size_t)std::min(capacity, h->vm.prm.length);
+    FLB_CUDA(h, cudaMemcpyAsync(out, h->vm.map_value.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FLB_OK;
+}
+
+int flb_vmap_dump(flb_handle* h, int cap_points, int cap_features, double* pos, float* value, int* n_obs, int* obs20, double* ft_geo17,
+                  float* ft_score, int* ft_level_id_img) {
+    FLB_CHECK_H(h);
+    if (!h->vm.on) return fail(h, FLB_ERR_STATE, "flb_vmap_dump: flb_vmap_reset first");
+    int np = 0, nf = 0;
+    { int rc = flb_vmap_counts(h, &np, &nf, nullptr, nullptr, nullptr); if (rc) return rc; }
+    np = std::min(np, cap_points);
+    nf = std::min(nf, cap_features);
+    std::vector<VmPoint> P((size_t)np);
+    std::vector<VmFeature> F((size_t)nf);
+    if (np) FLB_CUDA(h, cudaMemcpy(P.data(), h->vm.pts.p, (size_t)np * sizeof(VmPoint), cudaMemcpyDeviceToHost));
+    if (nf) FLB_CUDA(h, cudaMemcpy(F.data(), h->vm.fts.p, (size_t)nf * sizeof(VmFeature), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < np; ++j) {
+        if (pos) std::memcpy(pos + 3 * (size_t)j, P[j].pos, 3 * sizeof(double));
+        if (value) value[j] = P[j].value;
+        if (n_obs) n_obs[j] = P[j].n_obs;
+        if (obs20) for (int q = 0; q < 20; ++q) obs20[20 * (size_t)j + q] = q < P[j].n_obs ? P[j].obs[q] : -1;
+    }
+    for (int j = 0; j < nf; ++j) {
+        if (ft_geo17) {
+            double* g = ft_geo17 + 17 * (size_t)j;
+            g[0] = F[j].px[0]; g[1] = F[j].px[1];
+            std::memcpy(g + 2, F[j].f, 3 * sizeof(double));
+            std::memcpy(g + 5, F[j].R, 9 * sizeof(double));
+            std::memcpy(g + 14, F[j].t, 3 * sizeof(double));
+        }
+        if (ft_score) ft_score[j] = F[j].score;
+        if (ft_level_id_img) { ft_level_id_img[3 * (size_t)j] = F[j].level; ft_level_id_img[3 * (size_t)j + 1] = F[j].id; ft_level_id_img[3 * (size_t)j + 2] = F[j].img; }
+    }
     return FLB_OK;
 }
 

@@ -612,6 +612,8 @@ struct VioArgs {
     double* x_z;                 // Pn*64 or null
     double* x_H;                 // Pn*64*6 or null
     P2PArgs p2p;                 // world > 1 (persistent kernel only): per-patch errors are pushed to every rank
+    const int* Pn_dev;           // persistent kernel: when non-null the patch count is read from the device (the patch
+                                 // list was built there by the visual-map selection, flb_vmap_select) and Pn is its capacity
 };
 
 struct LatView {
@@ -1294,9 +1296,10 @@ template <int NT>
 __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSmem& sm, VioCtrl& c, float* s_err, bool first,
                                                  unsigned long long* pkt, unsigned flag, int resident,
                                                  unsigned long long* fine = nullptr, unsigned p2p_tag = 0u, int err_buf = 0,
-                                                 int err_cap = kErrChunk) {
+                                                 int err_cap = kErrChunk, int pn_override = -1) {
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     const int tid = threadIdx.x;
+    const int pn_total = pn_override >= 0 ? pn_override : s.Pn_total;
     const bool multi = p2p_tag != 0u;
     const int level = c.level;
     const float* errs_pass = s.errors + (size_t)err_buf * s.err_stride;     // this pass's half of the error buffer
@@ -1319,7 +1322,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                 sm.p2p_cnt[et] = (int)cnt;
             }
         } else if (et == 0) {
-            sm.p2p_cnt[0] = s.Pn_total;
+            sm.p2p_cnt[0] = pn_total;
         }
         asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
         int total = 0;
@@ -1857,9 +1860,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     extern __shared__ __align__(16) float s_err[];     // err_cap floats (dynamic): the leader's staging of the per-patch errors
     __shared__ unsigned long long s_seq_base;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (a.Pn <= 0 && s.p2p.world <= 1) return;                 // :969-970 (host also short-circuits)
     const int nworkers = (int)gridDim.x - 1;
     const bool is_leader = (int)blockIdx.x == nworkers;
+    const int Pn = a.Pn_dev ? min(*a.Pn_dev, a.Pn) : a.Pn;     // device-built patch list: its length lives on the device
+    if (Pn <= 0 && s.p2p.world <= 1) {                         // :969-970 (the host short-circuits when it knows)
+        if (is_leader && tid == 0) {
+            VioCtrl c;
+            c.level = 2; c.iteration = 0; c.stop = 1;
+            c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;
+            for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
+            c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0; c.err_buf = 0;
+            *s.ctrl = c;
+        }
+        return;
+    }
     const bool multi = s.p2p.world > 1;
     bool first = true;
     int pass_no = 0;
@@ -1876,9 +1890,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
         s_ctrl = c;
     }
     // every warp owns at most one patch: its pose-independent inputs stay in registers for all passes
-    const bool single = nworkers * NW >= a.Pn;
+    const bool single = nworkers * NW >= Pn;
     PatchIn pin;
-    if (single && !is_leader && blockIdx.x * NW + warp < a.Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
+    if (single && !is_leader && blockIdx.x * NW + warp < Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
     __syncthreads();
     int resident = 0;
     if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
@@ -1889,7 +1903,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             if (!leader_wait_arrivals(bar, (unsigned)nworkers * (unsigned)(pass_no + 1), s_bar)) return;
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[1 + 2 * pass_no] = global_ns();
             unsigned long long* fine = (trace && 32 + 8 * pass_no + 8 <= kTraceLen) ? trace + 32 + 8 * pass_no : nullptr;
-            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine, p2p_tag, pass_no & 1, err_cap);
+            vio_leader_solve<BLOCK>(s, sm, s_ctrl, s_err, first, pkt, flag, resident, fine, p2p_tag, pass_no & 1, err_cap, Pn);
             if (trace && tid == 0 && 2 + 2 * pass_no < kTraceLen) trace[2 + 2 * pass_no] = global_ns();
             vio_leader_finish<BLOCK>(s, sm, s_ctrl, first, false, resident);
             if (sm.flags[5]) {
@@ -1916,13 +1930,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 0] = global_ns();
             // fused multi-GPU mode: this rank's patch count of the pass goes out first (the leaders size their gather by it)
             if (multi && blockIdx.x == 0 && tid >= 32 && tid < 32 + s.p2p.world)
-                ll_store_line(&s.p2p.mail[tid - 32]->sums[p2p_tag & 1u][s.p2p.rank][31], (double)a.Pn, p2p_tag);
+                ll_store_line(&s.p2p.mail[tid - 32]->sums[p2p_tag & 1u][s.p2p.rank][31], (double)Pn, p2p_tag);
             if (tid == 0) vio_make_pose(a.prm.Rci, a.prm.Pci, a.prm.Jdphi_dR, a.prm.Jdp_dR, sm.x.rot, sm.x.pos, s_pose);
             __syncthreads();
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();
             const int level = s_ctrl.level;
             double accv = 0.0, n_meas = 0.0, skipped = 0.0;
-            for (int i = blockIdx.x * NW + warp; i < a.Pn; i += nworkers * NW) {
+            for (int i = blockIdx.x * NW + warp; i < Pn; i += nworkers * NW) {
                 if (!single) vio_patch_load(a, i, tid & 31, pin);
                 vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
                           dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1);

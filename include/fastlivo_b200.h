@@ -286,6 +286,50 @@ int flb_camera_set(flb_handle* h, const flb_camera* cam);
 int flb_visual_candidates(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* world_xyz, int n,
                           int stride_floats, int grid_size, int border, float* map_value, int* winner);
 
+/* ---- device-resident visual map ---------------------------------------
+ * The sparse visual map of LidarSelector -- feat_map (unordered_map<VOXEL_KEY, VOXEL_POINTS*>), its Points
+ * (include/point.h) with their observation lists of Features (include/feature.h) and the keyframe images those
+ * reference -- lives on the device.  Ids (points, features, images) are creation order.  The three calls are the
+ * three visual-map steps of LidarSelector::detect (src/lidar_selection.cpp:1027-1080); ComputeJ between them is
+ * flb_vio_update / flb_vio_update_enqueue, which consumes the patch list IN PLACE (no host round trip, no
+ * flb_patches_upload).  Rcw / Pcw = new_frame_->T_f_w_ (updateFrameState, :905-911); pass NULL for both to take
+ * it from the device state with the extrinsics given to flb_vmap_reset.  Single GPU.
+ * Needs flb_camera_set and the current frame uploaded with flb_image_upload. */
+typedef struct flb_vmap_params {
+    int    grid_size;          /* LidarSelector::grid_size (laserMapping.cpp:1198); one patch per grid cell */
+    int    ncc_en;             /* :549 */
+    double outlier_threshold;  /* :560 */
+    double ncc_thre;           /* :552 */
+    double Rcl[9], Pcl[3];     /* sparse_map->Rcl / Pcl */
+    double R_LI[9], t_LI[3];   /* set_extrinsic(transl, rot), :35-39 */
+} flb_vmap_params;
+/* clears the map (LidarSelector::init, :41-79) */
+int flb_vmap_reset(flb_handle* h, const flb_vmap_params* p);
+/* LidarSelector::addFromSparseMap (:346-587).  pg_down: the scan in the world frame after the caller's
+ * pcl::VoxelGrid (0.2 m, :7, :351-352), n x stride floats.  Builds sub_sparse_map on the device: positions, warped
+ * 3-level reference patches and search levels become the inputs of the next VIO update.  n_selected == NULL:
+ * enqueue-only (the count stays on the device); otherwise blocks and returns sub_sparse_map->index.size(). */
+int flb_vmap_select(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* pg_down, int n, int stride_floats,
+                    int* n_selected);
+/* sub_sparse_map of the last flb_vmap_select (blocking; any pointer may be NULL): index (grid cell), point (id),
+ * search_levels, propa_errors, voxel_points[i]->pos_, patch (3 x 64 floats each). */
+int flb_vmap_selected(flb_handle* h, int capacity, int* n, int* index, int* point, int* search_level, float* error, double* pos,
+                      float* patch);
+/* LidarSelector::addSparseMap (:142-202): Shi-Tomasi candidate per grid cell over pg (world frame, unfiltered scan),
+ * then one new Point + Feature per won cell (AddPoint, :204-230).  Enqueue-only. */
+int flb_vmap_grow(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* pg, int n, int stride_floats, int frame_id);
+/* LidarSelector::addObservation (:913-965) for the patches of the last flb_vmap_select, with the frame pose AFTER
+ * ComputeJ (NULL, NULL = the device state).  Enqueue-only. */
+int flb_vmap_add_observations(flb_handle* h, const double Rcw[9], const double Pcw[3], int frame_id);
+/* sizes (blocking): points, features, keyframe images, patches of the last selection, items appended by the last
+ * grow / add_observations call.  Any pointer may be NULL. */
+int flb_vmap_counts(flb_handle* h, int* points, int* features, int* images, int* selected, int* last_added);
+int flb_vmap_map_value(flb_handle* h, float* out, int capacity);       /* map_value[length] (:356, :455, :162) */
+/* the whole map (tests, debugging; blocking): per point pos (3 doubles), value, n_obs, newest-first feature ids
+ * (20, -1 padded); per feature px(2) f(3) T_f_w R(9) t(3) = 17 doubles, score, {level, frame id, image slot}. */
+int flb_vmap_dump(flb_handle* h, int cap_points, int cap_features, double* pos, float* value, int* n_obs, int* obs20, double* ft_geo17,
+                  float* ft_score, int* ft_level_id_img);
+
 /* One measurement pass of LidarSelector::UpdateState (src/lidar_selection.cpp:772-857)
  * at pose (R,p) and pyramid level `level`. */
 int flb_vio_pass(flb_handle* h, const flb_vio_params* prm, const double R[9], const double p[3], int level,
