@@ -199,7 +199,55 @@ inline flb_vio_report compute_j(flb_handle* h, const flb_vio_params& prm, const 
     to_abi(state_propagat, xp);
     check(h, flb_vio_update(h, &prm, &x, &xp, &rep));
     from_abi(x, state);
+    // sub_sparse_map->errors[i] = patch_error of the last executed pass (:851; display_keypatch reads it, :995)
+    std::vector<float> err(level.size());
+    check(h, flb_vio_errors(h, err.data(), (int)err.size()));
+    for (size_t k = 0; k < src.size(); ++k) sub_sparse_map.errors[src[k]] = err[k];
     return rep;
+}
+
+// ---- VIO: one pyramid level, float LidarSelector::UpdateState(cv::Mat img, float total_residual, int level)
+// (include/lidar_selection.h:72, src/lidar_selection.cpp:743-902).  The caller keeps its own ComputeJ loop (:974-981):
+//     for (level = 2; level >= 0; level--) now_error = flb::update_state(h, prm, img, *sub_sparse_map, *state, *state_propagat, error, level, G);
+//     if (now_error < error) state->cov -= G * state->cov;
+// G: the caller's 18 x 18 member (anything with operator()(i, j)); its first six columns are rewritten whenever a pass
+// of this call was accepted, exactly as :874 does.  The image / patch upload happens on the first level only
+// (level == 2) unless `upload` says otherwise.
+template <class Image, class SubMap, class StatesGroup, class Mat18>
+inline float update_state(flb_handle* h, const flb_vio_params& prm, const Image& img, SubMap& sub_sparse_map, StatesGroup& state,
+                          const StatesGroup& state_propagat, float total_residual, int level, Mat18& G, int upload = -1) {
+    const int total = (int)sub_sparse_map.index.size();
+    if (total == 0) return 0.f;                                    // :746
+    std::vector<int> src;
+    for (int i = 0; i < total; ++i)
+        if (sub_sparse_map.voxel_points[i] != nullptr) src.push_back(i);
+    if (upload > 0 || (upload < 0 && level == 2)) {
+        std::vector<double> pos;
+        std::vector<float> patch;
+        std::vector<int> lv;
+        for (int i : src) {
+            for (int k = 0; k < 3; ++k) pos.push_back(sub_sparse_map.voxel_points[i]->pos_(k));
+            patch.insert(patch.end(), sub_sparse_map.patch[i].begin(), sub_sparse_map.patch[i].begin() + 192);
+            lv.push_back(sub_sparse_map.search_levels[i]);
+        }
+        check(h, flb_image_upload(h, img.data, img.cols, img.rows, (int)img.step));
+        check(h, flb_patches_upload(h, pos.data(), patch.data(), lv.data(), (int)lv.size()));
+    }
+    flb_state18 x, xp;
+    to_abi(state, x);
+    to_abi(state_propagat, xp);
+    float last_error = 0.f;
+    double Gc[108];
+    flb_vio_report rep{};
+    check(h, flb_vio_update_level(h, &prm, level, total_residual, &x, &xp, &last_error, Gc, &rep));
+    from_abi(x, state);
+    if (rep.passes[level] > 0 && last_error < total_residual)     // at least one pass was accepted: G was rewritten (:874)
+        for (int i = 0; i < 18; ++i)
+            for (int j = 0; j < 6; ++j) G(i, j) = Gc[6 * i + j];
+    std::vector<float> err(src.size());
+    check(h, flb_vio_errors(h, err.data(), (int)err.size()));
+    for (size_t k = 0; k < src.size(); ++k) sub_sparse_map.errors[src[k]] = err[k];
+    return last_error;
 }
 
 // ---- IMU forward propagation + backward undistortion (src/IMU_Processing.cpp:655-808) ----------------

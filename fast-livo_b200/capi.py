@@ -162,8 +162,10 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
            "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach",
            "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
+           "flb_vio_update_level",
            "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
            "flb_vmap_map_value", "flb_vmap_dump",
+           "flb_batch_begin", "flb_batch_set_frame", "flb_batch_state_reset_enqueue", "flb_batch_update_enqueue", "flb_batch_state_download",
            "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps"]
 
 
@@ -221,6 +223,13 @@ def lib():
         L.flb_vio_pass.argtypes = [vp, C.POINTER(VioParams), vp, vp, C.c_int, C.POINTER(VioEq)]
         L.flb_vio_export.argtypes = [vp, vp, vp, vp]
         L.flb_vio_errors.argtypes = [vp, vp, C.c_int]
+        L.flb_vio_update_level.argtypes = [vp, C.POINTER(VioParams), C.c_int, C.c_float, C.POINTER(State18), C.POINTER(State18),
+                                           C.POINTER(C.c_float), vp, C.POINTER(VioReport)]
+        L.flb_batch_begin.argtypes = [vp, C.c_int, C.c_int]
+        L.flb_batch_set_frame.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.POINTER(State18), C.POINTER(State18)]
+        L.flb_batch_state_reset_enqueue.argtypes = [vp]
+        L.flb_batch_update_enqueue.argtypes = [vp, C.POINTER(LioParams), C.POINTER(VioParams)]
+        L.flb_batch_state_download.argtypes = [vp, C.c_int, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
         L.flb_vmap_reset.argtypes = [vp, C.POINTER(VmapParams)]
         L.flb_vmap_select.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
         L.flb_vmap_selected.argtypes = [vp, C.c_int, C.POINTER(C.c_int)] + [vp] * 6
@@ -429,6 +438,15 @@ class Handle:
             out.update(z=z, H_sub=H, errors=err)
         return out
 
+    def vio_update_level(self, prm: VioParams, level: int, total_residual: float, x: State18, x_prop: State18):
+        """flb_vio_update_level == LidarSelector::UpdateState.  Returns (last_error, G[18, 6], report)."""
+        rep = VioReport()
+        le = C.c_float()
+        G = np.zeros((18, 6))
+        self._ck(self.L.flb_vio_update_level(self.h, C.byref(prm), int(level), C.c_float(total_residual), C.byref(x), C.byref(x_prop),
+                                             C.byref(le), _p(G), C.byref(rep)))
+        return le.value, G, rep
+
     def vio_errors(self):
         """sub_sparse_map->errors as the last update's last pass left them (flb_vio_errors)."""
         err = np.zeros(self.Pn, np.float32)
@@ -453,6 +471,25 @@ class Handle:
                                               int(grid_size), int(border), mv.ctypes.data_as(C.c_void_p),
                                               win.ctypes.data_as(C.c_void_p)))
         return mv, win
+
+    # ---- batched frames
+    def batch_begin(self, B, max_points):
+        self._ck(self.L.flb_batch_begin(self.h, int(B), int(max_points)))
+
+    def batch_set_frame(self, b, body_xyz, x: State18, x_prop: State18):
+        a = np.ascontiguousarray(body_xyz, np.float32)
+        self._ck(self.L.flb_batch_set_frame(self.h, int(b), _p(a), a.shape[0], a.shape[1], C.byref(x), C.byref(x_prop)))
+
+    def batch_state_reset_enqueue(self):
+        self._ck(self.L.flb_batch_state_reset_enqueue(self.h))
+
+    def batch_update_enqueue(self, lprm, vprm=None):
+        self._ck(self.L.flb_batch_update_enqueue(self.h, C.byref(lprm), C.byref(vprm) if vprm is not None else None))
+
+    def batch_state_download(self, b):
+        x, lr, vr = State18(), LioReport(), VioReport()
+        self._ck(self.L.flb_batch_state_download(self.h, int(b), C.byref(x), C.byref(lr), C.byref(vr)))
+        return x, lr, vr
 
     # ---- device-resident visual map (rows f2 / f4)
     def vmap_reset(self, seq_or_frame, grid_size=40, outlier_threshold=100.0, ncc_en=0, ncc_thre=0.0):

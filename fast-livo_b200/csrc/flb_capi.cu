@@ -254,6 +254,28 @@ struct flb_handle {
     } vm;
     bool pn_on_device = false;   // the patch list was built on the device (flb_vmap_select without a count readback)
 
+    // batched frames: B independent frames per launch, all against the handle's map
+    struct Batch {
+        int B = 0, n_max = 0, n_cap = 0;
+        std::vector<int> N;                  // points per frame
+        DevBuf<float4> scan, plane;          // B x n_cap
+        DevBuf<unsigned char> sel, plane_ok;
+        DevBuf<double> partials;             // B x max(nb_lio * 29, nb_vio * 29)
+        size_t partials_per = 0;
+        DevBuf<State18> states;              // B x {x, x_prop, old_state, saved x, saved x_prop}
+        DevBuf<LioCtrl> lio_ctrl;
+        DevBuf<VioCtrl> vio_ctrl;
+        DevBuf<PriorBlock> prior;
+        DevBuf<double> G_last;               // B x 108
+        DevBuf<float> errors;                // B x 2 x err_stride
+        DevBuf<LioArgs> lio_args;
+        DevBuf<LioSolveArgs> lio_solve;
+        DevBuf<VioArgs> vio_args;
+        DevBuf<VioSolveArgs> vio_solve;
+        DevBuf<LioCtrl*> lio_ctrl_ptrs;
+        DevBuf<VioCtrl*> vio_ctrl_ptrs;
+    } batch;
+
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -344,6 +366,7 @@ void to_dev_params(const flb_vio_params* p, VioParamsDev& d) {
     d.conv_rot_deg = p->conv_rot_deg;
     d.conv_pos_cm = p->conv_pos_cm;
     d.force_all_passes = p->force_all_passes;
+    d.single_level = 0;
 }
 
 int lio_nblocks(const flb_handle* h) { return (h->N + kLioBlock - 1) / kLioBlock; }
@@ -775,6 +798,12 @@ int flb_destroy(flb_handle* h) {
         if (h->p2p_peer_ptr[r]) cudaIpcCloseMemHandle(h->p2p_peer_ptr[r]);
     h->mailbox.release();
     h->p2p_seq.release();
+    {
+        auto& b = h->batch;
+        b.scan.release(); b.plane.release(); b.sel.release(); b.plane_ok.release(); b.partials.release(); b.states.release();
+        b.lio_ctrl.release(); b.vio_ctrl.release(); b.prior.release(); b.G_last.release(); b.errors.release(); b.lio_args.release();
+        b.lio_solve.release(); b.vio_args.release(); b.vio_solve.release(); b.lio_ctrl_ptrs.release(); b.vio_ctrl_ptrs.release();
+    }
     {
         auto& vm = h->vm;
         vm.pts.release(); vm.fts.release(); vm.pool.release(); vm.counters.release(); vm.pose.release(); vm.rci.release(); vm.pg.release();
@@ -1723,6 +1752,83 @@ int flb_vio_errors(flb_handle* h, float* errors, int capacity) {
     return FLB_OK;
 }
 
+int flb_vio_update_level(flb_handle* h, const flb_vio_params* prm, int level, float total_residual, flb_state18* x,
+                         const flb_state18* x_prop, float* last_error, double* G18x6, flb_vio_report* rep) {
+    FLB_CHECK_H(h);
+    if (!prm || !x || !x_prop || level < 0 || level > 2) return fail(h, FLB_ERR_INVALID, "flb_vio_update_level: bad arguments");
+    if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update_level: camera and image must be set first");
+    if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
+    if (h->comm || h->p2p.world > 1) return fail(h, FLB_ERR_STATE, "flb_vio_update_level: single GPU");
+    { int rcp = resolve_pn(h); if (rcp) return rcp; }
+    if (last_error) *last_error = 0.f;                               // :746 (total_points == 0 returns 0.)
+    flb_vio_report r{};
+    if (h->Pn == 0) { if (rep) *rep = r; return FLB_OK; }
+    int rc = flb_state_upload(h, x, x_prop);
+    if (rc) return rc;
+    VioParamsDev d;
+    to_dev_params(prm, d);
+    d.single_level = 1;
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
+    VioSolveArgs s{};
+    s.state = &h->states.p[0];
+    s.state_prop = &h->states.p[1];
+    s.old_state = &h->states.p[2];
+    s.ctrl = h->vio_ctrl.p;
+    s.prior = h->prior.p;
+    s.G_last = h->G_last.p;
+    s.partials = h->partials.p;
+    s.nblocks = vio_nblocks(h);
+    s.errors = h->errors.p;
+    s.err_stride = h->err_stride;
+    s.Pn_total = h->Pn;
+    s.prm = d;
+    s.timeout_flag = &h->barrier.p->timeout;
+    VioArgs a{};
+    a.img = h->img.p;
+    a.cam = h->cam;
+    a.pos = h->patch_pos.p;
+    a.patch = h->patch_ref.p;
+    a.search_level = h->patch_level.p;
+    a.Pn = h->Pn;
+    a.state = &h->states.p[0];
+    a.prm = d;
+    a.ctrl = h->vio_ctrl.p;
+    a.force_level = -1;
+    a.errors = h->errors.p;
+    a.err_stride = h->err_stride;
+    a.partials = h->partials.p;
+    {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_vio_begin_level<<<1, 32, 0, h->stream>>>(h->vio_ctrl.p, h->Pn, level, total_residual);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    const int nb = vio_nblocks(h);
+    for (int it = 0; it < std::max(prm->max_iteration, 0); ++it) {      // later launches return at once when the level has ended
+        {
+            LaunchScope ls(h, FAM_VIO);
+            k_vio_pass<kVioBlock><<<nb, kVioBlock, 0, h->stream>>>(a);
+            FLB_CUDA(h, cudaGetLastError());
+        }
+        LaunchScope ls(h, FAM_SOLVE);
+        k_vio_finalize<<<1, kLeaderBlock, 0, h->stream>>>(s);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    if (G18x6) {
+        LaunchScope ls(h, FAM_SOLVE);
+        k_vio_export_gain<<<1, kLeaderBlock, 0, h->stream>>>(s, h->packed.p);
+        FLB_CUDA(h, cudaGetLastError());
+        FLB_CUDA(h, cudaMemcpyAsync(G18x6, h->packed.p, 108 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    { int rcq = vio_inputs_release(h); if (rcq) return rcq; }
+    h->last_vio_valid = false;
+    rc = flb_state_download(h, x, nullptr, &r);
+    if (rc) return rc;
+    if (rep) *rep = r;
+    if (last_error) *last_error = r.last_error[level];               // return last_error (:901)
+    if (r.status != 0) return fail(h, r.status, "flb_vio_update_level: device reported status %d", r.status);
+    return FLB_OK;
+}
+
 int flb_vio_update(flb_handle* h, const flb_vio_params* prm, flb_state18* x, const flb_state18* x_prop, flb_vio_report* rep) {
     FLB_CHECK_H(h);
     if (!prm || !x || !x_prop) return fail(h, FLB_ERR_INVALID, "flb_vio_update: null argument");
@@ -1898,6 +2004,234 @@ int flb_comm_destroy(flb_handle* h) {
     if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     h->world = 1;
     h->rank = 0;
+    return FLB_OK;
+}
+
+}  // extern "C"
+
+// =======================================================================================
+// Batched frames: B independent frames per launch
+// =======================================================================================
+extern "C" {
+
+int flb_batch_begin(flb_handle* h, int B, int max_points_per_frame) {
+    FLB_CHECK_H(h);
+    if (B < 1 || B > 4096 || max_points_per_frame < 1) return fail(h, FLB_ERR_INVALID, "flb_batch_begin: bad arguments");
+    if (h->M <= 0) return fail(h, FLB_ERR_STATE, "flb_batch_begin: upload the map first");
+    auto& b = h->batch;
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    b.B = B;
+    b.n_cap = (max_points_per_frame + kLioBlock - 1) / kLioBlock * kLioBlock;
+    b.N.assign(B, 0);
+    const size_t tot = (size_t)B * b.n_cap;
+    FLB_CUDA(h, b.scan.reserve(tot));
+    FLB_CUDA(h, b.plane.reserve(tot));
+    FLB_CUDA(h, b.sel.reserve(tot));
+    FLB_CUDA(h, b.plane_ok.reserve(tot));
+    FLB_CUDA(h, b.states.reserve((size_t)B * 5));
+    FLB_CUDA(h, b.lio_ctrl.reserve(B));
+    FLB_CUDA(h, b.vio_ctrl.reserve(B));
+    FLB_CUDA(h, b.prior.reserve(B));
+    FLB_CUDA(h, b.G_last.reserve((size_t)B * 108));
+    FLB_CUDA(h, b.lio_args.reserve(B));
+    FLB_CUDA(h, b.lio_solve.reserve(B));
+    FLB_CUDA(h, b.vio_args.reserve(B));
+    FLB_CUDA(h, b.vio_solve.reserve(B));
+    FLB_CUDA(h, b.lio_ctrl_ptrs.reserve(B));
+    FLB_CUDA(h, b.vio_ctrl_ptrs.reserve(B));
+    std::vector<LioCtrl*> lp(B);
+    std::vector<VioCtrl*> vp(B);
+    for (int i = 0; i < B; ++i) { lp[i] = b.lio_ctrl.p + i; vp[i] = b.vio_ctrl.p + i; }
+    FLB_CUDA(h, cudaMemcpy(b.lio_ctrl_ptrs.p, lp.data(), B * sizeof(LioCtrl*), cudaMemcpyHostToDevice));
+    FLB_CUDA(h, cudaMemcpy(b.vio_ctrl_ptrs.p, vp.data(), B * sizeof(VioCtrl*), cudaMemcpyHostToDevice));
+    FLB_CUDA(h, cudaMemset(b.lio_ctrl.p, 0, B * sizeof(LioCtrl)));
+    FLB_CUDA(h, cudaMemset(b.vio_ctrl.p, 0, B * sizeof(VioCtrl)));
+    return FLB_OK;
+}
+
+int flb_batch_set_frame(flb_handle* h, int frame, const float* body_xyz, int N, int stride, const flb_state18* x, const flb_state18* x_prop) {
+    FLB_CHECK_H(h);
+    auto& b = h->batch;
+    if (frame < 0 || frame >= b.B || !x || !x_prop || N < 1 || N > b.n_cap) return fail(h, FLB_ERR_INVALID, "flb_batch_set_frame: bad arguments");
+    int rc = flb_scan_upload(h, body_xyz, N, stride);      // validates, Morton-sorts into h->scan
+    if (rc) return rc;
+    const size_t off = (size_t)frame * b.n_cap;
+    FLB_CUDA(h, cudaMemcpyAsync(b.scan.p + off, h->scan.p, (size_t)N * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(b.sel.p + off, 1, N, h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(b.plane_ok.p + off, 0, N, h->stream));
+    rc = flb_state_upload(h, x, x_prop);                   // through the handle's staging, then into the frame's slots
+    if (rc) return rc;
+    State18* st = b.states.p + (size_t)frame * 5;
+    FLB_CUDA(h, cudaMemcpyAsync(st, &h->states.p[0], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(st + 3, &h->states.p[0], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    b.N[frame] = N;
+    b.n_max = *std::max_element(b.N.begin(), b.N.end());
+    return FLB_OK;
+}
+
+/* restore every frame's x / x_prop to what flb_batch_set_frame gave it (benchmark loop) */
+int flb_batch_state_reset_enqueue(flb_handle* h) {
+    FLB_CHECK_H(h);
+    auto& b = h->batch;
+    if (b.B < 1) return fail(h, FLB_ERR_STATE, "flb_batch_state_reset_enqueue: no batch");
+    FLB_CUDA(h, cudaMemcpy2DAsync(b.states.p, 5 * sizeof(State18), b.states.p + 3, 5 * sizeof(State18), 2 * sizeof(State18), b.B,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+    return FLB_OK;
+}
+
+int flb_batch_update_enqueue(flb_handle* h, const flb_lio_params* lprm, const flb_vio_params* vprm) {
+    FLB_CHECK_H(h);
+    auto& b = h->batch;
+    if (b.B < 1 || b.n_max < 1) return fail(h, FLB_ERR_STATE, "flb_batch_update_enqueue: flb_batch_begin / flb_batch_set_frame first");
+    if (!lprm) return fail(h, FLB_ERR_INVALID, "flb_batch_update_enqueue: null LIO params");
+    if (h->comm || h->p2p.world > 1) return fail(h, FLB_ERR_STATE, "batched frames: single GPU");
+    for (int i = 0; i < b.B; ++i)
+        if (b.N[i] < 1) return fail(h, FLB_ERR_STATE, "flb_batch_update_enqueue: frame %d not set", i);
+    const int B = b.B;
+    const bool vio = vprm != nullptr && h->Pn > 0 && vprm->max_iteration > 0;
+    if (vio) {
+        if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_batch_update_enqueue: camera and image must be set first");
+        if (h->pn_on_device) { int rc = resolve_pn(h); if (rc) return rc; }
+    }
+    const int nb_lio = (b.n_max + kLioBlock - 1) / kLioBlock;
+    const int nb_vio = (h->Pn + (kVioBlock / 32) - 1) / (kVioBlock / 32);
+    b.partials_per = (size_t)std::max(nb_lio * lio_packed(6), nb_vio * kVioPacked);
+    FLB_CUDA(h, b.partials.reserve((size_t)B * b.partials_per));
+    const int estride = std::max(h->Pn, 1);
+    FLB_CUDA(h, b.errors.reserve((size_t)B * 2 * estride));
+    LioParamsDev ld;
+    to_dev_params(lprm, ld);
+    std::vector<LioArgs> la(B);
+    std::vector<LioSolveArgs> ls(B);
+    for (int i = 0; i < B; ++i) {
+        const size_t off = (size_t)i * b.n_cap;
+        LioArgs a{};
+        a.scan = b.scan.p + off;
+        a.N = b.N[i];
+        a.grid = h->grid;
+        a.cell_start = h->cell_start.p;
+        a.map_pts = h->map_pts.p;
+        a.state = b.states.p + (size_t)i * 5;
+        a.prm = ld;
+        a.plane_thr = (float)h->cfg.plane_threshold;
+        a.ctrl = b.lio_ctrl.p + i;
+        a.force_rematch = -1;
+        a.sel = b.sel.p + off;
+        a.plane = b.plane.p + off;
+        a.plane_ok = b.plane_ok.p + off;
+        a.partials = b.partials.p + (size_t)i * b.partials_per;
+        a.M = h->M;
+        la[i] = a;
+        LioSolveArgs s{};
+        s.state = b.states.p + (size_t)i * 5;
+        s.state_prop = s.state + 1;
+        s.ctrl = b.lio_ctrl.p + i;
+        s.prior = b.prior.p + i;
+        s.partials = a.partials;
+        s.nblocks = (b.N[i] + kLioBlock - 1) / kLioBlock;
+        s.prm = ld;
+        s.timeout_flag = &h->barrier.p->timeout;
+        ls[i] = s;
+    }
+    // argument tables: pageable -> device through the stream (small; ordered before the launches that read them)
+    FLB_CUDA(h, cudaMemcpyAsync(b.lio_args.p, la.data(), B * sizeof(LioArgs), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(b.lio_solve.p, ls.data(), B * sizeof(LioSolveArgs), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));          // la / ls are stack-owned
+    {
+        LaunchScope lsx(h, FAM_SOLVE);
+        k_lio_begin_batched<<<(B + 127) / 128, 128, 0, h->stream>>>(b.lio_ctrl_ptrs.p, B);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    const int T = lprm->max_iteration;
+    for (int it = -1; it < T; ++it) {
+        {
+            // family tag: with early stop disabled the rematch passes are the first and the last (Appendix A)
+            LaunchScope lsx(h, (it == -1 || it == T - 1) ? FAM_LIO_KNN : FAM_LIO_PLAIN);
+            k_lio_pass_batched<6, kLioBlock><<<dim3(nb_lio, B), kLioBlock, 0, h->stream>>>(b.lio_args.p);
+            FLB_CUDA(h, cudaGetLastError());
+        }
+        LaunchScope lsx(h, FAM_SOLVE);
+        k_lio_finalize_batched<<<B, kLeaderBlock, 0, h->stream>>>(b.lio_solve.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    if (!vio) return FLB_OK;
+    // state_propagat := the LIO posterior (zero-motion propagation between the two updates), per frame
+    FLB_CUDA(h, cudaMemcpy2DAsync(b.states.p + 1, 5 * sizeof(State18), b.states.p, 5 * sizeof(State18), sizeof(State18), B,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+    { int rcq = vio_inputs_acquire(h); if (rcq) return rcq; }
+    VioParamsDev vd;
+    to_dev_params(vprm, vd);
+    std::vector<VioArgs> va(B);
+    std::vector<VioSolveArgs> vs(B);
+    for (int i = 0; i < B; ++i) {
+        VioArgs a{};
+        a.img = h->img.p;
+        a.cam = h->cam;
+        a.pos = h->patch_pos.p;
+        a.patch = h->patch_ref.p;
+        a.search_level = h->patch_level.p;
+        a.Pn = h->Pn;
+        a.state = b.states.p + (size_t)i * 5;
+        a.prm = vd;
+        a.ctrl = b.vio_ctrl.p + i;
+        a.force_level = -1;
+        a.errors = b.errors.p + (size_t)i * 2 * estride;
+        a.err_stride = estride;
+        a.partials = b.partials.p + (size_t)i * b.partials_per;
+        va[i] = a;
+        VioSolveArgs s{};
+        s.state = b.states.p + (size_t)i * 5;
+        s.state_prop = s.state + 1;
+        s.old_state = s.state + 2;
+        s.ctrl = b.vio_ctrl.p + i;
+        s.prior = b.prior.p + i;
+        s.G_last = b.G_last.p + (size_t)i * 108;
+        s.partials = a.partials;
+        s.nblocks = nb_vio;
+        s.errors = a.errors;
+        s.err_stride = estride;
+        s.Pn_total = h->Pn;
+        s.prm = vd;
+        s.timeout_flag = &h->barrier.p->timeout;
+        vs[i] = s;
+    }
+    FLB_CUDA(h, cudaMemcpyAsync(b.vio_args.p, va.data(), B * sizeof(VioArgs), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(b.vio_solve.p, vs.data(), B * sizeof(VioSolveArgs), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    {
+        LaunchScope lsx(h, FAM_SOLVE);
+        k_vio_begin_batched<<<(B + 127) / 128, 128, 0, h->stream>>>(b.vio_ctrl_ptrs.p, B, h->Pn);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    const int total = 3 * vprm->max_iteration;
+    for (int it = 0; it < total; ++it) {
+        {
+            LaunchScope lsx(h, FAM_VIO);
+            k_vio_pass_batched<kVioBlock><<<dim3(nb_vio, B), kVioBlock, 0, h->stream>>>(b.vio_args.p);
+            FLB_CUDA(h, cudaGetLastError());
+        }
+        LaunchScope lsx(h, FAM_SOLVE);
+        k_vio_finalize_batched<<<B, kLeaderBlock, 0, h->stream>>>(b.vio_solve.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    return vio_inputs_release(h);
+}
+
+int flb_batch_state_download(flb_handle* h, int frame, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio) {
+    FLB_CHECK_H(h);
+    auto& b = h->batch;
+    if (frame < 0 || frame >= b.B) return fail(h, FLB_ERR_INVALID, "flb_batch_state_download: bad frame");
+    State18 xs;
+    LioCtrl lc;
+    VioCtrl vc;
+    FLB_CUDA(h, cudaMemcpyAsync(&xs, b.states.p + (size_t)frame * 5, sizeof(State18), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(&lc, b.lio_ctrl.p + frame, sizeof(LioCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(&vc, b.vio_ctrl.p + frame, sizeof(VioCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (x) std::memcpy(x, &xs, sizeof(State18));
+    if (lio) fill_lio_report(lc, lio);
+    if (vio) fill_vio_report(vc, vio);
     return FLB_OK;
 }
 

@@ -64,6 +64,7 @@ struct VioParamsDev {
     int max_iteration;
     float conv_rot_deg, conv_pos_cm;
     int force_all_passes;
+    int single_level;                // UpdateState alone (one pyramid level, :743-902): stop when the level ends, no :980
 };
 
 // Packed sizes: W(W+1)/2 upper-triangular products + W (H^T z) + 2 scalars.
@@ -503,7 +504,7 @@ __device__ __forceinline__ void lio_accumulate(double (&acc)[lio_packed(W)], con
 
 // kernel-per-pass: one thread per scan point
 template <int W, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) {
+__device__ __forceinline__ void lio_pass_body(const LioArgs& a) {
     constexpr int K = lio_packed(W);
     __shared__ LioPose s_pose;
     __shared__ double s_acc[BLOCK / 32][K];
@@ -528,6 +529,24 @@ __global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) {
         if (active) lio_accumulate<W>(acc, row, z, absres);
     }
     block_reduce_store<K, BLOCK>(acc, s_acc, a.partials);
+}
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_lio_pass(LioArgs a) { lio_pass_body<W, BLOCK>(a); }
+
+// Batched frames: blockIdx.y = frame; every frame has its own scan, state, control
+// block and partial sums (args[frame]), all share the map.  The pass of B frames is ONE launch, so the grid is B times
+// larger than a frame's and the kernel runs where its throughput, not its latency, is what is measured.
+template <int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_lio_pass_batched(const LioArgs* __restrict__ args) {
+    __shared__ LioArgs s_a;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(args + blockIdx.y);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_a);
+        for (int e = threadIdx.x; e < (int)(sizeof(LioArgs) / sizeof(unsigned)); e += BLOCK) dst[e] = src[e];
+    }
+    __syncthreads();
+    if ((int)blockIdx.x * BLOCK >= s_a.N) return;
+    lio_pass_body<W, BLOCK>(s_a);
 }
 
 __global__ void __launch_bounds__(32) k_reduce_only(const double* partials, int nblocks, int K, double* out) {
@@ -770,7 +789,7 @@ __device__ __forceinline__ void vio_block_reduce_store(double accv, double n_mea
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_vio_pass(VioArgs a) {
+__device__ __forceinline__ void vio_pass_body(const VioArgs& a) {
     constexpr int NW = BLOCK / 32;
     __shared__ VioPose s_pose;
     __shared__ float s_lat[NW][128];
@@ -794,6 +813,20 @@ __global__ void __launch_bounds__(BLOCK) k_vio_pass(VioArgs a) {
         vio_patch(a, s_pose, level, i, in, s_lat[warp], s_res[warp], accv, n_meas, skipped);
     }
     vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
+}
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_vio_pass(VioArgs a) { vio_pass_body<BLOCK>(a); }
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_vio_pass_batched(const VioArgs* __restrict__ args) {
+    __shared__ VioArgs s_a;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(args + blockIdx.y);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_a);
+        for (int e = threadIdx.x; e < (int)(sizeof(VioArgs) / sizeof(unsigned)); e += BLOCK) dst[e] = src[e];
+    }
+    __syncthreads();
+    vio_pass_body<BLOCK>(s_a);
 }
 
 // =======================================================================================
@@ -1255,7 +1288,7 @@ __global__ void __launch_bounds__(32) k_lio_begin(LioCtrl* ctrl) {
     }
 }
 
-__global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize(LioSolveArgs s) {
+__device__ __forceinline__ void lio_finalize_body(const LioSolveArgs& s) {
     __shared__ LeaderSmem sm;
     __shared__ LioCtrl c;
     if (s.ctrl->stop) return;
@@ -1266,6 +1299,26 @@ __global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize(LioSolveArgs s) {
     const bool first = c.passes == 0;
     lio_leader_solve<kLeaderBlock>(s, sm, c, first, nullptr, 0u, 0);
     lio_leader_finish<kLeaderBlock>(s, sm, c, first, true, 0);
+}
+__global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize(LioSolveArgs s) { lio_finalize_body(s); }
+__global__ void __launch_bounds__(kLeaderBlock) k_lio_finalize_batched(const LioSolveArgs* __restrict__ args) {
+    __shared__ LioSolveArgs s_s;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(args + blockIdx.x);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_s);
+        for (int e = threadIdx.x; e < (int)(sizeof(LioSolveArgs) / sizeof(unsigned)); e += kLeaderBlock) dst[e] = src[e];
+    }
+    __syncthreads();
+    lio_finalize_body(s_s);
+}
+__global__ void k_lio_begin_batched(LioCtrl* const* ctrls, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    LioCtrl c;
+    c.iterCount = -1; c.rematch_num = 0; c.nearest_search_en = 1; c.stop = 0;
+    c.passes = c.knn_passes = c.n_eff_last = c.converged_last = 0; c.status = 0;
+    c.res_mean_last = 0.0; c.rows_total = 0;
+    *ctrls[b] = c;
 }
 
 struct VioSolveArgs {
@@ -1424,7 +1477,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                                     (norm3(sm.sol + 3) * 100.0f < s.prm.conv_pos_cm);
                 const int it1 = c.iteration + 1;
                 const bool done_p = conv_p || it1 >= s.prm.max_iteration;
-                const bool stop_p = !ok_p || (done_p && level - 1 < 0);
+                const bool stop_p = !ok_p || (done_p && (level - 1 < 0 || s.prm.single_level));
                 const int spec = (pkt != nullptr && !stop_p) ? 1 : 0;
                 sm.flags[4] = spec;
                 sm.flags[5] = 0;
@@ -1477,7 +1530,9 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                     c.iteration = 0;
                     c.last_error = 1e10f;
                     newlevel = 1;
-                    if (c.level < 0 || !ok) {
+                    if (s.prm.single_level) {
+                        c.stop = 1;                                                         // UpdateState returns (:900)
+                    } else if (c.level < 0 || !ok) {
                         c.stop = 1;
                         if (c.now_error < 1e10f && ok) { docov = 1; c.cov_updated = 1; }   // :978-981
                     }
@@ -1549,7 +1604,7 @@ __global__ void __launch_bounds__(32) k_vio_begin(VioCtrl* ctrl, int Pn_total) {
     }
 }
 
-__global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
+__device__ __forceinline__ void vio_finalize_body(const VioSolveArgs& s) {
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl c;
     __shared__ __align__(16) float s_err[kErrChunk];
@@ -1561,6 +1616,62 @@ __global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) {
     const bool first = (c.passes[0] + c.passes[1] + c.passes[2]) == 0;
     vio_leader_solve<kLeaderBlock>(s, sm, c, s_err, first, nullptr, 0u, 0);
     vio_leader_finish<kLeaderBlock>(s, sm, c, first, true, 0);
+}
+__global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize(VioSolveArgs s) { vio_finalize_body(s); }
+
+// UpdateState(img, total_residual, level) alone: the control block starts at `level` with last_error = total_residual.
+__global__ void __launch_bounds__(32) k_vio_begin_level(VioCtrl* ctrl, int Pn_total, int level, float total_residual) {
+    if (threadIdx.x == 0) {
+        VioCtrl c;
+        c.level = level;
+        c.iteration = 0;
+        c.stop = (Pn_total == 0) ? 1 : 0;
+        c.last_error = total_residual;
+        c.now_error = total_residual;
+        c.any_solved = 0;
+        for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = total_residual; }
+        c.rows_total = 0;
+        c.skipped_last = 0;
+        c.cov_updated = 0;
+        c.status = 0;
+        c.err_buf = 0;
+        *ctrl = c;
+    }
+}
+
+// The member G of LidarSelector (:874): K_1[:, :6] * H_T_H[:6, :6] of the last ACCEPTED pass, formed from the stored
+// H^T H block and the covariance the passes ran with.  out: 18 x 6 row-major (the other 12 columns of G are zero).
+__global__ void __launch_bounds__(kLeaderBlock) k_vio_export_gain(VioSolveArgs s, double* out) {
+    __shared__ LeaderSmem sm;
+    const int tid = threadIdx.x;
+    load_cov_l2<kLeaderBlock>(&sm.x, s.state, tid);
+    if (tid == 0) sm.flags[3] = 0;
+    if (tid < 36) sm.HTH[tid] = __ldcg(s.G_last + tid);
+    __syncthreads();
+    leader_prior<Team<kLeaderBlock, false>>(sm, s.prior, tid);
+    __syncthreads();
+    leader_gain<Team<kLeaderBlock, false>>(sm, s.prm.sigma, tid);
+    for (int e = tid; e < kDim * 6; e += kLeaderBlock) out[e] = sm.Gc[e];
+}
+__global__ void __launch_bounds__(kLeaderBlock) k_vio_finalize_batched(const VioSolveArgs* __restrict__ args) {
+    __shared__ VioSolveArgs s_s;
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(args + blockIdx.x);
+        unsigned* dst = reinterpret_cast<unsigned*>(&s_s);
+        for (int e = threadIdx.x; e < (int)(sizeof(VioSolveArgs) / sizeof(unsigned)); e += kLeaderBlock) dst[e] = src[e];
+    }
+    __syncthreads();
+    vio_finalize_body(s_s);
+}
+__global__ void k_vio_begin_batched(VioCtrl* const* ctrls, int B, int Pn_total) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    VioCtrl c;
+    c.level = 2; c.iteration = 0; c.stop = (Pn_total == 0) ? 1 : 0;
+    c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;
+    for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
+    c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0; c.err_buf = 0;
+    *ctrls[b] = c;
 }
 
 // =======================================================================================

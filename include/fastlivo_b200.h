@@ -342,6 +342,13 @@ int flb_vio_export(flb_handle* h, double* z, double* H_sub, float* errors);
  * for level = 2,1,0, then cov -= G*cov, all on the device. */
 int flb_vio_update(flb_handle* h, const flb_vio_params* prm, flb_state18* x, const flb_state18* x_prop,
                    flb_vio_report* rep);
+/* float LidarSelector::UpdateState(cv::Mat img, float total_residual, int level) (include/lidar_selection.h:72,
+ * src/lidar_selection.cpp:743-902) on its own: the iteration loop of ONE pyramid level starting from *x with
+ * last_error = total_residual; returns the level's last_error like the reference (0 when there are no patches).
+ * G18x6 (may be NULL): the non-zero block (columns 0..5) of the member G after the call (:874), which the caller's
+ * ComputeJ applies as state->cov -= G * state->cov (:980) -- this entry point leaves the covariance alone. */
+int flb_vio_update_level(flb_handle* h, const flb_vio_params* prm, int level, float total_residual, flb_state18* x,
+                         const flb_state18* x_prop, float* last_error, double* G18x6, flb_vio_report* rep);
 /* sub_sparse_map->errors[i] as ComputeJ leaves them (src/lidar_selection.cpp:851: the per-patch errors of the
  * LAST pass executed by the last flb_vio_update / flb_vio_update_enqueue; read by display_keypatch, :995).
  * errors: up to `capacity` floats, patch order. */
@@ -360,6 +367,21 @@ int flb_state_reset_enqueue(flb_handle* h);
 /* x_prop := x on the device: `state_propagat = state` (src/laserMapping.cpp:1292) with a
  * zero-motion IMU propagation between the LIO and the VIO update */
 int flb_state_set_prior_enqueue(flb_handle* h);
+
+/* ---- batched frames ------------------------------------------------------------
+ * B independent frames (own scan, own prior) against the handle's map -- and, for the VIO step, its image and
+ * patch list -- advanced together: every pass of the iterated update is ONE launch over all B frames (kernel-per-
+ * pass path, blockIdx.y = frame), so the grid is B times a frame's.  One frame's passes are latency-bound at the
+ * sizes of BASELINE.json; this is the mode in which the kernels run at their throughput
+ * (relocalisation against a map, multi-hypothesis tracking, offline batches).  Every frame's result is bit-identical
+ * to the same frame run alone through the kernel-per-pass path (flb_config.persistent = 0). */
+int flb_batch_begin(flb_handle* h, int B, int max_points_per_frame);
+int flb_batch_set_frame(flb_handle* h, int frame, const float* body_xyz, int N, int stride_floats, const flb_state18* x,
+                        const flb_state18* x_prop);
+int flb_batch_state_reset_enqueue(flb_handle* h);
+/* LIO update of every frame, then (vprm != NULL) VIO update with the LIO posterior as prior.  Enqueue-only. */
+int flb_batch_update_enqueue(flb_handle* h, const flb_lio_params* lprm, const flb_vio_params* vprm);
+int flb_batch_state_download(flb_handle* h, int frame, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio);
 
 /* Per-kernel-family device time of the work enqueued between start and stop,
  * measured with CUDA events on the handle's stream (adds one event pair per launch:

@@ -813,6 +813,55 @@ float flo_vio_pass(flo_vio* V, const flo_vio_params* prm, const double R[9], con
 
 void flo_vio_errors(const flo_vio* V, float* errors) { std::memcpy(errors, V->errors.data(), sizeof(float) * V->Pn); }
 
+// LidarSelector::UpdateState(img, total_residual, level), lidar_selection.cpp:743-902.  G is the member G (:874): it
+// keeps its value when no pass of this call is accepted.
+static float update_state(flo_vio* V, const VioConst& K, const flo_vio_params* prm, flo_state18* x, const flo_state18* x_prop,
+                          float total_residual, int level, double* G, flo_vio_report& r) {
+    // H_sub / z are resized + zeroed per UpdateState call (:759-768): mirror the allocation.
+    std::vector<double> z((size_t)V->Pn * 64, 0.0), H_sub((size_t)V->Pn * 64 * 6, 0.0);
+    flo_state18 old_state = *x;                        // :747
+    float last_error = total_residual;                 // :755
+    bool EKF_end = false;
+    for (int iteration = 0; iteration < prm->max_iteration; iteration++) {   // :772
+        double HTH6[36], HTz6[6];
+        int64_t n_meas = 0;
+        int skipped = 0;
+        const float error = vio_pass_core(V, K, x->rot, x->pos, level, z.data(), H_sub.data(), HTH6, HTz6,
+                                          &n_meas, &skipped);
+        r.passes[level]++;
+        r.rows_total += n_meas;
+        r.skipped_last = skipped;
+        if (prm->force_all_passes || error <= last_error) {               // :861
+            old_state = *x;
+            last_error = error;
+            double solution[kDim];
+            ekf18_step(x, x_prop, HTH6, HTz6, prm->img_point_cov, -1.0, G, solution);  // :871-880
+            if (!prm->force_all_passes &&
+                (norm3(solution) * 57.3f < prm->conv_rot_deg) && (norm3(solution + 3) * 100.0f < prm->conv_pos_cm))
+                EKF_end = true;                                              // :883-886
+        } else {
+            *x = old_state;                                                  // :890
+            EKF_end = true;
+            r.rejects++;
+        }
+        if (EKF_end) break;                                                  // :897
+    }
+    r.last_error[level] = last_error;
+    return last_error;                                                       // :901
+}
+
+// UpdateState alone (one pyramid level).  G324: in/out, the 18x18 member G.
+float flo_vio_update_level(flo_vio* V, const flo_vio_params* prm, int level, float total_residual, flo_state18* x,
+                           const flo_state18* x_prop, double* G324, flo_vio_report* rep) {
+    flo_vio_report r = {};
+    if (V->Pn == 0) { if (rep) *rep = r; return 0.f; }   // :746
+    VioConst K;
+    vio_constants(prm, &V->cam, &K);
+    const float e = update_state(V, K, prm, x, x_prop, total_residual, level, G324, r);
+    if (rep) *rep = r;
+    return e;
+}
+
 // ComputeJ (lidar_selection.cpp:967-983) driving UpdateState (:743-902) for level = 2,1,0.
 int flo_vio_update(flo_vio* V, const flo_vio_params* prm, flo_state18* x, const flo_state18* x_prop,
                    flo_vio_report* rep) {
@@ -823,39 +872,8 @@ int flo_vio_update(flo_vio* V, const flo_vio_params* prm, flo_state18* x, const 
     double G[kDim * kDim] = {0};
     const float error0 = 1e10f;                            // :971
     float now_error = error0;
-    // H_sub / z are resized + zeroed per UpdateState call (:759-768): mirror the allocation.
-    for (int level = 2; level >= 0; level--) {             // :974
-        std::vector<double> z((size_t)V->Pn * 64, 0.0), H_sub((size_t)V->Pn * 64 * 6, 0.0);
-        flo_state18 old_state = *x;                        // :747
-        float last_error = error0;                         // total_residual = 1e10 every level
-        bool EKF_end = false;
-        for (int iteration = 0; iteration < prm->max_iteration; iteration++) {   // :772
-            double HTH6[36], HTz6[6];
-            int64_t n_meas = 0;
-            int skipped = 0;
-            const float error = vio_pass_core(V, K, x->rot, x->pos, level, z.data(), H_sub.data(), HTH6, HTz6,
-                                              &n_meas, &skipped);
-            r.passes[level]++;
-            r.rows_total += n_meas;
-            r.skipped_last = skipped;
-            if (prm->force_all_passes || error <= last_error) {               // :861
-                old_state = *x;
-                last_error = error;
-                double solution[kDim];
-                ekf18_step(x, x_prop, HTH6, HTz6, prm->img_point_cov, -1.0, G, solution);  // :871-880
-                if (!prm->force_all_passes &&
-                    (norm3(solution) * 57.3f < prm->conv_rot_deg) && (norm3(solution + 3) * 100.0f < prm->conv_pos_cm))
-                    EKF_end = true;                                              // :883-886
-            } else {
-                *x = old_state;                                                  // :890
-                EKF_end = true;
-                r.rejects++;
-            }
-            if (EKF_end) break;                                                  // :897
-        }
-        r.last_error[level] = last_error;
-        now_error = last_error;                                                  // :976
-    }
+    for (int level = 2; level >= 0; level--)               // :974
+        now_error = update_state(V, K, prm, x, x_prop, error0, level, G, r);   // :976
     if (now_error < error0) {                                                    // :978
         // state->cov -= G * state->cov, :980
         double GP[kDim * kDim];

@@ -201,6 +201,10 @@ float flo_vio_pass(flo_vio*, const flo_vio_params*, const double R[9], const dou
 int flo_vio_update(flo_vio*, const flo_vio_params*, flo_state18* x, const flo_state18* x_prop,
                    flo_vio_report* rep);
 
+/* LidarSelector::UpdateState(img, total_residual, level) alone (lidar_selection.cpp:743-902); G324: the member G
+ * (18 x 18, in/out); returns last_error. */
+float flo_vio_update_level(flo_vio*, const flo_vio_params*, int level, float total_residual, flo_state18* x,
+                           const flo_state18* x_prop, double* G324, flo_vio_report* rep);
 /* sub_sparse_map->errors as the last pass executed left them (lidar_selection.cpp:851). */
 void flo_vio_errors(const flo_vio*, float* errors);
 

@@ -244,6 +244,9 @@ def lib():
         L.flo_vio_update.argtypes = [C.c_void_p, C.POINTER(VioParams), C.POINTER(State18), C.POINTER(State18),
                                      C.POINTER(VioReport)]
         L.flo_vio_errors.argtypes = [C.c_void_p, C.c_void_p]
+        L.flo_vio_update_level.restype = C.c_float
+        L.flo_vio_update_level.argtypes = [C.c_void_p, C.POINTER(VioParams), C.c_int, C.c_float, C.POINTER(State18), C.POINTER(State18),
+                                           C.c_void_p, C.POINTER(VioReport)]
         vp = C.c_void_p
         L.flo_vmap_create.restype = vp
         L.flo_vmap_create.argtypes = [C.POINTER(Cam), C.c_int, C.c_double, C.c_int, C.c_double]
@@ -504,6 +507,14 @@ class Vio:
         rep = VioReport()
         self.L.flo_vio_update(self.h, C.byref(prm), C.byref(x), C.byref(x_prop), C.byref(rep))
         return rep
+
+    def update_level(self, prm: VioParams, level: int, total_residual: float, x: State18, x_prop: State18, G=None):
+        """LidarSelector::UpdateState alone.  G (18x18, in/out) is the member G.  Returns (last_error, G, report)."""
+        G = np.zeros((18, 18)) if G is None else np.ascontiguousarray(G, np.float64)
+        rep = VioReport()
+        e = self.L.flo_vio_update_level(self.h, C.byref(prm), int(level), C.c_float(total_residual), C.byref(x), C.byref(x_prop),
+                                        _p(G), C.byref(rep))
+        return e, G, rep
 
     def errors(self):
         """sub_sparse_map->errors as the last executed pass left them (lidar_selection.cpp:851)."""

@@ -2,6 +2,8 @@
 // Eigen / PCL / OpenCV-shaped types.  Reads a frame dumped by the pytest driver, runs the
 // adapters against libfastlivo_b200.so and writes the results back for comparison with the oracle.
 // Mock types mirror only the members the adapters touch (Eigen is column-major: so are the mocks).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -123,11 +125,46 @@ int main(int argc, char** argv) {
             auto p = std::make_shared<Point>();
             for (int k = 0; k < 3; ++k) p->pos_(k) = ppos[3 * i + k];
             sub.voxel_points.push_back(i % 17 == 5 ? nullptr : p);   // a few null points, like the reference's map
+            sub.errors.push_back(-1.0f);                              // :569 (overwritten by every pass, :851)
         }
         Image im{img.data(), W, H, (size_t)W};
         flb_vio_params vp = flb::make_vio_params(Rcl, Pcl, R_LI, t_LI, covs[1], T);
         StatesGroup vprop = state;
+        // the same ComputeJ assembled from three UpdateState calls, as the reference's own loop does (:974-981)
+        StatesGroup state2 = state;
+        SubSparseMap sub2 = sub;
+        Mat<18, 18> G;
+        float now_error = 1e10f;
+        for (int level = 2; level >= 0; level--) now_error = flb::update_state(h, vp, im, sub2, state2, vprop, 1e10f, level, G);
+        if (now_error < 1e10f) {
+            Mat<18, 18> GP;
+            for (int i = 0; i < 18; ++i)
+                for (int j = 0; j < 18; ++j) {
+                    double acc = 0;
+                    for (int k = 0; k < 18; ++k) acc += G(i, k) * state2.cov(k, j);
+                    GP(i, j) = acc;
+                }
+            for (int i = 0; i < 18; ++i)
+                for (int j = 0; j < 18; ++j) state2.cov(i, j) -= GP(i, j);
+        }
         flb_vio_report vrep = flb::compute_j(h, vp, im, sub, state, vprop);
+        double lvl_diff = 0;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) lvl_diff = std::max(lvl_diff, std::fabs(state.rot_end(i, j) - state2.rot_end(i, j)));
+            lvl_diff = std::max(lvl_diff, std::fabs(state.pos_end(i) - state2.pos_end(i)));
+        }
+        double cov_diff = 0, cov_max = 0;
+        for (int i = 0; i < 18; ++i)
+            for (int j = 0; j < 18; ++j) {
+                cov_diff = std::max(cov_diff, std::fabs(state.cov(i, j) - state2.cov(i, j)));
+                cov_max = std::max(cov_max, std::fabs(state.cov(i, j)));
+            }
+        bool err_same = true;
+        for (int i = 0; i < Pn; ++i) err_same = err_same && (sub.errors[i] == sub2.errors[i]);
+        if (lvl_diff > 1e-12 || cov_diff > 1e-9 * cov_max || !err_same) {
+            fprintf(stderr, "update_state x3 != compute_j: state %.3e cov %.3e errors %d\n", lvl_diff, cov_diff, (int)err_same);
+            return 5;
+        }
 
         FILE* o = fopen(argv[2], "wb");
         int oh[8] = {effct, lrep.passes, lrep.n_eff_last, vrep.passes[0], vrep.passes[1], vrep.passes[2], vrep.cov_updated, (int)eidx.size()};
@@ -141,6 +178,7 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) out[3 * i + j] = state.rot_end(i, j); out[9 + i] = state.pos_end(i); }
         for (int i = 0; i < 18; ++i) for (int j = 0; j < 18; ++j) out[12 + 18 * i + j] = state.cov(i, j);
         fwrite(out, 8, 12 + 324, o);
+        fwrite(sub.errors.data(), sizeof(float), sub.errors.size(), o);
         fclose(o);
     } catch (const flb::Error& e) {
         fprintf(stderr, "flb error %d: %s\n", e.code, e.what());

@@ -63,6 +63,8 @@ def test_adapters_match_oracle(flb, po, frames, tmp_path):
     eidx = np.frombuffer(raw, np.int32, nidx, off)
     off += nidx * 4
     st = np.frombuffer(raw, np.float64, 12 + 324, off)
+    off += (12 + 324) * 8
+    errs = np.frombuffer(raw, np.float32, Pn, off)
 
     # oracle: same three steps
     lio = po.Lio(f["map_xyz"], f["scan_body"])
@@ -79,6 +81,8 @@ def test_adapters_match_oracle(flb, po, frames, tmp_path):
     vio = po.Vio(f["image"], f["patch_pos"][keep], f["patch_ref"][keep], f["patch_level"][keep], f["cam"])
     vrep = vio.update(po.vio_params(f, T), x, x.copy())
     assert [vp0, vp1, vp2] == list(vrep.passes) and covup == vrep.cov_updated
+    # sub_sparse_map->errors written back by compute_j (:851): the last pass's per-patch errors; null points keep theirs
+    assert (errs[keep].view(np.uint32) == vio.errors().view(np.uint32)).all() and (errs[~keep] == -1.0).all()
     ref = np.concatenate([x.R.ravel(), x.p, x.P.ravel()])
     assert np.abs(st[:12] - ref[:12]).max() / np.abs(ref[:12]).max() < 1e-9
     np.testing.assert_allclose(st[12:], ref[12:], rtol=1e-6, atol=1e-14)

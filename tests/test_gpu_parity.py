@@ -248,3 +248,35 @@ def test_gpu_matches_committed_golden(flb, handle):
     vrep = handle.vio_update(flb.capi.vio_params(frame, 4), xv, x.copy())
     assert [*vrep.passes, vrep.rows_total, vrep.cov_updated] == list(g["vio_report"])
     assert rel(xv.vector(), g["vio_state"]) < STATE_RTOL
+
+
+@pytest.mark.parametrize("name,T", [("T0", 10), ("T1", 4)])
+def test_vio_update_level_parity(flb, po, frames, name, T):
+    """flb_vio_update_level == LidarSelector::UpdateState alone: driving the three levels from the host with the
+    reference's own ComputeJ loop (:974-981) reproduces flb_vio_update and the oracle, level by level."""
+    f = frames(name)
+    h = flb.Handle(device=0)
+    h.load_frame(f)
+    vio = po.Vio(f["image"], f["patch_pos"], f["patch_ref"], f["patch_level"], f["cam"])
+    oprm, gprm = po.vio_params(f, T), flb.capi.vio_params(f, T)
+    xo, xg = _ostate(po, f), _gstate(flb, f)
+    xpo, xpg = xo.copy(), xg.copy()
+    Go = np.zeros((18, 18))
+    Gg = np.zeros((18, 18))
+    now_o = now_g = np.float32(1e10)
+    for level in (2, 1, 0):
+        now_o, Go, ro = vio.update_level(oprm, level, 1e10, xo, xpo, Go)
+        now_g, G6, rg = h.vio_update_level(gprm, level, 1e10, xg, xpg)
+        if rg.passes[level] > 0 and now_g < 1e10:
+            Gg[:, :6] = G6
+        assert list(rg.passes) == list(ro.passes)
+        assert abs(now_g - now_o) <= 1e-6 * abs(now_o)
+        assert rel(xg.vector(), xo.vector()) < STATE_RTOL
+        assert np.abs(Gg - Go).max() < 1e-9 * max(np.abs(Go).max(), 1e-30)
+        assert (bits(h.vio_errors()) == bits(vio.errors())).all()
+    # ... and the whole of ComputeJ assembled from the three calls equals flb_vio_update
+    Pg = xg.P - Gg @ xg.P
+    xw = _gstate(flb, f)
+    h.vio_update(gprm, xw, xw.copy())
+    assert rel(xg.vector(), xw.vector()) < 1e-12 and rel(Pg, xw.P) < 1e-9
+    h.close()
