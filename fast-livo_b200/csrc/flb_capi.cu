@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <dlfcn.h>
 
@@ -157,9 +158,13 @@ struct flb_handle {
     DevBuf<unsigned> keys, keys_sorted;
     DevBuf<int> vals, vals_sorted;
     DevBuf<unsigned char> cub_tmp;
-    DevBuf<float4> map_pts;
-    DevBuf<int> cell_start;
-    float map_lo[3] = {0, 0, 0}, map_hi[3] = {0, 0, 0};   // bounding box of everything ever in the map
+    DevBuf<float4> map_pts, map_pts_alt;       // sorted grid points (double-buffered for the incremental merge)
+    DevBuf<int> cell_start, cell_start_alt;
+    DevBuf<float> map_raw_alt;
+    DevBuf<unsigned char> dead, ins;
+    DevBuf<int> dead_before, merge_counts, bbox_dev;
+    float map_lo[3] = {0, 0, 0}, map_hi[3] = {0, 0, 0};   // tight bounding box of the live map points
+    float grid_lo[3] = {0, 0, 0}, grid_hi[3] = {0, 0, 0}; // box the kNN grid covers (= map box + a margin for growth)
     // map maintenance scratch
     DevBuf<float> map_comb, boxes;
     DevBuf<unsigned long long> vkeys, vkeys_sorted;
@@ -864,8 +869,15 @@ int64_t flb_launch_count(const flb_handle* h) { return h ? h->launches : 0; }
 // ---------------------------------------------------------------------------------------
 // Build the sorted uniform kNN grid over h->map_raw[0..M) with the bounding box h->map_lo/hi.
 static int rebuild_grid(flb_handle* h, int M) {
-    const float* lo = h->map_lo;
-    const float* hi = h->map_hi;
+    // the grid covers the map box plus a margin, so that points added next to the map (a moving sensor) fall inside
+    // it and take the incremental path of flb_map_add_points; kNN is exact for any cell geometry
+    for (int k = 0; k < 3; ++k) {
+        const float m = std::max(2.0f * (float)h->cfg.cell_size, 0.05f * (h->map_hi[k] - h->map_lo[k]));
+        h->grid_lo[k] = h->map_lo[k] - m;
+        h->grid_hi[k] = h->map_hi[k] + m;
+    }
+    const float* lo = h->grid_lo;
+    const float* hi = h->grid_hi;
     // grid geometry; enlarge the cell if the dense grid would exceed 2^25 cells (still exact, just slower)
     double cell = h->cfg.cell_size;
     for (;;) {
@@ -907,9 +919,10 @@ static int rebuild_grid(flb_handle* h, int M) {
     h->launches += 4;
     {
         LaunchScope ls(h, FAM_OTHER);
-        k_map_gather<<<nb, 256, 0, h->stream>>>(h->map_raw.p, M, 3, h->keys_sorted.p, h->vals_sorted.p, h->map_pts.p,
-                                                 h->cell_start.p, ncell);
+        k_map_gather<<<nb, 256, 0, h->stream>>>(h->map_raw.p, M, 3, h->vals_sorted.p, h->map_pts.p);
+        k_cell_starts<<<(ncell + 256) / 256, 256, 0, h->stream>>>(h->keys_sorted.p, M, h->cell_start.p, ncell);
         FLB_CUDA(h, cudaGetLastError());
+        h->launches++;
     }
     h->M = M;
     h->grid = g;
@@ -958,10 +971,25 @@ static int compact_and_rebuild(flb_handle* h, const int* idx_in, int total) {
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     if (count < 1) return fail(h, FLB_ERR_STATE, "map maintenance would leave an empty map");
     FLB_CUDA(h, h->map_raw.reserve((size_t)count * 3));   // never shrinks; grows only if count > capacity
+    FLB_CUDA(h, h->bbox_dev.reserve(6));
+    const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    FLB_CUDA(h, cudaMemcpyAsync(h->bbox_dev.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     {
         LaunchScope ls(h, FAM_OTHER);
         k_gather_xyz<<<(count + 255) / 256, 256, 0, h->stream>>>(h->map_comb.p, h->sel_idx.p, count, h->map_raw.p);
+        k_bbox<<<std::min((count + 255) / 256, 4 * std::max(h->num_sms, 1)), 256, 0, h->stream>>>(h->map_raw.p, count, h->bbox_dev.p);
         FLB_CUDA(h, cudaGetLastError());
+        h->launches++;
+    }
+    // the box follows the LIVE points: it shrinks when Delete_Point_Boxes drops the part of the map the sensor left
+    int box[6];
+    FLB_CUDA(h, cudaMemcpyAsync(box, h->bbox_dev.p, sizeof(box), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 6; ++k) {
+        const int b = box[k] >= 0 ? box[k] : (box[k] ^ 0x7fffffff);
+        float f;
+        std::memcpy(&f, &b, sizeof(f));
+        (k < 3 ? h->map_lo[k] : h->map_hi[k - 3]) = f;
     }
     return rebuild_grid(h, count);
 }

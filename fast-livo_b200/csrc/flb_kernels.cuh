@@ -141,9 +141,8 @@ __global__ void k_map_cell_ids(const float* __restrict__ xyz, int M, int stride,
 }
 
 // After the stable sort by cell: gather points (w = original index bits) and mark cell starts.
-__global__ void k_map_gather(const float* __restrict__ xyz, int M, int stride, const unsigned* __restrict__ keys_sorted,
-                             const int* __restrict__ vals_sorted, float4* __restrict__ pts, int* __restrict__ cell_start,
-                             int ncell) {
+__global__ void k_map_gather(const float* __restrict__ xyz, int M, int stride, const int* __restrict__ vals_sorted,
+                             float4* __restrict__ pts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int src = vals_sorted[i];
@@ -153,15 +152,48 @@ __global__ void k_map_gather(const float* __restrict__ xyz, int M, int stride, c
     p.z = xyz[(size_t)src * stride + 2];
     p.w = __int_as_float(src);
     pts[i] = p;
-    const unsigned k = keys_sorted[i];
-    const unsigned kprev = (i == 0) ? 0u : keys_sorted[i - 1];
-    if (i == 0) {
-        for (unsigned c = 0; c <= k; ++c) cell_start[c] = 0;
-    } else if (k != kprev) {
-        for (unsigned c = kprev + 1; c <= k; ++c) cell_start[c] = i;
+}
+
+// cell_start[c] = first sorted position whose cell id is >= c (c = 0 .. ncell): one binary search per cell, so long
+// runs of empty cells (a map that covers little of its bounding box) cost nothing extra.
+__device__ __forceinline__ int lower_bound_u32(const unsigned* __restrict__ a, int n, unsigned v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
     }
-    if (i == M - 1) {
-        for (unsigned c = k + 1; c <= (unsigned)ncell; ++c) cell_start[c] = M;
+    return lo;
+}
+__global__ void k_cell_starts(const unsigned* __restrict__ keys_sorted, int M, int* __restrict__ cell_start, int ncell) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncell) return;
+    cell_start[c] = lower_bound_u32(keys_sorted, M, (unsigned)c);
+}
+
+// bounding box of n packed xyz points: ordered-int atomics into box[6] = {min x, y, z, max x, y, z} (as ordered bits)
+__device__ __forceinline__ int f32_ordered_int(float f) {
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__global__ void k_bbox(const float* __restrict__ xyz, int n, int* __restrict__ box) {
+    int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int v = f32_ordered_int(xyz[3 * (size_t)i + a]);
+            mn[a] = min(mn[a], v);
+            mx[a] = max(mx[a], v);
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(box + a, mn[a]);
+            atomicMax(box + 3 + a, mx[a]);
+        }
     }
 }
 
@@ -276,6 +308,148 @@ __global__ void k_gather_xyz(const float* __restrict__ src, const int* __restric
     dst[3 * (size_t)i] = src[3 * (size_t)s];
     dst[3 * (size_t)i + 1] = src[3 * (size_t)s + 1];
     dst[3 * (size_t)i + 2] = src[3 * (size_t)s + 2];
+}
+
+// ---------------------------------------------------------------------------------------
+// Incremental Add_Points: only the voxels the NEW points fall into are looked at.  The new points are sorted by
+// downsample voxel; one thread per touched voxel finds the live points of its box through the kNN grid (a box overlaps
+// at most a handful of cells), replays the reference's sequential rule, marks the existing points that go and the one
+// new point that stays; the sorted grid is then MERGED (live existing points keep their order, inserts are appended to
+// their cells) instead of being re-sorted.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_axis_cell(float v, float o, float inv_cell, int n) {
+    const int c = (int)floorf((v - o) * inv_cell);
+    return min(max(c, 0), n - 1);
+}
+__global__ void k_vox_keys_rel(const float* __restrict__ xyz, int n, float ds, int bx, int by, int bz, int sy, int sz,
+                               unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // floor(p / ds) per axis (ikd_Tree.cpp:392-396) relative to the map box, packed x | y << sy | z << sz
+    const long long ix = (long long)floorf(xyz[3 * (size_t)i] / ds) - bx, iy = (long long)floorf(xyz[3 * (size_t)i + 1] / ds) - by,
+                    iz = (long long)floorf(xyz[3 * (size_t)i + 2] / ds) - bz;
+    keys[i] = (unsigned long long)ix | ((unsigned long long)iy << sy) | ((unsigned long long)iz << sz);
+    vals[i] = i;
+}
+__global__ void k_vox_resolve_incremental(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                          const float* __restrict__ nxyz, int n, float ds, GridDesc g, const int* __restrict__ cell_start,
+                                          const float4* __restrict__ pts, unsigned char* __restrict__ dead,
+                                          unsigned char* __restrict__ ins) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    if (i > 0 && keys[i - 1] == k) return;          // not a segment head
+    int end = i;
+    while (end < n && keys[end] == k) ++end;
+    const int v0 = vals[i];
+    float mn[3], mx[3], mid[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = floorf(nxyz[3 * (size_t)v0 + a] / ds) * ds;
+        mx[a] = mn[a] + ds;
+        mid[a] = (float)((double)mn[a] + (double)(mx[a] - mn[a]) / 2.0);
+    }
+    // Downsample_Storage = live points in the half-open box (Search_by_range, :1001)
+    const int cx0 = grid_axis_cell(mn[0], g.ox, g.inv_cell, g.nx), cx1 = grid_axis_cell(mx[0], g.ox, g.inv_cell, g.nx);
+    const int cy0 = grid_axis_cell(mn[1], g.oy, g.inv_cell, g.ny), cy1 = grid_axis_cell(mx[1], g.oy, g.inv_cell, g.ny);
+    const int cz0 = grid_axis_cell(mn[2], g.oz, g.inv_cell, g.nz), cz1 = grid_axis_cell(mx[2], g.oz, g.inv_cell, g.nz);
+    int c = 0, best = -1;                           // best >= 0: sorted position of an existing point; <= -2: -(j + 2) of a new one
+    float best_d = INFINITY;
+    for (int z = cz0; z <= cz1; ++z)
+        for (int y = cy0; y <= cy1; ++y) {
+            const int row = (z * g.ny + y) * g.nx;
+            const int s0 = cell_start[row + cx0], s1 = cell_start[row + cx1 + 1];
+            for (int m = s0; m < s1; ++m) {
+                const float4 p = pts[m];
+                if (mn[0] <= p.x && mx[0] > p.x && mn[1] <= p.y && mx[1] > p.y && mn[2] <= p.z && mx[2] > p.z) {
+                    ++c;
+                    const float d = dist2f(p.x, p.y, p.z, mid[0], mid[1], mid[2]);
+                    if (d < best_d) { best_d = d; best = m; }
+                }
+            }
+        }
+    bool replaced = false;
+    for (int j = i; j < end; ++j) {
+        const float* p = nxyz + 3 * (size_t)vals[j];
+        const float d = dist2f(p[0], p[1], p[2], mid[0], mid[1], mid[2]);
+        const bool p_wins = !(best_d < d);          // tmp_dist < min_dist, strict (:405)
+        if (c > 1 || p_wins) {                      // :412
+            if (p_wins) { best = -(j + 2); best_d = d; }
+            c = 1;
+            replaced = true;
+        }
+    }
+    if (!replaced) return;                          // the single existing point beat every new one: nothing changes
+    for (int z = cz0; z <= cz1; ++z)
+        for (int y = cy0; y <= cy1; ++y) {
+            const int row = (z * g.ny + y) * g.nx;
+            const int s0 = cell_start[row + cx0], s1 = cell_start[row + cx1 + 1];
+            for (int m = s0; m < s1; ++m) {
+                const float4 p = pts[m];
+                if (m != best && mn[0] <= p.x && mx[0] > p.x && mn[1] <= p.y && mx[1] > p.y && mn[2] <= p.z && mx[2] > p.z) dead[m] = 1;
+            }
+        }
+    if (best <= -2) ins[vals[-(best + 2)]] = 1;
+}
+// cell id of every new point (ncell = "not inserted": sorts behind every real cell)
+__global__ void k_insert_cells(const float* __restrict__ nxyz, int n, const unsigned char* __restrict__ ins, GridDesc g, int ncell,
+                               unsigned* __restrict__ keys, int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned key = (unsigned)ncell;
+    if (ins[i]) {
+        const int cx = grid_axis_cell(nxyz[3 * (size_t)i], g.ox, g.inv_cell, g.nx), cy = grid_axis_cell(nxyz[3 * (size_t)i + 1], g.oy, g.inv_cell, g.ny),
+                  cz = grid_axis_cell(nxyz[3 * (size_t)i + 2], g.oz, g.inv_cell, g.nz);
+        key = (unsigned)((cz * g.ny + cy) * g.nx + cx);
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+__global__ void k_dead_to_int(const unsigned char* __restrict__ dead, int M, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) out[i] = dead[i];
+}
+// counts[0] = dead points, counts[1] = inserted points (needs dead_before of the last element + its flag)
+__global__ void k_merge_counts(const int* __restrict__ dead_before, const unsigned char* __restrict__ dead, int M,
+                               const unsigned* __restrict__ ins_keys_sorted, int n, int ncell, int* __restrict__ counts) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        counts[0] = dead_before[M - 1] + dead[M - 1];
+        counts[1] = lower_bound_u32(ins_keys_sorted, n, (unsigned)ncell);
+    }
+}
+__global__ void k_merge_cell_starts(const int* __restrict__ cs_old, const int* __restrict__ dead_before, const int* __restrict__ counts,
+                                    int M, const unsigned* __restrict__ ins_keys_sorted, int n, int ncell, int* __restrict__ cs_new) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncell) return;
+    const int s = cs_old[c];
+    const int db = s < M ? dead_before[s] : counts[0];
+    cs_new[c] = s - db + lower_bound_u32(ins_keys_sorted, n, (unsigned)c);
+}
+__global__ void k_merge_existing(const float4* __restrict__ pts_old, const unsigned char* __restrict__ dead,
+                                 const int* __restrict__ dead_before, int M, GridDesc g, const unsigned* __restrict__ ins_keys_sorted, int n,
+                                 float4* __restrict__ pts_new, float* __restrict__ raw_new) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M || dead[m]) return;
+    float4 p = pts_old[m];
+    const int cx = grid_axis_cell(p.x, g.ox, g.inv_cell, g.nx), cy = grid_axis_cell(p.y, g.oy, g.inv_cell, g.ny),
+              cz = grid_axis_cell(p.z, g.oz, g.inv_cell, g.nz);
+    const unsigned cell = (unsigned)((cz * g.ny + cy) * g.nx + cx);
+    const int pos = m - dead_before[m] + lower_bound_u32(ins_keys_sorted, n, cell);
+    p.w = __int_as_float(pos);
+    pts_new[pos] = p;
+    raw_new[3 * (size_t)pos] = p.x; raw_new[3 * (size_t)pos + 1] = p.y; raw_new[3 * (size_t)pos + 2] = p.z;
+}
+__global__ void k_merge_inserts(const float* __restrict__ nxyz, const unsigned* __restrict__ ins_keys_sorted, const int* __restrict__ ins_vals_sorted,
+                                int n, const int* __restrict__ counts, const int* __restrict__ cs_new, float4* __restrict__ pts_new,
+                                float* __restrict__ raw_new) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= counts[1]) return;
+    const unsigned cell = ins_keys_sorted[k];
+    const int first = lower_bound_u32(ins_keys_sorted, n, cell), last = lower_bound_u32(ins_keys_sorted, n, cell + 1u);
+    const int pos = cs_new[cell + 1] - (last - first) + (k - first);     // inserts go behind the cell's surviving points
+    const float* q = nxyz + 3 * (size_t)ins_vals_sorted[k];
+    pts_new[pos] = make_float4(q[0], q[1], q[2], __int_as_float(pos));
+    raw_new[3 * (size_t)pos] = q[0]; raw_new[3 * (size_t)pos + 1] = q[1]; raw_new[3 * (size_t)pos + 2] = q[2];
 }
 
 // ---------------------------------------------------------------------------------------

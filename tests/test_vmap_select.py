@@ -96,6 +96,7 @@ def run_sequence(vm, seq, pose_after=None):
     out = []
     for fr in seq["frames"]:
         s = vm.select(fr["image"], fr["Rcw"], fr["Pcw"], fr["pg_down"])
+        s["map_value"] = vm.map_value()             # map_value as addFromSparseMap leaves it (:356, :455)
         g = vm.grow(fr["image"], fr["Rcw"], fr["Pcw"], fr["pg"], fr["frame_id"])
         mv = vm.map_value()
         a = vm.add_observations(fr["image"], fr["Rcw"], fr["Pcw"], fr["frame_id"])
@@ -111,8 +112,9 @@ def assert_same(a, b, exact_geo=True):
         assert (bits(sa["patch"]) == bits(sb["patch"])).all()
         assert (bits(sa["error"]) == bits(sb["error"])).all()
         assert (sa["pos"] == sb["pos"]).all()
+        assert (bits(sa["map_value"]) == bits(sb["map_value"])).all(), np.nonzero(sa["map_value"] != sb["map_value"])
+        assert (bits(mva) == bits(mvb)).all(), (np.nonzero(mva != mvb), mva[mva != mvb], mvb[mva != mvb])
         assert ga == gb and aa == ab
-        assert (bits(mva) == bits(mvb)).all()
     da, db = a[1], b[1]
     assert (da["pos"] == db["pos"]).all() and (bits(da["value"]) == bits(db["value"])).all()
     assert (da["n_obs"] == db["n_obs"]).all() and (da["obs"] == db["obs"]).all()
