@@ -820,6 +820,8 @@ int flb_destroy(flb_handle* h) {
     for (auto& ev : h->evs) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     h->map_raw.release(); h->keys.release(); h->keys_sorted.release(); h->vals.release(); h->vals_sorted.release();
     h->map_comb.release(); h->boxes.release(); h->vkeys.release(); h->vkeys_sorted.release(); h->keep.release(); h->sel_idx.release();
+    h->map_pts_alt.release(); h->cell_start_alt.release(); h->map_raw_alt.release(); h->dead.release(); h->ins.release();
+    h->dead_before.release(); h->merge_counts.release(); h->bbox_dev.release();
     h->cub_tmp.release(); h->map_pts.release(); h->cell_start.release(); h->scan.release(); h->sel.release();
     h->plane_ok.release(); h->plane.release(); h->x_world.release(); h->x_nn_d2.release(); h->x_pd2.release();
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
@@ -994,24 +996,10 @@ static int compact_and_rebuild(flb_handle* h, const int* idx_in, int total) {
     return rebuild_grid(h, count);
 }
 
-int flb_map_add_points(flb_handle* h, const float* world_xyz, int n, int stride, float downsample_size) {
-    FLB_CHECK_H(h);
-    if (h->M <= 0) return fail(h, FLB_ERR_STATE, "flb_map_add_points: no map uploaded");
-    if (!world_xyz || n < 0 || stride < 3 || !(downsample_size > 0)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: bad arguments");
-    if (n == 0) return FLB_OK;
+// Full path of Add_Points: (existing + new) points sorted by downsample voxel, one thread per voxel, compaction, grid
+// rebuilt from scratch.  Taken when a new point lies outside the box the kNN grid covers (the grid has to grow).
+static int map_add_points_full(flb_handle* h, const float* st, int n, float downsample_size) {
     const int M = h->M, total = M + n;
-    void* stv = nullptr;
-    FLB_CUDA(h, h->st_map.acquire((size_t)n * 3 * sizeof(float), &stv));
-    float* st = static_cast<float*>(stv);
-    for (int i = 0; i < n; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const float v = world_xyz[(size_t)i * stride + k];
-            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: non-finite coordinate at point %d", i);
-            if (std::fabs(v / downsample_size) > 1.0e6f) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: coordinate / downsample_size exceeds 2^20 voxels");
-            st[3 * (size_t)i + k] = v;
-            h->map_lo[k] = std::min(h->map_lo[k], v);
-            h->map_hi[k] = std::max(h->map_hi[k], v);
-        }
     FLB_CUDA(h, h->map_comb.reserve((size_t)total * 3));
     FLB_CUDA(h, h->vkeys.reserve(total));
     FLB_CUDA(h, h->vkeys_sorted.reserve(total));
@@ -1041,6 +1029,118 @@ int flb_map_add_points(flb_handle* h, const float* world_xyz, int n, int stride,
         FLB_CUDA(h, cudaGetLastError());
     }
     return compact_and_rebuild(h, h->vals_sorted.p, total);
+}
+
+static int bits_for(long long span) {
+    int b = 1;
+    while ((1ll << b) <= span) ++b;
+    return b;
+}
+
+int flb_map_add_points(flb_handle* h, const float* world_xyz, int n, int stride, float downsample_size) {
+    FLB_CHECK_H(h);
+    if (h->M <= 0) return fail(h, FLB_ERR_STATE, "flb_map_add_points: no map uploaded");
+    if (!world_xyz || n < 0 || stride < 3 || !(downsample_size > 0)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: bad arguments");
+    if (n == 0) return FLB_OK;
+    const int M = h->M;
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_map.acquire((size_t)n * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = world_xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: non-finite coordinate at point %d", i);
+            if (std::fabs(v / downsample_size) > 1.0e6f) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: coordinate / downsample_size exceeds 2^20 voxels");
+            st[3 * (size_t)i + k] = v;
+            lo[k] = std::min(lo[k], v);
+            hi[k] = std::max(hi[k], v);
+        }
+    // the input is valid from here on: only now does the map box take it in
+    bool inside = true;
+    for (int k = 0; k < 3; ++k) inside = inside && lo[k] >= h->grid_lo[k] && hi[k] <= h->grid_hi[k];
+    for (int k = 0; k < 3; ++k) { h->map_lo[k] = std::min(h->map_lo[k], lo[k]); h->map_hi[k] = std::max(h->map_hi[k], hi[k]); }
+    if (!inside) return map_add_points_full(h, st, n, downsample_size);
+
+    // ---- incremental path: every new point lies inside the box the grid covers
+    const GridDesc g = h->grid;
+    const int ncell = h->ncell;
+    const float ds = downsample_size;
+    // voxel keys relative to the grid box, packed into as few bits as the box needs (fewer radix passes)
+    const int bx = (int)std::floor(h->grid_lo[0] / ds) - 1, by = (int)std::floor(h->grid_lo[1] / ds) - 1, bz = (int)std::floor(h->grid_lo[2] / ds) - 1;
+    const int wx = bits_for((long long)std::floor(h->grid_hi[0] / ds) + 2 - bx), wy = bits_for((long long)std::floor(h->grid_hi[1] / ds) + 2 - by),
+              wz = bits_for((long long)std::floor(h->grid_hi[2] / ds) + 2 - bz);
+    if (wx + wy + wz > 62) return map_add_points_full(h, st, n, downsample_size);
+    FLB_CUDA(h, h->map_comb.reserve((size_t)n * 3));
+    FLB_CUDA(h, h->vkeys.reserve(n));
+    FLB_CUDA(h, h->vkeys_sorted.reserve(n));
+    FLB_CUDA(h, h->vals.reserve(std::max(n, M)));
+    FLB_CUDA(h, h->vals_sorted.reserve(std::max(n, M)));
+    FLB_CUDA(h, h->keys.reserve(std::max(n, M)));
+    FLB_CUDA(h, h->keys_sorted.reserve(std::max(n, M)));
+    FLB_CUDA(h, h->dead.reserve(M));
+    FLB_CUDA(h, h->ins.reserve(n));
+    FLB_CUDA(h, h->dead_before.reserve((size_t)M + 1));
+    FLB_CUDA(h, h->merge_counts.reserve(2));
+    FLB_CUDA(h, h->map_pts_alt.reserve((size_t)M + n));
+    FLB_CUDA(h, h->map_raw_alt.reserve(((size_t)M + n) * 3));
+    FLB_CUDA(h, h->cell_start_alt.reserve((size_t)ncell + 1));
+    float* nxyz = h->map_comb.p;
+    FLB_CUDA(h, cudaMemcpyAsync(nxyz, st, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_map.mark(h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(h->dead.p, 0, M, h->stream));
+    FLB_CUDA(h, cudaMemsetAsync(h->ins.p, 0, n, h->stream));
+    const int gn = (n + 255) / 256, gm = (M + 255) / 256;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vox_keys_rel<<<gn, 256, 0, h->stream>>>(nxyz, n, ds, bx, by, bz, wx, wx + wy, h->vkeys.p, h->vals.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    size_t tmp_bytes = 0, t2 = 0, t3 = 0;
+    int cell_bits = bits_for((long long)ncell);
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->vkeys.p, h->vkeys_sorted.p, h->vals.p, h->vals_sorted.p, n, 0,
+                                                wx + wy + wz, h->stream));
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, t2, h->keys.p, h->keys_sorted.p, h->vals.p, h->vals_sorted.p, n, 0, cell_bits, h->stream));
+    FLB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, t3, h->dead_before.p, h->dead_before.p, M, h->stream));
+    FLB_CUDA(h, h->cub_tmp.reserve(std::max(tmp_bytes, std::max(t2, t3))));
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->vkeys.p, h->vkeys_sorted.p, h->vals.p, h->vals_sorted.p, n, 0,
+                                                wx + wy + wz, h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vox_resolve_incremental<<<gn, 256, 0, h->stream>>>(h->vkeys_sorted.p, h->vals_sorted.p, nxyz, n, ds, g, h->cell_start.p, h->map_pts.p,
+                                                              h->dead.p, h->ins.p);
+        // inserted points sorted by grid cell (not-inserted ones sort behind every cell)
+        k_insert_cells<<<gn, 256, 0, h->stream>>>(nxyz, n, h->ins.p, g, ncell, h->keys.p, h->vals.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, t2, h->keys.p, h->keys_sorted.p, h->vals.p, h->vals_sorted.p, n, 0, cell_bits, h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_dead_to_int<<<gm, 256, 0, h->stream>>>(h->dead.p, M, h->dead_before.p);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    FLB_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, t3, h->dead_before.p, h->dead_before.p, M, h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_merge_counts<<<1, 32, 0, h->stream>>>(h->dead_before.p, h->dead.p, M, h->keys_sorted.p, n, ncell, h->merge_counts.p);
+        k_merge_cell_starts<<<(ncell + 256) / 256, 256, 0, h->stream>>>(h->cell_start.p, h->dead_before.p, h->merge_counts.p, M, h->keys_sorted.p, n,
+                                                                         ncell, h->cell_start_alt.p);
+        k_merge_existing<<<gm, 256, 0, h->stream>>>(h->map_pts.p, h->dead.p, h->dead_before.p, M, g, h->keys_sorted.p, n, h->map_pts_alt.p,
+                                                     h->map_raw_alt.p);
+        k_merge_inserts<<<gn, 256, 0, h->stream>>>(nxyz, h->keys_sorted.p, h->vals_sorted.p, n, h->merge_counts.p, h->cell_start_alt.p,
+                                                    h->map_pts_alt.p, h->map_raw_alt.p);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 10;
+    }
+    int counts[2] = {0, 0};
+    FLB_CUDA(h, cudaMemcpyAsync(counts, h->merge_counts.p, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::swap(h->map_pts, h->map_pts_alt);
+    std::swap(h->cell_start, h->cell_start_alt);
+    std::swap(h->map_raw, h->map_raw_alt);
+    h->M = M - counts[0] + counts[1];
+    h->last_pass_valid = false;
+    return FLB_OK;
 }
 
 int flb_map_delete_boxes(flb_handle* h, const float* boxes, int nb) {
