@@ -487,6 +487,95 @@ def measure_batched(flb, torch, name, B, local, dev, stream, flush, hbm, peak_sr
             "note": "kernel-per-pass path with blockIdx.y = frame; every frame bit-identical to the frame run alone (tests/test_gpu_batch.py)"}
 
 
+def measure_full_frame(flb, torch, name, local, dev, stream, flush, steps=20):
+    """One frame through EVERY stage that is on the device, host buffers in, state out (SURVEY.md section 8 rows a + f1-f4):
+    IMU propagation + undistortion -> LIO update -> map maintenance (Add_Points) -> visible-patch selection + warp ->
+    VIO update -> map growth -> new observations.  The patch list never crosses PCIe (it is built on the device)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from imu_util import product_inputs
+    cfg = flb.synth.CONFIGS[name]
+    seq = flb.synth.make_visual_sequence(cfg, 2, with_map=True)
+    f0, f1 = seq["frames"]
+    grid = 12 if cfg.img_w <= 640 else 16
+    h = flb.Handle(device=local, cell_size=cfg.cell_size)
+    h.set_stream(stream.cuda_stream)
+    fdict = dict(R_LI=seq["R_LI"], t_LI=seq["t_LI"], Rcl=seq["Rcl"], Pcl=seq["Pcl"], cfg=cfg)
+    pc = pass_counts(cfg)
+    lprm = flb.capi.lio_params(fdict, pc["lio_T"], early_stop=False)
+    vprm = flb.capi.vio_params(fdict, pc["vio_T"], early_stop=False, force_all_passes=True)
+    h.map_upload(seq["map_xyz"])
+    h.camera_set(seq["cam"])
+    h.image_upload(f0["image"])
+    h.vmap_reset(seq, grid_size=grid, outlier_threshold=300.0)
+    h.vmap_select(f0["Rcw"], f0["Pcw"], f0["pg_down"])
+    h.vmap_grow(f0["Rcw"], f0["Pcw"], f0["pg"], 0)          # the visual map now holds frame 0's points
+    base = h.vmap_counts()
+    fi = flb.synth.make_imu_frame(seed=41, n_points=cfg.n_scan)
+    packed = np.concatenate([f1["scan_body"], fi["offset_ms"][:len(f1["scan_body"]), None]], 1).astype(np.float32)
+    x0 = flb.capi.State18.make(f1["R_prop"], f1["p_prop"], cov=seq["cov"], grav=seq["grav"])
+    stage = {k: 0.0 for k in ("imu_undistort", "scan+lio_enqueue", "map_add_points", "image+select_enqueue", "vio+grow+observe_enqueue", "state_download")}
+    n_sel = 0
+
+    def frame(k, timed):
+        nonlocal n_sel
+        t = [time.perf_counter()]
+        Pg, Cg, xg = product_inputs(flb, fi)
+        h.state_upload(x0, x0.copy())
+        h.imu_undistort(Pg, Cg, fi["v_imu"], fi["pcl_beg_time"], fi["pcl_end_time"], packed, offset_index=3)
+        t.append(time.perf_counter())
+        h.state_upload(x0, x0.copy())                       # the synthetic IMU stream is not this trajectory's: restore the prior
+        h.scan_upload(f1["scan_body"])
+        h.lio_update_enqueue(lprm)
+        t.append(time.perf_counter())
+        h.map_add_points(f1["pg"], cfg.pitch)
+        t.append(time.perf_counter())
+        h.image_upload(f1["image"])
+        h.vmap_select(None, None, f1["pg_down"], blocking=False)
+        t.append(time.perf_counter())
+        h.vmap_grow(None, None, f1["pg"], k + 1)
+        h.state_set_prior_enqueue()
+        h.vio_update_enqueue(vprm)
+        h.vmap_add_observations(None, None, k + 1)
+        t.append(time.perf_counter())
+        x, lrep, vrep = h.state_download()
+        t.append(time.perf_counter())
+        if timed:
+            for key, a, b in zip(stage, t[:-1], t[1:]):
+                stage[key] += b - a
+        return x, lrep, vrep
+    for k in range(3):
+        x, lrep, vrep = frame(k, False)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        if flush is not None:
+            flush.zero_()
+        x, lrep, vrep = frame(3 + k, True)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if flush is not None:
+        torch.cuda.synchronize(dev)
+        tf = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+        torch.cuda.synchronize(dev)
+        dt -= time.perf_counter() - tf
+    c = h.vmap_counts()
+    h.close()
+    h2d = packed.nbytes + len(fi["v_imu"]) * 56 + f1["scan_body"].nbytes + f1["pg"].nbytes * 2 + f1["image"].size + f1["pg_down"].nbytes + 3 * 2 * 2736
+    return {"workload": f"{cfg.name}-shaped 2-frame sequence: {cfg.n_scan} scan pts, {cfg.n_map}-pt map, {cfg.img_w}x{cfg.img_h} image, "
+                        f"{grid} px grid ({(cfg.img_w // grid) * (cfg.img_h // grid)} cells), {c['selected']} patches selected on the device",
+            "value": steps / dt, "unit": UNIT, "ms_per_frame": 1e3 * dt / steps, "steps": steps,
+            "host_ms_per_stage": {k: 1e3 * v / steps for k, v in stage.items()},
+            "h2d_bytes_per_frame": int(h2d), "d2h_bytes_per_frame": int(len(packed) * 16 + 2736 + 128),
+            "patches": int(c["selected"]), "vio_rows_per_frame": int(vrep.rows_total), "lio_rows_per_frame": int(lrep.rows_total),
+            "visual_map": {"points_before": base["points"], "points_after": c["points"], "features_after": c["features"], "keyframe_images": c["images"]},
+            "note": "stages: flb_imu_undistort (blocking: the undistorted points go back to the caller's voxel filter), flb_scan_upload + "
+                    "flb_lio_update_enqueue, flb_map_add_points (incremental merge; one small sync), flb_image_upload + flb_vmap_select "
+                    "(enqueue-only, pose from the device state), flb_vmap_grow + flb_vio_update_enqueue + flb_vmap_add_observations, "
+                    "flb_state_download; L2 flushed between frames"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -809,6 +898,13 @@ def main():
             except Exception as e:
                 batched[f"{name}x{B}"] = {"error": repr(e)}
 
+    full_frame = None
+    if rank == 0 and world == 1 and not args.no_others and args.workload == "C2":
+        try:
+            full_frame = measure_full_frame(flb, torch, "C2", local, dev, stream, flush)
+        except Exception as e:
+            full_frame = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -831,7 +927,7 @@ def main():
                             "blocking_calls_value: flb_lio_update + flb_vio_update (two synchronisations and state round "
                             "trips per frame, the reference's call shape), no L2 flush"},
             "roofline": roofline, "kernels": fams, "pass_trace": trace, "map_maintenance": map_maint, "imu_undistort": imu_f3,
-            "cpu_baseline": cpu, "parity": parity, "nccl_collective": nccl_alt, "other_workloads": others, "batched": batched,
+            "cpu_baseline": cpu, "parity": parity, "nccl_collective": nccl_alt, "other_workloads": others, "batched": batched, "e2e_full_frame": full_frame,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

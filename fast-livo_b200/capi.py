@@ -164,7 +164,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
            "flb_vio_update_level",
            "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
-           "flb_vmap_map_value", "flb_vmap_dump",
+           "flb_vmap_map_value", "flb_vmap_dump", "flb_colorize",
            "flb_batch_begin", "flb_batch_set_frame", "flb_batch_state_reset_enqueue", "flb_batch_update_enqueue", "flb_batch_state_download",
            "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps"]
 
@@ -230,6 +230,7 @@ def lib():
         L.flb_batch_state_reset_enqueue.argtypes = [vp]
         L.flb_batch_update_enqueue.argtypes = [vp, C.POINTER(LioParams), C.POINTER(VioParams)]
         L.flb_batch_state_download.argtypes = [vp, C.c_int, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
+        L.flb_colorize.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.flb_vmap_reset.argtypes = [vp, C.POINTER(VmapParams)]
         L.flb_vmap_select.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
         L.flb_vmap_selected.argtypes = [vp, C.c_int, C.POINTER(C.c_int)] + [vp] * 6
@@ -541,6 +542,16 @@ class Handle:
     def vmap_add_observations(self, Rcw, Pcw, frame_id):
         R, P, pr, pp = self._pose(Rcw, Pcw)
         self._ck(self.L.flb_vmap_add_observations(self.h, pr, pp, int(frame_id)))
+
+    def colorize(self, Rcw, Pcw, bgr, world_xyz):
+        """flb_colorize: (rgb (n, 3) uint8, valid (n,) bool)."""
+        R, P, pr, pp = self._pose(Rcw, Pcw)
+        img = np.ascontiguousarray(bgr, np.uint8)
+        pts = np.ascontiguousarray(world_xyz, np.float32).reshape(-1, 3)
+        rgb = np.zeros((len(pts), 3), np.uint8)
+        val = np.zeros(len(pts), np.uint8)
+        self._ck(self.L.flb_colorize(self.h, pr, pp, _p(img), img.shape[1] * 3, _p(pts), len(pts), 3, _p(rgb), _p(val)))
+        return rgb, val.astype(bool)
 
     def vmap_counts(self):
         v = [C.c_int() for _ in range(5)]

@@ -2649,6 +2649,45 @@ int flb_vmap_add_observations(flb_handle* h, const double Rcw[9], const double P
     return vio_inputs_release(h);
 }
 
+int flb_colorize(flb_handle* h, const double Rcw[9], const double Pcw[3], const uint8_t* bgr, int stride_bytes, const float* world_xyz, int n,
+                 int stride, uint8_t* rgb, uint8_t* valid) {
+    FLB_CHECK_H(h);
+    if (!h->cam_set) return fail(h, FLB_ERR_STATE, "flb_colorize: flb_camera_set first");
+    const int W = h->cam.width, H = h->cam.height;
+    if (!bgr || stride_bytes < 3 * W || n < 0 || (n > 0 && (!world_xyz || !rgb || !valid)) || stride < 3)
+        return fail(h, FLB_ERR_INVALID, "flb_colorize: bad arguments");
+    if (n == 0) return FLB_OK;
+    auto& vm = h->vm;
+    FLB_CUDA(h, vm.pose.reserve(12));
+    FLB_CUDA(h, vm.rci.reserve(12));
+    if (!(Rcw && Pcw) && !vm.on) return fail(h, FLB_ERR_STATE, "flb_colorize: no pose given and no flb_vmap_reset (extrinsics)");
+    { int rc = vm_set_pose(h, Rcw, Pcw); if (rc) return rc; }
+    { int rc = vm_upload_points(h, world_xyz, n, stride); if (rc) return rc; }
+    const size_t img_bytes = (size_t)W * H * 3;
+    FLB_CUDA(h, h->x_rowmask.reserve(img_bytes + (size_t)n * 4));     // colour image | rgb | valid
+    unsigned char* d_img = h->x_rowmask.p;
+    unsigned char* d_rgb = d_img + img_bytes;
+    unsigned char* d_val = d_rgb + (size_t)n * 3;
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_img.acquire(img_bytes, &stv));
+    unsigned char* st = static_cast<unsigned char*>(stv);
+    for (int r = 0; r < H; ++r) std::memcpy(st + (size_t)r * W * 3, bgr + (size_t)r * stride_bytes, (size_t)W * 3);
+    FLB_CUDA(h, cudaMemcpyAsync(d_img, st, img_bytes, cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_img.mark(h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vm_colorize<<<(n + 255) / 256, 256, 0, h->stream>>>(h->cam, vm.pose.p, d_img, vm.pg.p, n, d_rgb, d_val);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    FLB_CUDA(h, h->pin_out.reserve((size_t)n * 4));
+    FLB_CUDA(h, cudaMemcpyAsync(h->pin_out.p, d_rgb, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(rgb, h->pin_out.p, (size_t)n * 3);
+    std::memcpy(valid, static_cast<unsigned char*>(h->pin_out.p) + (size_t)n * 3, n);
+    h->last_pass_valid = false;                       // the row-mask export buffer was reused
+    return FLB_OK;
+}
+
 int flb_vmap_counts(flb_handle* h, int* points, int* features, int* images, int* selected, int* last_added) {
     FLB_CHECK_H(h);
     if (!h->vm.on) return fail(h, FLB_ERR_STATE, "flb_vmap_counts: flb_vmap_reset first");

@@ -925,6 +925,37 @@ FLB_HD float vm_getpatch_pixel(const unsigned char* img, int width, const VmPatc
     return g.w_tl * p[0] + g.w_tr * p[1] + g.w_bl * p[width] + g.w_br * p[width + 1];
 }
 
+// One point of publish_frame_world_rgb (src/laserMapping.cpp:726-741): project into the current frame, bilinear BGR
+// sample (LidarSelector::getpixel, src/lidar_selection.cpp:1007-1025), stored as r, g, b bytes.  false: not coloured.
+FLB_HD bool vm_colorize_point(const CamModel& cam, const double* Rcw, const double* Pcw, const unsigned char* bgr, const float* p,
+                              unsigned char* rgb) {
+    const double p_w[3] = {(double)p[0], (double)p[1], (double)p[2]};
+    double pf[3], pc[2];
+    se3_apply(Rcw, Pcw, p_w, pf);
+    if (pf[2] < 0) return false;
+    world2cam(cam, pf, pc);
+    if (!vm_in_frame(cam, pc[0], pc[1], 0)) return false;
+    const int width = cam.width;
+    const float u_ref = pc[0];
+    const float v_ref = pc[1];
+    const int u_ref_i = floorf(pc[0]);
+    const int v_ref_i = floorf(pc[1]);
+    const float subpix_u_ref = (u_ref - u_ref_i);
+    const float subpix_v_ref = (v_ref - v_ref_i);
+    const float w_ref_tl = (1.0 - subpix_u_ref) * (1.0 - subpix_v_ref);
+    const float w_ref_tr = subpix_u_ref * (1.0 - subpix_v_ref);
+    const float w_ref_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
+    const float w_ref_br = subpix_u_ref * subpix_v_ref;
+    // the last row / column of the image has no bilinear neighbour (the reference reads past it): clamp the neighbour
+    const int du = (u_ref_i + 1 < cam.width) ? 3 : 0, dv = (v_ref_i + 1 < cam.height) ? width * 3 : 0;
+    const unsigned char* img_ptr = bgr + ((size_t)v_ref_i * width + u_ref_i) * 3;
+    const float B = w_ref_tl * img_ptr[0] + w_ref_tr * img_ptr[0 + du] + w_ref_bl * img_ptr[dv] + w_ref_br * img_ptr[dv + 0 + du];
+    const float G = w_ref_tl * img_ptr[1] + w_ref_tr * img_ptr[1 + du] + w_ref_bl * img_ptr[1 + dv] + w_ref_br * img_ptr[dv + 1 + du];
+    const float R = w_ref_tl * img_ptr[2] + w_ref_tr * img_ptr[2 + du] + w_ref_bl * img_ptr[2 + dv] + w_ref_br * img_ptr[dv + 2 + du];
+    rgb[0] = (unsigned char)(int)R; rgb[1] = (unsigned char)(int)G; rgb[2] = (unsigned char)(int)B;
+    return true;
+}
+
 // The device-resident visual map: Point (include/point.h) and Feature (include/feature.h) flattened.
 constexpr int kVmMaxObs = 20;            // addObservation keeps obs_.size() < 20 before adding one (:946-952)
 struct VmFeature {

@@ -358,4 +358,21 @@ __global__ void __launch_bounds__(1024) k_vm_observe(CamModel cam, const double*
     }
 }
 
+// publish_frame_world_rgb (src/laserMapping.cpp:710-745): per point, r g b + a validity flag
+__global__ void k_vm_colorize(CamModel cam, const double* __restrict__ pose12, const unsigned char* __restrict__ bgr,
+                              const float* __restrict__ xyz, int n, unsigned char* __restrict__ rgb, unsigned char* __restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double Rcw[9], Pcw[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rcw[k] = pose12[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Pcw[k] = pose12[9 + k];
+    unsigned char c[3] = {0, 0, 0};
+    const float p[3] = {xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]};
+    const bool ok = vm_colorize_point(cam, Rcw, Pcw, bgr, p, c);
+    rgb[3 * (size_t)i] = c[0]; rgb[3 * (size_t)i + 1] = c[1]; rgb[3 * (size_t)i + 2] = c[2];
+    valid[i] = ok ? 1 : 0;
+}
+
 }  // namespace flb

@@ -402,7 +402,7 @@ def voxel_centroids(xyz: np.ndarray, leaf: float) -> np.ndarray:
 
 
 def make_visual_sequence(cfg: FrameConfig | str = "T0", n_frames: int = 3, seed: int | None = None, step=(0.18, 0.06, 0.02),
-                         yaw_step_deg: float = 2.5) -> dict:
+                         yaw_step_deg: float = 2.5, with_map: bool = False) -> dict:
     """n_frames camera frames of one scene: image, camera pose T_f_w = (Rcw, Pcw) as LidarSelector::updateFrameState
     forms it (src/lidar_selection.cpp:905-911), the scan in WORLD coordinates (`pg` of LidarSelector::detect) and its
     0.2 m voxel-filtered version (`pg_down`, :7, :351-352)."""
@@ -412,6 +412,7 @@ def make_visual_sequence(cfg: FrameConfig | str = "T0", n_frames: int = 3, seed:
     rng = np.random.default_rng(np.random.PCG64(seed + 77))
     room_l = _room_for(cfg.n_map, cfg.pitch, cfg.room_h)
     scene = Scene(rng, room_l, cfg.room_h)
+    map_xyz = sample_map(np.random.default_rng(np.random.PCG64(seed + 78)), scene, cfg.pitch, cfg.n_map) if with_map else None
     yaw0 = rng.uniform(-np.pi, np.pi)
     p0 = np.array([rng.uniform(-0.04, 0.04) * room_l, rng.uniform(-0.04, 0.04) * room_l, rng.uniform(1.2, 1.8)])
     R_LI, t_LI = AVIA_EXTRINSIC_R.copy(), AVIA_EXTRINSIC_T.copy()
@@ -442,5 +443,10 @@ def make_visual_sequence(cfg: FrameConfig | str = "T0", n_frames: int = 3, seed:
         d_w = d_l @ (R @ R_LI).T
         rng_t = scene.raycast(o_w, d_w) + rng.normal(0.0, 0.01, size=cfg.n_scan)
         pg = (o_w + d_w * rng_t[:, None]).astype(np.float32)
-        frames.append(dict(image=image, Rcw=Rcw, Pcw=Pcw, R=R, p=p, pg=pg, pg_down=voxel_centroids(pg, 0.2), frame_id=k))
-    return dict(cfg=cfg, cam=cam, frames=frames, Rci=Rci, Pci=Pci, R_LI=R_LI, t_LI=t_LI, Rcl=AVIA_RCL.copy(), Pcl=AVIA_PCL.copy())
+        prng = np.random.default_rng(np.random.PCG64(seed + 1000 + k))
+        frames.append(dict(image=image, Rcw=Rcw, Pcw=Pcw, R=R, p=p, pg=pg, pg_down=voxel_centroids(pg, 0.2), frame_id=k,
+                           scan_body=(d_l * rng_t[:, None]).astype(np.float32),
+                           R_prop=R @ exp_so3(prng.normal(0.0, np.deg2rad(0.5), size=3)), p_prop=p + prng.normal(0.0, 0.03, size=3)))
+    return dict(cfg=cfg, cam=cam, frames=frames, Rci=Rci, Pci=Pci, R_LI=R_LI, t_LI=t_LI, Rcl=AVIA_RCL.copy(), Pcl=AVIA_PCL.copy(),
+                map_xyz=map_xyz, cov=np.diag(np.repeat([1e-4, 1e-3, 1e-2, 1e-4, 1e-3, 1e-4], 3)).astype(np.float64),
+                grav=np.array([0.0, 0.0, -9.81]))

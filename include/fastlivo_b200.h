@@ -321,6 +321,13 @@ int flb_vmap_grow(flb_handle* h, const double Rcw[9], const double Pcw[3], const
 /* LidarSelector::addObservation (:913-965) for the patches of the last flb_vmap_select, with the frame pose AFTER
  * ComputeJ (NULL, NULL = the device state).  Enqueue-only. */
 int flb_vmap_add_observations(flb_handle* h, const double Rcw[9], const double Pcw[3], int frame_id);
+/* publish_frame_world_rgb (src/laserMapping.cpp:710-745): colour every world point that projects into the current
+ * frame with the bilinear BGR sample of LidarSelector::getpixel (src/lidar_selection.cpp:1007-1025).  bgr: the
+ * colour frame (img_rgb), 3 bytes per pixel; rgb: n x 3 bytes (r, g, b as the reference stores them); valid[i] = 1
+ * for the points the reference pushes into laserCloudWorldRGB (in front of the camera, inside the image), whose order
+ * is the input order.  Rcw / Pcw NULL: from the device state (after flb_vmap_reset).  Blocking. */
+int flb_colorize(flb_handle* h, const double Rcw[9], const double Pcw[3], const uint8_t* bgr, int stride_bytes, const float* world_xyz, int n,
+                 int stride_floats, uint8_t* rgb, uint8_t* valid);
 /* sizes (blocking): points, features, keyframe images, patches of the last selection, items appended by the last
  * grow / add_observations call.  Any pointer may be NULL. */
 int flb_vmap_counts(flb_handle* h, int* points, int* features, int* images, int* selected, int* last_added);

@@ -547,6 +547,40 @@ int flo_vmap_add_observations(flo_vmap* vm, const uint8_t* img, const double* Rc
     return added;
 }
 
+/* publish_frame_world_rgb, src/laserMapping.cpp:710-745 + LidarSelector::getpixel, src/lidar_selection.cpp:1007-1025.
+ * The reference reads the bilinear neighbour even on the last row / column (past the buffer): clamped here. */
+void flo_colorize(const flo_cam* cam, const double* Rcw, const double* Pcw, const uint8_t* bgr, const float* xyz, int n, uint8_t* rgb,
+                  uint8_t* valid) {
+    const int width = cam->width;
+    for (int i = 0; i < n; i++) {
+        rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = 0;
+        valid[i] = 0;
+        const double p_w[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        double pf[3], pc[2];
+        se3_apply(Rcw, Pcw, p_w, pf);
+        if (pf[2] < 0) continue;
+        flo_world2cam(cam, pf, pc);
+        if (!in_frame(*cam, pc[0], pc[1], 0)) continue;
+        const float u_ref = pc[0];
+        const float v_ref = pc[1];
+        const int u_ref_i = floorf(pc[0]);
+        const int v_ref_i = floorf(pc[1]);
+        const float subpix_u_ref = (u_ref - u_ref_i);
+        const float subpix_v_ref = (v_ref - v_ref_i);
+        const float w_ref_tl = (1.0 - subpix_u_ref) * (1.0 - subpix_v_ref);
+        const float w_ref_tr = subpix_u_ref * (1.0 - subpix_v_ref);
+        const float w_ref_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
+        const float w_ref_br = subpix_u_ref * subpix_v_ref;
+        const int du = (u_ref_i + 1 < cam->width) ? 3 : 0, dv = (v_ref_i + 1 < cam->height) ? width * 3 : 0;
+        const uint8_t* img_ptr = bgr + ((size_t)v_ref_i * width + u_ref_i) * 3;
+        const float B = w_ref_tl * img_ptr[0] + w_ref_tr * img_ptr[0 + du] + w_ref_bl * img_ptr[dv] + w_ref_br * img_ptr[dv + 0 + du];
+        const float G = w_ref_tl * img_ptr[1] + w_ref_tr * img_ptr[1 + du] + w_ref_bl * img_ptr[1 + dv] + w_ref_br * img_ptr[dv + 1 + du];
+        const float R = w_ref_tl * img_ptr[2] + w_ref_tr * img_ptr[2 + du] + w_ref_bl * img_ptr[2 + dv] + w_ref_br * img_ptr[dv + 2 + du];
+        rgb[3 * i] = (uint8_t)(int)R; rgb[3 * i + 1] = (uint8_t)(int)G; rgb[3 * i + 2] = (uint8_t)(int)B;
+        valid[i] = 1;
+    }
+}
+
 /* Dump for tests: per point pos (3 doubles), value, n_obs and the newest-first feature ids (up to 20, -1 padded). */
 void flo_vmap_dump_points(const flo_vmap* vm, double* pos, float* value, int* n_obs, int* obs20) {
     for (size_t j = 0; j < vm->pts.size(); ++j) {

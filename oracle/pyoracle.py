@@ -259,6 +259,7 @@ def lib():
         L.flo_vmap_add_observations.argtypes = [vp, vp, vp, vp, C.c_int]
         L.flo_vmap_dump_points.argtypes = [vp] * 5
         L.flo_vmap_dump_features.argtypes = [vp] * 4
+        L.flo_colorize.argtypes = [C.POINTER(Cam)] + [vp] * 4 + [C.c_int, vp, vp]
         L.flo_world2cam.argtypes = [C.POINTER(Cam), C.c_void_p, C.c_void_p]
         L.flo_exp3.argtypes = [C.c_void_p, C.c_void_p]
         L.flo_log3.argtypes = [C.c_void_p, C.c_void_p]
@@ -577,6 +578,18 @@ class VMap:
         geo, score, lii = np.zeros((m, 17)), np.zeros(m, np.float32), np.zeros((m, 3), np.int32)
         self.L.flo_vmap_dump_features(self.h, _p(geo), _p(score), _p(lii))
         return dict(pos=pos, value=value, n_obs=n_obs, obs=obs, ft_geo=geo, ft_score=score, ft_level_id_img=lii)
+
+
+def colorize(cam: dict, Rcw, Pcw, bgr, world_xyz):
+    """flo_colorize: (rgb (n, 3) uint8, valid (n,) bool)."""
+    c = make_cam(cam)
+    img = np.ascontiguousarray(bgr, np.uint8)
+    pts = f32(world_xyz).reshape(-1, 3)
+    R, P = f64(Rcw), f64(Pcw)
+    rgb = np.zeros((len(pts), 3), np.uint8)
+    val = np.zeros(len(pts), np.uint8)
+    lib().flo_colorize(C.byref(c), _p(R), _p(P), _p(img), _p(pts), len(pts), _p(rgb), _p(val))
+    return rgb, val.astype(bool)
 
 
 def world2cam(cam: dict, pf):

@@ -278,3 +278,20 @@ def test_gpu_select_feeds_vio_in_place(flb, po):
     assert np.abs(xa.vector() - xo.vector()).max() / np.abs(xo.vector()).max() < 1e-9
     do = ovm.dump()
     assert (da["n_obs"] == do["n_obs"]).all() and (da["obs"] == do["obs"]).all()
+
+
+@pytest.mark.gpu
+def test_gpu_colorize_matches_oracle(flb, po):
+    """publish_frame_world_rgb (src/laserMapping.cpp:710-745): per-point bilinear colour, byte for byte."""
+    seq = flb.synth.make_visual_sequence("T1", 1)
+    fr = seq["frames"][0]
+    rng = np.random.default_rng(2)
+    bgr = np.stack([fr["image"], np.roll(fr["image"], 3, 1), 255 - fr["image"]], -1) ^ rng.integers(0, 8, fr["image"].shape + (3,), dtype=np.uint8)
+    pts = np.concatenate([fr["pg"], -fr["pg"][:50], fr["pg"][:50] * np.float32(40.0)])      # + behind the camera, + far off-axis
+    h = flb.Handle(device=0)
+    h.camera_set(seq["cam"])
+    rgb, val = h.colorize(fr["Rcw"], fr["Pcw"], bgr, pts)
+    orgb, oval = po.colorize(seq["cam"], fr["Rcw"], fr["Pcw"], bgr, pts)
+    assert (val == oval).all() and 100 < val.sum() < len(pts)
+    assert (rgb == orgb).all()
+    h.close()
