@@ -164,7 +164,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
            "flb_vio_update_level",
            "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
-           "flb_vmap_map_value", "flb_vmap_dump", "flb_colorize",
+           "flb_vmap_map_value", "flb_vmap_dump", "flb_colorize", "flb_voxel_grid",
            "flb_batch_begin", "flb_batch_set_frame", "flb_batch_state_reset_enqueue", "flb_batch_update_enqueue", "flb_batch_state_download",
            "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps"]
 
@@ -230,6 +230,7 @@ def lib():
         L.flb_batch_state_reset_enqueue.argtypes = [vp]
         L.flb_batch_update_enqueue.argtypes = [vp, C.POINTER(LioParams), C.POINTER(VioParams)]
         L.flb_batch_state_download.argtypes = [vp, C.c_int, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
+        L.flb_voxel_grid.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, vp, C.c_int, C.POINTER(C.c_int)]
         L.flb_colorize.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
         L.flb_vmap_reset.argtypes = [vp, C.POINTER(VmapParams)]
         L.flb_vmap_select.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
@@ -346,6 +347,14 @@ class Handle:
         m = C.c_int()
         self._ck(self.L.flb_map_download(self.h, _p(out), n, C.byref(m)))
         return out
+
+    def voxel_grid(self, xyz, leaf):
+        """flb_voxel_grid: pcl::VoxelGrid centroids (m, 3) float32."""
+        a = np.ascontiguousarray(xyz, np.float32)
+        out = np.zeros((len(a), 3), np.float32)
+        n = C.c_int()
+        self._ck(self.L.flb_voxel_grid(self.h, _p(a), len(a), a.shape[1] if a.ndim == 2 else 3, C.c_float(leaf), _p(out), len(a), C.byref(n)))
+        return out[:n.value].copy()
 
     def scan_upload(self, body_xyz):
         a = np.ascontiguousarray(body_xyz, np.float32)

@@ -235,6 +235,10 @@ struct flb_handle {
     DevBuf<double> x_z, x_H;
     bool cam_set = false;
     CamModel cam{};
+    TapMaps tapmaps{};           // TMA descriptors of the image (experiment: FLB_TMA=1)
+    const void* tapmaps_for = nullptr;
+    int tapmaps_w = 0, tapmaps_h = 0;
+    bool tapmaps_ok = false;
     bool last_vio_valid = false;
 
     // device-resident visual map (rows f2 / f4)
@@ -606,6 +610,35 @@ int resolve_pn(flb_handle* h) {
     return FLB_OK;
 }
 
+// TMA descriptors for the tap box (one per tap stride 1, 2, 4, 8); false when the driver entry point is missing or the
+// image geometry does not satisfy TMA's alignment rules (row pitch a multiple of 16 bytes).
+bool ensure_tapmaps(flb_handle* h) {
+    if (h->tapmaps_for == h->img.p && h->tapmaps_w == h->img_w && h->tapmaps_h == h->img_h) return h->tapmaps_ok;
+    h->tapmaps_for = h->img.p;
+    h->tapmaps_w = h->img_w;
+    h->tapmaps_h = h->img_h;
+    h->tapmaps_ok = false;
+    if (h->img_w % 16 != 0) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
+    EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+    for (int si = 0; si < 4; ++si) {
+        const int sc = 1 << si;
+        const cuuint64_t dims[2] = {(cuuint64_t)h->img_w, (cuuint64_t)h->img_h};
+        const cuuint64_t strides[1] = {(cuuint64_t)h->img_w};
+        const cuuint32_t box[2] = {(cuuint32_t)((10 * sc + 1 + 15) / 16 * 16), (cuuint32_t)(10 * sc + 1)};
+        const cuuint32_t estr[2] = {1u, (cuuint32_t)sc};
+        if (enc(&h->tapmaps.m[si], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->img.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    h->tapmaps_ok = true;
+    return true;
+}
+
 int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update: camera and image must be set first");
     if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
@@ -690,10 +723,13 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         }
         // staging capacity for the errors of ALL ranks (the peers' shard sizes are not known here: assume like ours + slack)
         int err_cap = (int)std::min<long long>(kVioErrCapMax, std::max<long long>(2048, ((long long)a.Pn * std::max(h->p2p.world, 1) * 5 / 4 + 319) / 256 * 256));
-        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap};
+        static const int env_tma = [] { const char* e = getenv("FLB_TMA"); return e ? atoi(e) : 0; }();
+        int use_tma = (env_tma && ensure_tapmaps(h)) ? 1 : 0;
+        const size_t dyn = std::max<size_t>((size_t)err_cap * sizeof(float), use_tma ? (size_t)(kVioPersBlock / 32) * kTapTileBytes : 0);
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap, &h->tapmaps, &use_tma};
         LaunchScope ls(h, FAM_VIO);
-        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args,
-                                                (size_t)err_cap * sizeof(float), h->stream));
+        FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args, dyn,
+                                                h->stream));
         h->last_vio_valid = false;
         return vio_inputs_release(h);
     }
@@ -1318,6 +1354,76 @@ int flb_visual_candidates(flb_handle* h, const double Rcw[9], const double Pcw[3
     std::memcpy(map_value, po, (size_t)ncell * sizeof(float));
     std::memcpy(winner, po + (size_t)ncell * sizeof(float), (size_t)ncell * sizeof(int));
     return vio_inputs_release(h);
+}
+
+int flb_voxel_grid(flb_handle* h, const float* xyz, int n, int stride, float leaf, float* out_xyz, int capacity, int* n_out) {
+    FLB_CHECK_H(h);
+    if (n < 0 || (n > 0 && !xyz) || stride < 3 || !(leaf > 0) || !n_out || capacity < 0 || (capacity > 0 && !out_xyz))
+        return fail(h, FLB_ERR_INVALID, "flb_voxel_grid: bad arguments");
+    *n_out = 0;
+    if (n == 0) return FLB_OK;
+    void* stv = nullptr;
+    FLB_CUDA(h, h->st_scan.acquire((size_t)n * 3 * sizeof(float), &stv));
+    float* st = static_cast<float*>(stv);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = xyz[(size_t)i * stride + k];
+            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_voxel_grid: non-finite coordinate at point %d", i);
+            st[3 * (size_t)i + k] = v;
+        }
+    FLB_CUDA(h, h->scan_raw.reserve((size_t)n * 3));
+    FLB_CUDA(h, h->skeys.reserve(n));
+    FLB_CUDA(h, h->skeys_sorted.reserve(n));
+    FLB_CUDA(h, h->svals.reserve(n));
+    FLB_CUDA(h, h->svals_sorted.reserve(n));
+    FLB_CUDA(h, h->dead_before.reserve((size_t)2 * n + 2));      // head flags | ranks
+    FLB_CUDA(h, h->map_comb.reserve((size_t)n * 3));             // centroids
+    FLB_CUDA(h, h->bbox_dev.reserve(8));
+    int* head = h->dead_before.p;
+    int* rank = h->dead_before.p + n;
+    const int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0, 0};
+    FLB_CUDA(h, cudaMemcpyAsync(h->bbox_dev.p, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FLB_CUDA(h, h->st_scan.mark(h->stream));
+    const float inv_leaf = 1.0f / leaf;                              // inverse_leaf_size_ = Array4f::Ones() / leaf_size_
+    const int g = (n + 255) / 256;
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_bbox<<<std::min(g, 4 * std::max(h->num_sms, 1)), 256, 0, h->stream>>>(h->scan_raw.p, n, h->bbox_dev.p);
+        k_vg_keys<<<g, 256, 0, h->stream>>>(h->scan_raw.p, n, h->bbox_dev.p, inv_leaf, h->skeys.p, h->svals.p, h->bbox_dev.p + 6);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    size_t t1 = 0, t2 = 0;
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, t1, h->skeys.p, h->skeys_sorted.p, h->svals.p, h->svals_sorted.p, n, 0, 31, h->stream));
+    FLB_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, t2, head, rank, n, h->stream));
+    FLB_CUDA(h, h->cub_tmp.reserve(std::max(t1, t2)));
+    FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, t1, h->skeys.p, h->skeys_sorted.p, h->svals.p, h->svals_sorted.p, n, 0, 31, h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vg_heads<<<g, 256, 0, h->stream>>>(h->skeys_sorted.p, n, head);
+        FLB_CUDA(h, cudaGetLastError());
+    }
+    FLB_CUDA(h, cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, t2, head, rank, n, h->stream));
+    {
+        LaunchScope ls(h, FAM_OTHER);
+        k_vg_centroids<<<g, 256, 0, h->stream>>>(h->scan_raw.p, h->skeys_sorted.p, h->svals_sorted.p, head, rank, n, h->map_comb.p,
+                                                  h->bbox_dev.p + 7);
+        FLB_CUDA(h, cudaGetLastError());
+        h->launches += 8;
+    }
+    int tail[2] = {0, 0};
+    FLB_CUDA(h, cudaMemcpyAsync(tail, h->bbox_dev.p + 6, sizeof(tail), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (tail[0]) return fail(h, FLB_ERR_INVALID, "flb_voxel_grid: leaf size too small for the cloud's extent (index overflow, as PCL warns)");
+    *n_out = tail[1];
+    const int m = std::min(tail[1], capacity);
+    if (m > 0) {
+        FLB_CUDA(h, cudaMemcpyAsync(out_xyz, h->map_comb.p, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    h->N = 0;                                    // the scan slot was used as scratch
+    h->last_pass_valid = false;
+    return FLB_OK;
 }
 
 int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {

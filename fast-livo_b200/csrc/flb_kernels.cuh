@@ -16,10 +16,39 @@
 // has a fixed order, so results are bit-reproducible run to run and identical across ranks.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "flb_device.cuh"
 
 namespace flb {
+
+// ---------------------------------------------------------------------------------------
+// TMA staging of the photometric tap box (north_star: "TMA-staged image tiles"; experiment, off by default --
+// DESIGN.md section 8 has the measurement).  One tiled tensor map per tap stride sc = 1, 2, 4, 8 over the uint8 image:
+// box = {round16(10 sc + 1) bytes, 10 sc + 1 rows} with traversal stride {1, sc}, i.e. the 11 tap ROWS arrive as 11
+// contiguous row segments (TMA has no stride on the innermost dimension and caps the others at 8, so sc = 16 patches
+// and the column stride stay with the scalar path / the shared-memory gather).
+// ---------------------------------------------------------------------------------------
+struct TapMaps { CUtensorMap m[4]; };
+constexpr int kTapTileBytes = 1152;      // 11 rows x 96 B (sc = 8), padded to a multiple of 128
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------
 // device-resident control blocks
@@ -453,6 +482,53 @@ __global__ void k_merge_inserts(const float* __restrict__ nxyz, const unsigned* 
 }
 
 // ---------------------------------------------------------------------------------------
+// pcl::VoxelGrid<PointType> (centroid per leaf; src/laserMapping.cpp:1398-1399 downSizeFilterSurf, src/lidar_selection.cpp:7,
+// :351-352 downSizeFilter): leaf index as PCL forms it (min_b from the cloud's minimum, idx = ijk . divb_mul), points of a
+// leaf summed in float in their ORIGINAL ORDER (PCL's own order inside a leaf is that of an unstable std::sort: unspecified),
+// output in ascending leaf index like PCL.  box = k_bbox's ordered-int {min, max}.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float ordered_int_f32(int v) { return __int_as_float(v >= 0 ? v : (v ^ 0x7fffffff)); }
+__global__ void k_vg_keys(const float* __restrict__ xyz, int n, const int* __restrict__ box, float inv_leaf, unsigned* __restrict__ keys,
+                          int* __restrict__ vals, int* __restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int min_b[3], div_b[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        min_b[a] = (int)floorf(ordered_int_f32(box[a]) * inv_leaf);
+        div_b[a] = (int)floorf(ordered_int_f32(box[3 + a]) * inv_leaf) - min_b[a] + 1;
+    }
+    if (i == 0 && (long long)div_b[0] * div_b[1] * div_b[2] > 0x7fffffffll) *status = 1;     // PCL: "leaf size is too small"
+    const int i0 = (int)(floorf(xyz[3 * (size_t)i] * inv_leaf) - (float)min_b[0]);
+    const int i1 = (int)(floorf(xyz[3 * (size_t)i + 1] * inv_leaf) - (float)min_b[1]);
+    const int i2 = (int)(floorf(xyz[3 * (size_t)i + 2] * inv_leaf) - (float)min_b[2]);
+    keys[i] = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
+    vals[i] = i;
+}
+__global__ void k_vg_heads(const unsigned* __restrict__ keys_sorted, int n, int* __restrict__ head) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || keys_sorted[i] != keys_sorted[i - 1]) ? 1 : 0;
+}
+__global__ void k_vg_centroids(const float* __restrict__ xyz, const unsigned* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
+                               const int* __restrict__ head, const int* __restrict__ rank, int n, float* __restrict__ out, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == n - 1) *count = rank[i] + head[i];
+    if (!head[i]) return;
+    const unsigned k = keys_sorted[i];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    int c = 0;
+    for (int j = i; j < n && keys_sorted[j] == k; ++j) {
+        const float* p = xyz + 3 * (size_t)vals_sorted[j];
+        sx += p[0]; sy += p[1]; sz += p[2];
+        ++c;
+    }
+    const float fc = (float)c;
+    float* o = out + 3 * (size_t)rank[i];
+    o[0] = sx / fc; o[1] = sy / fc; o[2] = sz / fc;
+}
+
+// ---------------------------------------------------------------------------------------
 // scan preparation: Morton order in the BODY frame.  A rigid transform preserves spatial
 // neighbourhoods, so the lanes of a warp query neighbouring map cells at every pose: similar trip
 // counts (less divergence) and shared cache lines.  w carries the original scan index.
@@ -848,7 +924,9 @@ __device__ __forceinline__ double round_to_f32_precision(double d) {
 // lane 0 also counts n_meas / skipped.
 __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
                                           float* s_lat, double* s_res, double& accv, double& n_meas, double& skipped,
-                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0) {
+                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0,
+                                          const TapMaps* tm = nullptr, unsigned char* tile = nullptr, unsigned long long* mbar = nullptr,
+                                          unsigned* tma_phase = nullptr) {
     const int lane = threadIdx.x & 31;
     float* const err_out = a.errors + (size_t)err_buf * a.err_stride;
     double acc[27];
@@ -860,13 +938,34 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
     if (g.valid) {
         // stage the 11x11 tap lattice (stride = scale px) as float
         const int W = a.cam.width;
-        const unsigned char* base = a.img + (size_t)(g.v_i - 5 * g.scale) * W + (g.u_i - 5 * g.scale);
+        if (tm != nullptr && g.scale <= 8) {
+            // TMA: the 11 tap rows as one tiled bulk copy (row stride = scale), then the strided column gather from the tile
+            const int si = (g.scale == 1) ? 0 : (g.scale == 2) ? 1 : (g.scale == 4) ? 2 : 3;
+            const int rowb = (10 * g.scale + 1 + 15) / 16 * 16;
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the tile's previous readers are done
+                mbar_expect_tx(mbar, (unsigned)(rowb * 11));
+                tma_load_2d(tile, &tm->m[si], g.u_i - 5 * g.scale, g.v_i - 5 * g.scale, mbar);
+            }
+            mbar_wait(mbar, *tma_phase);
+            *tma_phase ^= 1u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int e = lane + 32 * q;
-            if (e < 121) {
-                const int r = e / 11, c = e - r * 11;
-                s_lat[e] = (float)__ldg(base + (size_t)r * g.scale * W + c * g.scale);
+            for (int q = 0; q < 4; ++q) {
+                const int e = lane + 32 * q;
+                if (e < 121) {
+                    const int r = e / 11, c = e - r * 11;
+                    s_lat[e] = (float)tile[r * rowb + c * g.scale];
+                }
+            }
+        } else {
+            const unsigned char* base = a.img + (size_t)(g.v_i - 5 * g.scale) * W + (g.u_i - 5 * g.scale);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = lane + 32 * q;
+                if (e < 121) {
+                    const int r = e / 11, c = e - r * 11;
+                    s_lat[e] = (float)__ldg(base + (size_t)r * g.scale * W + c * g.scale);
+                }
             }
         }
         __syncwarp();
@@ -2132,7 +2231,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
                                                                     unsigned long long* pkt, unsigned epoch,
-                                                                    unsigned long long* trace, unsigned long long* dbg, int err_cap) {
+                                                                    unsigned long long* trace, unsigned long long* dbg, int err_cap,
+                                                                    const __grid_constant__ TapMaps tapmaps, int use_tma) {
     constexpr int NW = BLOCK / 32;
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     __shared__ VioPose s_pose;
@@ -2142,9 +2242,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl s_ctrl;
-    extern __shared__ __align__(16) float s_err[];     // err_cap floats (dynamic): the leader's staging of the per-patch errors
+    extern __shared__ __align__(128) float s_err[];    // dynamic: the LEADER's staging of the per-patch errors (err_cap floats);
+                                                       // the WORKERS' TMA tap tiles (NW x kTapTileBytes) when use_tma
     __shared__ unsigned long long s_seq_base;
+    __shared__ __align__(8) unsigned long long s_mbar[NW];
     const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned tma_phase = 0u;
+    if (use_tma && (tid & 31) == 0) mbar_init(&s_mbar[warp], 1u);
+    if (use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const int nworkers = (int)gridDim.x - 1;
     const bool is_leader = (int)blockIdx.x == nworkers;
     const int Pn = a.Pn_dev ? min(*a.Pn_dev, a.Pn) : a.Pn;     // device-built patch list: its length lives on the device
@@ -2224,7 +2329,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             for (int i = blockIdx.x * NW + warp; i < Pn; i += nworkers * NW) {
                 if (!single) vio_patch_load(a, i, tid & 31, pin);
                 vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
-                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1);
+                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1,
+                          use_tma ? &tapmaps : nullptr, reinterpret_cast<unsigned char*>(s_err) + (size_t)warp * kTapTileBytes, &s_mbar[warp],
+                          &tma_phase);
             }
             vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();

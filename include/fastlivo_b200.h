@@ -286,6 +286,14 @@ int flb_camera_set(flb_handle* h, const flb_camera* cam);
 int flb_visual_candidates(flb_handle* h, const double Rcw[9], const double Pcw[3], const float* world_xyz, int n,
                           int stride_floats, int grid_size, int border, float* map_value, int* winner);
 
+/* pcl::VoxelGrid<PointType>::filter on x, y, z (src/laserMapping.cpp:1398-1399 downSizeFilterSurf; src/lidar_selection.cpp:7,
+ * :351-352 downSizeFilter): one centroid per occupied leaf, leaves indexed and ordered as PCL does (min_b from the cloud's
+ * minimum, idx = ijk . divb_mul, output in ascending idx).  The points of a leaf are summed in float in their INPUT order:
+ * PCL's own within-leaf order is that of an unstable std::sort, i.e. unspecified, so this is a defined member of the family
+ * of results PCL can produce, not a bit-level reproduction of one PCL build.  out_xyz: up to `capacity` x 3 floats;
+ * *n_out = number of occupied leaves.  Uses the handle's scan slot as scratch (upload the scan afterwards).  Blocking. */
+int flb_voxel_grid(flb_handle* h, const float* xyz, int n, int stride_floats, float leaf, float* out_xyz, int capacity, int* n_out);
+
 /* ---- device-resident visual map ---------------------------------------
  * The sparse visual map of LidarSelector -- feat_map (unordered_map<VOXEL_KEY, VOXEL_POINTS*>), its Points
  * (include/point.h) with their observation lists of Features (include/feature.h) and the keyframe images those

@@ -230,6 +230,8 @@ void      flo_vmap_selected(const flo_vmap*, int* index, int* point, int* search
 int       flo_vmap_grow(flo_vmap*, const uint8_t* img, const double* Rcw, const double* Pcw, const float* pg, int n, int frame_id);
 /* LidarSelector::addObservation, :913-965 */
 int       flo_vmap_add_observations(flo_vmap*, const uint8_t* img, const double* Rcw, const double* Pcw, int frame_id);
+/* pcl::VoxelGrid centroids on x, y, z (laserMapping.cpp:1398-1399; lidar_selection.cpp:351-352); returns the leaf count */
+int       flo_voxel_grid(const float* xyz, int n, float leaf, float* out);
 /* publish_frame_world_rgb (laserMapping.cpp:710-745): r g b per point + validity */
 void      flo_colorize(const flo_cam* cam, const double* Rcw, const double* Pcw, const uint8_t* bgr, const float* xyz, int n, uint8_t* rgb,
                        uint8_t* valid);

@@ -83,6 +83,7 @@ extern "C" void flo_visual_candidates(const flo_cam* cam, const double* Rcw, con
  * Iteration order of the reference's unordered_map<VOXEL_KEY, ...> is implementation-defined; it only matters for
  * exact float ties of `cur_dist <= map_dist[index]` (:450).  Here: points are visited in insertion order.
  * ===================================================================================================== */
+#include <algorithm>
 #include <array>
 #include <cstring>
 #include <unordered_set>
@@ -579,6 +580,43 @@ void flo_colorize(const flo_cam* cam, const double* Rcw, const double* Pcw, cons
         rgb[3 * i] = (uint8_t)(int)R; rgb[3 * i + 1] = (uint8_t)(int)G; rgb[3 * i + 2] = (uint8_t)(int)B;
         valid[i] = 1;
     }
+}
+
+/* pcl::VoxelGrid<PointT>::applyFilter on x, y, z (PCL 1.8+, filters/include/pcl/filters/impl/voxel_grid.hpp; third-party,
+ * absent from /root/reference, restated): leaf index from the cloud minimum, points of a leaf summed in float and divided by
+ * the count, output in ascending leaf index.  PCL orders (leaf idx, point) pairs with std::sort on the leaf idx alone, so
+ * the order INSIDE a leaf -- and with it the last bits of the float sum -- is unspecified; this restatement uses the input
+ * order (a stable sort), which is one of the orders PCL can produce.  Returns the number of leaves. */
+int flo_voxel_grid(const float* xyz, int n, float leaf, float* out) {
+    if (n <= 0) return 0;
+    float mn[3] = {xyz[0], xyz[1], xyz[2]}, mx[3] = {xyz[0], xyz[1], xyz[2]};
+    for (int i = 1; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], xyz[3 * i + a]); mx[a] = std::max(mx[a], xyz[3 * i + a]); }
+    const float inv = 1.0f / leaf;
+    int min_b[3], div_b[3];
+    for (int a = 0; a < 3; ++a) {
+        min_b[a] = static_cast<int>(std::floor(mn[a] * inv));
+        div_b[a] = static_cast<int>(std::floor(mx[a] * inv)) - min_b[a] + 1;
+    }
+    std::vector<std::pair<int, int>> idx(n);
+    for (int i = 0; i < n; ++i) {
+        const int i0 = static_cast<int>(std::floor(xyz[3 * i] * inv) - static_cast<float>(min_b[0]));
+        const int i1 = static_cast<int>(std::floor(xyz[3 * i + 1] * inv) - static_cast<float>(min_b[1]));
+        const int i2 = static_cast<int>(std::floor(xyz[3 * i + 2] * inv) - static_cast<float>(min_b[2]));
+        idx[i] = {i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1], i};
+    }
+    std::stable_sort(idx.begin(), idx.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+    int m = 0;
+    for (int i = 0; i < n;) {
+        float s[3] = {0.f, 0.f, 0.f};
+        int c = 0, j = i;
+        for (; j < n && idx[j].first == idx[i].first; ++j, ++c)
+            for (int a = 0; a < 3; ++a) s[a] += xyz[3 * idx[j].second + a];
+        for (int a = 0; a < 3; ++a) out[3 * m + a] = s[a] / static_cast<float>(c);
+        ++m;
+        i = j;
+    }
+    return m;
 }
 
 /* Dump for tests: per point pos (3 doubles), value, n_obs and the newest-first feature ids (up to 20, -1 padded). */

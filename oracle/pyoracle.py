@@ -259,6 +259,7 @@ def lib():
         L.flo_vmap_add_observations.argtypes = [vp, vp, vp, vp, C.c_int]
         L.flo_vmap_dump_points.argtypes = [vp] * 5
         L.flo_vmap_dump_features.argtypes = [vp] * 4
+        L.flo_voxel_grid.argtypes = [vp, C.c_int, C.c_float, vp]
         L.flo_colorize.argtypes = [C.POINTER(Cam)] + [vp] * 4 + [C.c_int, vp, vp]
         L.flo_world2cam.argtypes = [C.POINTER(Cam), C.c_void_p, C.c_void_p]
         L.flo_exp3.argtypes = [C.c_void_p, C.c_void_p]
@@ -578,6 +579,14 @@ class VMap:
         geo, score, lii = np.zeros((m, 17)), np.zeros(m, np.float32), np.zeros((m, 3), np.int32)
         self.L.flo_vmap_dump_features(self.h, _p(geo), _p(score), _p(lii))
         return dict(pos=pos, value=value, n_obs=n_obs, obs=obs, ft_geo=geo, ft_score=score, ft_level_id_img=lii)
+
+
+def voxel_grid(xyz, leaf):
+    """flo_voxel_grid: pcl::VoxelGrid centroids, (m, 3) float32 in ascending leaf index."""
+    a = f32(xyz).reshape(-1, 3)
+    out = np.zeros((len(a), 3), np.float32)
+    m = lib().flo_voxel_grid(_p(a), len(a), C.c_float(leaf), _p(out))
+    return out[:m].copy()
 
 
 def colorize(cam: dict, Rcw, Pcw, bgr, world_xyz):
