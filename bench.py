@@ -589,6 +589,7 @@ def main():
                     help="N > 1: fused NVLink exchange inside the persistent kernels (default) or NCCL between per-pass kernels")
     ap.add_argument("--quick", action="store_true", help="profiling aid: skip the e2e / profile / cpu_baseline legs")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads (C3, C4) and batched legs")
+    ap.add_argument("--cell-size", type=float, default=0.0, help="experiment: kNN grid cell size (default 2 x the map pitch)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -613,7 +614,7 @@ def main():
     cfg = flb.synth.CONFIGS[args.workload]
     frame = flb.synth.make_frame(cfg)
     pc = pass_counts(cfg)
-    h = flb.Handle(device=local, cell_size=cfg.cell_size)
+    h = flb.Handle(device=local, cell_size=args.cell_size if args.cell_size > 0 else cfg.cell_size)
     # a dedicated (non-default) torch stream: the library's kernels, the L2 flush and the timing events
     # must all be on the SAME stream, and flb_set_stream(NULL) would mean "the handle's own stream"
     stream = torch.cuda.Stream(dev)

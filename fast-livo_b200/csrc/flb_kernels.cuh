@@ -1769,12 +1769,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
             FLB_STAMP(4);
             if (tid == 0) {
                 const bool ok = sm.flags[3] == 0;
-                if (first) {
-                    c.level = 2; c.iteration = 0; c.stop = 0;
-                    c.last_error = 1e10f; c.now_error = 1e10f; c.any_solved = 0;           // :971
-                    for (int l = 0; l < 3; ++l) { c.passes[l] = 0; c.level_error[l] = 1e10f; }
-                    c.rows_total = 0; c.skipped_last = 0; c.cov_updated = 0; c.status = 0; c.err_buf = 0;
-                }
+                // (the control block was initialised by k_vio_begin* / at kernel entry: level, last_error = total_residual, :755, :971)
                 const long long nm = (long long)sm.packed[27];
                 const float error = sm.error / (float)(unsigned long long)nm;              // :857
                 c.passes[level] += 1;
