@@ -162,7 +162,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
            "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach",
            "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
-           "flb_vio_update_level",
+           "flb_vio_update_level", "flb_state_download_enqueue", "flb_state_download_wait",
            "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
            "flb_vmap_map_value", "flb_vmap_dump", "flb_colorize", "flb_voxel_grid",
            "flb_batch_begin", "flb_batch_set_frame", "flb_batch_state_reset_enqueue", "flb_batch_update_enqueue", "flb_batch_state_download",
@@ -244,6 +244,8 @@ def lib():
         L.flb_state_upload.argtypes = [vp, C.POINTER(State18), C.POINTER(State18)]
         L.flb_state_download.argtypes = [vp, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
         L.flb_lio_update_enqueue.argtypes = [vp, C.POINTER(LioParams)]
+        L.flb_state_download_enqueue.argtypes = [vp, C.c_int]
+        L.flb_state_download_wait.argtypes = [vp, C.c_int, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
         L.flb_vio_update_enqueue.argtypes = [vp, C.POINTER(VioParams)]
         L.flb_state_reset_enqueue.argtypes = [vp]
         L.flb_state_set_prior_enqueue.argtypes = [vp]
@@ -605,6 +607,14 @@ class Handle:
     def state_download(self):
         x, lr, vr = State18(), LioReport(), VioReport()
         self._ck(self.L.flb_state_download(self.h, C.byref(x), C.byref(lr), C.byref(vr)))
+        return x, lr, vr
+
+    def state_download_enqueue(self, slot):
+        self._ck(self.L.flb_state_download_enqueue(self.h, int(slot)))
+
+    def state_download_wait(self, slot):
+        x, lr, vr = State18(), LioReport(), VioReport()
+        self._ck(self.L.flb_state_download_wait(self.h, int(slot), C.byref(x), C.byref(lr), C.byref(vr)))
         return x, lr, vr
 
     def lio_update_enqueue(self, prm):

@@ -220,6 +220,9 @@ struct flb_handle {
     int occ_lio = 0, occ_vio = 0;
     Staging st_map, st_scan, st_img, st_patch, st_state, st_misc;   // per-kind upload staging
     PinBuf pin_out;              // staging for downloads
+    PinBuf pin_res[2];           // flb_state_download_enqueue / _wait: two result slots in flight
+    cudaEvent_t ev_res[2] = {nullptr, nullptr};
+    bool res_pending[2] = {false, false};
     bool state_valid = false;
 
     // VIO inputs
@@ -866,6 +869,7 @@ int flb_destroy(flb_handle* h) {
     h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
+    for (int k = 0; k < 2; ++k) { h->pin_res[k].release(); if (h->ev_res[k]) cudaEventDestroy(h->ev_res[k]); }
     cudaStreamSynchronize(h->copy_stream);
     cudaEventDestroy(h->ev_vio_inputs);
     cudaEventDestroy(h->ev_vio_done);
@@ -910,7 +914,9 @@ static int rebuild_grid(flb_handle* h, int M) {
     // the grid covers the map box plus a margin, so that points added next to the map (a moving sensor) fall inside
     // it and take the incremental path of flb_map_add_points; kNN is exact for any cell geometry
     for (int k = 0; k < 3; ++k) {
-        const float m = std::max(2.0f * (float)h->cfg.cell_size, 0.05f * (h->map_hi[k] - h->map_lo[k]));
+        // a whole number of cells, so that the cell boundaries stay where a grid anchored at the map's own corner puts them
+        const float cs = (float)h->cfg.cell_size;
+        const float m = cs * std::ceil(std::max(2.0f * cs, 0.05f * (h->map_hi[k] - h->map_lo[k])) / cs);
         h->grid_lo[k] = h->map_lo[k] - m;
         h->grid_hi[k] = h->map_hi[k] + m;
     }
@@ -1685,6 +1691,45 @@ int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_v
         std::memcpy(&c, po + sizeof(State18) + sizeof(LioCtrl), sizeof(c));
         fill_vio_report(c, vio);
     }
+    return FLB_OK;
+}
+
+// Pipelined result read-back: enqueue the copy of (state, reports) of everything enqueued so far into result slot
+// `slot`, return at once; flb_state_download_wait blocks on that slot only, so frame k's result can be collected while
+// frame k+1 is already uploading / running.
+int flb_state_download_enqueue(flb_handle* h, int slot) {
+    FLB_CHECK_H(h);
+    if (slot < 0 || slot > 1) return fail(h, FLB_ERR_INVALID, "flb_state_download_enqueue: slot must be 0 or 1");
+    if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_download_enqueue: no state uploaded");
+    const size_t bytes = sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl) + sizeof(GridBarrier);
+    FLB_CUDA(h, h->pin_res[slot].reserve(bytes));
+    if (!h->ev_res[slot]) FLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_res[slot], cudaEventDisableTiming));
+    char* po = static_cast<char*>(h->pin_res[slot].p);
+    FLB_CUDA(h, cudaMemcpyAsync(po, &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18), h->lio_ctrl.p, sizeof(LioCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl), h->vio_ctrl.p, sizeof(VioCtrl), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl), h->barrier.p, sizeof(GridBarrier),
+                                cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaEventRecord(h->ev_res[slot], h->stream));
+    h->res_pending[slot] = true;
+    return FLB_OK;
+}
+
+int flb_state_download_wait(flb_handle* h, int slot, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio) {
+    FLB_CHECK_H(h);
+    if (slot < 0 || slot > 1 || !h->res_pending[slot]) return fail(h, FLB_ERR_STATE, "flb_state_download_wait: nothing enqueued in this slot");
+    FLB_CUDA(h, cudaEventSynchronize(h->ev_res[slot]));
+    h->res_pending[slot] = false;
+    const char* po = static_cast<const char*>(h->pin_res[slot].p);
+    GridBarrier b;
+    std::memcpy(&b, po + sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl), sizeof(b));
+    if (b.timeout) {
+        cudaMemset(h->barrier.p, 0, sizeof(GridBarrier));
+        return fail(h, FLB_ERR_TIMEOUT, "device-side grid barrier watchdog tripped");
+    }
+    if (x) std::memcpy(x, po, sizeof(State18));
+    if (lio) { LioCtrl c; std::memcpy(&c, po + sizeof(State18), sizeof(c)); fill_lio_report(c, lio); }
+    if (vio) { VioCtrl c; std::memcpy(&c, po + sizeof(State18) + sizeof(LioCtrl), sizeof(c)); fill_vio_report(c, vio); }
     return FLB_OK;
 }
 

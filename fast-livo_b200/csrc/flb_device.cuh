@@ -13,6 +13,11 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#if !defined(__CUDACC__)
+#include <algorithm>
+using std::max;
+using std::min;
+#endif
 
 #if defined(__CUDACC__)
 #define FLB_HD __host__ __device__ __forceinline__
@@ -946,9 +951,12 @@ FLB_HD bool vm_colorize_point(const CamModel& cam, const double* Rcw, const doub
     const float w_ref_tr = subpix_u_ref * (1.0 - subpix_v_ref);
     const float w_ref_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
     const float w_ref_br = subpix_u_ref * subpix_v_ref;
-    // the last row / column of the image has no bilinear neighbour (the reference reads past it): clamp the neighbour
-    const int du = (u_ref_i + 1 < cam.width) ? 3 : 0, dv = (v_ref_i + 1 < cam.height) ? width * 3 : 0;
-    const unsigned char* img_ptr = bgr + ((size_t)v_ref_i * width + u_ref_i) * 3;
+    // isInFrame(pc.cast<int>(), 0) lets pc in (-1, 0) through (its integer cast is 0) and the last row / column has no
+    // bilinear neighbour: the reference then reads outside the image.  Defined here: both taps are clamped into it.
+    const int u0 = min(max(u_ref_i, 0), cam.width - 1), u1 = min(max(u_ref_i + 1, 0), cam.width - 1);
+    const int v0 = min(max(v_ref_i, 0), cam.height - 1), v1 = min(max(v_ref_i + 1, 0), cam.height - 1);
+    const int du = (u1 - u0) * 3, dv = (v1 - v0) * width * 3;
+    const unsigned char* img_ptr = bgr + ((size_t)v0 * width + u0) * 3;
     const float B = w_ref_tl * img_ptr[0] + w_ref_tr * img_ptr[0 + du] + w_ref_bl * img_ptr[dv] + w_ref_br * img_ptr[dv + 0 + du];
     const float G = w_ref_tl * img_ptr[1] + w_ref_tr * img_ptr[1 + du] + w_ref_bl * img_ptr[1 + dv] + w_ref_br * img_ptr[dv + 1 + du];
     const float R = w_ref_tl * img_ptr[2] + w_ref_tr * img_ptr[2 + du] + w_ref_bl * img_ptr[2 + dv] + w_ref_br * img_ptr[dv + 2 + du];

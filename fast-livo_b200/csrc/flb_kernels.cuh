@@ -498,7 +498,12 @@ __global__ void k_vg_keys(const float* __restrict__ xyz, int n, const int* __res
         min_b[a] = (int)floorf(ordered_int_f32(box[a]) * inv_leaf);
         div_b[a] = (int)floorf(ordered_int_f32(box[3 + a]) * inv_leaf) - min_b[a] + 1;
     }
-    if (i == 0 && (long long)div_b[0] * div_b[1] * div_b[2] > 0x7fffffffll) *status = 1;     // PCL: "leaf size is too small"
+    if (i == 0) {                                    // PCL: "Leaf size is too small for the input dataset. Integer indices would overflow."
+        const long long dx = (long long)((ordered_int_f32(box[3]) - ordered_int_f32(box[0])) * inv_leaf) + 1;
+        const long long dy = (long long)((ordered_int_f32(box[4]) - ordered_int_f32(box[1])) * inv_leaf) + 1;
+        const long long dz = (long long)((ordered_int_f32(box[5]) - ordered_int_f32(box[2])) * inv_leaf) + 1;
+        if ((double)dx * (double)dy * (double)dz > 2147483647.0) *status = 1;
+    }
     const int i0 = (int)(floorf(xyz[3 * (size_t)i] * inv_leaf) - (float)min_b[0]);
     const int i1 = (int)(floorf(xyz[3 * (size_t)i + 1] * inv_leaf) - (float)min_b[1]);
     const int i2 = (int)(floorf(xyz[3 * (size_t)i + 2] * inv_leaf) - (float)min_b[2]);
@@ -2549,7 +2554,8 @@ __global__ void k_imu_undistort(const float* __restrict__ in_xyz, int stride, co
 // The reference walks the points in order and lets a point take its grid cell when its score is strictly above
 // the cell's current value.  The outcome per cell is "the first point that reaches the cell's maximum, if that
 // maximum exceeds the incoming value": one 64-bit atomicMax per point on {order-preserving score bits,
-// ~index}; the seed carries index bits 0xFFFFFFFF so that an equal score never displaces it.
+// ~index}; the seed carries index bits 0xFFFFFFFF so that an equal score never displaces it (a candidate's index bits
+// are 0xFFFFFFFE - i: point 0 must stay distinguishable from the seed).
 __device__ __forceinline__ unsigned ordered_f32(float f) {
     const unsigned b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -2575,7 +2581,7 @@ __global__ void k_vmap_candidates(CamModel cam, const double* __restrict__ Rcw_P
     const float p[3] = {xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]};
     const int cell = visual_candidate(cam, Rcw, Pcw, img, cam.width, p, grid_size, grid_n_height, border, &score);
     if (cell < 0) return;
-    atomicMax(key + cell, ((unsigned long long)ordered_f32(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i));
+    atomicMax(key + cell, ((unsigned long long)ordered_f32(score) << 32) | (unsigned long long)(0xFFFFFFFEu - (unsigned)i));
 }
 __global__ void k_vmap_resolve(const unsigned long long* __restrict__ key, int ncell, float* __restrict__ map_value,
                                int* __restrict__ winner) {
@@ -2583,7 +2589,7 @@ __global__ void k_vmap_resolve(const unsigned long long* __restrict__ key, int n
     if (c >= ncell) return;
     const unsigned long long k = key[c];
     const unsigned low = (unsigned)k;
-    winner[c] = (low == 0xFFFFFFFFu) ? -1 : (int)(0xFFFFFFFFu - low);
+    winner[c] = (low == 0xFFFFFFFFu) ? -1 : (int)(0xFFFFFFFEu - low);
     if (low != 0xFFFFFFFFu) map_value[c] = unordered_f32((unsigned)(k >> 32));
 }
 

@@ -375,6 +375,11 @@ int flb_vio_errors(flb_handle* h, float* errors, int capacity);
  * VIO update whose prior is the LIO posterior (zero-motion propagation). */
 int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_prop);
 int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio);
+/* Pipelined read-back (two result slots): _enqueue copies the state and both reports of everything enqueued so far and
+ * returns at once; _wait blocks on that slot only -- frame k's result is collected while frame k+1 already uploads
+ * and runs (uploads never overwrite what an enqueued kernel still reads: stream order, and events for the copy stream). */
+int flb_state_download_enqueue(flb_handle* h, int slot);
+int flb_state_download_wait(flb_handle* h, int slot, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio);
 int flb_lio_update_enqueue(flb_handle* h, const flb_lio_params* prm);
 int flb_vio_update_enqueue(flb_handle* h, const flb_vio_params* prm);
 /* restore x := x_prop := the state given to the last flb_state_upload (device-side copy) */

@@ -549,7 +549,7 @@ int flo_vmap_add_observations(flo_vmap* vm, const uint8_t* img, const double* Rc
 }
 
 /* publish_frame_world_rgb, src/laserMapping.cpp:710-745 + LidarSelector::getpixel, src/lidar_selection.cpp:1007-1025.
- * The reference reads the bilinear neighbour even on the last row / column (past the buffer): clamped here. */
+ * Out-of-image taps (see below) are clamped. */
 void flo_colorize(const flo_cam* cam, const double* Rcw, const double* Pcw, const uint8_t* bgr, const float* xyz, int n, uint8_t* rgb,
                   uint8_t* valid) {
     const int width = cam->width;
@@ -572,8 +572,12 @@ void flo_colorize(const flo_cam* cam, const double* Rcw, const double* Pcw, cons
         const float w_ref_tr = subpix_u_ref * (1.0 - subpix_v_ref);
         const float w_ref_bl = (1.0 - subpix_u_ref) * subpix_v_ref;
         const float w_ref_br = subpix_u_ref * subpix_v_ref;
-        const int du = (u_ref_i + 1 < cam->width) ? 3 : 0, dv = (v_ref_i + 1 < cam->height) ? width * 3 : 0;
-        const uint8_t* img_ptr = bgr + ((size_t)v_ref_i * width + u_ref_i) * 3;
+        /* pc in (-1, 0) passes isInFrame (its integer cast is 0) and the last row / column has no neighbour: the reference
+         * reads outside the image there; defined here as clamping both taps into it */
+        const int u0 = std::min(std::max(u_ref_i, 0), cam->width - 1), u1 = std::min(std::max(u_ref_i + 1, 0), cam->width - 1);
+        const int v0 = std::min(std::max(v_ref_i, 0), cam->height - 1), v1 = std::min(std::max(v_ref_i + 1, 0), cam->height - 1);
+        const int du = (u1 - u0) * 3, dv = (v1 - v0) * width * 3;
+        const uint8_t* img_ptr = bgr + ((size_t)v0 * width + u0) * 3;
         const float B = w_ref_tl * img_ptr[0] + w_ref_tr * img_ptr[0 + du] + w_ref_bl * img_ptr[dv] + w_ref_br * img_ptr[dv + 0 + du];
         const float G = w_ref_tl * img_ptr[1] + w_ref_tr * img_ptr[1 + du] + w_ref_bl * img_ptr[1 + dv] + w_ref_br * img_ptr[dv + 1 + du];
         const float R = w_ref_tl * img_ptr[2] + w_ref_tr * img_ptr[2 + du] + w_ref_bl * img_ptr[2 + dv] + w_ref_br * img_ptr[dv + 2 + du];
@@ -593,6 +597,10 @@ int flo_voxel_grid(const float* xyz, int n, float leaf, float* out) {
     for (int i = 1; i < n; ++i)
         for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], xyz[3 * i + a]); mx[a] = std::max(mx[a], xyz[3 * i + a]); }
     const float inv = 1.0f / leaf;
+    {   /* "Leaf size is too small for the input dataset. Integer indices would overflow." */
+        const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+        if ((double)dx * (double)dy * (double)dz > 2147483647.0) return -1;
+    }
     int min_b[3], div_b[3];
     for (int a = 0; a < 3; ++a) {
         min_b[a] = static_cast<int>(std::floor(mn[a] * inv));

@@ -408,3 +408,17 @@ void emu_vm_dump_features(void* h, double* geo17, float* score, int* level_id_im
 }
 
 }  // extern "C"
+
+extern "C" void emu_colorize(const double* camv, const double* Rcw, const double* Pcw, const unsigned char* bgr, const float* xyz, int n,
+                             unsigned char* rgb, unsigned char* valid) {
+    CamModel cam;
+    cam.width = (int)camv[0]; cam.height = (int)camv[1];
+    cam.fx = camv[2]; cam.fy = camv[3]; cam.cx = camv[4]; cam.cy = camv[5];
+    for (int i = 0; i < 5; ++i) cam.d[i] = camv[6 + i];
+    cam.jfx = cam.jfy = 0.0;
+    for (int i = 0; i < n; ++i) {
+        unsigned char c[3] = {0, 0, 0};
+        valid[i] = vm_colorize_point(cam, Rcw, Pcw, bgr, xyz + 3 * i, c) ? 1 : 0;
+        rgb[3 * i] = c[0]; rgb[3 * i + 1] = c[1]; rgb[3 * i + 2] = c[2];
+    }
+}

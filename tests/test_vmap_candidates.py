@@ -79,4 +79,10 @@ def test_visual_candidates_gpu_bit_exact(flb, po, name, n):
     assert (win0 == -1).all() and (mv0 == seed_vals).all()
     mv2, win2 = h.visual_candidates(Rcw, Pcw, pts, GRID, BORDER, mv)
     assert (win2 == -1).all() and (mv2.view(np.uint32) == mv.view(np.uint32)).all()
+    # the point with index 0 can win its cell (round 1 encoded "no winner" and "point 0" alike): put a winner first
+    k = int(win_o[win_o >= 0][0])
+    order = np.concatenate([[k], np.delete(np.arange(len(pts)), k)])
+    mv_o3, win_o3 = po.visual_candidates(f["cam"], Rcw, Pcw, f["image"], pts[order], GRID, BORDER, seed_vals)
+    mv3, win3 = h.visual_candidates(Rcw, Pcw, pts[order], GRID, BORDER, seed_vals)
+    assert (win_o3 == 0).sum() == 1 and (win3 == win_o3).all() and (mv3.view(np.uint32) == mv_o3.view(np.uint32)).all()
     h.close()

@@ -295,3 +295,19 @@ def test_gpu_colorize_matches_oracle(flb, po):
     assert (val == oval).all() and 100 < val.sum() < len(pts)
     assert (rgb == orgb).all()
     h.close()
+
+
+def test_colorize_device_math_matches_oracle(flb, po, hostemu):
+    seq = flb.synth.make_visual_sequence("T1", 1)
+    fr = seq["frames"][0]
+    rng = np.random.default_rng(2)
+    bgr = np.ascontiguousarray(np.stack([fr["image"], np.roll(fr["image"], 3, 1), 255 - fr["image"]], -1) ^ rng.integers(0, 8, fr["image"].shape + (3,), dtype=np.uint8))
+    pts = np.ascontiguousarray(np.concatenate([fr["pg"], -fr["pg"][:50], fr["pg"][:50] * np.float32(40.0)]), np.float32)
+    rgb = np.zeros((len(pts), 3), np.uint8)
+    val = np.zeros(len(pts), np.uint8)
+    cv = camv(seq["cam"])
+    R, P = np.ascontiguousarray(fr["Rcw"]), np.ascontiguousarray(fr["Pcw"])
+    hostemu.emu_colorize.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+    hostemu.emu_colorize(_p(cv), _p(R), _p(P), _p(bgr), _p(pts), len(pts), _p(rgb), _p(val))
+    orgb, oval = po.colorize(seq["cam"], fr["Rcw"], fr["Pcw"], bgr, pts)
+    assert (val.astype(bool) == oval).all() and (rgb == orgb).all()
