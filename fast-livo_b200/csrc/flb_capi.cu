@@ -224,6 +224,9 @@ struct flb_handle {
     cudaEvent_t ev_res[2] = {nullptr, nullptr};
     bool res_pending[2] = {false, false};
     bool state_valid = false;
+    // device-side state moves that the next persistent kernel performs itself instead of a separate D2D copy
+    bool reset_pending = false;   // flb_state_reset_enqueue: x, x_prop := the saved pair
+    bool prior_pending = false;   // flb_state_set_prior_enqueue: x_prop := x
 
     // VIO inputs
     int img_w = 0, img_h = 0;
@@ -505,6 +508,19 @@ int vio_inputs_release(flb_handle* h) {
     return FLB_OK;
 }
 
+// Perform the deferred device-side state moves with plain copies (every consumer other than the persistent kernels).
+int flush_state_ops(flb_handle* h) {
+    if (h->reset_pending) {
+        FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[0], &h->states.p[3], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+        h->reset_pending = false;
+    }
+    if (h->prior_pending) {
+        FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[1], &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+        h->prior_pending = false;
+    }
+    return FLB_OK;
+}
+
 // Flag base for one persistent launch: flags epoch+1 .. epoch+4095 belong to it alone.  On wrap-around the
 // packet is cleared (stream-ordered) so that no stale unit can ever match.
 int next_epoch(flb_handle* h, unsigned* epoch) {
@@ -538,7 +554,14 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
     s.p2p = h->p2p;
     s.timeout_flag = &h->barrier.p->timeout;
     LioArgs a = make_lio_args(h, d, false, 6);
-    if (h->cfg.persistent && (!h->comm || h->p2p.world > 1)) {
+    const bool lio_persistent = h->cfg.persistent && (!h->comm || h->p2p.world > 1);
+    if (h->prior_pending || (h->reset_pending && !lio_persistent)) { int rcf = flush_state_ops(h); if (rcf) return rcf; }
+    if (h->reset_pending) {              // the kernel starts from the saved pair and restores state / state_prop itself
+        s.init_x = &h->states.p[3];
+        s.init_xp = &h->states.p[4];
+        h->reset_pending = false;
+    }
+    if (lio_persistent) {
         // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
         // whole multiples of the SM count (<= co-resident capacity): chunks are dealt round-robin to blocks
         // worker blocks (one per SM, chunks dealt round-robin) + one leader block
@@ -674,6 +697,11 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         return fail(h, FLB_ERR_STATE, "the fused NVLink exchange lives in the persistent kernels (flb_config.persistent = 1)");
     if (fused && h->Pn > kP2PErrCap) return fail(h, FLB_ERR_INVALID, "fused multi-GPU mode: at most %d patches per rank", kP2PErrCap);
     const bool persistent = h->cfg.persistent && (fused || (!h->comm && (h->Pn > 0 || h->pn_on_device))) && prm->max_iteration > 0;
+    if (h->reset_pending || (h->prior_pending && !persistent)) { int rcf = flush_state_ops(h); if (rcf) return rcf; }
+    if (h->prior_pending) {              // the kernel takes state_propagat = state itself
+        s.prior_from_state = 1;
+        h->prior_pending = false;
+    }
     if (!persistent) {
         LaunchScope ls(h, FAM_SOLVE);
         k_vio_begin<<<1, 32, 0, h->stream>>>(h->vio_ctrl.p, h->Pn);
@@ -1229,6 +1257,7 @@ int flb_imu_undistort(flb_handle* h, const flb_imu_params* prm, flb_imu_carry* c
         offset_index < 3 || offset_index >= stride)
         return fail(h, FLB_ERR_INVALID, "flb_imu_undistort: bad arguments");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_imu_undistort: no device state (flb_state_upload)");
+    { int rcf = flush_state_ops(h); if (rcf) return rcf; }
     for (int i = 0; i + 1 < n_imu; ++i)
         if (!(v_imu[i + 1].t >= v_imu[i].t)) return fail(h, FLB_ERR_INVALID, "flb_imu_undistort: IMU times must be non-decreasing");
     static_assert(sizeof(ImuSampleDev) == sizeof(flb_imu_sample) && sizeof(ImuCarryDev) == sizeof(flb_imu_carry), "ABI layout");
@@ -1644,26 +1673,30 @@ int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_p
     FLB_CUDA(h, h->st_state.mark(h->stream));
     FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[3], &h->states.p[0], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
     h->state_valid = true;
+    h->reset_pending = h->prior_pending = false;     // both superseded by the upload
     return FLB_OK;
 }
 
 int flb_state_reset_enqueue(flb_handle* h) {
     FLB_CHECK_H(h);
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_reset_enqueue: no state uploaded");
-    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[0], &h->states.p[3], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    h->prior_pending = false;            // overwritten by the reset
+    h->reset_pending = true;             // performed by the next LIO kernel (or flushed as a copy by any other consumer)
     return FLB_OK;
 }
 
 int flb_state_set_prior_enqueue(flb_handle* h) {
     FLB_CHECK_H(h);
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_set_prior_enqueue: no state uploaded");
-    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[1], &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
+    { int rcf = flush_state_ops(h); if (rcf) return rcf; }      // an earlier pending reset / prior comes first
+    h->prior_pending = true;             // performed by the next VIO kernel (or flushed as a copy by any other consumer)
     return FLB_OK;
 }
 
 int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio) {
     FLB_CHECK_H(h);
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_download: no state uploaded");
+    { int rcf = flush_state_ops(h); if (rcf) return rcf; }
     char* po = static_cast<char*>(h->pin_out.p);
     FLB_CUDA(h, cudaMemcpyAsync(po, &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToHost, h->stream));
     FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18), h->lio_ctrl.p, sizeof(LioCtrl), cudaMemcpyDeviceToHost, h->stream));
@@ -1701,6 +1734,7 @@ int flb_state_download_enqueue(flb_handle* h, int slot) {
     FLB_CHECK_H(h);
     if (slot < 0 || slot > 1) return fail(h, FLB_ERR_INVALID, "flb_state_download_enqueue: slot must be 0 or 1");
     if (!h->state_valid) return fail(h, FLB_ERR_STATE, "flb_state_download_enqueue: no state uploaded");
+    { int rcf = flush_state_ops(h); if (rcf) return rcf; }
     const size_t bytes = sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl) + sizeof(GridBarrier);
     FLB_CUDA(h, h->pin_res[slot].reserve(bytes));
     if (!h->ev_res[slot]) FLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_res[slot], cudaEventDisableTiming));
@@ -2540,6 +2574,7 @@ int vm_set_pose(flb_handle* h, const double* Rcw, const double* Pcw) {
         FLB_CUDA(h, h->st_misc.mark(h->stream));
     } else {
         if (!h->state_valid) return fail(h, FLB_ERR_STATE, "visual map: no pose given and no device state");
+        { int rcf = flush_state_ops(h); if (rcf) return rcf; }
         LaunchScope ls(h, FAM_OTHER);
         k_vm_pose_from_state<<<1, 32, 0, h->stream>>>(&h->states.p[0], h->vm.rci.p, h->vm.pose.p);
         FLB_CUDA(h, cudaGetLastError());

@@ -1441,6 +1441,10 @@ struct LioSolveArgs {
     LioParamsDev prm;
     P2PArgs p2p;             // world <= 1: single GPU
     int* timeout_flag;       // GridBarrier::timeout
+    // persistent kernel: where the update STARTS from when that is not *state / *state_prop (a pending
+    // flb_state_reset_enqueue: the saved pair).  The leader copies both into state / state_prop first.
+    const State18* init_x;
+    const State18* init_xp;
 };
 
 // Warp-level publication of the pose packet (see "Pose packet" below): 8-byte units {word, flag}.
@@ -1614,6 +1618,7 @@ struct VioSolveArgs {
     VioParamsDev prm;
     P2PArgs p2p;             // world <= 1: single GPU
     int* timeout_flag;
+    int prior_from_state;    // persistent kernel: state_propagat = state (a pending flb_state_set_prior_enqueue, laserMapping.cpp:1292)
 };
 
 constexpr int kErrChunk = 2048;          // staging capacity of the kernel-per-pass finalize kernel (static shared memory)
@@ -2150,8 +2155,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
     if (tid == 96) s_seq_base = multi ? *s.p2p.seq : 0ull;     // exchange counter: identical on every rank
     // every block keeps the pose/bias part of state and state_propagat resident in shared memory
-    if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(s.state)[tid];
-    else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(s.state_prop)[tid - 24];
+    const State18* x_src = s.init_x ? s.init_x : s.state;
+    const State18* xp_src = s.init_xp ? s.init_xp : s.state_prop;
+    if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(x_src)[tid];
+    else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(xp_src)[tid - 24];
     if (tid == 64) {
         LioCtrl c;
         c.iterCount = -1; c.rematch_num = 0; c.nearest_search_en = 1; c.stop = 0;
@@ -2161,8 +2168,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     }
     __syncthreads();
     int resident = 0;
-    if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
-    else if (a.prefetch) {
+    if (is_leader) {
+        if (s.init_x) {                  // the pending reset: state / state_prop take the saved pair (whole structs)
+            const double* a0 = reinterpret_cast<const double*>(s.init_x);
+            const double* a1 = reinterpret_cast<const double*>(s.init_xp);
+            double* d0 = reinterpret_cast<double*>(s.state);
+            double* d1 = reinterpret_cast<double*>(const_cast<State18*>(s.state_prop));
+            for (int e = tid; e < (int)(sizeof(State18) / sizeof(double)); e += BLOCK) { d0[e] = a0[e]; d1[e] = a1[e]; }
+        }
+        resident = leader_prepare<BLOCK>(sm, x_src, s.prior);
+    } else if (a.prefetch) {
         // A map larger than a few MB is cold in L2 when the frame starts (other work ran in between): the kNN walk
         // would then pay one DRAM latency per dependent step.  Stream the sorted points and the cell table into L2
         // with bulk prefetches (asynchronous: nobody waits for them), 4 KB per instruction.
@@ -2254,6 +2269,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     const bool is_leader = (int)blockIdx.x == nworkers;
     const int Pn = a.Pn_dev ? min(*a.Pn_dev, a.Pn) : a.Pn;     // device-built patch list: its length lives on the device
     if (Pn <= 0 && s.p2p.world <= 1) {                         // :969-970 (the host short-circuits when it knows)
+        if (is_leader && s.prior_from_state) {
+            const double* a0 = reinterpret_cast<const double*>(s.state);
+            double* d1 = reinterpret_cast<double*>(const_cast<State18*>(s.state_prop));
+            for (int e = tid; e < (int)(sizeof(State18) / sizeof(double)); e += BLOCK) d1[e] = a0[e];
+        }
         if (is_leader && tid == 0) {
             VioCtrl c;
             c.level = 2; c.iteration = 0; c.stop = 1;
@@ -2269,8 +2289,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     int pass_no = 0;
     if (trace && blockIdx.x == 0 && tid == 0) trace[0] = global_ns();
     if (tid == 96) s_seq_base = multi ? *s.p2p.seq : 0ull;     // exchange counter: identical on every rank
+    const State18* xp_src = s.prior_from_state ? s.state : s.state_prop;
     if (tid < 24) reinterpret_cast<double*>(&sm.x)[tid] = reinterpret_cast<const double*>(s.state)[tid];
-    else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(s.state_prop)[tid - 24];
+    else if (tid < 48) reinterpret_cast<double*>(&sm.xp)[tid - 24] = reinterpret_cast<const double*>(xp_src)[tid - 24];
     if (tid == 64) {
         VioCtrl c;
         c.level = 2; c.iteration = 0; c.stop = 0;
@@ -2285,7 +2306,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     if (single && !is_leader && blockIdx.x * NW + warp < Pn) vio_patch_load(a, blockIdx.x * NW + warp, tid & 31, pin);
     __syncthreads();
     int resident = 0;
-    if (is_leader) resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
+    if (is_leader) {
+        if (s.prior_from_state) {        // the pending `state_propagat = state`: the whole struct, before anything writes *state
+            const double* a0 = reinterpret_cast<const double*>(s.state);
+            double* d1 = reinterpret_cast<double*>(const_cast<State18*>(s.state_prop));
+            for (int e = tid; e < (int)(sizeof(State18) / sizeof(double)); e += BLOCK) d1[e] = a0[e];
+        }
+        resident = leader_prepare<BLOCK>(sm, s.state, s.prior);
+    }
     for (;;) {
         const unsigned flag = epoch + (unsigned)pass_no + 1u;
         const unsigned p2p_tag = multi ? ((unsigned)(s_seq_base + (unsigned long long)pass_no + 1ull) | 0x80000000u) : 0u;

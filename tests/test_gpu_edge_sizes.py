@@ -97,3 +97,38 @@ def test_packet_flag_wraparound(flb, po, frames):
         h.vio_update(flb.capi.vio_params(f, 3), xg, xpg)
         assert rel(xg.vector(), xv.vector()) < STATE_RTOL, it
     h.close()
+
+
+def test_deferred_state_moves(flb, frames):
+    """flb_state_reset_enqueue / flb_state_set_prior_enqueue are carried out by the next persistent kernel (no separate
+    device copy); every other consumer sees them as if they had been plain copies."""
+    f = frames("T1")
+    h = flb.Handle(device=0)
+    h.load_frame(f)
+    lprm, vprm = flb.capi.lio_params(f, 3), flb.capi.vio_params(f, 3)
+    x0 = flb.capi.State18.from_frame(f)
+    h.state_upload(x0, x0.copy())
+    h.lio_update_enqueue(lprm)
+    h.state_set_prior_enqueue()
+    h.vio_update_enqueue(vprm)
+    x1, _, _ = h.state_download()
+    # reset consumed by the LIO kernel, prior by the VIO kernel: the same frame again, bit for bit
+    h.state_reset_enqueue()
+    h.lio_update_enqueue(lprm)
+    h.state_set_prior_enqueue()
+    h.vio_update_enqueue(vprm)
+    x2, _, _ = h.state_download()
+    assert (x2.vector() == x1.vector()).all() and (np.array(x2.cov[:]) == np.array(x1.cov[:])).all()
+    # a reset nobody consumes is flushed by the download
+    h.state_reset_enqueue()
+    x3, _, _ = h.state_download()
+    assert (x3.vector() == x0.vector()).all() and (np.array(x3.cov[:]) == np.array(x0.cov[:])).all()
+    # reset followed directly by the VIO update (no LIO kernel to consume it): flushed as a copy first
+    h.state_reset_enqueue()
+    h.state_set_prior_enqueue()
+    h.vio_update_enqueue(vprm)
+    xa, _, _ = h.state_download()
+    xb = x0.copy()
+    h.vio_update(vprm, xb, x0)
+    assert (xa.vector() == xb.vector()).all()
+    h.close()
