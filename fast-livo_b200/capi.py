@@ -143,6 +143,14 @@ class VioReport(C.Structure):
                 ("skipped_last", C.c_int), ("cov_updated", C.c_int), ("status", C.c_int)]
 
 
+class FrameInputs(C.Structure):
+    """flb_frame_inputs (include/fastlivo_b200.h)."""
+    _fields_ = [("scan_xyz", C.c_void_p), ("n_scan", C.c_int), ("scan_stride", C.c_int),
+                ("gray", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("stride_bytes", C.c_int),
+                ("patch_pos", C.c_void_p), ("patch", C.c_void_p), ("search_level", C.c_void_p), ("Pn", C.c_int),
+                ("x", C.POINTER(State18)), ("x_prop", C.POINTER(State18))]
+
+
 class VmapParams(C.Structure):
     """flb_vmap_params (include/fastlivo_b200.h)."""
     _fields_ = [("grid_size", C.c_int), ("ncc_en", C.c_int), ("outlier_threshold", C.c_double), ("ncc_thre", C.c_double),
@@ -162,7 +170,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_vio_update_enqueue", "flb_state_reset_enqueue", "flb_state_set_prior_enqueue", "flb_profile_start", "flb_profile_stop",
            "flb_launch_count", "flb_trace_enable", "flb_trace_download", "flb_comm_unique_id", "flb_comm_init", "flb_comm_destroy", "flb_p2p_export", "flb_p2p_attach", "flb_p2p_detach",
            "flb_imu_undistort", "flb_visual_candidates", "flb_vio_errors",
-           "flb_vio_update_level", "flb_state_download_enqueue", "flb_state_download_wait",
+           "flb_vio_update_level", "flb_state_download_enqueue", "flb_state_download_wait", "flb_frame_enqueue",
            "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
            "flb_vmap_map_value", "flb_vmap_dump", "flb_colorize", "flb_voxel_grid",
            "flb_batch_begin", "flb_batch_set_frame", "flb_batch_state_reset_enqueue", "flb_batch_update_enqueue", "flb_batch_state_download",
@@ -244,6 +252,7 @@ def lib():
         L.flb_state_upload.argtypes = [vp, C.POINTER(State18), C.POINTER(State18)]
         L.flb_state_download.argtypes = [vp, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
         L.flb_lio_update_enqueue.argtypes = [vp, C.POINTER(LioParams)]
+        L.flb_frame_enqueue.argtypes = [vp, C.POINTER(FrameInputs), C.POINTER(LioParams), C.POINTER(VioParams), C.c_int]
         L.flb_state_download_enqueue.argtypes = [vp, C.c_int]
         L.flb_state_download_wait.argtypes = [vp, C.c_int, C.POINTER(State18), C.POINTER(LioReport), C.POINTER(VioReport)]
         L.flb_vio_update_enqueue.argtypes = [vp, C.POINTER(VioParams)]
@@ -608,6 +617,24 @@ class Handle:
         x, lr, vr = State18(), LioReport(), VioReport()
         self._ck(self.L.flb_state_download(self.h, C.byref(x), C.byref(lr), C.byref(vr)))
         return x, lr, vr
+
+    def frame_inputs(self, scan, x, x_prop, image=None, pos=None, patch=None, level=None):
+        """A reusable flb_frame_inputs over caller-owned numpy arrays (keep them alive; pass page-locked arrays from
+        pinned_like() to let the copy engine read them in place)."""
+        fi = FrameInputs()
+        fi._keep = (scan, image, pos, patch, level, x, x_prop)
+        fi.scan_xyz, fi.n_scan, fi.scan_stride = scan.ctypes.data, scan.shape[0], scan.shape[1]
+        if image is not None:
+            fi.gray, fi.width, fi.height, fi.stride_bytes = image.ctypes.data, image.shape[1], image.shape[0], image.shape[1]
+        if pos is not None:
+            fi.patch_pos, fi.patch, fi.search_level, fi.Pn = pos.ctypes.data, patch.ctypes.data, level.ctypes.data, len(pos)
+            self.Pn = len(pos)
+        fi.x, fi.x_prop = C.pointer(x), C.pointer(x_prop)
+        self.N = scan.shape[0]
+        return fi
+
+    def frame_enqueue(self, fi, lprm, vprm=None, slot=-1):
+        self._ck(self.L.flb_frame_enqueue(self.h, C.byref(fi), C.byref(lprm), C.byref(vprm) if vprm is not None else None, int(slot)))
 
     def state_download_enqueue(self, slot):
         self._ck(self.L.flb_state_download_enqueue(self.h, int(slot)))

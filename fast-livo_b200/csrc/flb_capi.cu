@@ -241,10 +241,7 @@ struct flb_handle {
     DevBuf<double> x_z, x_H;
     bool cam_set = false;
     CamModel cam{};
-    TapMaps tapmaps{};           // TMA descriptors of the image (experiment: FLB_TMA=1)
-    const void* tapmaps_for = nullptr;
-    int tapmaps_w = 0, tapmaps_h = 0;
-    bool tapmaps_ok = false;
+
     bool last_vio_valid = false;
 
     // device-resident visual map (rows f2 / f4)
@@ -636,35 +633,6 @@ int resolve_pn(flb_handle* h) {
     return FLB_OK;
 }
 
-// TMA descriptors for the tap box (one per tap stride 1, 2, 4, 8); false when the driver entry point is missing or the
-// image geometry does not satisfy TMA's alignment rules (row pitch a multiple of 16 bytes).
-bool ensure_tapmaps(flb_handle* h) {
-    if (h->tapmaps_for == h->img.p && h->tapmaps_w == h->img_w && h->tapmaps_h == h->img_h) return h->tapmaps_ok;
-    h->tapmaps_for = h->img.p;
-    h->tapmaps_w = h->img_w;
-    h->tapmaps_h = h->img_h;
-    h->tapmaps_ok = false;
-    if (h->img_w % 16 != 0) return false;
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
-    EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
-    for (int si = 0; si < 4; ++si) {
-        const int sc = 1 << si;
-        const cuuint64_t dims[2] = {(cuuint64_t)h->img_w, (cuuint64_t)h->img_h};
-        const cuuint64_t strides[1] = {(cuuint64_t)h->img_w};
-        const cuuint32_t box[2] = {(cuuint32_t)((10 * sc + 1 + 15) / 16 * 16), (cuuint32_t)(10 * sc + 1)};
-        const cuuint32_t estr[2] = {1u, (cuuint32_t)sc};
-        if (enc(&h->tapmaps.m[si], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->img.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-    }
-    h->tapmaps_ok = true;
-    return true;
-}
-
 int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     if (!h->cam_set || h->img_w <= 0) return fail(h, FLB_ERR_STATE, "flb_vio_update: camera and image must be set first");
     if (h->cam.width != h->img_w || h->cam.height != h->img_h) return fail(h, FLB_ERR_STATE, "camera / image size mismatch");
@@ -755,9 +723,9 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         // staging capacity for the errors of ALL ranks (the peers' shard sizes are not known here: assume like ours + slack)
         int err_cap = (int)std::min<long long>(kVioErrCapMax, std::max<long long>(2048, ((long long)a.Pn * std::max(h->p2p.world, 1) * 5 / 4 + 319) / 256 * 256));
         static const int env_tma = [] { const char* e = getenv("FLB_TMA"); return e ? atoi(e) : 0; }();
-        int use_tma = (env_tma && ensure_tapmaps(h)) ? 1 : 0;
+        int use_tma = env_tma ? 1 : 0;       // experiment: tap rows staged by the bulk async-copy engine
         const size_t dyn = std::max<size_t>((size_t)err_cap * sizeof(float), use_tma ? (size_t)(kVioPersBlock / 32) * kTapTileBytes : 0);
-        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap, &h->tapmaps, &use_tma};
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap, &use_tma};
         LaunchScope ls(h, FAM_VIO);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args, dyn,
                                                 h->stream));
@@ -1117,15 +1085,42 @@ int flb_map_add_points(flb_handle* h, const float* world_xyz, int n, int stride,
     FLB_CUDA(h, h->st_map.acquire((size_t)n * 3 * sizeof(float), &stv));
     float* st = static_cast<float*>(stv);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = 0; i < n; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const float v = world_xyz[(size_t)i * stride + k];
-            if (!std::isfinite(v)) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: non-finite coordinate at point %d", i);
-            if (std::fabs(v / downsample_size) > 1.0e6f) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: coordinate / downsample_size exceeds 2^20 voxels");
-            st[3 * (size_t)i + k] = v;
-            lo[k] = std::min(lo[k], v);
-            hi[k] = std::max(hi[k], v);
+    if (stride == 3) std::memcpy(st, world_xyz, (size_t)n * 3 * sizeof(float));
+    else
+        for (int i = 0; i < n; ++i) {
+            st[3 * (size_t)i] = world_xyz[(size_t)i * stride];
+            st[3 * (size_t)i + 1] = world_xyz[(size_t)i * stride + 1];
+            st[3 * (size_t)i + 2] = world_xyz[(size_t)i * stride + 2];
         }
+    {
+        // bounds + finiteness over the packed floats, 24 (= 8 points) at a time into independent accumulators (vectorises)
+        float mn[24], mx[24];
+        for (int j = 0; j < 24; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+        unsigned bad = 0;
+        const size_t n3 = (size_t)n * 3;
+        size_t i = 0;
+        for (; i + 24 <= n3; i += 24)
+            for (int j = 0; j < 24; ++j) {
+                const float v = st[i + j];
+                unsigned bits;
+                std::memcpy(&bits, &v, sizeof(bits));
+                bad |= ((bits & 0x7F800000u) == 0x7F800000u) ? 1u : 0u;
+                mn[j] = v < mn[j] ? v : mn[j];
+                mx[j] = v > mx[j] ? v : mx[j];
+            }
+        for (; i < n3; ++i) {
+            const float v = st[i];
+            const int j = (int)(i % 24);
+            bad |= std::isfinite(v) ? 0u : 1u;
+            mn[j] = v < mn[j] ? v : mn[j];
+            mx[j] = v > mx[j] ? v : mx[j];
+        }
+        if (bad) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: non-finite coordinate");
+        for (int j = 0; j < 24; ++j) { lo[j % 3] = std::min(lo[j % 3], mn[j]); hi[j % 3] = std::max(hi[j % 3], mx[j]); }
+        const float lim = 1.0e6f * downsample_size;
+        for (int k = 0; k < 3; ++k)
+            if (lo[k] < -lim || hi[k] > lim) return fail(h, FLB_ERR_INVALID, "flb_map_add_points: coordinate / downsample_size exceeds 2^20 voxels");
+    }
     // the input is valid from here on: only now does the map box take it in
     bool inside = true;
     for (int k = 0; k < 3; ++k) inside = inside && lo[k] >= h->grid_lo[k] && hi[k] <= h->grid_hi[k];
@@ -1469,7 +1464,9 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CUDA(h, h->st_scan.acquire(n1 * 3 * sizeof(float), &stv));
     float* st = static_cast<float*>(stv);
     float lo[3] = {INFINITY, INFINITY, INFINITY};
-    if (stride == 3) std::memcpy(st, body_xyz, (size_t)N * 3 * sizeof(float));
+    const bool direct = N > 0 && stride == 3 && is_pinned(body_xyz);      // page-locked packed source: no staging copy
+    if (direct) st = const_cast<float*>(body_xyz);
+    else if (stride == 3) std::memcpy(st, body_xyz, (size_t)N * 3 * sizeof(float));
     else
         for (int i = 0; i < N; ++i) {
             st[3 * (size_t)i] = body_xyz[(size_t)i * stride];
@@ -1514,7 +1511,7 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>(nb * lio_packed(12), h->partials.cap)));
     if (N > 0) {
         FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        FLB_CUDA(h, h->st_scan.mark(h->stream));
+        if (!direct) FLB_CUDA(h, h->st_scan.mark(h->stream));
         // Morton order in the body frame (cell = twice the map grid's cell): spatially coherent warps at any pose
         const float inv_cell = 0.5f / (float)h->cfg.cell_size;
         const int g = (N + 255) / 256;
@@ -1777,6 +1774,28 @@ int flb_vio_update_enqueue(flb_handle* h, const flb_vio_params* prm) {
     FLB_CHECK_H(h);
     if (!prm) return fail(h, FLB_ERR_INVALID, "null params");
     return enqueue_vio_update(h, prm);
+}
+
+// One frame in one call: uploads + both updates enqueued + (optionally) the pipelined read-back.
+int flb_frame_enqueue(flb_handle* h, const flb_frame_inputs* in, const flb_lio_params* lprm, const flb_vio_params* vprm, int result_slot) {
+    FLB_CHECK_H(h);
+    if (!in || !lprm || !in->x || !in->x_prop) return fail(h, FLB_ERR_INVALID, "flb_frame_enqueue: null argument");
+    int rc = flb_scan_upload(h, in->scan_xyz, in->n_scan, in->scan_stride);
+    if (rc) return rc;
+    rc = flb_state_upload(h, in->x, in->x_prop);
+    if (rc) return rc;
+    rc = enqueue_lio_update(h, lprm);
+    if (rc) return rc;
+    if (vprm) {
+        if (in->gray) { rc = flb_image_upload(h, in->gray, in->width, in->height, in->stride_bytes); if (rc) return rc; }
+        if (in->patch_pos) { rc = flb_patches_upload(h, in->patch_pos, in->patch, in->search_level, in->Pn); if (rc) return rc; }
+        rc = flb_state_set_prior_enqueue(h);          // state_propagat = state (src/laserMapping.cpp:1292), zero-motion propagation
+        if (rc) return rc;
+        rc = enqueue_vio_update(h, vprm);
+        if (rc) return rc;
+    }
+    if (result_slot >= 0) return flb_state_download_enqueue(h, result_slot);
+    return FLB_OK;
 }
 
 int flb_lio_update(flb_handle* h, const flb_lio_params* prm, flb_state18* x, const flb_state18* x_prop, flb_lio_report* rep) {

@@ -16,21 +16,22 @@
 // has a fixed order, so results are bit-reproducible run to run and identical across ranks.
 #pragma once
 
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include "flb_device.cuh"
 
 namespace flb {
 
 // ---------------------------------------------------------------------------------------
-// TMA staging of the photometric tap box (north_star: "TMA-staged image tiles"; experiment, off by default --
-// DESIGN.md section 8 has the measurement).  One tiled tensor map per tap stride sc = 1, 2, 4, 8 over the uint8 image:
-// box = {round16(10 sc + 1) bytes, 10 sc + 1 rows} with traversal stride {1, sc}, i.e. the 11 tap ROWS arrive as 11
-// contiguous row segments (TMA has no stride on the innermost dimension and caps the others at 8, so sc = 16 patches
-// and the column stride stay with the scalar path / the shared-memory gather).
+// TMA staging of the photometric tap box (north_star: "TMA-staged image tiles"; an experiment, off by default --
+// DESIGN.md section 8 and profiles/r02_tma_experiment.md have the measurement).  The 11 tap rows of a patch are fetched
+// by the bulk async-copy engine (cp.async.bulk shared <- global, SASS UBLKCP), one 16-byte-aligned row segment per
+// lane 0..10, completion on a per-warp mbarrier; the strided column gather then reads shared memory.  (A tiled tensor
+// map per tap stride -- box = 11 row segments with row traversal stride = scale; TMA has no stride on the innermost
+// dimension and caps the others at 8 -- was built first and faulted with "illegal instruction" at UTMALDG on the box
+// (not root-caused); the descriptor-less form below has none of the descriptor's constraints.)
 // ---------------------------------------------------------------------------------------
-struct TapMaps { CUtensorMap m[4]; };
-constexpr int kTapTileBytes = 1152;      // 11 rows x 96 B (sc = 8), padded to a multiple of 128
+constexpr int kTapRowBytes = 128;        // one staged row: up to 15 bytes of alignment slack + 10 * 8 + 1 taps, rounded to 16
+constexpr int kTapTileBytes = 11 * kTapRowBytes;
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -45,9 +46,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-                 "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -930,8 +931,7 @@ __device__ __forceinline__ double round_to_f32_precision(double d) {
 __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
                                           float* s_lat, double* s_res, double& accv, double& n_meas, double& skipped,
                                           unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0,
-                                          const TapMaps* tm = nullptr, unsigned char* tile = nullptr, unsigned long long* mbar = nullptr,
-                                          unsigned* tma_phase = nullptr) {
+                                          unsigned char* tile = nullptr, unsigned long long* mbar = nullptr, unsigned* tma_phase = nullptr) {
     const int lane = threadIdx.x & 31;
     float* const err_out = a.errors + (size_t)err_buf * a.err_stride;
     double acc[27];
@@ -943,15 +943,21 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
     if (g.valid) {
         // stage the 11x11 tap lattice (stride = scale px) as float
         const int W = a.cam.width;
-        if (tm != nullptr && g.scale <= 8) {
-            // TMA: the 11 tap rows as one tiled bulk copy (row stride = scale), then the strided column gather from the tile
-            const int si = (g.scale == 1) ? 0 : (g.scale == 2) ? 1 : (g.scale == 4) ? 2 : 3;
-            const int rowb = (10 * g.scale + 1 + 15) / 16 * 16;
+        if (tile != nullptr && g.scale <= 8) {
+            // bulk async copies: row r of the tap box = one aligned segment of image row v_i + (r - 5) scale
+            const unsigned char* row0 = a.img + (size_t)(g.v_i - 5 * g.scale) * W + (g.u_i - 5 * g.scale);
+            const unsigned char* rowp = row0 + (size_t)(lane < 11 ? lane : 0) * g.scale * W;
+            const unsigned off = (unsigned)(reinterpret_cast<size_t>(rowp) & 15u);
+            const unsigned bytes = (off + 10u * (unsigned)g.scale + 1u + 15u) & ~15u;
+            unsigned total = (lane < 11) ? bytes : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             if (lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the tile's previous readers are done
-                mbar_expect_tx(mbar, (unsigned)(rowb * 11));
-                tma_load_2d(tile, &tm->m[si], g.u_i - 5 * g.scale, g.v_i - 5 * g.scale, mbar);
+                mbar_expect_tx(mbar, total);
             }
+            __syncwarp();
+            if (lane < 11) bulk_load(tile + lane * kTapRowBytes, rowp - off, bytes, mbar);
             mbar_wait(mbar, *tma_phase);
             *tma_phase ^= 1u;
 #pragma unroll
@@ -959,7 +965,8 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
                 const int e = lane + 32 * q;
                 if (e < 121) {
                     const int r = e / 11, c = e - r * 11;
-                    s_lat[e] = (float)tile[r * rowb + c * g.scale];
+                    const unsigned offr = (unsigned)(reinterpret_cast<size_t>(row0 + (size_t)r * g.scale * W) & 15u);
+                    s_lat[e] = (float)tile[r * kTapRowBytes + offr + c * g.scale];
                 }
             }
         } else {
@@ -2247,7 +2254,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
                                                                     unsigned long long* pkt, unsigned epoch,
                                                                     unsigned long long* trace, unsigned long long* dbg, int err_cap,
-                                                                    const __grid_constant__ TapMaps tapmaps, int use_tma) {
+                                                                    int use_tma) {
     constexpr int NW = BLOCK / 32;
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     __shared__ VioPose s_pose;
@@ -2358,8 +2365,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
                 if (!single) vio_patch_load(a, i, tid & 31, pin);
                 vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
                           dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1,
-                          use_tma ? &tapmaps : nullptr, reinterpret_cast<unsigned char*>(s_err) + (size_t)warp * kTapTileBytes, &s_mbar[warp],
-                          &tma_phase);
+                          use_tma ? reinterpret_cast<unsigned char*>(s_err) + (size_t)warp * kTapTileBytes : nullptr, &s_mbar[warp], &tma_phase);
             }
             vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();

@@ -375,6 +375,18 @@ int flb_vio_errors(flb_handle* h, float* errors, int capacity);
  * VIO update whose prior is the LIO posterior (zero-motion propagation). */
 int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_prop);
 int flb_state_download(flb_handle* h, flb_state18* x, flb_lio_report* lio, flb_vio_report* vio);
+/* One frame in ONE call (the reference's per-frame work on this path: sync_packages -> LIO update -> VIO update,
+ * src/laserMapping.cpp:1269-1460): scan upload, state upload, LIO update, and -- when vprm != NULL -- image upload,
+ * patch-list upload (patch_pos == NULL: keep the list already on the device, e.g. one built by flb_vmap_select),
+ * state_propagat = state, VIO update; result_slot >= 0 also enqueues the read-back into that slot
+ * (flb_state_download_wait collects it).  Everything is enqueue-only. */
+typedef struct flb_frame_inputs {
+    const float*   scan_xyz;  int n_scan, scan_stride;                 /* feats_down_body, floats per point */
+    const uint8_t* gray;      int width, height, stride_bytes;         /* NULL: keep the image on the device */
+    const double*  patch_pos; const float* patch; const int* search_level; int Pn;
+    const flb_state18* x; const flb_state18* x_prop;
+} flb_frame_inputs;
+int flb_frame_enqueue(flb_handle* h, const flb_frame_inputs* in, const flb_lio_params* lprm, const flb_vio_params* vprm, int result_slot);
 /* Pipelined read-back (two result slots): _enqueue copies the state and both reports of everything enqueued so far and
  * returns at once; _wait blocks on that slot only -- frame k's result is collected while frame k+1 already uploads
  * and runs (uploads never overwrite what an enqueued kernel still reads: stream order, and events for the copy stream). */

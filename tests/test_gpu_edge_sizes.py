@@ -132,3 +132,43 @@ def test_deferred_state_moves(flb, frames):
     h.vio_update(vprm, xb, x0)
     assert (xa.vector() == xb.vector()).all()
     h.close()
+
+
+def test_frame_enqueue_equals_separate_calls(flb, frames):
+    """flb_frame_enqueue (one call per frame, pipelined read-back) == the separate upload / update / download calls;
+    page-locked caller buffers are read in place."""
+    f = frames("T1")
+    lprm, vprm = flb.capi.lio_params(f, 3), flb.capi.vio_params(f, 3)
+    x0 = flb.capi.State18.from_frame(f)
+    h = flb.Handle(device=0)
+    h.load_frame(f)
+    h.state_upload(x0, x0.copy())
+    h.lio_update_enqueue(lprm)
+    h.state_set_prior_enqueue()
+    h.vio_update_enqueue(vprm)
+    xs, ls, vs = h.state_download()
+    h.close()
+    h = flb.Handle(device=0)
+    h.map_upload(f["map_xyz"])
+    h.camera_set(f["cam"])
+    scan = h.pinned_like(np.ascontiguousarray(f["scan_body"], np.float32))
+    img = h.pinned_like(f["image"])
+    pos = h.pinned_like(np.ascontiguousarray(f["patch_pos"], np.float64))
+    ref = h.pinned_like(np.ascontiguousarray(f["patch_ref"], np.float32).reshape(len(pos), 192))
+    lev = h.pinned_like(np.ascontiguousarray(f["patch_level"], np.int32))
+    fi = h.frame_inputs(scan, x0, x0.copy(), img, pos, ref, lev)
+    for k in range(3):                                   # three frames in flight over two result slots
+        h.frame_enqueue(fi, lprm, vprm, k & 1)
+        if k:
+            xk, lk, vk = h.state_download_wait((k - 1) & 1)
+            assert (xk.vector() == xs.vector()).all() and (np.array(xk.cov[:]) == np.array(xs.cov[:])).all()
+            assert lk.rows_total == ls.rows_total and list(vk.passes) == list(vs.passes)
+    xk, _, _ = h.state_download_wait(0)
+    assert (xk.vector() == xs.vector()).all()
+    # LIO only
+    h.frame_enqueue(fi, lprm, None, 1)
+    xl, ll, _ = h.state_download_wait(1)
+    x1 = x0.copy()
+    h.lio_update(lprm, x1, x0)
+    assert (xl.vector() == x1.vector()).all() and ll.rows_total == ls.rows_total
+    h.close()
