@@ -379,20 +379,30 @@ struct map_pt { float x, y, z, w; };
 #define FLB_LDGI(ptr) (*(ptr))
 #endif
 
-// Scan one contiguous run of sorted map points [s, e): four independent 16-B loads in flight per
-// step (the loads do not depend on the insertions), candidates inserted in index order.
-FLB_HD void knn_scan_run(const map_pt* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t) {
-    int m = s;
-    for (; m + 4 <= e; m += 4) {
-        const map_pt P0 = FLB_LDG4(pts + m), P1 = FLB_LDG4(pts + m + 1), P2 = FLB_LDG4(pts + m + 2), P3 = FLB_LDG4(pts + m + 3);
+// Walk `nruns` (<= 9) runs of sorted map points whose [start, end) bounds sit in the per-thread scratch (start of run k
+// at rows[k * rstride], end at rows[(9 + k) * rstride]) as ONE candidate sequence, up to four points (independent 16-B
+// loads) per step, in run order then index order.  A lane's trip count is its own candidate count / 4, so lanes whose
+// non-empty runs differ do not wait on each other run by run.
+FLB_HD void knn_walk_runs(const map_pt* __restrict__ pts, const int* rows, int rstride, int nruns, float qx, float qy, float qz,
+                          Top5& t) {
+    int k = -1, m = 0, e = 0;
+    for (;;) {
+        while (m >= e) {
+            if (++k >= nruns) break;
+            m = rows[k * rstride];
+            e = rows[(9 + k) * rstride];
+        }
+        if (k >= nruns) break;
+        const int n = e - m;
+        const map_pt P0 = FLB_LDG4(pts + m);
+        const map_pt P1 = FLB_LDG4(pts + (n > 1 ? m + 1 : m));
+        const map_pt P2 = FLB_LDG4(pts + (n > 2 ? m + 2 : m));
+        const map_pt P3 = FLB_LDG4(pts + (n > 3 ? m + 3 : m));
         top5_insert(t, dist2f(qx, qy, qz, P0.x, P0.y, P0.z), m);
-        top5_insert(t, dist2f(qx, qy, qz, P1.x, P1.y, P1.z), m + 1);
-        top5_insert(t, dist2f(qx, qy, qz, P2.x, P2.y, P2.z), m + 2);
-        top5_insert(t, dist2f(qx, qy, qz, P3.x, P3.y, P3.z), m + 3);
-    }
-    for (; m < e; ++m) {
-        const map_pt P = FLB_LDG4(pts + m);
-        top5_insert(t, dist2f(qx, qy, qz, P.x, P.y, P.z), m);
+        if (n > 1) top5_insert(t, dist2f(qx, qy, qz, P1.x, P1.y, P1.z), m + 1);
+        if (n > 2) top5_insert(t, dist2f(qx, qy, qz, P2.x, P2.y, P2.z), m + 2);
+        if (n > 3) top5_insert(t, dist2f(qx, qy, qz, P3.x, P3.y, P3.z), m + 3);
+        m += (n > 4 ? 4 : n);
     }
 }
 
@@ -403,9 +413,11 @@ FLB_HD void knn_scan_run(const map_pt* __restrict__ pts, int s, int e, float qx,
 // bound (minus a float slack that also covers points binned across a face by
 // rounding), or when the bound passes sqrt(max_d2).  Returns sorted positions in t.i.
 //
-// Rings 0 and 1 (the 3x3x3 block, where almost every query ends) are scanned as nine 3-cell
-// x-rows whose 18 cell-table entries are fetched up front (independent loads: one memory round
-// trip instead of nine dependent ones); farther rings use the generic shell walk.
+// Every ring is walked as x-runs of cells whose cell-table bounds are fetched nine runs at a time (18 independent
+// loads: one memory round trip per batch instead of one per run): rings 0 and 1 (the 3x3x3 block, where a query next to
+// a surface ends) are nine 3-cell rows; the shell of ring r >= 2 is (2r+1)-cell rows on its z / y faces and single cells
+// at x = cx -+ r elsewhere.  (A query displaced from the surfaces by the prior's error -- the first pass of a frame --
+// needs ring 2 or 3: round 1 walked those shells one run and one dependent round trip at a time.)
 FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, const map_pt* __restrict__ pts,
                       float qx, float qy, float qz, Top5& t, int* rows, int rstride) {
     // rows: per-thread scratch for 18 ints, element k at rows[k * rstride] (shared memory on the device,
@@ -423,8 +435,7 @@ FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, con
     float mz = fminf(fz - (float)cz, (float)(cz + 1) - fz);
     const float margin = fmaxf(fminf(mx, fminf(my, mz)) * g.cell - 1e-3f * g.cell, 0.f);
     {
-        // rings 0+1: rows (dz, dy) in {-1,0,1}^2, x-range [cx-1, cx+1] clipped to the grid.  All 18
-        // cell-table entries are fetched up front (independent loads).
+        // rings 0+1: rows (dz, dy) in {-1,0,1}^2, x-range [cx-1, cx+1] clipped to the grid
         const int xa = cx - 1 < 0 ? 0 : cx - 1, xb = cx + 1 >= g.nx ? g.nx - 1 : cx + 1;
         FLB_UNROLL
         for (int k = 0; k < 9; ++k) {
@@ -434,28 +445,7 @@ FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, con
             rows[k * rstride] = in ? FLB_LDGI(cell_start + rowbase + xa) : 0;
             rows[(9 + k) * rstride] = in ? FLB_LDGI(cell_start + rowbase + xb + 1) : 0;
         }
-        // Walk the nine runs as ONE sequence, up to four points (independent 16-B loads) per step, in
-        // row order then index order.  A lane's trip count is its own candidate count / 4, so lanes whose
-        // non-empty rows differ (sparse, far-range chunks) no longer wait on each other row by row.
-        int k = -1, m = 0, e = 0;
-        for (;;) {
-            while (m >= e) {
-                if (++k >= 9) break;
-                m = rows[k * rstride];
-                e = rows[(9 + k) * rstride];
-            }
-            if (k >= 9) break;
-            const int n = e - m;
-            const map_pt P0 = FLB_LDG4(pts + m);
-            const map_pt P1 = FLB_LDG4(pts + (n > 1 ? m + 1 : m));
-            const map_pt P2 = FLB_LDG4(pts + (n > 2 ? m + 2 : m));
-            const map_pt P3 = FLB_LDG4(pts + (n > 3 ? m + 3 : m));
-            top5_insert(t, dist2f(qx, qy, qz, P0.x, P0.y, P0.z), m);
-            if (n > 1) top5_insert(t, dist2f(qx, qy, qz, P1.x, P1.y, P1.z), m + 1);
-            if (n > 2) top5_insert(t, dist2f(qx, qy, qz, P2.x, P2.y, P2.z), m + 2);
-            if (n > 3) top5_insert(t, dist2f(qx, qy, qz, P3.x, P3.y, P3.z), m + 3);
-            m += (n > 4 ? 4 : n);
-        }
+        knn_walk_runs(pts, rows, rstride, 9, qx, qy, qz, t);
         const float bound = g.cell + margin;
         const float b2 = bound * bound;
         if (t.d[4] <= b2) return;                 // 5th best is certainly final
@@ -463,28 +453,33 @@ FLB_HD void knn5_grid(const GridDesc& g, const int* __restrict__ cell_start, con
     }
     for (int r = 2; r <= g.max_ring; ++r) {
         const int z0 = cz - r, z1 = cz + r, y0 = cy - r, y1 = cy + r, x0 = cx - r, x1 = cx + r;
+        const int xa = x0 < 0 ? 0 : x0, xb = x1 >= g.nx ? g.nx - 1 : x1;
+        int cnt = 0;
         for (int z = (z0 < 0 ? 0 : z0); z <= (z1 >= g.nz ? g.nz - 1 : z1); ++z) {
             const bool zface = (z == z0) || (z == z1);
             for (int y = (y0 < 0 ? 0 : y0); y <= (y1 >= g.ny ? g.ny - 1 : y1); ++y) {
                 const int rowbase = (z * g.ny + y) * g.nx;
-                const int xa = x0 < 0 ? 0 : x0, xb = x1 >= g.nx ? g.nx - 1 : x1;
                 if (zface || y == y0 || y == y1) {
                     if (xa <= xb) {
-                        const int s = FLB_LDGI(cell_start + rowbase + xa), e = FLB_LDGI(cell_start + rowbase + xb + 1);
-                        knn_scan_run(pts, s, e, qx, qy, qz, t);
+                        rows[cnt * rstride] = FLB_LDGI(cell_start + rowbase + xa);
+                        rows[(9 + cnt) * rstride] = FLB_LDGI(cell_start + rowbase + xb + 1);
+                        if (++cnt == 9) { knn_walk_runs(pts, rows, rstride, 9, qx, qy, qz, t); cnt = 0; }
                     }
                 } else {
                     if (x0 >= 0 && x0 < g.nx) {
-                        const int s = FLB_LDGI(cell_start + rowbase + x0), e = FLB_LDGI(cell_start + rowbase + x0 + 1);
-                        knn_scan_run(pts, s, e, qx, qy, qz, t);
+                        rows[cnt * rstride] = FLB_LDGI(cell_start + rowbase + x0);
+                        rows[(9 + cnt) * rstride] = FLB_LDGI(cell_start + rowbase + x0 + 1);
+                        if (++cnt == 9) { knn_walk_runs(pts, rows, rstride, 9, qx, qy, qz, t); cnt = 0; }
                     }
                     if (x1 >= 0 && x1 < g.nx) {
-                        const int s = FLB_LDGI(cell_start + rowbase + x1), e = FLB_LDGI(cell_start + rowbase + x1 + 1);
-                        knn_scan_run(pts, s, e, qx, qy, qz, t);
+                        rows[cnt * rstride] = FLB_LDGI(cell_start + rowbase + x1);
+                        rows[(9 + cnt) * rstride] = FLB_LDGI(cell_start + rowbase + x1 + 1);
+                        if (++cnt == 9) { knn_walk_runs(pts, rows, rstride, 9, qx, qy, qz, t); cnt = 0; }
                     }
                 }
             }
         }
+        if (cnt) knn_walk_runs(pts, rows, rstride, cnt, qx, qy, qz, t);
         const float bound = (float)r * g.cell + margin;
         const float b2 = bound * bound;
         if (t.d[4] <= b2) break;             // 5th best is certainly final

@@ -54,13 +54,16 @@ def test_knn_grid_matches_bruteforce(hostemu, po, frames, name):
     assert (~(d2[~ok][:, 4] <= 5.0)).all()
 
 
-def test_knn_grid_far_and_outside_queries(hostemu, po, frames):
+@pytest.mark.parametrize("cell", [0.6, 0.25])
+def test_knn_grid_far_and_outside_queries(hostemu, po, frames, cell):
+    """Queries anywhere in (and around) the map volume: most are far from every surface, so the walk goes through the
+    ring >= 2 shells (nine-run batches, grid clipping) up to the search radius -- exact against brute force."""
     f = frames("T0")
     rng = np.random.default_rng(5)
     lo, hi = f["map_xyz"].min(0), f["map_xyz"].max(0)
-    q = rng.uniform(lo - 6, hi + 6, size=(4000, 3)).astype(np.float32)
+    q = rng.uniform(lo - 6, hi + 6, size=(4000 if cell > 0.5 else 1500, 3)).astype(np.float32)
     bi, bd = po.knn_brute(f["map_xyz"], q)
-    gridf, gridi, cell_start, pts4, order = grid_build(f["map_xyz"], 0.6)
+    gridf, gridi, cell_start, pts4, order = grid_build(f["map_xyz"], cell)
     pos = np.empty((len(q), 5), np.int32)
     d2 = np.empty((len(q), 5), np.float32)
     hostemu.emu_knn(_p(gridf), _p(gridi), _p(cell_start), _p(pts4), _p(q), len(q), _p(pos), _p(d2))
