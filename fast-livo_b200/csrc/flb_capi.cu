@@ -575,6 +575,18 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         a.probe = h->tracing ? h->trace.p + 112 : nullptr;
         a.chunk = std::max(1, std::min(32, (h->N + workers * (kLioPersBlock / 32) - 1) / (workers * (kLioPersBlock / 32))));
         {
+            static const int env_warm = [] { const char* e = getenv("FLB_WARM"); return e ? atoi(e) : 1; }();
+            if (env_warm) {
+                WarmList& w = a.warm;
+                const size_t n1 = (size_t)std::max(h->N, 1);
+                const void* ptr[] = {h->scan.p, h->map_pts.p, h->cell_start.p, h->plane.p, h->sel.p, h->plane_ok.p, h->partials.p, h->states.p};
+                const size_t len[] = {n1 * 16, (size_t)h->M * 16, ((size_t)h->ncell + 1) * 4, n1 * 16, n1, n1, (size_t)grid * lio_packed(6) * 8,
+                                      5 * sizeof(State18)};
+                w.n = 8;
+                for (int k = 0; k < 8; ++k) { w.p[k] = ptr[k]; w.bytes[k] = len[k]; }
+            }
+        }
+        {
             // L2 prefetch of the map: on by default for maps above 8 MB (points + cell table); FLB_PREFETCH=0/1 overrides
             const size_t bytes = (size_t)h->M * 16 + ((size_t)h->ncell + 1) * 4;
             static const int env = [] { const char* e = getenv("FLB_PREFETCH"); return e ? atoi(e) : -1; }();
@@ -722,6 +734,17 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         }
         // staging capacity for the errors of ALL ranks (the peers' shard sizes are not known here: assume like ours + slack)
         int err_cap = (int)std::min<long long>(kVioErrCapMax, std::max<long long>(2048, ((long long)a.Pn * std::max(h->p2p.world, 1) * 5 / 4 + 319) / 256 * 256));
+        {
+            static const int env_warm = [] { const char* e = getenv("FLB_WARM"); return e ? atoi(e) : 1; }();
+            if (env_warm) {
+                WarmList& w = a.warm;
+                const size_t pn = (size_t)std::max(a.Pn, 1);
+                const void* ptr[] = {h->img.p, h->patch_pos.p, h->patch_ref.p, h->patch_level.p, h->errors.p, h->partials.p};
+                const size_t len[] = {(size_t)h->img_w * h->img_h, pn * 24, pn * 768, pn * 4, 2 * (size_t)h->err_stride * 4, (size_t)grid * kVioPacked * 8};
+                w.n = 6;
+                for (int k = 0; k < 6; ++k) { w.p[k] = ptr[k]; w.bytes[k] = len[k]; }
+            }
+        }
         static const int env_tma = [] { const char* e = getenv("FLB_TMA"); return e ? atoi(e) : 0; }();
         int use_tma = env_tma ? 1 : 0;       // experiment: tap rows staged by the bulk async-copy engine
         const size_t dyn = std::max<size_t>((size_t)err_cap * sizeof(float), use_tma ? (size_t)(kVioPersBlock / 32) * kTapTileBytes : 0);

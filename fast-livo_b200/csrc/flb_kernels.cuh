@@ -51,6 +51,31 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                  "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// After an L2 flush (or simply other work) the first pass of a frame finds neither its data nor the translations of
+// its pages cached, and it discovers the pages one dependent step at a time (scan -> cell table -> map points ->
+// plane cache ...).  The leader block, idle until the first pass arrives, touches one word of every 2 MB page of every
+// buffer the update will use, all at once, so the page walks overlap instead of queueing behind each other.
+struct WarmList {
+    const void* p[10];
+    unsigned long long bytes[10];
+    int n;
+};
+__device__ __forceinline__ void warm_pages(const WarmList& w, int tid, int nt) {
+    constexpr unsigned long long kPage = 2ull << 20;
+    int slot = 0;
+    for (int b = 0; b < w.n; ++b) {
+        const char* base = static_cast<const char*>(w.p[b]);
+        if (!base) continue;
+        const unsigned long long npages = (w.bytes[b] + kPage - 1) / kPage;
+        for (unsigned long long pg = 0; pg < npages; ++pg, ++slot)
+            if (slot % nt == tid) {
+                const unsigned long long off = pg * kPage;
+                unsigned v;
+                asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(base + (off < w.bytes[b] ? (off & ~3ull) : 0ull)) : "memory");
+            }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // device-resident control blocks
 // ---------------------------------------------------------------------------------------
@@ -623,6 +648,7 @@ struct LioArgs {
     int chunk;                   // persistent kernel: points per warp-chunk (1..32)
     int M;                       // map points (for the L2 prefetch)
     int prefetch;                // persistent kernel: stream the map + cell table into L2 before the first pass
+    WarmList warm;               // persistent kernel: pages to touch before the first pass (n = 0: none)
 };
 
 template <int W>
@@ -887,6 +913,7 @@ struct VioArgs {
     double* x_z;                 // Pn*64 or null
     double* x_H;                 // Pn*64*6 or null
     P2PArgs p2p;                 // world > 1 (persistent kernel only): per-patch errors are pushed to every rank
+    WarmList warm;               // persistent kernel: pages to touch before the first pass (n = 0: none)
     const int* Pn_dev;           // persistent kernel: when non-null the patch count is read from the device (the patch
                                  // list was built there by the visual-map selection, flb_vmap_select) and Pn is its capacity
 };
@@ -2176,6 +2203,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
     __syncthreads();
     int resident = 0;
     if (is_leader) {
+        warm_pages(a.warm, tid, BLOCK);
         if (s.init_x) {                  // the pending reset: state / state_prop take the saved pair (whole structs)
             const double* a0 = reinterpret_cast<const double*>(s.init_x);
             const double* a1 = reinterpret_cast<const double*>(s.init_xp);
@@ -2314,6 +2342,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __syncthreads();
     int resident = 0;
     if (is_leader) {
+        warm_pages(a.warm, tid, BLOCK);
         if (s.prior_from_state) {        // the pending `state_propagat = state`: the whole struct, before anything writes *state
             const double* a0 = reinterpret_cast<const double*>(s.state);
             double* d1 = reinterpret_cast<double*>(const_cast<State18*>(s.state_prop));
