@@ -179,6 +179,17 @@ struct flb_handle {
     DevBuf<float4> scan;
     DevBuf<unsigned char> sel, plane_ok;
     DevBuf<float4> plane;
+    // the scan is double-buffered: flb_scan_upload fills the OTHER set on `scan_stream` (copy + ordering kernel) while
+    // updates already enqueued on `stream` still read this one, then swaps the two and makes `stream` wait for it
+    DevBuf<float4> scan_alt, plane_alt;
+    DevBuf<unsigned char> sel_alt, plane_ok_alt;
+    cudaStream_t scan_stream = nullptr;
+    cudaEvent_t ev_scan_ready = nullptr;
+    cudaEvent_t ev_scan_free[2] = {nullptr, nullptr};   // [slot]: everything on `stream` that reads that slot has been enqueued before it
+    bool scan_free_valid[2] = {false, false};
+    int scan_slot = 0;
+    DevBuf<unsigned char> scan_cub_tmp;                 // the upload's own sort scratch (cub_tmp belongs to `stream`)
+    int pers_sms = 0;                                   // SMs the persistent kernels may fill (one is left to the scan stream)
 
     // LIO exports (lazily allocated)
     DevBuf<float> x_world, x_nn_d2, x_pd2, x_pabcd;
@@ -401,6 +412,12 @@ int ensure_common(flb_handle* h) {
     FLB_CUDA(h, cudaMemset(h->lio_ctrl.p, 0, sizeof(LioCtrl)));
     FLB_CUDA(h, cudaMemset(h->vio_ctrl.p, 0, sizeof(VioCtrl)));
     FLB_CUDA(h, cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    {
+        // the per-frame persistent kernels fill all SMs but one: the next frame's scan ordering (one block on `scan_stream`)
+        // runs there concurrently.  FLB_RESERVE_SM=0 gives that SM back (A/B measurement).
+        static const int env_reserve = [] { const char* e = getenv("FLB_RESERVE_SM"); return e ? atoi(e) : 1; }();
+        h->pers_sms = (env_reserve && h->num_sms > 2) ? h->num_sms - 1 : h->num_sms;
+    }
     FLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_lio, k_lio_update_persistent<kLioPersBlock>, kLioPersBlock, 0));
     FLB_CUDA(h, h->ik_states.reserve(2));
     FLB_CUDA(h, h->ik_ctrl.reserve(1));
@@ -562,7 +579,7 @@ int enqueue_lio_update(flb_handle* h, const flb_lio_params* prm) {
         // one cooperative launch for the whole iterated update; grid = min(needed, co-resident capacity)
         // whole multiples of the SM count (<= co-resident capacity): chunks are dealt round-robin to blocks
         // worker blocks (one per SM, chunks dealt round-robin) + one leader block
-        const int cap = std::min(h->occ_lio * h->num_sms, h->num_sms);
+        const int cap = std::min(h->occ_lio * h->num_sms, h->pers_sms);
         if (cap < 2) return fail(h, FLB_ERR_STATE, "persistent mode needs two co-resident blocks");
         const int workers = std::max(1, std::min((h->N + 31) / 32, cap - 1));
         const int grid = workers + 1;
@@ -712,7 +729,7 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
     const int nb = vio_nblocks(h);
     if (persistent) {
         // patches are dealt warp-round-robin over the worker blocks; one more block is the leader
-        const int cap = h->occ_vio * h->num_sms;
+        const int cap = std::min(h->occ_vio * h->num_sms, h->pers_sms);
         if (cap < 2) return fail(h, FLB_ERR_STATE, "persistent mode needs two co-resident blocks");
         const int workers = std::max(1, std::min(std::max(a.Pn, 1), cap - 1));
         const int grid = workers + 1;
@@ -802,6 +819,21 @@ void fill_vio_report(const VioCtrl& c, flb_vio_report* rep) {
 
 }  // namespace
 
+template <int kScanSortBlock, int ITEMS>
+static int launch_scan_sort_block(flb_handle* h, cudaStream_t ss, int N, const float lo[3], float inv_cell) {
+    using Sort = cub::BlockRadixSort<unsigned, kScanSortBlock, ITEMS, int, 6>;
+    const size_t smem = std::max(sizeof(typename Sort::TempStorage), (size_t)kScanSortBlock * ITEMS * sizeof(unsigned));
+    static bool attr_set = false;       // per process is enough: one device per process (flb_create enforces nothing else here)
+    if (!attr_set) {
+        FLB_CUDA(h, cudaFuncSetAttribute(k_scan_sort_block<kScanSortBlock, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_scan_sort_block<kScanSortBlock, ITEMS><<<1, kScanSortBlock, smem, ss>>>(h->scan_raw.p, N, lo[0], lo[1], lo[2], inv_cell, h->scan_alt.p, h->sel_alt.p,
+                                                             h->plane_ok_alt.p);
+    FLB_CUDA(h, cudaGetLastError());
+    return FLB_OK;
+}
+
 extern "C" {
 
 int flb_abi_version(void) { return FLB_ABI_VERSION; }
@@ -834,7 +866,11 @@ int flb_create(const flb_config* cfg, flb_handle** out) {
         return fail(nullptr, FLB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     h->stream = h->own_stream;
-    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&h->scan_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_scan_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_scan_free[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_scan_free[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_vio_inputs, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_vio_done, cudaEventDisableTiming) != cudaSuccess) {
         cudaStreamDestroy(h->own_stream);
@@ -890,6 +926,13 @@ int flb_destroy(flb_handle* h) {
     h->st_misc.release(); h->pin_out.release();
     for (int k = 0; k < 2; ++k) { h->pin_res[k].release(); if (h->ev_res[k]) cudaEventDestroy(h->ev_res[k]); }
     cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->scan_stream);
+    h->scan_alt.release(); h->plane_alt.release(); h->sel_alt.release(); h->plane_ok_alt.release();
+    cudaEventDestroy(h->ev_scan_ready);
+    cudaEventDestroy(h->ev_scan_free[0]);
+    cudaEventDestroy(h->ev_scan_free[1]);
+    h->scan_cub_tmp.release();
+    cudaStreamDestroy(h->scan_stream);
     cudaEventDestroy(h->ev_vio_inputs);
     cudaEventDestroy(h->ev_vio_done);
     cudaStreamDestroy(h->copy_stream);
@@ -908,6 +951,7 @@ int flb_set_stream(flb_handle* h, void* cuda_stream) {
 int flb_synchronize(flb_handle* h) {
     FLB_CHECK_H(h);
     FLB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->scan_stream));
     FLB_CUDA(h, cudaStreamSynchronize(h->stream));
     return FLB_OK;
 }
@@ -1521,44 +1565,73 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
         for (int j = 0; j < 24; ++j) lo[j % 3] = std::min(lo[j % 3], mn[j]);
         if (bad) return fail(h, FLB_ERR_INVALID, "flb_scan_upload: non-finite coordinate");
     }
+    // The copy and the ordering run on `scan_stream` into the slot that is NOT being read: updates of the previous frame
+    // still queued or running on `stream` keep their scan, and -- because the persistent kernels leave one SM free and
+    // the ordering is one block (k_scan_sort_block) -- this frame's upload overlaps them instead of queueing behind them.
+    const int cur = h->scan_slot, alt = cur ^ 1;
+    cudaStream_t ss = h->scan_stream;
+    FLB_CUDA(h, cudaEventRecord(h->ev_scan_free[cur], h->stream));     // all readers of the current slot are enqueued before this
+    h->scan_free_valid[cur] = true;
+    if (h->scan_free_valid[alt]) FLB_CUDA(h, cudaStreamWaitEvent(ss, h->ev_scan_free[alt], 0));
+    // (scan_raw / skeys / svals double as flb_voxel_grid's scratch on `stream`; that call ends with a stream synchronise)
     FLB_CUDA(h, h->scan_raw.reserve(n1 * 3));
-    FLB_CUDA(h, h->skeys.reserve(n1));
-    FLB_CUDA(h, h->skeys_sorted.reserve(n1));
-    FLB_CUDA(h, h->svals.reserve(n1));
-    FLB_CUDA(h, h->svals_sorted.reserve(n1));
-    FLB_CUDA(h, h->scan.reserve(n1));
-    FLB_CUDA(h, h->sel.reserve(n1));
-    FLB_CUDA(h, h->plane_ok.reserve(n1));
-    FLB_CUDA(h, h->plane.reserve(n1));
+    FLB_CUDA(h, h->scan_alt.reserve(n1));
+    FLB_CUDA(h, h->sel_alt.reserve(n1));
+    FLB_CUDA(h, h->plane_ok_alt.reserve(n1));
+    FLB_CUDA(h, h->plane_alt.reserve(n1));
     const size_t nb = (n1 + kLioBlock - 1) / kLioBlock;
     FLB_CUDA(h, h->partials.reserve(std::max<size_t>(nb * lio_packed(12), h->partials.cap)));
+    bool flags_done = false;
     if (N > 0) {
-        FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        if (!direct) FLB_CUDA(h, h->st_scan.mark(h->stream));
+        FLB_CUDA(h, cudaMemcpyAsync(h->scan_raw.p, st, (size_t)N * 3 * sizeof(float), cudaMemcpyHostToDevice, ss));
+        if (!direct) FLB_CUDA(h, h->st_scan.mark(ss));
         // Morton order in the body frame (cell = twice the map grid's cell): spatially coherent warps at any pose
         const float inv_cell = 0.5f / (float)h->cfg.cell_size;
-        const int g = (N + 255) / 256;
-        {
+        static const int env_block_sort = [] { const char* e = getenv("FLB_BLOCK_SORT"); return e ? atoi(e) : 1; }();
+        if (env_block_sort && N <= 1024 * 25) {
             LaunchScope ls(h, FAM_OTHER);
-            k_scan_keys<<<g, 256, 0, h->stream>>>(h->scan_raw.p, N, lo[0], lo[1], lo[2], inv_cell, h->skeys.p, h->svals.p);
-            FLB_CUDA(h, cudaGetLastError());
-        }
-        size_t tmp_bytes = 0;
-        FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
-                                                    h->svals_sorted.p, N, 0, 24, h->stream));
-        FLB_CUDA(h, h->cub_tmp.reserve(tmp_bytes));
-        FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
-                                                    h->svals_sorted.p, N, 0, 24, h->stream));
-        h->launches += 3;
-        {
-            LaunchScope ls(h, FAM_OTHER);
-            k_scan_gather<<<g, 256, 0, h->stream>>>(h->scan_raw.p, N, h->svals_sorted.p, h->scan.p);
-            FLB_CUDA(h, cudaGetLastError());
+            int rcs = N <= 512 * 17   ? launch_scan_sort_block<512, 17>(h, ss, N, lo, inv_cell)
+                      : N <= 512 * 33 ? launch_scan_sort_block<512, 33>(h, ss, N, lo, inv_cell)
+                                      : launch_scan_sort_block<1024, 25>(h, ss, N, lo, inv_cell);
+            if (rcs) return rcs;
+            flags_done = true;
+        } else {
+            FLB_CUDA(h, h->skeys.reserve(n1));
+            FLB_CUDA(h, h->skeys_sorted.reserve(n1));
+            FLB_CUDA(h, h->svals.reserve(n1));
+            FLB_CUDA(h, h->svals_sorted.reserve(n1));
+            const int g = (N + 255) / 256;
+            {
+                LaunchScope ls(h, FAM_OTHER);
+                k_scan_keys<<<g, 256, 0, ss>>>(h->scan_raw.p, N, lo[0], lo[1], lo[2], inv_cell, h->skeys.p, h->svals.p);
+                FLB_CUDA(h, cudaGetLastError());
+            }
+            size_t tmp_bytes = 0;
+            FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
+                                                        h->svals_sorted.p, N, 0, 24, ss));
+            FLB_CUDA(h, h->scan_cub_tmp.reserve(tmp_bytes));
+            FLB_CUDA(h, cub::DeviceRadixSort::SortPairs(h->scan_cub_tmp.p, tmp_bytes, h->skeys.p, h->skeys_sorted.p, h->svals.p,
+                                                        h->svals_sorted.p, N, 0, 24, ss));
+            h->launches += 3;
+            {
+                LaunchScope ls(h, FAM_OTHER);
+                k_scan_gather<<<g, 256, 0, ss>>>(h->scan_raw.p, N, h->svals_sorted.p, h->scan_alt.p);
+                FLB_CUDA(h, cudaGetLastError());
+            }
         }
     }
-    // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
-    FLB_CUDA(h, cudaMemsetAsync(h->sel.p, 1, n1, h->stream));
-    FLB_CUDA(h, cudaMemsetAsync(h->plane_ok.p, 0, n1, h->stream));
+    if (!flags_done) {
+        // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
+        FLB_CUDA(h, cudaMemsetAsync(h->sel_alt.p, 1, n1, ss));
+        FLB_CUDA(h, cudaMemsetAsync(h->plane_ok_alt.p, 0, n1, ss));
+    }
+    FLB_CUDA(h, cudaEventRecord(h->ev_scan_ready, ss));
+    FLB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_scan_ready, 0));
+    std::swap(h->scan, h->scan_alt);
+    std::swap(h->sel, h->sel_alt);
+    std::swap(h->plane_ok, h->plane_ok_alt);
+    std::swap(h->plane, h->plane_alt);
+    h->scan_slot = alt;
     h->N = N;     // enqueue-only: everything later on this handle's stream is ordered after the upload
     h->last_pass_valid = false;
     return FLB_OK;
@@ -2253,6 +2326,18 @@ int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks,
     if (n > 0) FLB_CUDA(h, cudaMemcpy(out, h->dbg_vio.p, (size_t)n * kVioDbg * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     *nblocks = n;
     *words_per_block = kVioDbg;
+    return FLB_OK;
+}
+
+// Test aid: the uploaded scan's order -- src_index[i] = index (in the caller's array) of the point at sorted position i.
+int flb_debug_scan_order(flb_handle* h, int* src_index, int capacity) {
+    FLB_CHECK_H(h);
+    if (!src_index || capacity < h->N) return fail(h, FLB_ERR_INVALID, "flb_debug_scan_order: bad arguments");
+    if (h->N == 0) return FLB_OK;
+    std::vector<float4> tmp((size_t)h->N);
+    FLB_CUDA(h, cudaMemcpyAsync(tmp.data(), h->scan.p, (size_t)h->N * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    FLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->N; ++i) std::memcpy(&src_index[i], &tmp[(size_t)i].w, sizeof(int));
     return FLB_OK;
 }
 

@@ -17,6 +17,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cub/block/block_radix_sort.cuh>
 #include "flb_device.cuh"
 
 namespace flb {
@@ -592,6 +593,57 @@ __global__ void k_scan_gather(const float* __restrict__ xyz, int N, const int* _
     if (i >= N) return;
     const int src = vals_sorted[i];
     scan[i] = make_float4(xyz[3 * (size_t)src], xyz[3 * (size_t)src + 1], xyz[3 * (size_t)src + 2], __int_as_float(src));
+}
+
+// The whole upload ordering (keys, stable sort, gather, flag reset) in ONE block, for scans of up to BLOCK * ITEMS
+// points: the per-frame persistent kernels leave one SM free (flb_capi.cu, `pers_cap`), and this kernel -- launched on
+// the handle's scan stream -- orders frame k+1's scan on that SM while frame k's VIO update still runs on the other 147.
+// Same keys and same tie order (stable, by input index) as k_scan_keys + the device-wide radix sort + k_scan_gather.
+// Layout: item j of thread t is input index t * ITEMS + j ("blocked"; ITEMS odd so that the shared-memory transpose
+// below is conflict-free); the sort's last pass leaves the output "striped" (position j * BLOCK + t), so the 16-byte
+// stores are coalesced.
+template <int kScanSortBlock, int ITEMS>
+__global__ void __launch_bounds__(kScanSortBlock) k_scan_sort_block(const float* __restrict__ xyz, int N, float ox, float oy, float oz,
+                                                                    float inv_cell, float4* __restrict__ scan,
+                                                                    unsigned char* __restrict__ sel, unsigned char* __restrict__ plane_ok) {
+    using Sort = cub::BlockRadixSort<unsigned, kScanSortBlock, ITEMS, int, 6>;
+    extern __shared__ __align__(16) unsigned char s_sort[];
+    unsigned* s_keys = reinterpret_cast<unsigned*>(s_sort);                       // dead before the sort reuses the bytes
+    typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(s_sort);
+    const int t = threadIdx.x;
+    // keys with coalesced reads, transposed through shared memory into the blocked arrangement
+#pragma unroll 4
+    for (int j = 0; j < ITEMS; ++j) {
+        const int i = j * kScanSortBlock + t;
+        unsigned key = 0x00FFFFFFu;                                               // padding: sorts last (stable: after real ties)
+        if (i < N) {
+            const unsigned cx = (unsigned)fminf(fmaxf((xyz[3 * (size_t)i] - ox) * inv_cell, 0.f), 255.f);
+            const unsigned cy = (unsigned)fminf(fmaxf((xyz[3 * (size_t)i + 1] - oy) * inv_cell, 0.f), 255.f);
+            const unsigned cz = (unsigned)fminf(fmaxf((xyz[3 * (size_t)i + 2] - oz) * inv_cell, 0.f), 255.f);
+            key = morton_spread10(cx) | (morton_spread10(cy) << 1) | (morton_spread10(cz) << 2);
+        }
+        s_keys[i] = key;
+    }
+    __syncthreads();
+    unsigned keys[ITEMS];
+    int vals[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        keys[j] = s_keys[t * ITEMS + j];
+        vals[j] = t * ITEMS + j;
+    }
+    __syncthreads();
+    Sort(tmp).SortBlockedToStriped(keys, vals, 0, 24);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int pos = j * kScanSortBlock + t;
+        if (pos < N) {
+            const int src = vals[j];
+            scan[pos] = make_float4(xyz[3 * (size_t)src], xyz[3 * (size_t)src + 1], xyz[3 * (size_t)src + 2], __int_as_float(src));
+            sel[pos] = 1;               // point_selected_surf.resize(N, true) (src/laserMapping.cpp:1469)
+            plane_ok[pos] = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------

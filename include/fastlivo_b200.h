@@ -459,6 +459,9 @@ int flb_p2p_detach(flb_handle* h);
 int flb_debug_set_packet_epoch(flb_handle* h, unsigned epoch);
 int flb_debug_block_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks);
 int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks, int* nblocks, int* words_per_block);
+/* flb_debug_scan_order: src_index[i] = index in the caller's scan array of the point at position i of the uploaded
+ * (Morton-ordered) scan; capacity >= the scan's point count.  Test aid for the upload's two ordering paths. */
+int flb_debug_scan_order(flb_handle* h, int* src_index, int capacity);
 
 #ifdef __cplusplus
 }
