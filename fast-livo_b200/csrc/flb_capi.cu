@@ -762,10 +762,8 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
                 for (int k = 0; k < 6; ++k) { w.p[k] = ptr[k]; w.bytes[k] = len[k]; }
             }
         }
-        static const int env_tma = [] { const char* e = getenv("FLB_TMA"); return e ? atoi(e) : 0; }();
-        int use_tma = env_tma ? 1 : 0;       // experiment: tap rows staged by the bulk async-copy engine
-        const size_t dyn = std::max<size_t>((size_t)err_cap * sizeof(float), use_tma ? (size_t)(kVioPersBlock / 32) * kTapTileBytes : 0);
-        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap, &use_tma};
+        const size_t dyn = (size_t)err_cap * sizeof(float);
+        void* args[] = {&a, &s, &bar, &pkt, &epoch, &trace, &dbg, &err_cap};
         LaunchScope ls(h, FAM_VIO);
         FLB_CUDA(h, cudaLaunchCooperativeKernel((void*)k_vio_update_persistent<kVioPersBlock>, dim3(grid), dim3(kVioPersBlock), args, dyn,
                                                 h->stream));

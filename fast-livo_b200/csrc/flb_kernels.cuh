@@ -22,36 +22,6 @@
 
 namespace flb {
 
-// ---------------------------------------------------------------------------------------
-// TMA staging of the photometric tap box (north_star: "TMA-staged image tiles"; an experiment, off by default --
-// DESIGN.md section 8 and profiles/r02_tma_experiment.md have the measurement).  The 11 tap rows of a patch are fetched
-// by the bulk async-copy engine (cp.async.bulk shared <- global, SASS UBLKCP), one 16-byte-aligned row segment per
-// lane 0..10, completion on a per-warp mbarrier; the strided column gather then reads shared memory.  (A tiled tensor
-// map per tap stride -- box = 11 row segments with row traversal stride = scale; TMA has no stride on the innermost
-// dimension and caps the others at 8 -- was built first and faulted with "illegal instruction" at UTMALDG on the box
-// (not root-caused); the descriptor-less form below has none of the descriptor's constraints.)
-// ---------------------------------------------------------------------------------------
-constexpr int kTapRowBytes = 128;        // one staged row: up to 15 bytes of alignment slack + 10 * 8 + 1 taps, rounded to 16
-constexpr int kTapTileBytes = 11 * kTapRowBytes;
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // After an L2 flush (or simply other work) the first pass of a frame finds neither its data nor the translations of
 // its pages cached, and it discovers the pages one dependent step at a time (scan -> cell table -> map points ->
 // plane cache ...).  The leader block, idle until the first pass arrives, touches one word of every 2 MB page of every
@@ -1009,8 +979,7 @@ __device__ __forceinline__ double round_to_f32_precision(double d) {
 // lane 0 also counts n_meas / skipped.
 __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
                                           float* s_lat, double* s_res, double& accv, double& n_meas, double& skipped,
-                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0,
-                                          unsigned char* tile = nullptr, unsigned long long* mbar = nullptr, unsigned* tma_phase = nullptr) {
+                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0) {
     const int lane = threadIdx.x & 31;
     float* const err_out = a.errors + (size_t)err_buf * a.err_stride;
     double acc[27];
@@ -1022,33 +991,7 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
     if (g.valid) {
         // stage the 11x11 tap lattice (stride = scale px) as float
         const int W = a.cam.width;
-        if (tile != nullptr && g.scale <= 8) {
-            // bulk async copies: row r of the tap box = one aligned segment of image row v_i + (r - 5) scale
-            const unsigned char* row0 = a.img + (size_t)(g.v_i - 5 * g.scale) * W + (g.u_i - 5 * g.scale);
-            const unsigned char* rowp = row0 + (size_t)(lane < 11 ? lane : 0) * g.scale * W;
-            const unsigned off = (unsigned)(reinterpret_cast<size_t>(rowp) & 15u);
-            const unsigned bytes = (off + 10u * (unsigned)g.scale + 1u + 15u) & ~15u;
-            unsigned total = (lane < 11) ? bytes : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the tile's previous readers are done
-                mbar_expect_tx(mbar, total);
-            }
-            __syncwarp();
-            if (lane < 11) bulk_load(tile + lane * kTapRowBytes, rowp - off, bytes, mbar);
-            mbar_wait(mbar, *tma_phase);
-            *tma_phase ^= 1u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int e = lane + 32 * q;
-                if (e < 121) {
-                    const int r = e / 11, c = e - r * 11;
-                    const unsigned offr = (unsigned)(reinterpret_cast<size_t>(row0 + (size_t)r * g.scale * W) & 15u);
-                    s_lat[e] = (float)tile[r * kTapRowBytes + offr + c * g.scale];
-                }
-            }
-        } else {
+        {
             const unsigned char* base = a.img + (size_t)(g.v_i - 5 * g.scale) * W + (g.u_i - 5 * g.scale);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -2333,8 +2276,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_lio_update_persistent(LioArgs a, L
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, VioSolveArgs s, GridBarrier* bar,
                                                                     unsigned long long* pkt, unsigned epoch,
-                                                                    unsigned long long* trace, unsigned long long* dbg, int err_cap,
-                                                                    int use_tma) {
+                                                                    unsigned long long* trace, unsigned long long* dbg, int err_cap) {
     constexpr int NW = BLOCK / 32;
     constexpr int NC = (int)(sizeof(VioCtrl) / sizeof(unsigned));
     __shared__ VioPose s_pose;
@@ -2344,14 +2286,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
     __shared__ unsigned s_bar[2];
     __shared__ LeaderSmem sm;
     __shared__ VioCtrl s_ctrl;
-    extern __shared__ __align__(128) float s_err[];    // dynamic: the LEADER's staging of the per-patch errors (err_cap floats);
-                                                       // the WORKERS' TMA tap tiles (NW x kTapTileBytes) when use_tma
+    extern __shared__ __align__(128) float s_err[];    // dynamic: the LEADER's staging of the per-patch errors (err_cap floats)
     __shared__ unsigned long long s_seq_base;
-    __shared__ __align__(8) unsigned long long s_mbar[NW];
     const int tid = threadIdx.x, warp = tid >> 5;
-    unsigned tma_phase = 0u;
-    if (use_tma && (tid & 31) == 0) mbar_init(&s_mbar[warp], 1u);
-    if (use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const int nworkers = (int)gridDim.x - 1;
     const bool is_leader = (int)blockIdx.x == nworkers;
     const int Pn = a.Pn_dev ? min(*a.Pn_dev, a.Pn) : a.Pn;     // device-built patch list: its length lives on the device
@@ -2445,8 +2382,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             for (int i = blockIdx.x * NW + warp; i < Pn; i += nworkers * NW) {
                 if (!single) vio_patch_load(a, i, tid & 31, pin);
                 vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
-                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1,
-                          use_tma ? reinterpret_cast<unsigned char*>(s_err) + (size_t)warp * kTapTileBytes : nullptr, &s_mbar[warp], &tma_phase);
+                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1);
             }
             vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();

@@ -6,7 +6,7 @@
 mkdir -p gpurun_out
 SAN="compute-sanitizer --target-processes all --print-limit 5"
 T1="tests/test_gpu_parity.py -k update"
-T2="tests/test_vmap_select.py tests/test_gpu_batch.py tests/test_gpu_edge_sizes.py"
+T2="tests/test_vmap_select.py tests/test_gpu_batch.py tests/test_gpu_edge_sizes.py tests/test_gpu_scan_order.py"
 for tool in memcheck racecheck; do
   timeout 900 $SAN --tool $tool python -m pytest $T1 -m gpu -q -x > gpurun_out/san_${tool}_updates.txt 2>&1
   timeout 900 $SAN --tool $tool python -m pytest $T2 -m gpu -q -x > gpurun_out/san_${tool}_vmap_batch.txt 2>&1
