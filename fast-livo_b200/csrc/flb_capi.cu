@@ -58,7 +58,7 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocMapped);   // mapped: small kernels read / write it in place
         if (e == cudaSuccess) cap = bytes;
         return e;
     }
@@ -147,6 +147,13 @@ struct flb_handle {
     cudaEvent_t ev_vio_inputs = nullptr;   // recorded on copy_stream after the last image / patch copy
     cudaEvent_t ev_vio_done = nullptr;     // recorded on `stream` after the last kernel that reads them
     bool vio_inputs_pending = false, vio_done_pending = false;
+    // The image and the host-built patch list are double-buffered like the scan: an upload fills the set that no kernel
+    // reads (on copy_stream), then swaps it in; frame k + 1's copies (2 MB at C2) run under frame k's VIO update.
+    struct InSlot {
+        cudaEvent_t free_ev[2] = {nullptr, nullptr};   // [slot]: recorded on `stream` once every reader of that slot has been enqueued
+        bool valid[2] = {false, false};
+        int slot = 0;
+    } img_slot, patch_slot;
     std::string err;
     int64_t launches = 0;
 
@@ -241,11 +248,11 @@ struct flb_handle {
 
     // VIO inputs
     int img_w = 0, img_h = 0;
-    DevBuf<unsigned char> img;
+    DevBuf<unsigned char> img, img_alt;
     int Pn = 0;
-    DevBuf<double> patch_pos;
-    DevBuf<float> patch_ref;
-    DevBuf<int> patch_level;
+    DevBuf<double> patch_pos, patch_pos_alt;
+    DevBuf<float> patch_ref, patch_ref_alt;
+    DevBuf<int> patch_level, patch_level_alt;
     DevBuf<float> errors;        // 2 x err_stride (local shard; the persistent kernel's passes alternate between the halves)
     int err_stride = 0;
     DevBuf<float> errors_all;    // padded shard * world (multi-GPU)
@@ -495,12 +502,15 @@ bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// copy_stream must not overwrite the image / patches while a VIO kernel on `stream` still reads them
-int vio_copy_begin(flb_handle* h) {
-    if (h->vio_done_pending) {
-        FLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_vio_done, 0));
-        h->vio_done_pending = false;
-    }
+// copy_stream is about to fill the OTHER set of a double-buffered input.  Every reader of the current set has been
+// enqueued on `stream` by now (record its event); the other set's readers were all enqueued before the previous upload,
+// whose event the copy waits for.
+int vio_copy_begin(flb_handle* h, flb_handle::InSlot& s) {
+    for (int k = 0; k < 2; ++k)
+        if (!s.free_ev[k]) FLB_CUDA(h, cudaEventCreateWithFlags(&s.free_ev[k], cudaEventDisableTiming));
+    FLB_CUDA(h, cudaEventRecord(s.free_ev[s.slot], h->stream));
+    s.valid[s.slot] = true;
+    if (s.valid[s.slot ^ 1]) FLB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, s.free_ev[s.slot ^ 1], 0));
     return FLB_OK;
 }
 int vio_copy_end(flb_handle* h) {
@@ -516,11 +526,7 @@ int vio_inputs_acquire(flb_handle* h) {
     }
     return FLB_OK;
 }
-int vio_inputs_release(flb_handle* h) {
-    FLB_CUDA(h, cudaEventRecord(h->ev_vio_done, h->stream));
-    h->vio_done_pending = true;
-    return FLB_OK;
-}
+int vio_inputs_release(flb_handle*) { return FLB_OK; }   // (readers are fenced per slot at the next upload: vio_copy_begin)
 
 // Perform the deferred device-side state moves with plain copies (every consumer other than the persistent kernels).
 int flush_state_ops(flb_handle* h) {
@@ -926,6 +932,11 @@ int flb_destroy(flb_handle* h) {
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamSynchronize(h->scan_stream);
     h->scan_alt.release(); h->plane_alt.release(); h->sel_alt.release(); h->plane_ok_alt.release();
+    h->img_alt.release(); h->patch_pos_alt.release(); h->patch_ref_alt.release(); h->patch_level_alt.release();
+    for (int k = 0; k < 2; ++k) {
+        if (h->img_slot.free_ev[k]) cudaEventDestroy(h->img_slot.free_ev[k]);
+        if (h->patch_slot.free_ev[k]) cudaEventDestroy(h->patch_slot.free_ev[k]);
+    }
     cudaEventDestroy(h->ev_scan_ready);
     cudaEventDestroy(h->ev_scan_free[0]);
     cudaEventDestroy(h->ev_scan_free[1]);
@@ -1760,9 +1771,14 @@ int flb_state_upload(flb_handle* h, const flb_state18* x, const flb_state18* x_p
     State18* st = static_cast<State18*>(stv);
     std::memcpy(&st[0], x, sizeof(State18));
     std::memcpy(&st[1], x_prop, sizeof(State18));
-    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[0], st, 2 * sizeof(State18), cudaMemcpyHostToDevice, h->stream));
+    {
+        void* dsrc = nullptr;
+        FLB_CUDA(h, cudaHostGetDevicePointer(&dsrc, st, 0));
+        LaunchScope ls(h, FAM_OTHER);
+        k_state_install<<<1, 256, 0, h->stream>>>(static_cast<const double*>(dsrc), h->states.p);   // [0..1] and the saved pair [3..4]
+        FLB_CUDA(h, cudaGetLastError());
+    }
     FLB_CUDA(h, h->st_state.mark(h->stream));
-    FLB_CUDA(h, cudaMemcpyAsync(&h->states.p[3], &h->states.p[0], 2 * sizeof(State18), cudaMemcpyDeviceToDevice, h->stream));
     h->state_valid = true;
     h->reset_pending = h->prior_pending = false;     // both superseded by the upload
     return FLB_OK;
@@ -1830,11 +1846,17 @@ int flb_state_download_enqueue(flb_handle* h, int slot) {
     FLB_CUDA(h, h->pin_res[slot].reserve(bytes));
     if (!h->ev_res[slot]) FLB_CUDA(h, cudaEventCreateWithFlags(&h->ev_res[slot], cudaEventDisableTiming));
     char* po = static_cast<char*>(h->pin_res[slot].p);
-    FLB_CUDA(h, cudaMemcpyAsync(po, &h->states.p[0], sizeof(State18), cudaMemcpyDeviceToHost, h->stream));
-    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18), h->lio_ctrl.p, sizeof(LioCtrl), cudaMemcpyDeviceToHost, h->stream));
-    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl), h->vio_ctrl.p, sizeof(VioCtrl), cudaMemcpyDeviceToHost, h->stream));
-    FLB_CUDA(h, cudaMemcpyAsync(po + sizeof(State18) + sizeof(LioCtrl) + sizeof(VioCtrl), h->barrier.p, sizeof(GridBarrier),
-                                cudaMemcpyDeviceToHost, h->stream));
+    {
+        static_assert(sizeof(State18) % 4 == 0 && sizeof(LioCtrl) % 4 == 0 && sizeof(VioCtrl) % 4 == 0 && sizeof(GridBarrier) % 4 == 0, "word copies");
+        void* dout = nullptr;
+        FLB_CUDA(h, cudaHostGetDevicePointer(&dout, po, 0));
+        LaunchScope ls(h, FAM_OTHER);
+        k_pack_result<<<1, 256, 0, h->stream>>>(&h->states.p[0], reinterpret_cast<const unsigned*>(h->lio_ctrl.p), (int)(sizeof(LioCtrl) / 4),
+                                                reinterpret_cast<const unsigned*>(h->vio_ctrl.p), (int)(sizeof(VioCtrl) / 4),
+                                                reinterpret_cast<const unsigned*>(h->barrier.p), (int)(sizeof(GridBarrier) / 4),
+                                                static_cast<unsigned*>(dout));
+        FLB_CUDA(h, cudaGetLastError());
+    }
     FLB_CUDA(h, cudaEventRecord(h->ev_res[slot], h->stream));
     h->res_pending[slot] = true;
     return FLB_OK;
@@ -1973,7 +1995,7 @@ int flb_lio_update_ikfom(flb_handle* h, const flb_ikfom_params* prm, flb_state_i
 int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, int stride) {
     FLB_CHECK_H(h);
     if (!gray || width < 16 || height < 16 || stride < width) return fail(h, FLB_ERR_INVALID, "flb_image_upload: bad arguments");
-    FLB_CUDA(h, h->img.reserve((size_t)width * height));
+    FLB_CUDA(h, h->img_alt.reserve((size_t)width * height));
     const unsigned char* src = gray;
     const bool direct = (stride == width) && is_pinned(gray);     // page-locked caller buffer: no staging copy
     if (!direct) {
@@ -1984,10 +2006,12 @@ int flb_image_upload(flb_handle* h, const uint8_t* gray, int width, int height, 
         else for (int r = 0; r < height; ++r) std::memcpy(st + (size_t)r * width, gray + (size_t)r * stride, width);
         src = st;
     }
-    { int rcq = vio_copy_begin(h); if (rcq) return rcq; }
-    FLB_CUDA(h, cudaMemcpyAsync(h->img.p, src, (size_t)width * height, cudaMemcpyHostToDevice, h->copy_stream));
+    { int rcq = vio_copy_begin(h, h->img_slot); if (rcq) return rcq; }
+    FLB_CUDA(h, cudaMemcpyAsync(h->img_alt.p, src, (size_t)width * height, cudaMemcpyHostToDevice, h->copy_stream));
     if (!direct) FLB_CUDA(h, h->st_img.mark(h->copy_stream));
     { int rcq = vio_copy_end(h); if (rcq) return rcq; }
+    std::swap(h->img, h->img_alt);
+    h->img_slot.slot ^= 1;
     h->img_w = width;
     h->img_h = height;
     h->last_vio_valid = false;
@@ -2000,9 +2024,9 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     for (int i = 0; i < Pn; ++i)
         if (search_level[i] < 0 || search_level[i] > 2) return fail(h, FLB_ERR_INVALID, "search_level[%d] = %d outside [0,2]", i, search_level[i]);
     const size_t n = (size_t)std::max(Pn, 1);
-    FLB_CUDA(h, h->patch_pos.reserve(n * 3));
-    FLB_CUDA(h, h->patch_ref.reserve(n * 192));
-    FLB_CUDA(h, h->patch_level.reserve(n));
+    FLB_CUDA(h, h->patch_pos_alt.reserve(n * 3));
+    FLB_CUDA(h, h->patch_ref_alt.reserve(n * 192));
+    FLB_CUDA(h, h->patch_level_alt.reserve(n));
     FLB_CUDA(h, h->errors.reserve(2 * n));
     h->err_stride = (int)n;
     const int nb = (Pn + 7) / 8;
@@ -2010,11 +2034,11 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
     const size_t bytes = n * (3 * sizeof(double) + 192 * sizeof(float) + sizeof(int)) + 16;
     if (Pn > 0) {
         const bool direct = is_pinned(pos) && is_pinned(patch) && is_pinned(search_level);
-        { int rcq = vio_copy_begin(h); if (rcq) return rcq; }
+        { int rcq = vio_copy_begin(h, h->patch_slot); if (rcq) return rcq; }
         if (direct) {
-            FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, pos, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
-            FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p, patch, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
-            FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, search_level, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos_alt.p, pos, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref_alt.p, patch, (size_t)Pn * 192 * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_level_alt.p, search_level, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
         } else {
             // pageable caller buffers: pack into pinned staging and hand each piece to the copy engine as soon
             // as it is packed, the reference patches (96 % of the bytes) in four slices, so that the transfer
@@ -2023,21 +2047,25 @@ int flb_patches_upload(flb_handle* h, const double* pos, const float* patch, con
             FLB_CUDA(h, h->st_patch.acquire(bytes, &stv));
             char* b = static_cast<char*>(stv);
             std::memcpy(b, pos, (size_t)Pn * 3 * sizeof(double));
-            FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos.p, b, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_pos_alt.p, b, (size_t)Pn * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
             char* b3 = b + (size_t)Pn * 3 * sizeof(double);
             std::memcpy(b3, search_level, (size_t)Pn * sizeof(int));
-            FLB_CUDA(h, cudaMemcpyAsync(h->patch_level.p, b3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+            FLB_CUDA(h, cudaMemcpyAsync(h->patch_level_alt.p, b3, (size_t)Pn * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
             char* b2 = b3 + (((size_t)Pn * sizeof(int) + 15) & ~(size_t)15);
             const size_t total = (size_t)Pn * 192, slice = (total + 3) / 4;
             for (size_t o = 0; o < total; o += slice) {
                 const size_t cnt = std::min(slice, total - o);
                 std::memcpy(b2 + o * sizeof(float), patch + o, cnt * sizeof(float));
-                FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref.p + o, b2 + o * sizeof(float), cnt * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+                FLB_CUDA(h, cudaMemcpyAsync(h->patch_ref_alt.p + o, b2 + o * sizeof(float), cnt * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
             }
         }
         if (!direct) FLB_CUDA(h, h->st_patch.mark(h->copy_stream));
         { int rcq = vio_copy_end(h); if (rcq) return rcq; }
     }
+    std::swap(h->patch_pos, h->patch_pos_alt);
+    std::swap(h->patch_ref, h->patch_ref_alt);
+    std::swap(h->patch_level, h->patch_level_alt);
+    h->patch_slot.slot ^= 1;
     if (h->comm) {
         // agree on the largest shard so every rank contributes an equal-size block to ncclAllGather;
         // the padding entries stay 0.0f, and adding 0.0f to the sequential float sum is exact.

@@ -382,27 +382,50 @@ struct map_pt { float x, y, z, w; };
 // Walk `nruns` (<= 9) runs of sorted map points whose [start, end) bounds sit in the per-thread scratch (start of run k
 // at rows[k * rstride], end at rows[(9 + k) * rstride]) as ONE candidate sequence, up to four points (independent 16-B
 // loads) per step, in run order then index order.  A lane's trip count is its own candidate count / 4, so lanes whose
-// non-empty runs differ do not wait on each other run by run.
+// non-empty runs differ do not wait on each other run by run.  The walk is one memory round trip per step (the insert
+// needs the loaded points), so the loads of step s + 1 are issued BEFORE step s is consumed: two steps in flight.
+struct KnnCursor {
+    int k, m, e;
+};
+// next group of <= 4 consecutive candidates: returns their count (0: the sequence is exhausted) and the first index
+FLB_HD int knn_cursor_next(KnnCursor& c, const int* rows, int rstride, int nruns, int& first) {
+    while (c.m >= c.e) {
+        if (++c.k >= nruns) return 0;
+        c.m = rows[c.k * rstride];
+        c.e = rows[(9 + c.k) * rstride];
+    }
+    const int left = c.e - c.m;
+    const int n = left > 4 ? 4 : left;
+    first = c.m;
+    c.m += n;
+    return n;
+}
 FLB_HD void knn_walk_runs(const map_pt* __restrict__ pts, const int* rows, int rstride, int nruns, float qx, float qy, float qz,
                           Top5& t) {
-    int k = -1, m = 0, e = 0;
+    KnnCursor c{-1, 0, 0};
+    int m = 0;
+    int n = knn_cursor_next(c, rows, rstride, nruns, m);
+    if (n == 0) return;
+    map_pt P0 = FLB_LDG4(pts + m);
+    map_pt P1 = FLB_LDG4(pts + (n > 1 ? m + 1 : m));
+    map_pt P2 = FLB_LDG4(pts + (n > 2 ? m + 2 : m));
+    map_pt P3 = FLB_LDG4(pts + (n > 3 ? m + 3 : m));
     for (;;) {
-        while (m >= e) {
-            if (++k >= nruns) break;
-            m = rows[k * rstride];
-            e = rows[(9 + k) * rstride];
-        }
-        if (k >= nruns) break;
-        const int n = e - m;
-        const map_pt P0 = FLB_LDG4(pts + m);
-        const map_pt P1 = FLB_LDG4(pts + (n > 1 ? m + 1 : m));
-        const map_pt P2 = FLB_LDG4(pts + (n > 2 ? m + 2 : m));
-        const map_pt P3 = FLB_LDG4(pts + (n > 3 ? m + 3 : m));
+        int m1 = m;
+        const int n1 = knn_cursor_next(c, rows, rstride, nruns, m1);
+        // (n1 == 0: harmless re-load of the current group's first point)
+        const map_pt Q0 = FLB_LDG4(pts + m1);
+        const map_pt Q1 = FLB_LDG4(pts + (n1 > 1 ? m1 + 1 : m1));
+        const map_pt Q2 = FLB_LDG4(pts + (n1 > 2 ? m1 + 2 : m1));
+        const map_pt Q3 = FLB_LDG4(pts + (n1 > 3 ? m1 + 3 : m1));
         top5_insert(t, dist2f(qx, qy, qz, P0.x, P0.y, P0.z), m);
         if (n > 1) top5_insert(t, dist2f(qx, qy, qz, P1.x, P1.y, P1.z), m + 1);
         if (n > 2) top5_insert(t, dist2f(qx, qy, qz, P2.x, P2.y, P2.z), m + 2);
         if (n > 3) top5_insert(t, dist2f(qx, qy, qz, P3.x, P3.y, P3.z), m + 3);
-        m += (n > 4 ? 4 : n);
+        if (n1 == 0) break;
+        P0 = Q0; P1 = Q1; P2 = Q2; P3 = Q3;
+        m = m1;
+        n = n1;
     }
 }
 

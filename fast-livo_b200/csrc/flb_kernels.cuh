@@ -565,6 +565,30 @@ __global__ void k_scan_gather(const float* __restrict__ xyz, int N, const int* _
     scan[i] = make_float4(xyz[3 * (size_t)src], xyz[3 * (size_t)src + 1], xyz[3 * (size_t)src + 2], __int_as_float(src));
 }
 
+// State in / result out as ONE launch each, reading / writing the page-locked host buffer directly (mapped memory):
+// k_state_install replaces a host-to-device copy + a device-to-device copy (state pair + its saved copy),
+// k_pack_result four small device-to-host copies -- on a 200 us frame every queued operation is 2-3 us of stream time.
+__global__ void __launch_bounds__(256) k_state_install(const double* __restrict__ host_pair, State18* __restrict__ states) {
+    constexpr int n = (int)(2 * sizeof(State18) / sizeof(double));
+    double* d0 = reinterpret_cast<double*>(&states[0]);
+    double* d3 = reinterpret_cast<double*>(&states[3]);
+    for (int e = threadIdx.x; e < n; e += 256) {
+        const double v = host_pair[e];
+        d0[e] = v;
+        d3[e] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_pack_result(const State18* __restrict__ x, const unsigned* __restrict__ lio_ctrl, int lio_words,
+                                                     const unsigned* __restrict__ vio_ctrl, int vio_words,
+                                                     const unsigned* __restrict__ barrier, int bar_words, unsigned* __restrict__ host_out) {
+    constexpr int nx = (int)(sizeof(State18) / sizeof(unsigned));
+    const unsigned* xs = reinterpret_cast<const unsigned*>(x);
+    for (int e = threadIdx.x; e < nx; e += 256) host_out[e] = xs[e];
+    for (int e = threadIdx.x; e < lio_words; e += 256) host_out[nx + e] = lio_ctrl[e];
+    for (int e = threadIdx.x; e < vio_words; e += 256) host_out[nx + lio_words + e] = vio_ctrl[e];
+    for (int e = threadIdx.x; e < bar_words; e += 256) host_out[nx + lio_words + vio_words + e] = barrier[e];
+}
+
 // The whole upload ordering (keys, stable sort, gather, flag reset) in ONE block, for scans of up to BLOCK * ITEMS
 // points: the per-frame persistent kernels leave one SM free (flb_capi.cu, `pers_cap`), and this kernel -- launched on
 // the handle's scan stream -- orders frame k+1's scan on that SM while frame k's VIO update still runs on the other 147.
