@@ -861,6 +861,26 @@ def main():
                     "note": "kernel-per-pass path with ncclAllReduce(29 doubles) + ncclAllGather(per-patch errors) between the "
                             "pass and finalize kernels: the baseline collective BASELINE.json names"}
 
+    # ---- N > 1: independent frames, one whole (unsharded) frame stream per GPU, no exchange: the throughput mode next to
+    # the sharded single-frame mode above (a frame's passes are narrower than one GPU, so sharding
+    # cannot shorten them; frames are independent, so replicas scale)
+    replicas = None
+    if world > 1:
+        barrier()
+        h2 = flb.Handle(device=local, cell_size=args.cell_size if args.cell_size > 0 else cfg.cell_size)
+        h2.set_stream(stream.cuda_stream)
+        rig2 = Rig(flb, torch, cfg, frame, h2, dev, stream, 0, 1, dist, flush)     # rank 0 of 1: the whole frame; dist only for the barrier
+        rig2.upload()
+        for _ in range(3):
+            rig2.enqueue_frame()
+        barrier()
+        n_steps = max(min(args.steps, 200), 3)
+        ms_r, _, _ = rig2.time_resident(n_steps)       # max over ranks
+        h2.close()
+        replicas = {"value": world * n_steps / (ms_r * 1e-3), "unit": UNIT, "per_gpu": n_steps / (ms_r * 1e-3), "steps": n_steps,
+                    "scaling": "weak", "note": "every GPU runs its own whole frames (same kernels, no exchange); aggregate = "
+                                               "N x the slowest rank's rate"}
+
     # ---- cpu_baseline (rank 0, N == 1 only): bounded sample on the host cores
     cpu = None
     po = None
@@ -1001,7 +1021,7 @@ def main():
                             "blocking_calls_value: flb_lio_update + flb_vio_update (two synchronisations and state round "
                             "trips per frame, the reference's call shape), no L2 flush"},
             "roofline": roofline, "kernels": fams, "pass_trace": trace, "map_maintenance": map_maint, "imu_undistort": imu_f3,
-            "cpu_baseline": cpu, "parity": parity, "nccl_collective": nccl_alt, "other_workloads": others, "batched": batched, "e2e_full_frame": full_frame,
+            "cpu_baseline": cpu, "parity": parity, "nccl_collective": nccl_alt, "replicas": replicas, "other_workloads": others, "batched": batched, "e2e_full_frame": full_frame,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

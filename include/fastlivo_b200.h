@@ -73,8 +73,11 @@ int         flb_synchronize(flb_handle* h);
 /* Optional page-locked host buffers.  Upload calls detect page-locked sources (these, cudaHostAlloc or
  * cudaHostRegister memory) and let the copy engine read them directly instead of staging through the
  * handle's own pinned area; such a buffer must then stay unmodified until the next blocking call on the
- * handle (flb_*_update, flb_*_pass, flb_synchronize) returns.  Pageable buffers keep the plain contract:
- * free to reuse as soon as the upload call returns. */
+ * handle (flb_*_update, flb_*_pass, flb_synchronize; for a pipelined frame: the flb_state_download_wait that
+ * collects THAT frame's result) returns.  Pageable buffers keep the plain contract: free to reuse as soon as the
+ * upload call returns.
+ * Uploads never wait for the update that is running: scan, image and patch list each have two device sets, an
+ * upload fills the idle one on its own stream and the handle switches sets for everything enqueued afterwards. */
 int         flb_host_alloc(flb_handle* h, size_t bytes, void** out);
 int         flb_host_free(flb_handle* h, void* p);
 
