@@ -774,6 +774,8 @@ def main():
     # the one-call frame API with page-locked caller buffers, pipelined: the contract's e2e (inputs from PINNED host
     # memory, the call a user makes), and what the line reports as e2e.value at N = 1
     e2e_frame_api_fps = None
+    e2e_frame_api_serial_fps = None
+    e2e_live_fps = None
     if world == 1 and has_vio:
         pin_scan = h.pinned_like(np.ascontiguousarray(scan, np.float32))
         fi = h.frame_inputs(pin_scan, x0, x0.copy(), pin_img, pin_pos, pin_ref, pin_lev)
@@ -801,6 +803,64 @@ def main():
             barrier()
             dtf -= time.perf_counter() - tf
         e2e_frame_api_fps = e2e_steps / dtf
+        # the same call, but every frame's result is collected before the next frame is enqueued: the call pattern of a live
+        # odometry loop, whose next prior depends on this posterior
+        for k in range(3):
+            h.frame_enqueue(fi, lprm, vprm, 0)
+            xf, _, _ = h.state_download_wait(0)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            if flush is not None:
+                flush.zero_()
+            h.frame_enqueue(fi, lprm, vprm, 0)
+            xf, _, _ = h.state_download_wait(0)
+        barrier()
+        dts = time.perf_counter() - t0
+        if flush is not None:
+            barrier()
+            tf = time.perf_counter()
+            for _ in range(e2e_steps):
+                flush.zero_()
+            barrier()
+            dts -= time.perf_counter() - tf
+        e2e_frame_api_serial_fps = e2e_steps / dts
+        # live loop with look-ahead on the SENSOR data only: frame k+1's scan / image / patch list do not depend on frame k's
+        # posterior, so they are uploaded (own streams, idle device sets) while frame k runs; the prior of frame k+1 is set
+        # only after frame k's posterior has been read back
+        def sensor_uploads():
+            h.scan_upload(pin_scan)
+            h.image_upload(pin_img)
+            h.patches_upload(pin_pos, pin_ref, pin_lev)
+
+        def live_frame():
+            h.state_upload(x0, x0)              # (a real loop: the IMU-propagated posterior of the previous frame)
+            h.lio_update_enqueue(lprm)
+            h.state_set_prior_enqueue()
+            h.vio_update_enqueue(vprm)
+            h.state_download_enqueue(0)
+            sensor_uploads()                    # next frame's sensor data, under this frame's updates
+            return h.state_download_wait(0)
+        sensor_uploads()
+        for k in range(3):
+            xl, _, _ = live_frame()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            if flush is not None:
+                flush.zero_()
+            xl, _, _ = live_frame()
+        barrier()
+        dtl = time.perf_counter() - t0
+        if flush is not None:
+            barrier()
+            tf = time.perf_counter()
+            for _ in range(e2e_steps):
+                flush.zero_()
+            barrier()
+            dtl -= time.perf_counter() - tf
+        e2e_live_fps = e2e_steps / dtl
+        assert np.array_equal(np.array(xl.rot[:]), np.array(xe.rot[:])), "the live-loop e2e must give the same state"
         assert np.array_equal(np.array(xf.rot[:]), np.array(xe.rot[:])) and np.array_equal(np.array(xf.cov[:]), np.array(xe.cov[:])), \
             "flb_frame_enqueue must give the same state as the separate calls"
     e2e_blocking_fps = None
@@ -1007,11 +1067,16 @@ def main():
                     "residuals_per_sec": rows_per_frame * (e2e_frame_api_fps if e2e_frame_api_fps else e2e_fps),
                     "api": "flb_frame_enqueue + flb_state_download_wait (one call per frame, page-locked caller buffers, result read back one "
                            "frame behind)" if e2e_frame_api_fps else "separate upload / update calls, one blocking flb_state_download per frame",
+                    "frame_api_serial_value": e2e_frame_api_serial_fps, "live_loop_value": e2e_live_fps,
                     "separate_calls_serial_value": e2e_fps, "pipelined_value": e2e_pipe_fps,
                     "pinned_caller_buffers_value": e2e_pinned_fps, "blocking_calls_value": e2e_blocking_fps,
                     "note": "value (N = 1): every frame moves scan + image + patch list + two states H2D from page-locked host memory and its "
                             "state + reports D2H inside the timed region, through ONE C-ABI call per frame, with the read-back pipelined by one "
-                            "frame; separate_calls_serial_value: pageable buffers, separate calls, blocking download each frame.  "
+                            "frame (the frames are independent: each prior is given up front).  frame_api_serial_value: the same call with "
+                            "every result collected before the next frame is enqueued -- the pattern of a live odometry loop whose next "
+                            "prior depends on this posterior.  live_loop_value: that dependency kept (the state of frame k+1 is uploaded only "
+                            "after frame k's posterior has been read back) but frame k+1's scan / image / patch list -- which do not depend "
+                            "on it -- uploaded while frame k runs (separate calls, page-locked buffers).  "
                             "pipelined_value: the same calls with the result read-back one frame behind (flb_state_download_enqueue / "
                             "_wait, two slots): frame k+1 uploads and sorts while frame k runs; every frame still moves its inputs "
                             "H2D and its state + reports D2H inside the timed region.  "
