@@ -1193,6 +1193,7 @@ struct LeaderSmem {
     float error;
     VioCtrl cspec;            // VIO: the control block of the speculated next pass
     int p2p_cnt[8];           // VIO: per-rank patch counts of this pass (kP2PMaxWorld)
+    int err_prog[4];          // VIO: slices of per-patch errors staged so far, per staging warp of the error team
 };
 
 // The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
@@ -1713,6 +1714,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         } else if (et == 0) {
             sm.p2p_cnt[0] = pn_total;
         }
+        if (et >= kErrTeam - 4) sm.err_prog[et - (kErrTeam - 4)] = 0;
         asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
         int total = 0;
         for (int r = 0; r < nsrc; ++r) total += sm.p2p_cnt[r];
@@ -1729,54 +1731,83 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
             }
             return __uint_as_float((unsigned)u);
         };
-        // stage (the first err_cap of) them: independent loads, a few L2 round trips for the whole team
-        {
-            const int n0 = min(err_cap, total);
-            int e = et;
-            for (; e + 3 * kErrTeam < n0; e += 4 * kErrTeam) {
-                const float v0 = fetch(e), v1 = fetch(e + kErrTeam), v2 = fetch(e + 2 * kErrTeam), v3 = fetch(e + 3 * kErrTeam);
-                s_err[e] = v0; s_err[e + kErrTeam] = v1; s_err[e + 2 * kErrTeam] = v2; s_err[e + 3 * kErrTeam] = v3;
-            }
-            for (; e < n0; e += kErrTeam) s_err[e] = fetch(e);
-        }
-        asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
-        if (tid >= NT - 32) {
-        // The last warp forms the exact sequential float sum of the per-patch errors (:852): a serial
-        // chain of one FADD latency per patch, hidden behind the other warps' reduce + solve -- and, in the
-        // persistent kernel, behind the next pass, which has already been started on the accept branch.
-        const int lane = tid - (NT - 32);
-        float e_run = 0.0f;
-        {
-            for (int base = 0; base < total; base += err_cap) {
-                const int nchunk = min(err_cap, total - base);
-                if (base > 0) {            // beyond the staged capacity: this warp stages the next chunk itself
-                    for (int e = lane; e < nchunk; e += 32) s_err[e] = fetch(base + e);
+        // Gather and sum are PIPELINED: the first three warps of the team stage the errors into shared memory in
+        // slices of kErrSlice (each thread 16 independent loads per slice: one L2 round trip for 1536 errors) and publish
+        // their progress; lane 0 of the last warp runs the exact sequential float sum (:852) behind them, one FADD
+        // latency per patch, 16 addends per step with the next 16 already fetched from shared memory.  The chain is the
+        // longer of the two (2 k patches: 4 us, 10 k: 20 us), so the gather costs one round trip, not one per slice.
+        // Both are hidden behind the other threads' reduce + solve and -- in the persistent kernel -- behind the next
+        // pass, which has already been started on the accept branch.
+        constexpr int kStagers = kErrTeam - 32, kPer = 16, kErrSlice = kStagers * kPer;
+        const int n0 = min(err_cap, total);
+        const int nslices = (n0 + kErrSlice - 1) / kErrSlice;
+        volatile int* prog = sm.err_prog;
+        if (et < kStagers) {
+            const int w = et >> 5;
+            for (int c = 0; c < nslices; ++c) {
+                const int b0 = c * kErrSlice + et;
+#pragma unroll
+                for (int g = 0; g < kPer; g += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = b0 + (g + u) * kStagers;
+                        v[u] = (e < n0) ? fetch(e) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = b0 + (g + u) * kStagers;
+                        if (e < n0) s_err[e] = v[u];
+                    }
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    // 16 addends per step, the next 16 fetched from shared memory while these are added:
-                    // the chain then runs at one FADD latency per patch
-                    float e = e_run;
-                    const float4* s4 = reinterpret_cast<const float4*>(s_err);
-                    int i = 0;
-                    float4 n0, n1, n2, n3;
-                    if (nchunk >= 16) { n0 = s4[0]; n1 = s4[1]; n2 = s4[2]; n3 = s4[3]; }
-                    for (; i + 16 <= nchunk; i += 16) {
-                        const float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-                        {   // unconditional, index clamped into the array (unused past the end of the chunk)
-                            const int q = min((i >> 2) + 4, err_cap / 4 - 4);
-                            n0 = s4[q]; n1 = s4[q + 1]; n2 = s4[q + 2]; n3 = s4[q + 3];
+                if ((et & 31) == 0) {
+                    __threadfence_block();
+                    prog[w] = c + 1;
+                }
+            }
+        } else {
+        const int lane = et - kStagers;
+        float e_run = 0.0f;
+        if (lane == 0) {
+            float e = 0.0f;
+            for (int c = 0; c < nslices; ++c) {
+                while (prog[0] <= c || prog[1] <= c || prog[2] <= c) {}
+                __threadfence_block();
+                const int i0 = c * kErrSlice, i1 = min(i0 + kErrSlice, n0);
+                const float4* s4 = reinterpret_cast<const float4*>(s_err);
+                int i = i0;
+                if (i1 - i0 >= 16) {
+                    float4 n0v = s4[i0 >> 2], n1v = s4[(i0 >> 2) + 1], n2v = s4[(i0 >> 2) + 2], n3v = s4[(i0 >> 2) + 3];
+                    for (; i + 16 <= i1; i += 16) {
+                        const float4 c0 = n0v, c1 = n1v, c2 = n2v, c3 = n3v;
+                        {   // unconditional, index clamped into this slice (unused past its end)
+                            const int q = min((i >> 2) + 4, (i1 >> 2) - 4);
+                            n0v = s4[q]; n1v = s4[q + 1]; n2v = s4[q + 2]; n3v = s4[q + 3];
                         }
                         e = e + c0.x; e = e + c0.y; e = e + c0.z; e = e + c0.w;
                         e = e + c1.x; e = e + c1.y; e = e + c1.z; e = e + c1.w;
                         e = e + c2.x; e = e + c2.y; e = e + c2.z; e = e + c2.w;
                         e = e + c3.x; e = e + c3.y; e = e + c3.z; e = e + c3.w;
                     }
-                    for (; i < nchunk; ++i) e = e + s_err[i];
-                    e_run = e;
                 }
-                __syncwarp();
+                for (; i < i1; ++i) e = e + s_err[i];
             }
+            e_run = e;
+        }
+        __syncwarp();
+        // beyond the staged capacity (more patches than err_cap): this warp stages and sums the rest chunk by chunk
+        for (int base = err_cap; base < total; base += err_cap) {
+            const int nchunk = min(err_cap, total - base);
+            e_run = __shfl_sync(0xffffffffu, e_run, 0);
+            for (int e = lane; e < nchunk; e += 32) s_err[e] = fetch(base + e);
+            __syncwarp();
+            if (lane == 0) {
+                float e = e_run;
+                for (int i = 0; i < nchunk; ++i) e = e + s_err[i];
+                e_run = e;
+            }
+            __syncwarp();
         }
         if (lane == 0) sm.error = e_run;
         if (fine && lane == 0) fine[3] = global_ns();
