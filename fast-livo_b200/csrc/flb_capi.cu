@@ -254,6 +254,7 @@ struct flb_handle {
     DevBuf<float> patch_ref, patch_ref_alt;
     DevBuf<int> patch_level, patch_level_alt;
     DevBuf<float> errors;        // 2 x err_stride (local shard; the persistent kernel's passes alternate between the halves)
+    DevBuf<unsigned long long> err_units;   // 2 x err_stride {tag : error} units (persistent kernel, single GPU: what its leader polls)
     int err_stride = 0;
     DevBuf<float> errors_all;    // padded shard * world (multi-GPU)
     DevBuf<double> x_z, x_H;
@@ -734,6 +735,16 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         s.Pn_total = a.Pn;
     }
     const int nb = vio_nblocks(h);
+    if (persistent && !fused) {
+        // per-patch errors as self-validating units (zeroed once per allocation: a tag always has its top bit set)
+        const size_t need = 2 * (size_t)std::max(h->err_stride, 1);
+        if (need > h->err_units.cap) {
+            FLB_CUDA(h, h->err_units.reserve(need));
+            FLB_CUDA(h, cudaMemsetAsync(h->err_units.p, 0, h->err_units.cap * sizeof(unsigned long long), h->stream));
+        }
+        a.err_units = h->err_units.p;
+        s.err_units = h->err_units.p;
+    }
     if (persistent) {
         // patches are dealt warp-round-robin over the worker blocks; one more block is the leader
         const int cap = std::min(h->occ_vio * h->num_sms, h->pers_sms);
@@ -926,7 +937,7 @@ int flb_destroy(flb_handle* h) {
     h->x_nn_idx.release(); h->x_rowmask.release(); h->x_rows.release(); h->x_meas.release(); h->partials.release();
     h->packed.release(); h->pose12.release(); h->prior.release(); h->scan_raw.release(); h->skeys.release(); h->skeys_sorted.release(); h->svals.release(); h->svals_sorted.release(); h->x_pabcd.release(); h->G_last.release(); h->states.release();
     h->lio_ctrl.release(); h->vio_ctrl.release(); h->ik_states.release(); h->ik_ctrl.release(); h->barrier.release(); h->pkt.release(); h->trace.release(); h->dbg.release(); h->dbg_vio.release(); h->imu_buf.release(); h->imu_pts.release(); h->imu_heads.release(); h->vm_key.release(); h->vm_val.release(); h->vm_pts.release(); h->vm_win.release(); h->vm_pose.release(); h->img.release(); h->patch_pos.release(); h->patch_ref.release();
-    h->patch_level.release(); h->errors.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
+    h->patch_level.release(); h->errors.release(); h->err_units.release(); h->errors_all.release(); h->x_z.release(); h->x_H.release();
     h->st_map.release(); h->st_scan.release(); h->st_img.release(); h->st_patch.release(); h->st_state.release();
     h->st_misc.release(); h->pin_out.release();
     for (int k = 0; k < 2; ++k) { h->pin_res[k].release(); if (h->ev_res[k]) cudaEventDestroy(h->ev_res[k]); }

@@ -962,6 +962,8 @@ struct VioArgs {
     WarmList warm;               // persistent kernel: pages to touch before the first pass (n = 0: none)
     const int* Pn_dev;           // persistent kernel: when non-null the patch count is read from the device (the patch
                                  // list was built there by the visual-map selection, flb_vmap_select) and Pn is its capacity
+    unsigned long long* err_units;   // persistent kernel, single GPU: 2 x err_stride self-validating {tag : error} units the leader
+                                     // polls (the per-patch error of a warp's last patch is formed AFTER the block has arrived)
 };
 
 struct LatView {
@@ -1001,11 +1003,40 @@ __device__ __forceinline__ double round_to_f32_precision(double d) {
 // One patch by one warp.  The 21 + 6 sums of the patch are reduced across the warp right away: lane l < 27
 // adds the patch total of sum l to `accv` (so only one double per lane is carried from patch to patch);
 // lane 0 also counts n_meas / skipped.
-__device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
+// Publish one per-patch error: the plain buffer (sub_sparse_map->errors), and -- persistent kernel -- the self-validating
+// unit the leader(s) poll: every rank's mailbox in the fused multi-GPU mode, the local unit array otherwise.
+__device__ __forceinline__ void vio_publish_error(const VioArgs& a, int i, float pe, unsigned p2p_tag, unsigned utag, int err_buf) {
+    a.errors[(size_t)err_buf * a.err_stride + i] = pe;                            // :851
+    if (p2p_tag) p2p_push_error(a.p2p, p2p_tag, i, pe);
+    else if (utag) ll_store_u64(a.err_units + (size_t)err_buf * a.err_stride + i, ((unsigned long long)utag << 32) | (unsigned long long)__float_as_uint(pe));
+}
+
+// patch_error += res*res over the 64 pixels: float accumulator, double addend (:843) -- sequential, exact.  Lane 0.
+__device__ __forceinline__ void vio_patch_error(const VioArgs& a, int i, const double* s_res, bool tiny, unsigned p2p_tag, unsigned utag,
+                                                int err_buf, unsigned long long* wdbg) {
+    if ((threadIdx.x & 31) == 0) {
+        double ped = 0.0;
+#pragma unroll 8
+        for (int e = 0; e < 64; ++e) ped = round_to_f32_precision(ped + s_res[e]);
+        float pe = (float)ped;
+        if (tiny || !(ped < 3.0e38)) {                          // outside the shortcut's domain: literal form
+            pe = 0.0f;
+            for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[e]);
+        }
+        vio_publish_error(a, i, pe, p2p_tag, utag, err_buf);
+        if (wdbg) wdbg[3] = global_ns();
+    }
+}
+
+// `defer` (persistent kernel, last patch of this warp in the pass): the per-patch error chain is NOT run here; the caller
+// runs vio_patch_error after its block has arrived at the pass barrier -- the chain (64 dependent steps by one lane,
+// ~1.3 us) feeds only the leader's error sum, which is off the critical path, while the barrier is on it.  Returns true
+// when a chain is pending (`tiny_out` is its argument; s_res must stay untouched until then).
+__device__ __forceinline__ bool vio_patch(const VioArgs& a, const VioPose& pose, int level, int i, const PatchIn& in,
                                           float* s_lat, double* s_res, double& accv, double& n_meas, double& skipped,
-                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0) {
+                                          unsigned long long* wdbg = nullptr, unsigned p2p_tag = 0u, int err_buf = 0,
+                                          unsigned utag = 0u, bool defer = false, bool* tiny_out = nullptr) {
     const int lane = threadIdx.x & 31;
-    float* const err_out = a.errors + (size_t)err_buf * a.err_stride;
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0.0;
@@ -1062,28 +1093,16 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
         tiny = __any_sync(0xffffffffu, tiny);
         __syncwarp();
         if (wdbg && lane == 0) wdbg[2] = global_ns();
-        if (lane == 0) {
-            // patch_error += res*res : float accumulator, double addend (:843) -- sequential, exact
-            double ped = 0.0;
-#pragma unroll 8
-            for (int e = 0; e < 64; ++e) ped = round_to_f32_precision(ped + s_res[e]);
-            float pe = (float)ped;
-            if (tiny || !(ped < 3.0e38)) {                          // outside the shortcut's domain: literal form
-                pe = 0.0f;
-                for (int e = 0; e < 64; ++e) pe = (float)((double)pe + s_res[e]);
-            }
-            err_out[i] = pe;                                        // :851
-            if (p2p_tag) p2p_push_error(a.p2p, p2p_tag, i, pe);
-            n_meas += 64.0;
-            if (wdbg) wdbg[3] = global_ns();
-        }
+        if (lane == 0) n_meas += 64.0;
+        if (defer) *tiny_out = tiny;
+        else vio_patch_error(a, i, s_res, tiny, p2p_tag, utag, err_buf, wdbg);
         __syncwarp();
         accv += warp_transpose_reduce<27>(acc);
+        return defer;
     } else {
         if (lane == 0) {
-            err_out[i] = 0.0f;
             skipped += 1.0;
-            if (p2p_tag) p2p_push_error(a.p2p, p2p_tag, i, 0.0f);
+            vio_publish_error(a, i, 0.0f, p2p_tag, utag, err_buf);
         }
         if (a.x_z) {
             for (int e = lane; e < 64; e += 32) {
@@ -1092,6 +1111,7 @@ __device__ __forceinline__ void vio_patch(const VioArgs& a, const VioPose& pose,
             }
         }
     }
+    return false;
 }
 
 __device__ __forceinline__ void vio_make_pose_from(const VioArgs& a, VioPose& pose, bool through_l2) {
@@ -1673,6 +1693,7 @@ struct VioSolveArgs {
     P2PArgs p2p;             // world <= 1: single GPU
     int* timeout_flag;
     int prior_from_state;    // persistent kernel: state_propagat = state (a pending flb_state_set_prior_enqueue, laserMapping.cpp:1292)
+    const unsigned long long* err_units;   // see VioArgs::err_units (null: read `errors`)
 };
 
 constexpr int kErrChunk = 2048;          // staging capacity of the kernel-per-pass finalize kernel (static shared memory)
@@ -1718,14 +1739,20 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
         int total = 0;
         for (int r = 0; r < nsrc; ++r) total += sm.p2p_cnt[r];
+        const unsigned want_tag = multi ? p2p_tag : (flag | 0x80000000u);
         auto fetch = [&](int e) -> float {
-            if (!multi) return __ldcg(errs_pass + e);
-            int r = 0;
-            while (r + 1 < nsrc && e >= sm.p2p_cnt[r]) { e -= sm.p2p_cnt[r]; ++r; }
-            const unsigned long long* unit = &s.p2p.mail[s.p2p.rank]->errs[par][r][e];
+            if (!multi && s.err_units == nullptr) return __ldcg(errs_pass + e);
+            const unsigned long long* unit;
+            if (multi) {
+                int r = 0;
+                while (r + 1 < nsrc && e >= sm.p2p_cnt[r]) { e -= sm.p2p_cnt[r]; ++r; }
+                unit = &s.p2p.mail[s.p2p.rank]->errs[par][r][e];
+            } else {
+                unit = s.err_units + (size_t)err_buf * s.err_stride + e;
+            }
             unsigned long long u = ll_load_u64(unit);
             unsigned long long spins = 0;
-            while ((unsigned)(u >> 32) != p2p_tag) {
+            while ((unsigned)(u >> 32) != want_tag) {
                 if (++spins > kP2PSpinLimit) { *s.timeout_flag = 1; break; }
                 u = ll_load_u64(unit);
             }
@@ -2434,15 +2461,25 @@ __global__ void __launch_bounds__(BLOCK, 1) k_vio_update_persistent(VioArgs a, V
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 1] = global_ns();
             const int level = s_ctrl.level;
             double accv = 0.0, n_meas = 0.0, skipped = 0.0;
+            // the leader reads the per-patch errors as self-validating units, so the error chain of a warp's LAST patch of
+            // the pass can run after the block has arrived (it only feeds the error sum, which is off the critical path)
+            const unsigned utag = (!multi && a.err_units) ? (flag | 0x80000000u) : 0u;
+            const bool can_defer = multi || utag != 0u;
+            int pend_i = -1;
+            bool pend_tiny = false;
+            unsigned long long* wd = dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr;
             for (int i = blockIdx.x * NW + warp; i < Pn; i += nworkers * NW) {
                 if (!single) vio_patch_load(a, i, tid & 31, pin);
-                vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped,
-                          dbg ? dbg + blockIdx.x * kVioDbg + 8 + 4 * warp : nullptr, p2p_tag, pass_no & 1);
+                const bool last = can_defer && (i + nworkers * NW >= Pn);
+                if (vio_patch(a, s_pose, level, i, pin, s_lat[warp], s_res[warp], accv, n_meas, skipped, wd, p2p_tag, pass_no & 1, utag, last,
+                              &pend_tiny))
+                    pend_i = i;
             }
             vio_block_reduce_store<BLOCK>(accv, n_meas, skipped, s_acc, a.partials);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 2] = global_ns();
             grid_arrive_release(bar);
             if (dbg && tid == 0) dbg[blockIdx.x * kVioDbg + 3] = global_ns();
+            if (pend_i >= 0) vio_patch_error(a, pend_i, s_res[warp], pend_tiny, p2p_tag, utag, pass_no & 1, wd);
             if (!pkt_wait<NC>(pkt, sm.x, &s_ctrl, flag, bar, s_bar, multi ? 40000000ull : 3000000ull)) return;
         }
         first = false;
