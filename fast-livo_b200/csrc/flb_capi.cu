@@ -735,7 +735,8 @@ int enqueue_vio_update(flb_handle* h, const flb_vio_params* prm) {
         s.Pn_total = a.Pn;
     }
     const int nb = vio_nblocks(h);
-    if (persistent && !fused) {
+    static const int env_defer = [] { const char* e = getenv("FLB_DEFER"); return e ? atoi(e) : 1; }();
+    if (persistent && !fused && env_defer) {
         // per-patch errors as self-validating units (zeroed once per allocation: a tag always has its top bit set)
         const size_t need = 2 * (size_t)std::max(h->err_stride, 1);
         if (need > h->err_units.cap) {
