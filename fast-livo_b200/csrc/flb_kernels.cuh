@@ -1213,7 +1213,7 @@ struct LeaderSmem {
     float error;
     VioCtrl cspec;            // VIO: the control block of the speculated next pass
     int p2p_cnt[8];           // VIO: per-rank patch counts of this pass (kP2PMaxWorld)
-    int err_prog[4];          // VIO: slices of per-patch errors staged so far, per staging warp of the error team
+    int err_prog[8];          // VIO: slices of per-patch errors staged so far, per staging warp of the error team
 };
 
 // The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
@@ -1697,7 +1697,7 @@ struct VioSolveArgs {
 };
 
 constexpr int kErrChunk = 2048;          // staging capacity of the kernel-per-pass finalize kernel (static shared memory)
-constexpr int kErrTeam = 128;            // threads of the leader block that gather the per-patch errors
+// threads of the leader block that gather + sum the per-patch errors: 256 of the persistent kernel's 512, 128 of the finalize kernel's 256
 constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 
 // One VIO leader step (whole block, NT threads), in two halves like the LIO one.  Requires the 24
@@ -1720,6 +1720,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
     // partition).  Single GPU: this rank's error buffer.  Fused multi-GPU mode: every rank's worker warps pushed
     // {error, tag} units into this rank's mailbox while the pass was running, and each rank's patch count came
     // with the first block of its pass (line 31); every unit is validated by its tag.
+    constexpr int kErrTeam = NT >= 512 ? 256 : 128;
     static_assert(NT - kErrTeam >= kDim * 6 && NT - kErrTeam >= 64, "solve team too small");
     if (tid >= NT - kErrTeam) {
         // ---- error team (the last kErrTeam threads): gather, then its last warp sums
@@ -1735,11 +1736,17 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         } else if (et == 0) {
             sm.p2p_cnt[0] = pn_total;
         }
-        if (et >= kErrTeam - 4) sm.err_prog[et - (kErrTeam - 4)] = 0;
+        if (et >= kErrTeam - 8) sm.err_prog[et - (kErrTeam - 8)] = 0;
         asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
         int total = 0;
         for (int r = 0; r < nsrc; ++r) total += sm.p2p_cnt[r];
         const unsigned want_tag = multi ? p2p_tag : (flag | 0x80000000u);
+        auto unit_of = [&](int e) -> const unsigned long long* {
+            if (!multi) return s.err_units + (size_t)err_buf * s.err_stride + e;
+            int r = 0;
+            while (r + 1 < nsrc && e >= sm.p2p_cnt[r]) { e -= sm.p2p_cnt[r]; ++r; }
+            return &s.p2p.mail[s.p2p.rank]->errs[par][r][e];
+        };
         auto fetch = [&](int e) -> float {
             if (!multi && s.err_units == nullptr) return __ldcg(errs_pass + e);
             const unsigned long long* unit;
@@ -1765,26 +1772,52 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         // longer of the two (2 k patches: 4 us, 10 k: 20 us), so the gather costs one round trip, not one per slice.
         // Both are hidden behind the other threads' reduce + solve and -- in the persistent kernel -- behind the next
         // pass, which has already been started on the accept branch.
-        constexpr int kStagers = kErrTeam - 32, kPer = 16, kErrSlice = kStagers * kPer;
+        constexpr int kStagers = kErrTeam - 32, kPer = 16, kErrSlice = kStagers * kPer, kStageWarps = kStagers / 32;
+        static_assert(kStageWarps <= 8, "err_prog");
         const int n0 = min(err_cap, total);
         const int nslices = (n0 + kErrSlice - 1) / kErrSlice;
         volatile int* prog = sm.err_prog;
         if (et < kStagers) {
             const int w = et >> 5;
+            const bool units = multi || s.err_units != nullptr;
             for (int c = 0; c < nslices; ++c) {
                 const int b0 = c * kErrSlice + et;
+                if (!units) {
+                    // plain floats, complete when the blocks arrived: 16 independent loads
+                    float v[kPer];
 #pragma unroll
-                for (int g = 0; g < kPer; g += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int e = b0 + (g + u) * kStagers;
-                        v[u] = (e < n0) ? fetch(e) : 0.f;
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = b0 + u * kStagers;
+                        v[u] = (e < n0) ? __ldcg(errs_pass + e) : 0.f;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int e = b0 + (g + u) * kStagers;
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = b0 + u * kStagers;
                         if (e < n0) s_err[e] = v[u];
+                    }
+                } else {
+                    // self-validating units, still being written when the poll starts: all of this thread's units of the
+                    // slice are polled together (one round trip per attempt for the lot), each re-polled until its tag is right
+                    const unsigned long long* up[kPer];
+                    unsigned pending = 0u;
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = b0 + u * kStagers;
+                        up[u] = unit_of(e < n0 ? e : 0);
+                        if (e < n0) pending |= 1u << u;
+                    }
+                    unsigned long long spins = 0;
+                    while (pending) {
+                        unsigned long long uv[kPer];
+#pragma unroll
+                        for (int u = 0; u < kPer; ++u) uv[u] = (pending >> u & 1u) ? ll_load_u64(up[u]) : 0ull;
+#pragma unroll
+                        for (int u = 0; u < kPer; ++u)
+                            if ((pending >> u & 1u) && (unsigned)(uv[u] >> 32) == want_tag) {
+                                s_err[b0 + u * kStagers] = __uint_as_float((unsigned)uv[u]);
+                                pending &= ~(1u << u);
+                            }
+                        if (pending && ++spins > kP2PSpinLimit) { *s.timeout_flag = 1; break; }
                     }
                 }
                 __syncwarp();
@@ -1799,7 +1832,8 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         if (lane == 0) {
             float e = 0.0f;
             for (int c = 0; c < nslices; ++c) {
-                while (prog[0] <= c || prog[1] <= c || prog[2] <= c) {}
+                for (int w = 0; w < kStageWarps; ++w)
+                    while (prog[w] <= c) {}
                 __threadfence_block();
                 const int i0 = c * kErrSlice, i1 = min(i0 + kErrSlice, n0);
                 const float4* s4 = reinterpret_cast<const float4*>(s_err);
