@@ -1259,12 +1259,12 @@ __device__ __forceinline__ void team_reduce_vec(const double* partials, int nblo
         const int per = (nblocks + PARTS - 1) / PARTS;
         const int b0 = part * per, b1 = min(nblocks, b0 + per);
         double s = 0.0;
-        for (int b = b0; b < b1; b += 16) {
-            double v[16];
+        for (int b = b0; b < b1; b += 24) {       // 24 loads in flight: one round trip for a slice of up to 24 blocks
+            double v[24];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = (b + u < b1) ? __ldcg(partials + (size_t)(b + u) * K + q) : 0.0;
+            for (int u = 0; u < 24; ++u) v[u] = (b + u < b1) ? __ldcg(partials + (size_t)(b + u) * K + q) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) s += v[u];
+            for (int u = 0; u < 24; ++u) s += v[u];
         }
         sm.part[part][q] = s;
     }
@@ -1697,7 +1697,8 @@ struct VioSolveArgs {
 };
 
 constexpr int kErrChunk = 2048;          // staging capacity of the kernel-per-pass finalize kernel (static shared memory)
-// threads of the leader block that gather + sum the per-patch errors: 256 of the persistent kernel's 512, 128 of the finalize kernel's 256
+// threads of the leader block that gather + sum the per-patch errors: 160 of the persistent kernel's 512 (the other 352 reduce
+// the 146 block partials in ten slices of 15: one round trip), 128 of the finalize kernel's 256
 constexpr int kVioDbg = 8 + 4 * 16;   // debug stamps per block (tracing only)
 
 // One VIO leader step (whole block, NT threads), in two halves like the LIO one.  Requires the 24
@@ -1720,7 +1721,7 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
     // partition).  Single GPU: this rank's error buffer.  Fused multi-GPU mode: every rank's worker warps pushed
     // {error, tag} units into this rank's mailbox while the pass was running, and each rank's patch count came
     // with the first block of its pass (line 31); every unit is validated by its tag.
-    constexpr int kErrTeam = NT >= 512 ? 256 : 128;
+    constexpr int kErrTeam = NT >= 512 ? 160 : 128;
     static_assert(NT - kErrTeam >= kDim * 6 && NT - kErrTeam >= 64, "solve team too small");
     if (tid >= NT - kErrTeam) {
         // ---- error team (the last kErrTeam threads): gather, then its last warp sums
