@@ -1213,7 +1213,6 @@ struct LeaderSmem {
     float error;
     VioCtrl cspec;            // VIO: the control block of the speculated next pass
     int p2p_cnt[8];           // VIO: per-rank patch counts of this pass (kP2PMaxWorld)
-    int err_prog[8];          // VIO: slices of per-patch errors staged so far, per staging warp of the error team
 };
 
 // The 24 leading doubles (rot, pos, vel, bg, ba, grav) of x and xp: one L2 round trip for both.
@@ -1737,7 +1736,6 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
         } else if (et == 0) {
             sm.p2p_cnt[0] = pn_total;
         }
-        if (et >= kErrTeam - 8) sm.err_prog[et - (kErrTeam - 8)] = 0;
         asm volatile("bar.sync 4, %0;" ::"n"(kErrTeam) : "memory");
         int total = 0;
         for (int r = 0; r < nsrc; ++r) total += sm.p2p_cnt[r];
@@ -1766,22 +1764,25 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
             }
             return __uint_as_float((unsigned)u);
         };
-        // Gather and sum are PIPELINED: the first three warps of the team stage the errors into shared memory in
-        // slices of kErrSlice (each thread 16 independent loads per slice: one L2 round trip for 1536 errors) and publish
-        // their progress; lane 0 of the last warp runs the exact sequential float sum (:852) behind them, one FADD
-        // latency per patch, 16 addends per step with the next 16 already fetched from shared memory.  The chain is the
-        // longer of the two (2 k patches: 4 us, 10 k: 20 us), so the gather costs one round trip, not one per slice.
-        // Both are hidden behind the other threads' reduce + solve and -- in the persistent kernel -- behind the next
-        // pass, which has already been started on the accept branch.
-        constexpr int kStagers = kErrTeam - 32, kPer = 16, kErrSlice = kStagers * kPer, kStageWarps = kStagers / 32;
-        static_assert(kStageWarps <= 8, "err_prog");
+        // Gather and sum are PIPELINED: all warps of the team but the last stage the errors into shared memory in slices
+        // of kErrSlice (each thread 16 independent loads / unit polls per slice: one L2 round trip per attempt) and hand
+        // each slice over through a named barrier (arrive / sync pairs, two ids alternating); lane 0 of the last warp runs
+        // the exact sequential float sum (:852) behind them, one FADD latency per patch, 16 addends per step with the next
+        // 16 already fetched from shared memory.  The chain is the longer of the two (2 k patches: 4 us, 10 k: 20 us), so
+        // the gather costs one round trip, not one per slice.  Both are hidden behind the other threads' reduce + solve
+        // and -- in the persistent kernel -- behind the next pass, which has already been started on the accept branch.
+        constexpr int kStagers = kErrTeam - 32, kPer = 16, kErrSlice = kStagers * kPer;
         const int n0 = min(err_cap, total);
         const int nslices = (n0 + kErrSlice - 1) / kErrSlice;
-        volatile int* prog = sm.err_prog;
         if (et < kStagers) {
-            const int w = et >> 5;
             const bool units = multi || s.err_units != nullptr;
             for (int c = 0; c < nslices; ++c) {
+                // a barrier id is reused every other slice: do not arrive for slice c before the chain warp has taken slice
+                // c - 2 (EMPTY[c & 1]: the chain warp arrives, the stagers sync)
+                if (c >= 2) {
+                    if (c & 1) asm volatile("bar.sync 8, %0;" ::"n"(kErrTeam) : "memory");
+                    else asm volatile("bar.sync 7, %0;" ::"n"(kErrTeam) : "memory");
+                }
                 const int b0 = c * kErrSlice + et;
                 if (!units) {
                     // plain floats, complete when the blocks arrived: 16 independent loads
@@ -1821,39 +1822,44 @@ __device__ __forceinline__ void vio_leader_solve(const VioSolveArgs& s, LeaderSm
                         if (pending && ++spins > kP2PSpinLimit) { *s.timeout_flag = 1; break; }
                     }
                 }
-                __syncwarp();
-                if ((et & 31) == 0) {
-                    __threadfence_block();
-                    prog[w] = c + 1;
-                }
+                // hand slice c to the chain warp: named barrier FULL[c & 1] (stagers arrive, the chain warp syncs)
+                if (c & 1) asm volatile("bar.arrive 6, %0;" ::"n"(kErrTeam) : "memory");
+                else asm volatile("bar.arrive 5, %0;" ::"n"(kErrTeam) : "memory");
             }
         } else {
         const int lane = et - kStagers;
         float e_run = 0.0f;
-        if (lane == 0) {
+        {
             float e = 0.0f;
             for (int c = 0; c < nslices; ++c) {
-                for (int w = 0; w < kStageWarps; ++w)
-                    while (prog[w] <= c) {}
-                __threadfence_block();
-                const int i0 = c * kErrSlice, i1 = min(i0 + kErrSlice, n0);
-                const float4* s4 = reinterpret_cast<const float4*>(s_err);
-                int i = i0;
-                if (i1 - i0 >= 16) {
-                    float4 n0v = s4[i0 >> 2], n1v = s4[(i0 >> 2) + 1], n2v = s4[(i0 >> 2) + 2], n3v = s4[(i0 >> 2) + 3];
-                    for (; i + 16 <= i1; i += 16) {
-                        const float4 c0 = n0v, c1 = n1v, c2 = n2v, c3 = n3v;
-                        {   // unconditional, index clamped into this slice (unused past its end)
-                            const int q = min((i >> 2) + 4, (i1 >> 2) - 4);
-                            n0v = s4[q]; n1v = s4[q + 1]; n2v = s4[q + 2]; n3v = s4[q + 3];
+                if (c & 1) asm volatile("bar.sync 6, %0;" ::"n"(kErrTeam) : "memory");
+                else asm volatile("bar.sync 5, %0;" ::"n"(kErrTeam) : "memory");
+                if (fine && c == 0 && lane == 0) fine[0] = global_ns();
+                if (lane == 0) {
+                    const int i0 = c * kErrSlice, i1 = min(i0 + kErrSlice, n0);
+                    const float4* s4 = reinterpret_cast<const float4*>(s_err);
+                    int i = i0;
+                    if (i1 - i0 >= 16) {
+                        float4 n0v = s4[i0 >> 2], n1v = s4[(i0 >> 2) + 1], n2v = s4[(i0 >> 2) + 2], n3v = s4[(i0 >> 2) + 3];
+                        for (; i + 16 <= i1; i += 16) {
+                            const float4 c0 = n0v, c1 = n1v, c2 = n2v, c3 = n3v;
+                            {   // unconditional, index clamped into this slice (unused past its end)
+                                const int q = min((i >> 2) + 4, (i1 >> 2) - 4);
+                                n0v = s4[q]; n1v = s4[q + 1]; n2v = s4[q + 2]; n3v = s4[q + 3];
+                            }
+                            e = e + c0.x; e = e + c0.y; e = e + c0.z; e = e + c0.w;
+                            e = e + c1.x; e = e + c1.y; e = e + c1.z; e = e + c1.w;
+                            e = e + c2.x; e = e + c2.y; e = e + c2.z; e = e + c2.w;
+                            e = e + c3.x; e = e + c3.y; e = e + c3.z; e = e + c3.w;
                         }
-                        e = e + c0.x; e = e + c0.y; e = e + c0.z; e = e + c0.w;
-                        e = e + c1.x; e = e + c1.y; e = e + c1.z; e = e + c1.w;
-                        e = e + c2.x; e = e + c2.y; e = e + c2.z; e = e + c2.w;
-                        e = e + c3.x; e = e + c3.y; e = e + c3.z; e = e + c3.w;
                     }
+                    for (; i < i1; ++i) e = e + s_err[i];
                 }
-                for (; i < i1; ++i) e = e + s_err[i];
+                __syncwarp();
+                if (c + 2 < nslices) {
+                    if (c & 1) asm volatile("bar.arrive 8, %0;" ::"n"(kErrTeam) : "memory");
+                    else asm volatile("bar.arrive 7, %0;" ::"n"(kErrTeam) : "memory");
+                }
             }
             e_run = e;
         }
