@@ -487,7 +487,7 @@ def measure_batched(flb, torch, name, B, local, dev, stream, flush, hbm, peak_sr
             "note": "kernel-per-pass path with blockIdx.y = frame; every frame bit-identical to the frame run alone (tests/test_gpu_batch.py)"}
 
 
-def measure_full_frame(flb, torch, name, local, dev, stream, flush, steps=20):
+def measure_full_frame(flb, torch, name, local, dev, stream, flush, steps=20, raw=None):
     """One frame through EVERY stage that is on the device, host buffers in, state out (SURVEY.md section 8 rows a + f1-f4):
     IMU propagation + undistortion -> LIO update -> map maintenance (Add_Points) -> visible-patch selection + warp ->
     VIO update -> map growth -> new observations.  The patch list never crosses PCIe (it is built on the device)."""
@@ -542,6 +542,8 @@ def measure_full_frame(flb, torch, name, local, dev, stream, flush, steps=20):
         if timed:
             for key, a, b in zip(stage, t[:-1], t[1:]):
                 stage[key] += b - a
+            if raw is not None:
+                raw.append([round(1e3 * (b - a), 3) for a, b in zip(t[:-1], t[1:])])
         return x, lrep, vrep
     for k in range(3):
         x, lrep, vrep = frame(k, False)
