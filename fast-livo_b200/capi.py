@@ -174,7 +174,7 @@ SYMBOLS = ["flb_abi_version", "flb_create", "flb_destroy", "flb_last_error", "fl
            "flb_vmap_reset", "flb_vmap_select", "flb_vmap_selected", "flb_vmap_grow", "flb_vmap_add_observations", "flb_vmap_counts",
            "flb_vmap_map_value", "flb_vmap_dump", "flb_colorize", "flb_voxel_grid",
            "flb_batch_begin", "flb_batch_set_frame", "flb_batch_state_reset_enqueue", "flb_batch_update_enqueue", "flb_batch_state_download",
-           "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps", "flb_debug_scan_order"]
+           "flb_debug_set_packet_epoch", "flb_debug_block_stamps", "flb_debug_vio_stamps", "flb_debug_scan_order", "flb_debug_set_scan_sort"]
 
 
 def lib_path() -> str:
@@ -232,6 +232,7 @@ def lib():
         L.flb_vio_export.argtypes = [vp, vp, vp, vp]
         L.flb_vio_errors.argtypes = [vp, vp, C.c_int]
         L.flb_debug_scan_order.argtypes = [vp, vp, C.c_int]
+        L.flb_debug_set_scan_sort.argtypes = [vp, C.c_int]
         L.flb_vio_update_level.argtypes = [vp, C.POINTER(VioParams), C.c_int, C.c_float, C.POINTER(State18), C.POINTER(State18),
                                            C.POINTER(C.c_float), vp, C.POINTER(VioReport)]
         L.flb_batch_begin.argtypes = [vp, C.c_int, C.c_int]
@@ -372,6 +373,10 @@ class Handle:
         a = np.ascontiguousarray(body_xyz, np.float32)
         self._ck(self.L.flb_scan_upload(self.h, _p(a), a.shape[0], a.shape[1] if a.ndim == 2 else 3))
         self.N = a.shape[0]
+
+    def debug_set_scan_sort(self, mode):
+        """0 automatic, 1 one-block ordering kernel, 2 device-wide sort (test aid)."""
+        self._ck(self.L.flb_debug_set_scan_sort(self.h, int(mode)))
 
     def debug_scan_order(self):
         """Index in the caller's array of the point at each position of the uploaded (ordered) scan (test aid)."""

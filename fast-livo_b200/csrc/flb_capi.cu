@@ -197,6 +197,7 @@ struct flb_handle {
     int scan_slot = 0;
     DevBuf<unsigned char> scan_cub_tmp;                 // the upload's own sort scratch (cub_tmp belongs to `stream`)
     int pers_sms = 0;                                   // SMs the persistent kernels may fill (one is left to the scan stream)
+    int scan_sort_mode = 0;                             // 0 auto, 1 one-block ordering kernel, 2 device-wide sort (flb_debug_set_scan_sort)
 
     // LIO exports (lazily allocated)
     DevBuf<float> x_world, x_nn_d2, x_pd2, x_pabcd;
@@ -1609,8 +1610,21 @@ int flb_scan_upload(flb_handle* h, const float* body_xyz, int N, int stride) {
         if (!direct) FLB_CUDA(h, h->st_scan.mark(ss));
         // Morton order in the body frame (cell = twice the map grid's cell): spatially coherent warps at any pose
         const float inv_cell = 0.5f / (float)h->cfg.cell_size;
+        // One-block ordering vs keys + device-wide radix sort + gather (identical order).  Measured on an idle GPU
+        // (profiles/scan_upload_probe.py, copy included): 8 k points 45 vs 76 us, 16 k 78 vs 82, 24 k 116 vs 89 -- but the
+        // one-block kernel runs on the SM the persistent kernels leave free, so when an update is still running on
+        // `stream` (a pipelined caller) it costs nothing, while the device-wide kernels would queue behind the update.
+        // So: one block up to 16 896 points always, up to 25 600 when `stream` is busy; FLB_BLOCK_SORT=0 / 2 or
+        // flb_debug_set_scan_sort force the device-wide / one-block path.
         static const int env_block_sort = [] { const char* e = getenv("FLB_BLOCK_SORT"); return e ? atoi(e) : 1; }();
-        if (env_block_sort && N <= 1024 * 25) {
+        const int mode = h->scan_sort_mode ? h->scan_sort_mode : (env_block_sort == 0 ? 2 : (env_block_sort == 2 ? 1 : 0));
+        bool use_block = N <= 1024 * 25 && mode != 2;
+        if (use_block && mode == 0 && N > 512 * 33) {
+            const cudaError_t q = cudaStreamQuery(h->stream);
+            (void)cudaGetLastError();
+            use_block = (q == cudaErrorNotReady);
+        }
+        if (use_block) {
             LaunchScope ls(h, FAM_OTHER);
             int rcs = N <= 512 * 17   ? launch_scan_sort_block<512, 17>(h, ss, N, lo, inv_cell)
                       : N <= 512 * 33 ? launch_scan_sort_block<512, 33>(h, ss, N, lo, inv_cell)
@@ -2365,6 +2379,14 @@ int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks,
     if (n > 0) FLB_CUDA(h, cudaMemcpy(out, h->dbg_vio.p, (size_t)n * kVioDbg * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     *nblocks = n;
     *words_per_block = kVioDbg;
+    return FLB_OK;
+}
+
+// Test aid: force the scan ordering path of the following uploads (0 automatic, 1 one-block kernel, 2 device-wide sort).
+int flb_debug_set_scan_sort(flb_handle* h, int mode) {
+    FLB_CHECK_H(h);
+    if (mode < 0 || mode > 2) return fail(h, FLB_ERR_INVALID, "flb_debug_set_scan_sort: mode 0, 1 or 2");
+    h->scan_sort_mode = mode;
     return FLB_OK;
 }
 

@@ -465,6 +465,9 @@ int flb_debug_vio_stamps(flb_handle* h, unsigned long long* out, int max_blocks,
 /* flb_debug_scan_order: src_index[i] = index in the caller's scan array of the point at position i of the uploaded
  * (Morton-ordered) scan; capacity >= the scan's point count.  Test aid for the upload's two ordering paths. */
 int flb_debug_scan_order(flb_handle* h, int* src_index, int capacity);
+/* flb_debug_set_scan_sort: ordering path of the following flb_scan_upload calls -- 0 automatic (by size and by
+ * whether the handle's stream is busy), 1 the one-block kernel (scans of <= 25 600 points), 2 the device-wide sort. */
+int flb_debug_set_scan_sort(flb_handle* h, int mode);
 
 #ifdef __cplusplus
 }

@@ -27,13 +27,15 @@ def _expected_order(xyz, cell_size):
     return np.argsort(key, kind="stable").astype(np.int32)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("n", [1, 31, 512 * 17, 512 * 17 + 1, 512 * 33, 512 * 33 + 1, 24000, 1024 * 25, 1024 * 25 + 1, 40000])
-def test_scan_order_matches_stable_morton(flb, n):
+def test_scan_order_matches_stable_morton(flb, n, mode):
     rng = np.random.default_rng(n)
     # few occupied cells => long runs of equal keys: the tie order (caller's index) is what is being tested
     xyz = (rng.integers(0, 6, size=(n, 3)) * 1.2 + rng.uniform(0, 0.3, size=(n, 3))).astype(np.float32)
     h = flb.Handle(cell_size=0.6)
     try:
+        h.debug_set_scan_sort(mode)     # 0: by size / stream state; 1: the one-block kernel where it applies; 2: device-wide
         h.scan_upload(xyz)
         got = h.debug_scan_order()
         assert np.array_equal(got, _expected_order(xyz, 0.6))
