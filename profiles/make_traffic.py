@@ -20,7 +20,7 @@ def main(args):
         col = {n: i for i, n in enumerate(hdr)}
         per = {}
         for r in rows[2:]:
-            name = r[col["Kernel Name"]].split("<")[0].split("(")[0]
+            name = r[col["Kernel Name"]].split("<")[0].split("(")[0].replace("void ", "").replace("flb::", "").strip()
             tot = 0.0
             for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(r[col[m]].replace(",", "")) * UNIT.get(units[col[m]], 1)
