@@ -198,6 +198,7 @@ struct flb_handle {
     DevBuf<unsigned char> scan_cub_tmp;                 // the upload's own sort scratch (cub_tmp belongs to `stream`)
     int pers_sms = 0;                                   // SMs the persistent kernels may fill (one is left to the scan stream)
     int scan_sort_mode = 0;                             // 0 auto, 1 one-block ordering kernel, 2 device-wide sort (flb_debug_set_scan_sort)
+    bool sort_attr_set[3] = {false, false, false};      // dynamic shared memory opt-in of the three k_scan_sort_block instances
 
     // LIO exports (lazily allocated)
     DevBuf<float> x_world, x_nn_d2, x_pd2, x_pabcd;
@@ -841,7 +842,7 @@ template <int kScanSortBlock, int ITEMS>
 static int launch_scan_sort_block(flb_handle* h, cudaStream_t ss, int N, const float lo[3], float inv_cell) {
     using Sort = cub::BlockRadixSort<unsigned, kScanSortBlock, ITEMS, int, 6>;
     const size_t smem = std::max(sizeof(typename Sort::TempStorage), (size_t)kScanSortBlock * ITEMS * sizeof(unsigned));
-    static bool attr_set = false;       // per process is enough: one device per process (flb_create enforces nothing else here)
+    bool& attr_set = h->sort_attr_set[ITEMS == 17 ? 0 : (ITEMS == 33 ? 1 : 2)];      // per handle: the attribute is per device
     if (!attr_set) {
         FLB_CUDA(h, cudaFuncSetAttribute(k_scan_sort_block<kScanSortBlock, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
