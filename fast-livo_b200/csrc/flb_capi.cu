@@ -1,6 +1,7 @@
 // flb_capi.cu -- the C ABI of include/fastlivo_b200.h over the sm_100a kernels.
-// Host side is plain C++ (no Eigen / PCL / torch); the handle owns device memory,
-// one stream, CUDA events and an optional NCCL communicator (dlopen'ed lazily).
+// Host side is plain C++ (no Eigen / PCL / torch); the handle owns device memory, three streams (updates; image + patch
+// copies; scan copy + ordering -- every input has two device sets, so an upload never waits for the update that is
+// running: DESIGN.md section 4.8), CUDA events and an optional NCCL communicator (dlopen'ed lazily).
 #include "../../include/fastlivo_b200.h"
 
 #include <cuda_runtime.h>

@@ -11,7 +11,13 @@
 //   persistent      one cooperative launch per update: worker blocks run the passes, ONE leader block (no
 //                   points / patches of its own) reduces, solves and publishes the next pose as a flagged
 //                   packet the workers poll (k_lio_update_persistent / k_vio_update_persistent)
-//   kernel-per-pass k_*_pass + k_*_finalize (one block running the same leader code)
+//   kernel-per-pass k_*_pass + k_*_finalize (one block running the same leader code); with blockIdx.y = frame the same
+//                   bodies are the batched-frames kernels (k_*_pass_batched / k_*_finalize_batched)
+// What sits OFF the critical path of a VIO pass: the exact sequential float sum over the
+// per-patch errors (the leader publishes the accept branch before it is known and discards the running pass if it
+// says "reject") and the exact 64-step chain inside a patch (run by the worker after its block has arrived; the leader
+// polls self-validating {tag : error} units).  Multi-GPU: the same units and 16-byte {payload, tag} lines written
+// straight into the peers' mailboxes over NVLink (p2p_exchange), no separate flag, no fence.
 // No tensor cores: nothing here is a dense contraction.  No floating-point atomics: every reduction
 // has a fixed order, so results are bit-reproducible run to run and identical across ranks.
 #pragma once
